@@ -1,0 +1,95 @@
+"""Seeded synthetic inputs for the decode hot path: emissions, unique-spelling
+lexicons and well-formed back-off ARPA files. numpy only; used by tests/ and bench.py.
+"""
+import os
+
+import numpy as np
+
+
+def emissions(B, T, N, seed=1234, sigma=1.0):
+    """emis[b,t,:] = log_softmax(sigma * z), z ~ N(0,1), fp32, row-major [B,T,N]."""
+    rng = np.random.default_rng(seed)
+    z = rng.standard_normal((B, T, N), dtype=np.float32) * np.float32(sigma)
+    m = z.max(axis=-1, keepdims=True)
+    lse = m + np.log(np.exp(z - m).sum(axis=-1, keepdims=True, dtype=np.float32))
+    return (z - lse).astype(np.float32)
+
+
+def lexicon(W, N, min_len=2, max_len=5, seed=7, exclude=()):
+    """W distinct spellings (so every terminal trie node has exactly one label: no homophone
+    ties), tokens uniform in [0,N) minus `exclude` (sil / blank)."""
+    rng = np.random.default_rng(seed)
+    allowed = np.array([t for t in range(N) if t not in set(exclude)], dtype=np.int32)
+    seen, out = set(), []
+    while len(out) < W:
+        need = W - len(out)
+        lens = rng.integers(min_len, max_len + 1, size=need + 16)
+        toks = allowed[rng.integers(0, len(allowed), size=(need + 16, max_len))]
+        for L, row in zip(lens, toks):
+            sp = tuple(int(x) for x in row[:L])
+            if sp not in seen:
+                seen.add(sp)
+                out.append(np.array(sp, dtype=np.int32))
+                if len(out) == W:
+                    break
+    return out
+
+
+def word_names(W):
+    return [f"w{i}" for i in range(W)]
+
+
+def write_arpa(path, W, order=4, counts=None, seed=11, with_unk=True):
+    """Well-formed synthetic back-off LM over words w0..w{W-1} (+ <unk>, <s>, </s>): every
+    n-gram's (n-1)-word prefix is itself listed, log10 probs in [-6,-0.1], back-offs in [-1,0]
+    (none on the highest order). Returns the list of n-gram counts per order."""
+    rng = np.random.default_rng(seed)
+    counts = list(counts or [])
+    vocab = (["<unk>"] if with_unk else []) + ["<s>", "</s>"] + word_names(W)
+    V = len(vocab)
+    bos = vocab.index("<s>")
+    eos = vocab.index("</s>")
+    levels = []  # levels[k] = int array [n_k, k+1] of vocab ids
+    uni = np.arange(V, dtype=np.int64)[:, None]
+    levels.append(uni)
+    for k in range(1, order):
+        want = counts[k] if k < len(counts) else max(1, len(levels[-1]) // 2)
+        prev = levels[-1]
+        # contexts must not end in </s>; extend a random existing (k)-gram by one word
+        ok = prev[prev[:, -1] != eos]
+        pick = ok[rng.integers(0, len(ok), size=int(want * 1.15) + 8)]
+        nxt = rng.integers(0, V, size=len(pick))
+        nxt[nxt == bos] = eos
+        cand = np.concatenate([pick, nxt[:, None]], axis=1)
+        cand = np.unique(cand, axis=0)
+        rng.shuffle(cand)
+        levels.append(cand[:want])
+    with open(path, "w") as f:
+        f.write("\\data\\\n")
+        for k, lv in enumerate(levels):
+            f.write(f"ngram {k + 1}={len(lv)}\n")
+        for k, lv in enumerate(levels):
+            f.write(f"\n\\{k + 1}-grams:\n")
+            probs = -(rng.random(len(lv)) * 5.9 + 0.1)
+            bows = -rng.random(len(lv))
+            last = k == order - 1
+            lines = []
+            for i, row in enumerate(lv):
+                ws = " ".join(vocab[j] for j in row)
+                if k == 0 and vocab[row[0]] == "<s>":
+                    lines.append(f"-99\t{ws}\t{bows[i]:.6f}\n")
+                elif last or vocab[row[-1]] == "</s>":
+                    lines.append(f"{probs[i]:.6f}\t{ws}\n")
+                else:
+                    lines.append(f"{probs[i]:.6f}\t{ws}\t{bows[i]:.6f}\n")
+            f.writelines(lines)
+        f.write("\n\\end\\\n")
+    return [len(lv) for lv in levels]
+
+
+def cache_dir():
+    import tempfile
+
+    d = os.environ.get("TEXT_B200_CACHE", os.path.join(tempfile.gettempdir(), "text_b200_cache"))
+    os.makedirs(d, exist_ok=True)
+    return d
