@@ -1,0 +1,140 @@
+/* flt_decoder.h — C-ABI of the B200-native beam-search decode hot path.
+ *
+ * Drop-in boundary for flashlight/text's LexiconDecoder / LexiconFreeDecoder decode path.
+ * Plain pointers and sizes only (no torch / STL types). Every entry point names the reference
+ * interface it replaces (paths relative to the reference root, flashlight/lib/text/...).
+ * All functions return 0 on success, non-zero on error (message: flt_last_error(), thread-local);
+ * nothing throws across this boundary. The C++ mirror classes (text_b200/csrc/host/) map codes
+ * back to the exception types the reference throws.
+ *
+ * Threading: a decoder handle owns one CUDA stream and is single-owner, like the reference's
+ * decoders (decoder/Utils.h:60-63). Tries and LMs are immutable once a decoder is created from
+ * them and may be shared by several decoders.
+ */
+#ifndef FLT_DECODER_H
+#define FLT_DECODER_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLT_OK 0
+#define FLT_ERR_INVALID 1      /* std::invalid_argument in the C++ mirror            */
+#define FLT_ERR_OUT_OF_RANGE 2 /* std::out_of_range   (Trie.cpp:31-34)                */
+#define FLT_ERR_RUNTIME 3      /* std::runtime_error  (lm/KenLM.cpp:36,40,67)         */
+#define FLT_ERR_CUDA 4         /* CUDA runtime failure / no device                   */
+#define FLT_ERR_UNSUPPORTED 5  /* configuration not implemented on the device path   */
+
+typedef struct flt_trie flt_trie;
+typedef struct flt_lm flt_lm;
+typedef struct flt_decoder flt_decoder;
+
+/* CriterionType, decoder/Decoder.h:16 */
+#define FLT_CRITERION_ASG 0
+#define FLT_CRITERION_CTC 1
+/* SmearingMode, decoder/Trie.h:21-25 */
+#define FLT_SMEAR_NONE 0
+#define FLT_SMEAR_MAX 1
+#define FLT_SMEAR_LOGADD 2
+
+/* LexiconDecoderOptions (decoder/LexiconDecoder.h:21-31); LexiconFreeDecoderOptions
+ * (decoder/LexiconFreeDecoder.h:20-28) is the same minus wordScore / unkScore, which the
+ * lexicon-free decoder ignores. */
+typedef struct {
+  int32_t beamSize;
+  int32_t beamSizeToken;
+  double beamThreshold;
+  double lmWeight;
+  double wordScore;
+  double unkScore;
+  double silScore;
+  int32_t logAdd;
+  int32_t criterionType;
+} flt_options;
+
+const char* flt_last_error(void);
+
+/* ---- Trie: decoder/Trie.h:66-86 (Trie::Trie / insert / search / smear). Built on the host with
+ * the reference's semantics (<= 6 labels per node, Trie.cpp:40-46; out-of-range token ->
+ * FLT_ERR_OUT_OF_RANGE, Trie.cpp:31-34), flattened to CSR tables in HBM when the first decoder
+ * is created from it. */
+int flt_trie_create(int32_t maxChildren, int32_t rootIdx, flt_trie** out);
+int flt_trie_insert(flt_trie* trie, const int32_t* indices, int32_t n, int32_t label, float score);
+int flt_trie_smear(flt_trie* trie, int32_t mode);
+/* found = 0/1; maxScore / labels (<= 6) / scores of the node reached by `indices` */
+int flt_trie_search(const flt_trie* trie, const int32_t* indices, int32_t n, int32_t* found,
+                    float* maxScore, int32_t* nLabels, int32_t* labels6, float* scores6);
+int flt_trie_num_nodes(const flt_trie* trie, int64_t* out);
+void flt_trie_destroy(flt_trie* trie);
+
+/* ---- LM: decoder/lm/LM.h:52-85. Two device-resident models:
+ *   zero  = ZeroLM (lm/ZeroLM.cpp:14-26): score 0, a child state per (state, index)
+ *   ngram = the KenLM adapter's role (lm/KenLM.cpp:32-83) for ARPA back-off models: log10 scores,
+ *           usr index -> LM vocabulary map built from `usrWords` (OOV -> <unk>, id 0),
+ *           start = <s> context, finish scores </s>. KenLM binary files are not supported. */
+int flt_lm_zero_create(flt_lm** out);
+int flt_lm_ngram_load_arpa(const char* path, const char* const* usrWords, int32_t nUsrWords,
+                           flt_lm** out);
+/* LM::start(false) then LM::score per index (and LM::finish when withFinish): host-side query used
+ * for Trie insertion scores (test/decoder/DecoderTest.cpp:126-141) and tests. out[n(+1)]. */
+int flt_lm_score_seq(const flt_lm* lm, const int32_t* usrIdx, int32_t n, int32_t withFinish,
+                     float* out);
+void flt_lm_destroy(flt_lm* lm);
+
+/* ---- Decoders: LexiconFreeDecoder(opt, lm, sil, blank, transitions)
+ * (decoder/LexiconFreeDecoder.h:102-112) and LexiconDecoder(opt, trie, lm, sil, blank, unk,
+ * transitions, isLmToken) (decoder/LexiconDecoder.h:117-133). `device` = CUDA ordinal. */
+int flt_decoder_create_lexfree(const flt_options* opt, const flt_lm* lm, int32_t sil, int32_t blank,
+                               const float* transitions, int64_t nTransitions, int32_t device,
+                               flt_decoder** out);
+int flt_decoder_create_lexicon(const flt_options* opt, const flt_trie* trie, const flt_lm* lm,
+                               int32_t sil, int32_t blank, int32_t unk, const float* transitions,
+                               int64_t nTransitions, int32_t isLmToken, int32_t device,
+                               flt_decoder** out);
+void flt_decoder_destroy(flt_decoder* dec);
+
+/* How many of the final hypotheses are materialised (tokens / words backtrace) per utterance by
+ * flt_decode_batch*. Default: beamSize, i.e. everything getAllFinalHypothesis returns. */
+int flt_decoder_set_nbest(flt_decoder* dec, int32_t nbest);
+
+/* Decoder::decode (decoder/Decoder.h:51-57: decodeBegin + decodeStep + decodeEnd +
+ * getAllFinalHypothesis) for B utterances at once. `emissions` is row-major [B,T,N] fp32
+ * (e[(b*T+t)*N+n], decoder/LexiconDecoder.cpp:50,69), HOST or DEVICE memory (detected with
+ * cudaPointerGetAttributes), borrowed until the call returns. `lengths` (host, may be NULL =
+ * all T) gives the number of valid frames per utterance. The n-best lists stay on the device
+ * until flt_nbest_copy. B = 1 is the reference's single-utterance decode(). */
+int flt_decode_batch(flt_decoder* dec, const float* emissions, int32_t B, int32_t T, int32_t N,
+                     const int32_t* lengths);
+/* Same, device emissions, enqueue only (no host synchronisation): for timing on a stream. */
+int flt_decode_batch_async(flt_decoder* dec, const float* dEmissions, int32_t B, int32_t T,
+                           int32_t N, const int32_t* dLengths);
+int flt_decoder_synchronize(flt_decoder* dec);
+/* cudaStream_t the decoder enqueues on (for CUDA-event timing by the caller). */
+void* flt_decoder_stream(flt_decoder* dec);
+
+/* getAllFinalHypothesis (decoder/Utils.h:229-266) for the last batch: for utterance b, hypothesis
+ * r < counts[b] (sorted by score, best first), tokens/words hold T+2 entries
+ * (seed, T frames, finish record; -1 padded past lengths[b]+2):
+ *   tokens[(b*nbest + r)*(T+2) + i], words[...], scores[(b*nbest + r)*3 + {0: score,
+ *   1: emittingModelScore, 2: lmScore}]. nbest <= beamSize; host buffers. counts[b] is the
+ * total number of final hypotheses (may exceed nbest). */
+int flt_nbest_copy(flt_decoder* dec, int32_t nbest, int32_t* tokens, int32_t* words,
+                   double* scores, int32_t* counts);
+
+/* Introspection for benchmarks: kernels launched by the last flt_decode_batch* call, and device
+ * bytes currently held by the decoder workspace. */
+int flt_decoder_last_launches(const flt_decoder* dec, int32_t* out);
+int flt_decoder_workspace_bytes(const flt_decoder* dec, int64_t* out);
+
+/* Stand-alone entry to the token-beam select kernel (decoder/LexiconFreeDecoder.cpp:39-51:
+ * iota + partial_sort of one emission row), for kernel-level tests and roofline timing.
+ * dEmissions [rows,N] device; outputs device: dTok/dVal [rows,M] sorted by value descending. */
+int flt_topm_rows(const float* dEmissions, int64_t rows, int32_t N, int32_t M, int32_t* dTok,
+                  float* dVal, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLT_DECODER_H */

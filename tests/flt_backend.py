@@ -1,0 +1,59 @@
+"""Adapter giving the product's C-ABI (text_b200.capi.Api) the same surface as oracle.pyoracle.Oracle
+so `cases.Built` can instantiate one spec on the oracle and on the product.
+
+`kind="cuda"` loads the shipped CUDA library (GPU tests). `kind="model"` loads tests/model's g++
+build of the same kernel sources (a GPU-less logic harness, NOT a product path)."""
+import os
+import subprocess
+
+import numpy as np
+
+from text_b200 import capi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+MODEL_LIB = os.path.join(_HERE, "model", "libflt_model.so")
+
+
+def build_model():
+    subprocess.run(["make", "-s", "-C", os.path.join(_HERE, "model")], check=True)
+
+
+class FltBackend:
+    def __init__(self, kind="cuda"):
+        if kind == "model":
+            build_model()
+            self.api = capi.Api(MODEL_LIB)
+        else:
+            self.api = capi.Api()
+        self.kind = kind
+        a = self.api
+        for name in ("trie_create", "trie_insert", "trie_smear", "trie_search", "trie_destroy",
+                     "lm_zero", "lm_arpa", "lm_score_seq", "lm_destroy", "decoder_destroy"):
+            setattr(self, name, getattr(a, name))
+
+    @staticmethod
+    def _opt(o):
+        return capi.Options(o.beamSize, o.beamSizeToken, o.beamThreshold, o.lmWeight, o.wordScore,
+                            o.unkScore, o.silScore, o.logAdd, o.criterion)
+
+    def decoder_lexfree(self, opt, lm, sil, blank, transitions=None):
+        return self.api.decoder_lexfree(self._opt(opt), lm, sil, blank, transitions)
+
+    def decoder_lexicon(self, opt, trie, lm, sil, blank, unk, transitions=None, is_lm_token=False):
+        return self.api.decoder_lexicon(self._opt(opt), trie, lm, sil, blank, unk, transitions,
+                                        is_lm_token)
+
+    def decode(self, dec, emissions, max_hyp):
+        """single utterance [T,N] -> same dict as pyoracle.Oracle.decode"""
+        return self.decode_batch(dec, np.asarray(emissions)[None], max_hyp)[0]
+
+    def decode_batch(self, dec, emissions, max_hyp, lengths=None):
+        B, T, N = self.api.decode_batch(dec, emissions, lengths)
+        r = self.api.nbest(dec, B, T, max_hyp)
+        out = []
+        for b in range(B):
+            n = min(int(r["counts"][b]), max_hyp)
+            L = T + 2 if lengths is None else int(lengths[b]) + 2
+            out.append(dict(n=n, scores=r["scores"][b, :n], tokens=r["tokens"][b, :n, :L],
+                            words=r["words"][b, :n, :L], total=int(r["counts"][b])))
+        return out

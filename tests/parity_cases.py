@@ -1,0 +1,88 @@
+"""The parity case list shared by the GPU tests (product CUDA library vs oracle) and the CPU
+logic-harness tests (tests/model build of the same kernels vs oracle)."""
+import os
+
+import numpy as np
+
+from cases import spec_lexfree, spec_lexicon
+from oracle import pyoracle as po
+from text_b200 import synth
+
+NEG_INF = float("-inf")
+
+
+def _arpa(name, W, order, counts, seed):
+    path = os.path.join(synth.cache_dir(), name)
+    if not os.path.exists(path):
+        synth.write_arpa(path, W, order=order, counts=counts, seed=seed)
+    return path, synth.word_names(W) + ["<unk>"]
+
+
+def lexfree_cases():
+    # name, N, T, B, beam, bst, thr, criterion, sil_score, sigma
+    rows = [
+        ("cfg1_shape", 29, 200, 2, 10, 29, 1e9, po.CTC, 0.0, 1.0),
+        ("bst_small", 29, 80, 2, 10, 5, 1e9, po.CTC, 0.0, 1.0),
+        ("thr_silneg", 29, 80, 2, 10, 29, 8.0, po.CTC, -0.5, 1.0),
+        ("sil_positive", 40, 60, 2, 12, 40, 1e9, po.CTC, 0.7, 1.0),
+        ("sil_positive_bst", 40, 60, 2, 12, 9, 20.0, po.CTC, 0.7, 2.0),
+        ("asg", 40, 60, 2, 12, 40, 1e9, po.ASG, 0.0, 1.0),
+        ("asg_bst_thr", 40, 60, 2, 12, 6, 20.0, po.ASG, -1.0, 1.0),
+        ("cfg2_scaled_bstN", 500, 40, 2, 50, 500, 1e9, po.CTC, 0.0, 1.0),
+        ("cfg2_scaled_bstK", 500, 40, 2, 50, 50, 1e9, po.CTC, 0.0, 1.0),
+        ("chunk_path_bstN", 5000, 12, 2, 50, 5000, 1e9, po.CTC, 0.0, 1.0),
+        ("chunk_path_bst300", 5000, 12, 2, 20, 300, 1e9, po.CTC, 0.0, 1.0),
+        ("peaky", 300, 60, 2, 30, 300, 25.0, po.CTC, 0.0, 4.0),
+        ("tiny_vocab", 3, 30, 2, 4, 3, 1e9, po.CTC, 0.0, 1.0),
+        ("one_frame", 10, 1, 2, 5, 10, 1e9, po.CTC, 0.0, 1.0),
+        ("beam1", 20, 30, 2, 1, 20, 1e9, po.CTC, 0.0, 1.0),
+        ("beam_gt_cands", 6, 10, 2, 200, 6, 1e9, po.CTC, 0.0, 1.0),
+    ]
+    out = []
+    for name, N, T, B, beam, bst, thr, crit, sil_score, sigma in rows:
+        tr = np.random.default_rng(5).random(N * N, dtype=np.float32) if crit == po.ASG else None
+        spec = spec_lexfree(N, beam, bst, thr, sil=0, blank=(N - 1 if crit == po.CTC else -1),
+                            criterion=crit, sil_score=sil_score, transitions=tr)
+        em = synth.emissions(B, T, N, seed=1000 + len(out), sigma=sigma)
+        out.append((name, spec, em))
+    return out
+
+
+def lexicon_cases():
+    # name, N, T, B, W, (minlen,maxlen), beam, bst, thr, criterion, sil_score, word_score, unk_score, lm
+    rows = [
+        ("zero_ctc", 30, 60, 2, 200, (2, 4), 20, 30, 1e9, po.CTC, 0.0, 0.0, NEG_INF, "zero"),
+        ("zero_ctc_bst_thr", 30, 60, 2, 200, (2, 4), 20, 8, 15.0, po.CTC, -0.2, 1.0, NEG_INF, "zero"),
+        ("zero_ctc_silpos", 30, 60, 2, 200, (2, 4), 20, 30, 1e9, po.CTC, 0.4, 0.3, NEG_INF, "zero"),
+        ("zero_ctc_words1", 30, 60, 2, 200, (1, 4), 20, 30, 1e9, po.CTC, 0.0, 0.37, NEG_INF, "zero"),
+        ("zero_unk", 30, 60, 2, 200, (2, 4), 20, 30, 1e9, po.CTC, 0.0, 0.0, -2.0, "zero"),
+        ("zero_asg", 30, 50, 2, 200, (2, 4), 20, 30, 1e9, po.ASG, -0.3, 0.7, NEG_INF, "zero"),
+        ("cfg3_scaled_bstN", 200, 40, 2, 2000, (2, 4), 50, 200, 1e9, po.CTC, 0.0, 0.0, NEG_INF, "zero"),
+        ("cfg3_scaled_bstK", 200, 40, 2, 2000, (2, 4), 50, 50, 25.0, po.CTC, 0.0, 0.0, NEG_INF, "zero"),
+        ("cfg3_mid", 2000, 30, 2, 20000, (2, 5), 100, 2000, 1e9, po.CTC, 0.0, 0.0, NEG_INF, "zero"),
+        ("arpa3_ctc", 40, 80, 2, 300, (1, 3), 40, 40, 30.0, po.CTC, 0.0, 0.5, NEG_INF, "arpa4"),
+        ("arpa3_ctc_bst", 40, 80, 2, 300, (1, 3), 40, 12, 30.0, po.CTC, -0.1, 0.5, NEG_INF, "arpa4"),
+        ("arpa_asg", 40, 60, 2, 300, (1, 3), 40, 40, 30.0, po.ASG, 0.0, 0.5, NEG_INF, "arpa4"),
+        ("arpa_unk", 40, 60, 2, 300, (2, 3), 30, 40, 30.0, po.CTC, 0.0, 0.5, -3.0, "arpa4"),
+        ("cfg4_scaled", 300, 60, 2, 3000, (2, 5), 200, 300, 25.0, po.CTC, 0.0, 0.0, NEG_INF, "arpa4big"),
+    ]
+    out = []
+    for (name, N, T, B, W, (mn, mx), beam, bst, thr, crit, sil_score, word_score, unk_score,
+         lm) in rows:
+        sp = synth.lexicon(W, N, mn, mx, seed=7, exclude=(0, N - 1))
+        if lm == "zero":
+            lmspec, lmw = ("zero",), 0.0
+        elif lm == "arpa4":
+            path, words = _arpa("p_small4.arpa", 300, 4, [0, 3000, 3000, 2000], 3)
+            lmspec, lmw = ("arpa", path, words), 1.5
+        else:
+            path, words = _arpa("p_mid4.arpa", 3000, 4, [0, 30000, 30000, 20000], 4)
+            lmspec, lmw = ("arpa", path, words), 2.0
+        tr = np.random.default_rng(5).random(N * N, dtype=np.float32) if crit == po.ASG else None
+        spec = spec_lexicon(N, beam, bst, sp, thr, sil=0, blank=(N - 1 if crit == po.CTC else -1),
+                            criterion=crit, sil_score=sil_score, lm_weight=lmw,
+                            word_score=word_score, unk_score=unk_score, lm=lmspec, transitions=tr,
+                            unk=W)
+        em = synth.emissions(B, T, N, seed=2000 + len(out), sigma=2.0)
+        out.append((name, spec, em))
+    return out

@@ -1,0 +1,238 @@
+"""ctypes binding of the C-ABI in include/flt_decoder.h (text_b200/lib/libflt_decoder.so).
+
+This is the only native entry into the product. There is no CPU implementation behind it: if the
+CUDA library is missing or no device is present, calls fail loudly (FltError / OSError).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libflt_decoder.so")
+
+OK, ERR_INVALID, ERR_OUT_OF_RANGE, ERR_RUNTIME, ERR_CUDA, ERR_UNSUPPORTED = range(6)
+CRITERION_ASG, CRITERION_CTC = 0, 1
+SMEAR_NONE, SMEAR_MAX, SMEAR_LOGADD = 0, 1, 2
+
+
+class Options(C.Structure):
+    """flt_options == LexiconDecoderOptions (decoder/LexiconDecoder.h:21-31)."""
+    _fields_ = [
+        ("beamSize", C.c_int32),
+        ("beamSizeToken", C.c_int32),
+        ("beamThreshold", C.c_double),
+        ("lmWeight", C.c_double),
+        ("wordScore", C.c_double),
+        ("unkScore", C.c_double),
+        ("silScore", C.c_double),
+        ("logAdd", C.c_int32),
+        ("criterionType", C.c_int32),
+    ]
+
+
+class FltError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[flt:{code}] {msg}")
+        self.code = code
+        self.msg = msg
+
+
+SYMBOLS = {
+    # name: (restype, argtypes)
+    "flt_last_error": (C.c_char_p, []),
+    "flt_trie_create": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "flt_trie_insert": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_float]),
+    "flt_trie_smear": (C.c_int, [C.c_void_p, C.c_int32]),
+    "flt_trie_search": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32),
+                                  C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                  C.POINTER(C.c_float)]),
+    "flt_trie_num_nodes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "flt_trie_destroy": (None, [C.c_void_p]),
+    "flt_lm_zero_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "flt_lm_ngram_load_arpa": (C.c_int, [C.c_char_p, C.POINTER(C.c_char_p), C.c_int32,
+                                         C.POINTER(C.c_void_p)]),
+    "flt_lm_score_seq": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_int32,
+                                   C.POINTER(C.c_float)]),
+    "flt_lm_destroy": (None, [C.c_void_p]),
+    "flt_decoder_create_lexfree": (C.c_int, [C.POINTER(Options), C.c_void_p, C.c_int32, C.c_int32,
+                                             C.POINTER(C.c_float), C.c_int64, C.c_int32,
+                                             C.POINTER(C.c_void_p)]),
+    "flt_decoder_create_lexicon": (C.c_int, [C.POINTER(Options), C.c_void_p, C.c_void_p, C.c_int32,
+                                             C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int64,
+                                             C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "flt_decoder_destroy": (None, [C.c_void_p]),
+    "flt_decoder_set_nbest": (C.c_int, [C.c_void_p, C.c_int32]),
+    "flt_decode_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                   C.POINTER(C.c_int32)]),
+    "flt_decode_batch_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_void_p]),
+    "flt_decoder_synchronize": (C.c_int, [C.c_void_p]),
+    "flt_decoder_stream": (C.c_void_p, [C.c_void_p]),
+    "flt_nbest_copy": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                 C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+    "flt_decoder_last_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "flt_decoder_workspace_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "flt_topm_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                C.c_void_p]),
+}
+
+_libs = {}
+
+
+def load(path=None):
+    """dlopen the C-ABI library and type its entry points. `path` other than the product library is
+    used only by tests (the GPU-less logic harness, tests/model)."""
+    path = path or LIB_PATH
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise OSError(f"{path} not found: build it with `make -C text_b200/csrc` "
+                      "(there is no CPU fallback)")
+    lib = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        f = getattr(lib, name)  # AttributeError if the library does not export the symbol
+        f.restype = res
+        f.argtypes = args
+    _libs[path] = lib
+    return lib
+
+
+def _i32p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _f32p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class Api:
+    """Object wrapper over the C entry points; raises FltError on non-zero status."""
+
+    def __init__(self, path=None, device=0):
+        self.lib = load(path)
+        self.device = device
+
+    def _ck(self, code):
+        if code != OK:
+            raise FltError(code, (self.lib.flt_last_error() or b"").decode())
+
+    # ---- Trie
+    def trie_create(self, max_children, root_idx):
+        h = C.c_void_p()
+        self._ck(self.lib.flt_trie_create(max_children, root_idx, C.byref(h)))
+        return h
+
+    def trie_insert(self, trie, indices, label, score):
+        a = np.ascontiguousarray(indices, np.int32)
+        self._ck(self.lib.flt_trie_insert(trie, _i32p(a), len(a), label, score))
+
+    def trie_smear(self, trie, mode):
+        self._ck(self.lib.flt_trie_smear(trie, mode))
+
+    def trie_search(self, trie, indices):
+        a = np.ascontiguousarray(indices, np.int32)
+        found, ms, nl = C.c_int32(), C.c_float(), C.c_int32()
+        labels = np.zeros(6, np.int32)
+        scores = np.zeros(6, np.float32)
+        self._ck(self.lib.flt_trie_search(trie, _i32p(a), len(a), C.byref(found), C.byref(ms),
+                                          C.byref(nl), _i32p(labels), _f32p(scores)))
+        if not found.value:
+            return None
+        return dict(maxScore=ms.value, labels=labels[:nl.value].copy(), scores=scores[:nl.value].copy())
+
+    def trie_num_nodes(self, trie):
+        n = C.c_int64()
+        self._ck(self.lib.flt_trie_num_nodes(trie, C.byref(n)))
+        return n.value
+
+    def trie_destroy(self, trie):
+        self.lib.flt_trie_destroy(trie)
+
+    # ---- LM
+    def lm_zero(self):
+        h = C.c_void_p()
+        self._ck(self.lib.flt_lm_zero_create(C.byref(h)))
+        return h
+
+    def lm_arpa(self, path, words):
+        arr = (C.c_char_p * len(words))(*[w.encode() for w in words])
+        h = C.c_void_p()
+        self._ck(self.lib.flt_lm_ngram_load_arpa(path.encode(), arr, len(words), C.byref(h)))
+        return h
+
+    def lm_score_seq(self, lm, usr_idx, with_finish=False):
+        a = np.ascontiguousarray(usr_idx, np.int32)
+        out = np.zeros(len(a) + 1, np.float32)
+        self._ck(self.lib.flt_lm_score_seq(lm, _i32p(a), len(a), int(with_finish), _f32p(out)))
+        return out if with_finish else out[:-1]
+
+    def lm_destroy(self, lm):
+        self.lib.flt_lm_destroy(lm)
+
+    # ---- decoders
+    def decoder_lexfree(self, opt, lm, sil, blank, transitions=None):
+        tr = np.ascontiguousarray(transitions if transitions is not None else [], np.float32)
+        h = C.c_void_p()
+        self._ck(self.lib.flt_decoder_create_lexfree(C.byref(opt), lm, sil, blank, _f32p(tr), tr.size,
+                                                     self.device, C.byref(h)))
+        return h
+
+    def decoder_lexicon(self, opt, trie, lm, sil, blank, unk, transitions=None, is_lm_token=False):
+        tr = np.ascontiguousarray(transitions if transitions is not None else [], np.float32)
+        h = C.c_void_p()
+        self._ck(self.lib.flt_decoder_create_lexicon(C.byref(opt), trie, lm, sil, blank, unk,
+                                                     _f32p(tr), tr.size, int(is_lm_token),
+                                                     self.device, C.byref(h)))
+        return h
+
+    def decoder_destroy(self, dec):
+        self.lib.flt_decoder_destroy(dec)
+
+    def set_nbest(self, dec, nbest):
+        self._ck(self.lib.flt_decoder_set_nbest(dec, nbest))
+
+    def decode_batch(self, dec, emissions, lengths=None):
+        """emissions: C-contiguous fp32 numpy array [B,T,N] (host)."""
+        e = np.ascontiguousarray(emissions, np.float32)
+        B, T, N = e.shape
+        ln = None if lengths is None else np.ascontiguousarray(lengths, np.int32)
+        self._ck(self.lib.flt_decode_batch(dec, e.ctypes.data, B, T, N,
+                                           None if ln is None else _i32p(ln)))
+        return B, T, N
+
+    def decode_batch_ptr(self, dec, ptr, B, T, N, lengths=None):
+        """Raw pointer (host or device address) form, as the reference's Python decode takes."""
+        ln = None if lengths is None else np.ascontiguousarray(lengths, np.int32)
+        self._ck(self.lib.flt_decode_batch(dec, ptr, B, T, N, None if ln is None else _i32p(ln)))
+
+    def decode_batch_async(self, dec, dev_ptr, B, T, N, dev_lengths_ptr=None):
+        self._ck(self.lib.flt_decode_batch_async(dec, dev_ptr, B, T, N, dev_lengths_ptr))
+
+    def synchronize(self, dec):
+        self._ck(self.lib.flt_decoder_synchronize(dec))
+
+    def stream(self, dec):
+        return self.lib.flt_decoder_stream(dec)
+
+    def nbest(self, dec, B, T, nbest):
+        tokens = np.empty((B, nbest, T + 2), np.int32)
+        words = np.empty((B, nbest, T + 2), np.int32)
+        scores = np.empty((B, nbest, 3), np.float64)
+        counts = np.empty(B, np.int32)
+        self._ck(self.lib.flt_nbest_copy(dec, nbest, _i32p(tokens), _i32p(words),
+                                         scores.ctypes.data_as(C.POINTER(C.c_double)), _i32p(counts)))
+        return dict(tokens=tokens, words=words, scores=scores, counts=counts)
+
+    def last_launches(self, dec):
+        n = C.c_int32()
+        self._ck(self.lib.flt_decoder_last_launches(dec, C.byref(n)))
+        return n.value
+
+    def workspace_bytes(self, dec):
+        n = C.c_int64()
+        self._ck(self.lib.flt_decoder_workspace_bytes(dec, C.byref(n)))
+        return n.value
+
+    def topm_rows(self, dev_emis_ptr, rows, N, M, dev_tok_ptr, dev_val_ptr, stream=None):
+        self._ck(self.lib.flt_topm_rows(dev_emis_ptr, rows, N, M, dev_tok_ptr, dev_val_ptr, stream))

@@ -1,0 +1,1038 @@
+// flt_abi.cu — implementation of include/flt_decoder.h: host-side Trie / ARPA builders with the
+// reference's semantics, table upload, launch planning, and the three kernels (token-beam select,
+// beam step, n-best backtrace). Compiled by nvcc for sm_100a into text_b200/lib/libflt_decoder.so.
+// (tests/model builds the same file with g++ -DFLT_HOST_MODEL as a GPU-less logic harness; see
+// spmd.h. That build is not shipped and nothing in the package loads it.)
+#include "../../include/flt_decoder.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <fstream>
+#include <limits>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "runtime.h"
+#include "beam_core.h"
+#include "topm_core.h"
+
+using namespace flt;
+
+/* =============================================================================== kernels ==== */
+#if FLT_DEVICE_BUILD
+__global__ void __launch_bounds__(256) flt_k_topm(TopMCfg c, TopMArgs a) {
+  extern __shared__ __align__(16) char smem[];
+  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
+  topmCta(cta, c, a, smem);
+}
+__global__ void __launch_bounds__(256) flt_k_decode(DecCfg c, BatchArgs a) {
+  extern __shared__ __align__(16) char smem[];
+  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
+  decodeCta(cta, c, a, smem);
+}
+__global__ void flt_k_backtrace(BacktraceArgs a) {
+  const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item < (long long)a.B * a.nbest) backtraceItem(a, item);
+}
+#endif
+
+namespace {
+
+thread_local std::string gErr;
+int fail(int code, const std::string& msg) {
+  gErr = msg;
+  return code;
+}
+struct FltError : std::runtime_error {
+  int code;
+  FltError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+constexpr int kThreads = 256;
+constexpr int kTrieMaxLabel = 6; // decoder/Trie.h:19
+
+/* ------------------------------------------------------------------ launches ---------- */
+void launchTopM(const TopMCfg& c, const TopMArgs& a, int grid, size_t smem, rt::Stream s) {
+#if FLT_DEVICE_BUILD
+  flt_k_topm<<<grid, kThreads, smem, s>>>(c, a);
+  FLT_RT_TRY(cudaGetLastError());
+#else
+  std::vector<char> sm(smem + 16);
+  for (int b = 0; b < grid; ++b) {
+    Cta cta{0, 1, b, grid};
+    topmCta(cta, c, a, sm.data());
+  }
+  (void)s;
+#endif
+}
+void launchDecode(const DecCfg& c, const BatchArgs& a, int grid, size_t smem, rt::Stream s) {
+#if FLT_DEVICE_BUILD
+  flt_k_decode<<<grid, kThreads, smem, s>>>(c, a);
+  FLT_RT_TRY(cudaGetLastError());
+#else
+  std::vector<char> sm(smem + 16);
+  for (int b = 0; b < grid; ++b) {
+    Cta cta{0, 1, b, grid};
+    decodeCta(cta, c, a, sm.data());
+  }
+  (void)s;
+#endif
+}
+void launchBacktrace(const BacktraceArgs& a, rt::Stream s) {
+  const long long items = (long long)a.B * a.nbest;
+  if (items == 0) return;
+#if FLT_DEVICE_BUILD
+  flt_k_backtrace<<<(unsigned)((items + 127) / 128), 128, 0, s>>>(a);
+  FLT_RT_TRY(cudaGetLastError());
+#else
+  for (long long i = 0; i < items; ++i) backtraceItem(a, i);
+  (void)s;
+#endif
+}
+
+template <class T>
+T* upload(rt::DevBuf& buf, const std::vector<T>& v, rt::Stream s) {
+  buf.reserve(sizeof(T) * std::max<size_t>(v.size(), 1));
+  rt::h2d(buf.p, v.data(), sizeof(T) * v.size(), s);
+  return buf.as<T>();
+}
+
+} // namespace
+
+/* ================================================================================= Trie ===== */
+struct HNode {
+  std::map<int, int> kids; // token -> node, ascending (also the CSR edge order)
+  std::vector<int> labels;
+  std::vector<float> scores;
+  float maxScore = 0;
+};
+
+struct flt_trie {
+  int maxChildren, rootIdx;
+  std::vector<HNode> nodes;
+  // device image (built on first use)
+  mutable bool uploaded = false;
+  mutable TrieDev dev{};
+  mutable rt::DevBuf dChildOff, dChildTok, dChildNode, dMaxScore, dLabelOff, dLabels, dRootChild,
+      dRootLabTok;
+  mutable std::vector<int> rootChildHost;
+
+  static double logAdd(double a, double b) { // Trie.cpp:66-77
+    if (a < b) std::swap(a, b);
+    const double d = b - a;
+    if (d < -39.14) return a;
+    return a + std::log1p(std::exp(d));
+  }
+  void smearNode(int n, int mode) { // Trie.cpp:79-95; maxScore is a float after every step
+    nodes[n].maxScore = -std::numeric_limits<float>::infinity();
+    for (float s : nodes[n].scores) nodes[n].maxScore = (float)logAdd(nodes[n].maxScore, s);
+    for (auto& kv : nodes[n].kids) {
+      smearNode(kv.second, mode);
+      const float cm = nodes[kv.second].maxScore;
+      if (mode == FLT_SMEAR_LOGADD) nodes[n].maxScore = (float)logAdd(nodes[n].maxScore, cm);
+      else if (mode == FLT_SMEAR_MAX && cm > nodes[n].maxScore) nodes[n].maxScore = cm;
+    }
+  }
+  void ensureUploaded(rt::Stream s) const {
+    if (uploaded) return;
+    const int nn = (int)nodes.size();
+    std::vector<int> childOff(nn + 1, 0), childTok, childNode, labelOff(nn + 1, 0), labels;
+    std::vector<float> maxScore(nn);
+    for (int i = 0; i < nn; ++i) {
+      childOff[i] = (int)childTok.size();
+      for (auto& kv : nodes[i].kids) {
+        childTok.push_back(kv.first);
+        childNode.push_back(kv.second);
+      }
+      labelOff[i] = (int)labels.size();
+      for (int l : nodes[i].labels) labels.push_back(l);
+      maxScore[i] = nodes[i].maxScore;
+    }
+    childOff[nn] = (int)childTok.size();
+    labelOff[nn] = (int)labels.size();
+    rootChildHost.assign(std::max(maxChildren, 1), -1);
+    std::vector<int> rootLabTok;
+    for (auto& kv : nodes[0].kids) {
+      if (kv.first >= 0 && kv.first < maxChildren) rootChildHost[kv.first] = kv.second;
+      if (!nodes[kv.second].labels.empty()) rootLabTok.push_back(kv.first);
+    }
+    dev.nNodes = nn;
+    dev.childOff = upload(dChildOff, childOff, s);
+    dev.childTok = upload(dChildTok, childTok, s);
+    dev.childNode = upload(dChildNode, childNode, s);
+    dev.maxScore = upload(dMaxScore, maxScore, s);
+    dev.labelOff = upload(dLabelOff, labelOff, s);
+    dev.labels = upload(dLabels, labels, s);
+    dev.rootChild = upload(dRootChild, rootChildHost, s);
+    dev.nRootLab = (int)rootLabTok.size();
+    dev.rootLabTok = upload(dRootLabTok, rootLabTok, s);
+    rt::sync(s);
+    uploaded = true;
+  }
+  ~flt_trie() {
+    dChildOff.release(), dChildTok.release(), dChildNode.release(), dMaxScore.release();
+    dLabelOff.release(), dLabels.release(), dRootChild.release(), dRootLabTok.release();
+  }
+};
+
+/* =================================================================================== LM ===== */
+struct flt_lm {
+  int kind = 0; // 0 zero, 1 ngram
+  int order = 0, vocab = 0, bos = -1, eos = -1;
+  std::vector<F2> uni;
+  std::vector<uint64_t> keys[kMaxOrder + 1];
+  std::vector<F2> vals[kMaxOrder + 1];
+  std::vector<int> usr2lm;
+  LmDev host{}; // view over the host vectors (host-side scoring)
+  mutable bool uploaded = false;
+  mutable LmDev dev{};
+  mutable rt::DevBuf dUni, dUsr, dKeys[kMaxOrder + 1], dVals[kMaxOrder + 1];
+
+  void makeHostView() {
+    host = LmDev{};
+    host.kind = kind;
+    host.order = order;
+    host.vocab = vocab;
+    host.bos = bos;
+    host.eos = eos;
+    host.nUsr = (int)usr2lm.size();
+    host.usr2lm = usr2lm.data();
+    host.uni = uni.data();
+    for (int n = 2; n <= kMaxOrder; ++n) {
+      host.keys[n] = keys[n].empty() ? nullptr : keys[n].data();
+      host.vals[n] = vals[n].empty() ? nullptr : vals[n].data();
+      host.mask[n] = keys[n].empty() ? 0 : (uint32_t)keys[n].size() - 1;
+    }
+  }
+  void ensureUploaded(rt::Stream s) const {
+    if (uploaded) return;
+    dev = host;
+    if (kind == 1) {
+      dev.usr2lm = upload(dUsr, usr2lm, s);
+      dev.uni = upload(dUni, uni, s);
+      for (int n = 2; n <= kMaxOrder; ++n) {
+        if (keys[n].empty()) continue;
+        dev.keys[n] = upload(dKeys[n], keys[n], s);
+        dev.vals[n] = upload(dVals[n], vals[n], s);
+      }
+      rt::sync(s);
+    }
+    uploaded = true;
+  }
+  ~flt_lm() {
+    dUni.release(), dUsr.release();
+    for (int n = 0; n <= kMaxOrder; ++n) dKeys[n].release(), dVals[n].release();
+  }
+};
+
+namespace {
+
+// ARPA reader: vocabulary ids in unigram order with <unk> forced to id 0 (KenLM convention), log10
+// values kept as parsed floats, n-grams of order >= 2 hashed into per-order tables.
+void loadArpa(const std::string& path, const char* const* usrWords, int nUsr, flt_lm& lm) {
+  std::ifstream in(path);
+  if (!in) throw FltError(FLT_ERR_RUNTIME, "[KenLM] LM loading failed: cannot open " + path);
+  std::unordered_map<std::string, int> vocab;
+  std::vector<long> counts(kMaxOrder + 2, 0);
+  struct Entry {
+    uint64_t key;
+    F2 v;
+  };
+  std::vector<Entry> pending[kMaxOrder + 1];
+  std::string line;
+  bool inData = false;
+  int section = 0;
+  std::vector<std::string> toks;
+  lm.kind = 1;
+  while (std::getline(in, line)) {
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    if (line.empty()) continue;
+    if (line == "\\data\\") {
+      inData = true;
+      continue;
+    }
+    if (line == "\\end\\") break;
+    if (line[0] == '\\') {
+      section = atoi(line.c_str() + 1);
+      if (section < 1 || section > kMaxOrder)
+        throw FltError(FLT_ERR_RUNTIME, "[KenLM] unsupported n-gram order in " + line);
+      if (section == 1) {
+        vocab["<unk>"] = 0;
+        lm.uni.push_back(F2{-100.0f, 0.0f});
+      } else {
+        pending[section].reserve((size_t)counts[section]);
+      }
+      inData = false;
+      continue;
+    }
+    if (inData) {
+      if (line.compare(0, 6, "ngram ") == 0) {
+        const int n = atoi(line.c_str() + 6);
+        const size_t eq = line.find('=');
+        if (n >= 1 && n <= kMaxOrder && eq != std::string::npos) {
+          counts[n] = atol(line.c_str() + eq + 1);
+          lm.order = std::max(lm.order, n);
+        }
+      }
+      continue;
+    }
+    if (section == 0) continue;
+    toks.clear();
+    size_t p = 0;
+    while (p < line.size()) {
+      size_t q = line.find_first_of(" \t", p);
+      if (q == std::string::npos) q = line.size();
+      if (q > p) toks.emplace_back(line.substr(p, q - p));
+      p = q + 1;
+    }
+    if ((int)toks.size() < section + 1) continue;
+    F2 v;
+    v.x = strtof(toks[0].c_str(), nullptr);
+    v.y = (int)toks.size() > section + 1 ? strtof(toks[section + 1].c_str(), nullptr) : 0.0f;
+    if (section == 1) {
+      if (toks[1] == "<unk>") {
+        lm.uni[0] = v;
+      } else {
+        vocab[toks[1]] = (int)lm.uni.size();
+        lm.uni.push_back(v);
+      }
+    } else {
+      // chain over the words in reversed order (tables.h)
+      uint64_t h = 0;
+      for (int i = section; i >= 1; --i) {
+        auto it = vocab.find(toks[i]);
+        const int w = it == vocab.end() ? 0 : it->second;
+        h = i == section ? ngramChainStart(w) : ngramChainExtend(h, w);
+      }
+      pending[section].push_back(Entry{ngramFinalKey(h), v});
+    }
+  }
+  if (lm.order < 1 || lm.uni.empty()) throw FltError(FLT_ERR_RUNTIME, "[KenLM] LM loading failed: empty model");
+  auto b = vocab.find("<s>"), e = vocab.find("</s>");
+  if (b == vocab.end() || e == vocab.end())
+    throw FltError(FLT_ERR_RUNTIME, "[KenLM] LM vocabulary loading failed: missing <s> or </s>");
+  lm.bos = b->second;
+  lm.eos = e->second;
+  lm.vocab = (int)lm.uni.size();
+  for (int n = 2; n <= lm.order; ++n) {
+    if (pending[n].empty()) continue;
+    size_t cap = 16;
+    while (cap < pending[n].size() * 2) cap <<= 1;
+    lm.keys[n].assign(cap, 0);
+    lm.vals[n].assign(cap, F2{0, 0});
+    const uint32_t mask = (uint32_t)cap - 1;
+    for (const Entry& en : pending[n]) {
+      uint32_t s = (uint32_t)(en.key >> 17) & mask;
+      while (lm.keys[n][s] != 0 && lm.keys[n][s] != en.key) s = (s + 1) & mask;
+      lm.keys[n][s] = en.key; // a repeated n-gram keeps the last value, like a rebuilt table
+      lm.vals[n][s] = en.v;
+    }
+    std::vector<Entry>().swap(pending[n]);
+  }
+  lm.usr2lm.resize(nUsr);
+  for (int i = 0; i < nUsr; ++i) {
+    auto it = vocab.find(usrWords[i]);
+    lm.usr2lm[i] = it == vocab.end() ? 0 : it->second; // Vocabulary::Index: OOV -> <unk>
+  }
+  lm.makeHostView();
+}
+
+} // namespace
+
+/* ============================================================================== decoder ===== */
+struct flt_decoder {
+  int lexicon = 0;
+  flt_options opt{};
+  const flt_trie* trie = nullptr;
+  const flt_lm* lm = nullptr;
+  int sil = 0, blank = -1, unk = -1;
+  std::vector<float> trans;
+  int isLmToken = 0;
+  int device = 0;
+  int nbest = 0;
+  rt::Stream stream{};
+  rt::Stream copyStream{};
+#if FLT_DEVICE_BUILD
+  cudaEvent_t evCopied[2]{}, evFree[2]{};
+  int numSMs = 148;
+#endif
+  // plan
+  int planN = -1;
+  DecCfg cfg{};
+  TopMCfg tcfg{};
+  bool needTopM = false;
+  size_t wsBytes = 0, topmSmem = 0;
+  int gridMax = 1, topmGridMax = 1;
+  std::vector<int> wideOffHost;
+  rt::DevBuf dWideOff, dBias, dTrans;
+  // batch buffers
+  rt::DevBuf topTok, topVal, thr, hPar, hTok, hWord, finScore, finCount, status, ws, stateTab,
+      outTok, outWord, dLengths, staging[2];
+  long long stateCap = 0;
+  int lastB = 0, lastT = 0, launches = 0;
+  int capBoost = 1; // candidate-capacity multiplier, grown after an overflow
+  bool useSmemFlag = false;
+  std::vector<int> lastLengths;
+  bool haveLengths = false;
+
+  ~flt_decoder() {
+    for (rt::DevBuf* b : {&dWideOff, &dBias, &dTrans, &topTok, &topVal, &thr, &hPar, &hTok, &hWord,
+                          &finScore, &finCount, &status, &ws, &stateTab, &outTok, &outWord,
+                          &dLengths, &staging[0], &staging[1]})
+      b->release();
+#if FLT_DEVICE_BUILD
+    for (int i = 0; i < 2; ++i) {
+      if (evCopied[i]) cudaEventDestroy(evCopied[i]);
+      if (evFree[i]) cudaEventDestroy(evFree[i]);
+    }
+    if (stream) cudaStreamDestroy(stream);
+    if (copyStream) cudaStreamDestroy(copyStream);
+#endif
+  }
+};
+
+namespace {
+
+void planFor(flt_decoder& d, int N) {
+  if (d.planN == N) return;
+  const flt_options& o = d.opt;
+  DecCfg c{};
+  c.lexicon = d.lexicon;
+  c.K = o.beamSize;
+  c.N = N;
+  c.setAll = o.beamSizeToken >= N;
+  c.beamThreshold = o.beamThreshold;
+  c.lmWeight = o.lmWeight;
+  c.wordScore = o.wordScore;
+  c.unkScore = o.unkScore;
+  c.silScore = o.silScore;
+  c.logAdd = o.logAdd;
+  c.ctc = o.criterionType == FLT_CRITERION_CTC;
+  c.hasUnk = d.lexicon && o.unkScore > -std::numeric_limits<double>::infinity();
+  c.sil = d.sil;
+  c.blank = d.blank;
+  c.unk = d.unk;
+  if (o.beamSize < 1) throw FltError(FLT_ERR_INVALID, "beamSize must be >= 1");
+  if (o.beamSizeToken < 1) throw FltError(FLT_ERR_INVALID, "beamSizeToken must be >= 1");
+  if (o.criterionType != FLT_CRITERION_CTC && o.criterionType != FLT_CRITERION_ASG)
+    throw FltError(FLT_ERR_UNSUPPORTED, "criterion type must be ASG or CTC for these decoders");
+  if (o.logAdd)
+    throw FltError(FLT_ERR_UNSUPPORTED, "logAdd=true is not implemented on the device path yet");
+  if (d.isLmToken)
+    throw FltError(FLT_ERR_UNSUPPORTED, "token-level LM (isLmToken) is not implemented on the device path yet");
+  if (!d.lexicon && d.lm->kind != 0)
+    throw FltError(FLT_ERR_UNSUPPORTED, "LexiconFreeDecoder with an n-gram LM is not implemented on the device path yet");
+  if (d.sil < 0 || d.sil >= N) throw FltError(FLT_ERR_INVALID, "sil index out of range for N");
+  if (c.ctc && (d.blank < 0 || d.blank >= N))
+    throw FltError(FLT_ERR_INVALID, "blank index out of range for N (CTC)");
+  if (!c.ctc && !d.trans.empty() && (long long)d.trans.size() < (long long)N * N)
+    throw FltError(FLT_ERR_INVALID, "transitions must hold N*N entries (ASG)");
+  if (d.lexicon && d.trie->maxChildren < 1) throw FltError(FLT_ERR_INVALID, "empty trie");
+  if (d.lm->kind == 1) {
+    int maxIdx = -1;
+    for (auto& nd : d.trie->nodes)
+      for (int l : nd.labels) maxIdx = std::max(maxIdx, l);
+    if (c.hasUnk) maxIdx = std::max(maxIdx, d.unk);
+    if (maxIdx >= (int)d.lm->usr2lm.size() || (c.hasUnk && d.unk < 0))
+      throw FltError(FLT_ERR_RUNTIME, "[KenLM] Invalid user token index: " + std::to_string(maxIdx));
+  }
+
+  const int K = c.K;
+  const int bstEff = std::min(o.beamSizeToken, N);
+  c.wideRanked = d.lexicon ? (c.ctc && !c.hasUnk) : 1;
+  if (!c.ctc && !d.lexicon) c.wideRanked = 1; // ASG transitions never touch the lexicon-free score
+  d.needTopM = c.wideRanked || !c.setAll;
+  TopMCfg t{};
+  t.N = N;
+  t.bst = c.setAll ? N : bstEff;
+  t.capS = 2048;
+  if (c.wideRanked) {
+    const int slack = d.lexicon ? 2 : 0; // fp32 rank keys of e+bias may swap near-equal neighbours
+    c.Mwide = std::min(K + 3 + slack, bstEff);
+    c.M = (d.lexicon || c.setAll) ? c.Mwide : bstEff; // lexicon-free restricted: list = whole set
+  } else {
+    c.Mwide = 0;
+    c.M = 1;
+  }
+  const int want = c.setAll ? c.M : bstEff;
+  if (want > 2048)
+    throw FltError(FLT_ERR_UNSUPPORTED,
+                   "beamSize / beamSizeToken combination needs a token list longer than 2048 "
+                   "(beamSizeToken < N and > 2048, or beamSize > 2040 in ranked mode)");
+  t.M = c.M;
+  t.P = std::max(kThreads, nextPow2(want));
+  t.stage = (size_t)N * 4 <= 100 * 1024;
+  // wide offsets
+  d.wideOffHost.assign(K + 1, 0);
+  for (int r = 1; r <= K; ++r)
+    d.wideOffHost[r] = d.wideOffHost[r - 1] + std::min(c.Mwide, K / r + 3 + (d.lexicon ? 2 : 0));
+  const long long narrowBudget = d.lexicon ? std::max<long long>(4096, 24LL * K) : 0;
+  long long capC = (long long)(c.wideRanked ? d.wideOffHost[K] : 0) + 3LL * K + narrowBudget * d.capBoost;
+  capC = (capC + 63) / 64 * 64;
+  if (capC > (1LL << 26)) throw FltError(FLT_ERR_RUNTIME, "candidate capacity exceeded");
+  c.capC = (int)capC;
+  c.capH = nextPow2((int)std::min<long long>(2 * capC, 1LL << 27));
+  c.capRH = nextPow2(2 * K);
+  c.capP = nextPow2(K);
+
+  rt::Stream s = d.stream;
+  c.wideOff = upload(d.dWideOff, d.wideOffHost, s);
+  c.trans = nullptr;
+  if (!c.ctc && !d.trans.empty()) c.trans = upload(d.dTrans, d.trans, s);
+  if (d.lexicon) {
+    d.trie->ensureUploaded(s);
+    c.trie = d.trie->dev;
+  }
+  d.lm->ensureUploaded(s);
+  c.lm = d.lm->dev;
+  t.bias = nullptr;
+  if (d.lexicon && c.wideRanked) {
+    // rank key offset of a root child: lmWeight * smeared score; -inf = not expandable as (1a)
+    std::vector<float> bias(N, -std::numeric_limits<float>::infinity());
+    const flt_trie& tr = *d.trie;
+    for (auto& kv : tr.nodes[0].kids) {
+      if (kv.first < 0 || kv.first >= N) continue;
+      if (tr.nodes[kv.second].kids.empty()) continue;
+      bias[kv.first] = (float)(o.lmWeight * (double)tr.nodes[kv.second].maxScore);
+    }
+    t.bias = upload(d.dBias, bias, s);
+  }
+  rt::sync(s);
+
+  Ws w;
+  d.wsBytes = carveWs(nullptr, c, w);
+  TopMSmem ts;
+  d.topmSmem = carveTopM(nullptr, t, ts);
+  d.cfg = c;
+  d.tcfg = t;
+#if FLT_DEVICE_BUILD
+  int dev = d.device;
+  cudaDeviceProp prop;
+  FLT_RT_TRY(cudaGetDeviceProperties(&prop, dev));
+  d.numSMs = prop.multiProcessorCount;
+  const size_t smemMax = prop.sharedMemPerBlockOptin;
+  FLT_RT_TRY(cudaFuncSetAttribute(flt_k_topm, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)std::min(d.topmSmem, smemMax)));
+  if (d.topmSmem > smemMax) throw FltError(FLT_ERR_UNSUPPORTED, "N too large for the select kernel's shared memory");
+  int occ = 1;
+  FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, flt_k_topm, kThreads, d.topmSmem));
+  d.topmGridMax = std::max(1, occ) * d.numSMs;
+  const bool smemOk = d.wsBytes <= std::min<size_t>(smemMax, 110 * 1024);
+  d.cfg.capC = c.capC;
+  int occ2 = 1;
+  if (smemOk) {
+    FLT_RT_TRY(cudaFuncSetAttribute(flt_k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.wsBytes));
+    FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode, kThreads, d.wsBytes));
+  } else {
+    FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode, kThreads, 0));
+    occ2 = std::min(occ2, 4);
+  }
+  d.gridMax = std::max(1, occ2) * d.numSMs;
+  d.wsBytes = (d.wsBytes + 255) / 256 * 256;
+  d.cfg.capP = c.capP;
+  d.useSmemFlag = smemOk;
+#else
+  d.gridMax = 4;
+  d.topmGridMax = 4;
+  d.useSmemFlag = true;
+#endif
+  d.planN = N;
+}
+
+} // namespace
+
+namespace {
+
+// Run the three kernels over `Bc` utterances whose emissions are device-resident at dEmis, writing
+// n-best rows [outBase, outBase+Bc) of the decoder's output buffers.
+void runChunk(flt_decoder& d, const float* dEmis, int Bc, int T, int N, const int* dLen,
+              long long outBase) {
+  const DecCfg& c = d.cfg;
+  const int K = c.K;
+  rt::Stream s = d.stream;
+  const long long rows = (long long)Bc * T;
+  BatchArgs a{};
+  a.emis = dEmis;
+  a.B = Bc;
+  a.T = T;
+  a.lengths = dLen;
+  if (d.needTopM) {
+    d.topTok.reserve(sizeof(int) * rows * c.M);
+    d.topVal.reserve(sizeof(float) * rows * c.M);
+    if (!c.setAll) d.thr.reserve(sizeof(float) * rows);
+    TopMArgs ta{};
+    ta.emis = dEmis;
+    ta.rows = rows;
+    ta.outTok = d.topTok.as<int>();
+    ta.outVal = d.topVal.as<float>();
+    ta.outThr = c.setAll ? nullptr : d.thr.as<float>();
+    const int grid = (int)std::min<long long>(rows, d.topmGridMax * 8LL);
+    if (rows > 0) {
+      launchTopM(d.tcfg, ta, grid, d.topmSmem, s);
+      d.launches++;
+    }
+    a.topTok = ta.outTok;
+    a.topVal = ta.outVal;
+    a.thrVal = ta.outThr;
+  }
+  const long long hist = (long long)Bc * (T + 2) * K;
+  d.hPar.reserve(sizeof(int) * hist);
+  d.hTok.reserve(sizeof(int) * hist);
+  if (d.lexicon) d.hWord.reserve(sizeof(int) * hist);
+  a.hParent = d.hPar.as<int>();
+  a.hTok = d.hTok.as<int>();
+  a.hWord = d.lexicon ? d.hWord.as<int>() : nullptr;
+  a.finScore = d.finScore.as<double>() + outBase * K * 3;
+  a.finCount = d.finCount.as<int>() + outBase;
+  a.status = d.status.as<int>() + outBase;
+  const int grid = std::max(1, std::min(Bc, d.gridMax));
+  long long cap = 64;
+  while (cap < 2LL * ((long long)K * (T + 1) + 2)) cap <<= 1;
+  d.stateCap = cap;
+  d.stateTab.reserve(sizeof(unsigned long long) * cap * grid);
+  a.stateTab = d.stateTab.as<unsigned long long>();
+  a.stateCap = cap;
+  a.useSmem = d.useSmemFlag ? 1 : 0;
+  if (!d.useSmemFlag) {
+    d.ws.reserve(d.wsBytes * grid);
+    a.wsGlobal = d.ws.as<char>();
+    a.wsStride = (long long)d.wsBytes;
+  }
+  launchDecode(c, a, grid, d.useSmemFlag ? d.wsBytes : 0, s);
+  d.launches++;
+  BacktraceArgs b{};
+  b.hParent = a.hParent;
+  b.hTok = a.hTok;
+  b.hWord = a.hWord;
+  b.finCount = a.finCount;
+  b.lengths = dLen;
+  b.B = Bc;
+  b.T = T;
+  b.K = K;
+  b.nbest = d.nbest;
+  b.outTok = d.outTok.as<int>() + outBase * d.nbest * (T + 2);
+  b.outWord = d.outWord.as<int>() + outBase * d.nbest * (T + 2);
+  launchBacktrace(b, s);
+  d.launches++;
+}
+
+void prepareBatch(flt_decoder& d, int B, int T, int N) {
+  if (B < 0 || T < 0 || N < 1) throw FltError(FLT_ERR_INVALID, "bad batch shape");
+  planFor(d, N);
+  const int K = d.cfg.K;
+  d.finScore.reserve(sizeof(double) * (size_t)std::max(B, 1) * K * 3);
+  d.finCount.reserve(sizeof(int) * (size_t)std::max(B, 1));
+  d.status.reserve(sizeof(int) * (size_t)std::max(B, 1));
+  d.outTok.reserve(sizeof(int) * (size_t)std::max(B, 1) * d.nbest * (T + 2));
+  d.outWord.reserve(sizeof(int) * (size_t)std::max(B, 1) * d.nbest * (T + 2));
+  d.lastB = B;
+  d.lastT = T;
+  d.launches = 0;
+}
+
+// device-resident emissions: whole batch in slices that bound the history / list buffers
+void decodeDevice(flt_decoder& d, const float* dEmis, int B, int T, int N, const int* dLen) {
+  const long long perUtt = (long long)(T + 2) * d.cfg.K * 12 + (long long)T * d.cfg.M * 8 + 64;
+  long long slice = std::max<long long>(1, (8LL << 30) / perUtt);
+  slice = std::min<long long>(slice, B);
+  if (slice >= d.gridMax) slice = slice / d.gridMax * d.gridMax; // whole waves
+  for (long long b0 = 0; b0 < B; b0 += slice) {
+    const int Bc = (int)std::min<long long>(slice, B - b0);
+    runChunk(d, dEmis + b0 * T * N, Bc, T, N, dLen ? dLen + b0 : nullptr, b0);
+  }
+}
+
+template <class F>
+int guarded(F&& f) {
+  try {
+    f();
+    return FLT_OK;
+  } catch (const FltError& e) {
+    return fail(e.code, e.what());
+  } catch (const std::bad_alloc&) {
+    return fail(FLT_ERR_RUNTIME, "out of host memory");
+  } catch (const std::exception& e) {
+    return fail(FLT_DEVICE_BUILD ? FLT_ERR_CUDA : FLT_ERR_RUNTIME, e.what());
+  }
+}
+
+void requireDevice(int device) {
+#if FLT_DEVICE_BUILD
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    throw FltError(FLT_ERR_CUDA, "no CUDA device available: the decoder has no CPU path");
+  }
+  if (device < 0 || device >= n) throw FltError(FLT_ERR_INVALID, "bad CUDA device ordinal");
+  FLT_RT_TRY(cudaSetDevice(device));
+#else
+  (void)device;
+#endif
+}
+
+flt_decoder* makeDecoder(int lexicon, const flt_options* opt, const flt_trie* trie, const flt_lm* lm,
+                         int sil, int blank, int unk, const float* trans, long long nTrans,
+                         int isLmToken, int device) {
+  if (!opt || !lm) throw FltError(FLT_ERR_INVALID, "null options or LM");
+  if (lexicon && !trie) throw FltError(FLT_ERR_INVALID, "null trie");
+  requireDevice(device);
+  std::unique_ptr<flt_decoder> d(new flt_decoder);
+  d->lexicon = lexicon;
+  d->opt = *opt;
+  d->trie = trie;
+  d->lm = lm;
+  d->sil = sil;
+  d->blank = blank;
+  d->unk = unk;
+  if (trans && nTrans > 0) d->trans.assign(trans, trans + nTrans);
+  d->isLmToken = isLmToken;
+  d->device = device;
+  d->nbest = std::max(1, opt->beamSize);
+#if FLT_DEVICE_BUILD
+  FLT_RT_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  FLT_RT_TRY(cudaStreamCreateWithFlags(&d->copyStream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    FLT_RT_TRY(cudaEventCreateWithFlags(&d->evCopied[i], cudaEventDisableTiming));
+    FLT_RT_TRY(cudaEventCreateWithFlags(&d->evFree[i], cudaEventDisableTiming));
+  }
+#endif
+  return d.release();
+}
+
+void checkStatus(flt_decoder& d) {
+  std::vector<int> st(std::max(d.lastB, 1));
+  rt::d2h(st.data(), d.status.p, sizeof(int) * d.lastB, d.stream);
+  rt::sync(d.stream);
+  int bits = 0;
+  for (int b = 0; b < d.lastB; ++b) bits |= st[b];
+  if (bits & 2) throw FltError(FLT_ERR_RUNTIME, "LM-state table overflow (internal sizing error)");
+  if (bits & 1) throw FltError(FLT_ERR_RUNTIME, "candidate capacity exceeded");
+}
+
+} // namespace
+
+/* ================================================================================ C ABI ===== */
+extern "C" {
+
+const char* flt_last_error(void) { return gErr.c_str(); }
+
+int flt_trie_create(int32_t maxChildren, int32_t rootIdx, flt_trie** out) {
+  return guarded([&] {
+    if (!out) throw FltError(FLT_ERR_INVALID, "null out");
+    auto* t = new flt_trie;
+    t->maxChildren = maxChildren;
+    t->rootIdx = rootIdx;
+    t->nodes.emplace_back();
+    *out = t;
+  });
+}
+int flt_trie_insert(flt_trie* trie, const int32_t* indices, int32_t n, int32_t label, float score) {
+  return guarded([&] {
+    if (!trie) throw FltError(FLT_ERR_INVALID, "null trie");
+    if (trie->uploaded) throw FltError(FLT_ERR_INVALID, "trie is frozen: a decoder already uses it");
+    int cur = 0;
+    for (int i = 0; i < n; ++i) {
+      const int idx = indices[i];
+      if (idx < 0 || idx >= trie->maxChildren) // Trie.cpp:31-34 (nodes created so far stay)
+        throw FltError(FLT_ERR_OUT_OF_RANGE, "[Trie] Invalid letter index: " + std::to_string(idx));
+      auto it = trie->nodes[cur].kids.find(idx);
+      if (it == trie->nodes[cur].kids.end()) {
+        const int nn = (int)trie->nodes.size();
+        trie->nodes[cur].kids.emplace(idx, nn);
+        trie->nodes.emplace_back();
+        cur = nn;
+      } else {
+        cur = it->second;
+      }
+    }
+    if ((int)trie->nodes[cur].labels.size() < kTrieMaxLabel) { // Trie.cpp:40-46
+      trie->nodes[cur].labels.push_back(label);
+      trie->nodes[cur].scores.push_back(score);
+    } else {
+      fprintf(stderr, "[Trie] Trie label number reached limit: %d\n", kTrieMaxLabel);
+    }
+  });
+}
+int flt_trie_smear(flt_trie* trie, int32_t mode) {
+  return guarded([&] {
+    if (!trie) throw FltError(FLT_ERR_INVALID, "null trie");
+    if (trie->uploaded) throw FltError(FLT_ERR_INVALID, "trie is frozen: a decoder already uses it");
+    if (mode != FLT_SMEAR_NONE) trie->smearNode(0, mode);
+  });
+}
+int flt_trie_search(const flt_trie* trie, const int32_t* indices, int32_t n, int32_t* found,
+                    float* maxScore, int32_t* nLabels, int32_t* labels6, float* scores6) {
+  return guarded([&] {
+    if (!trie || !found) throw FltError(FLT_ERR_INVALID, "null argument");
+    int cur = 0;
+    *found = 0;
+    for (int i = 0; i < n; ++i) {
+      const int idx = indices[i];
+      if (idx < 0 || idx >= trie->maxChildren)
+        throw FltError(FLT_ERR_OUT_OF_RANGE, "[Trie] Invalid letter index: " + std::to_string(idx));
+      auto it = trie->nodes[cur].kids.find(idx);
+      if (it == trie->nodes[cur].kids.end()) return;
+      cur = it->second;
+    }
+    const HNode& nd = trie->nodes[cur];
+    *found = 1;
+    if (maxScore) *maxScore = nd.maxScore;
+    if (nLabels) *nLabels = (int)nd.labels.size();
+    for (size_t i = 0; i < nd.labels.size() && i < 6; ++i) {
+      if (labels6) labels6[i] = nd.labels[i];
+      if (scores6) scores6[i] = nd.scores[i];
+    }
+  });
+}
+int flt_trie_num_nodes(const flt_trie* trie, int64_t* out) {
+  return guarded([&] {
+    if (!trie || !out) throw FltError(FLT_ERR_INVALID, "null argument");
+    *out = (int64_t)trie->nodes.size();
+  });
+}
+void flt_trie_destroy(flt_trie* trie) { delete trie; }
+
+int flt_lm_zero_create(flt_lm** out) {
+  return guarded([&] {
+    if (!out) throw FltError(FLT_ERR_INVALID, "null out");
+    auto* m = new flt_lm;
+    m->kind = 0;
+    m->makeHostView();
+    *out = m;
+  });
+}
+int flt_lm_ngram_load_arpa(const char* path, const char* const* usrWords, int32_t nUsrWords,
+                           flt_lm** out) {
+  return guarded([&] {
+    if (!out || !path) throw FltError(FLT_ERR_INVALID, "null argument");
+    std::unique_ptr<flt_lm> m(new flt_lm);
+    loadArpa(path, usrWords, nUsrWords, *m);
+    *out = m.release();
+  });
+}
+int flt_lm_score_seq(const flt_lm* lm, const int32_t* usrIdx, int32_t n, int32_t withFinish,
+                     float* out) {
+  return guarded([&] {
+    if (!lm || !out) throw FltError(FLT_ERR_INVALID, "null argument");
+    if (lm->kind == 0) {
+      for (int i = 0; i < n + (withFinish ? 1 : 0); ++i) out[i] = 0.0f;
+      return;
+    }
+    int ctx[kMaxCtx], nctx = 0, nxt[kMaxCtx];
+    if (lm->order > 1) {
+      ctx[0] = lm->bos;
+      nctx = 1;
+    }
+    for (int i = 0; i < n + (withFinish ? 1 : 0); ++i) {
+      int w;
+      if (i < n) {
+        if (usrIdx[i] < 0 || usrIdx[i] >= (int)lm->usr2lm.size()) // lm/KenLM.cpp:66-69
+          throw FltError(FLT_ERR_RUNTIME, "[KenLM] Invalid user token index: " + std::to_string(usrIdx[i]));
+        w = lm->usr2lm[usrIdx[i]];
+      } else {
+        w = lm->eos;
+      }
+      out[i] = ngramScore(lm->host, ctx, nctx, w);
+      nctx = ngramAdvanceCtx(lm->host, ctx, nctx, w, nxt);
+      for (int k = 0; k < nctx; ++k) ctx[k] = nxt[k];
+    }
+  });
+}
+void flt_lm_destroy(flt_lm* lm) { delete lm; }
+
+int flt_decoder_create_lexfree(const flt_options* opt, const flt_lm* lm, int32_t sil, int32_t blank,
+                               const float* transitions, int64_t nTransitions, int32_t device,
+                               flt_decoder** out) {
+  return guarded([&] {
+    if (!out) throw FltError(FLT_ERR_INVALID, "null out");
+    *out = makeDecoder(0, opt, nullptr, lm, sil, blank, -1, transitions, nTransitions, 0, device);
+  });
+}
+int flt_decoder_create_lexicon(const flt_options* opt, const flt_trie* trie, const flt_lm* lm,
+                               int32_t sil, int32_t blank, int32_t unk, const float* transitions,
+                               int64_t nTransitions, int32_t isLmToken, int32_t device,
+                               flt_decoder** out) {
+  return guarded([&] {
+    if (!out) throw FltError(FLT_ERR_INVALID, "null out");
+    *out = makeDecoder(1, opt, trie, lm, sil, blank, unk, transitions, nTransitions, isLmToken, device);
+  });
+}
+void flt_decoder_destroy(flt_decoder* dec) { delete dec; }
+
+int flt_decoder_set_nbest(flt_decoder* dec, int32_t nbest) {
+  return guarded([&] {
+    if (!dec || nbest < 1) throw FltError(FLT_ERR_INVALID, "nbest must be >= 1");
+    dec->nbest = std::min(nbest, dec->opt.beamSize);
+  });
+}
+
+int flt_decode_batch_async(flt_decoder* dec, const float* dEmissions, int32_t B, int32_t T,
+                           int32_t N, const int32_t* dLengths) {
+  return guarded([&] {
+    if (!dec || (!dEmissions && (long long)B * T > 0)) throw FltError(FLT_ERR_INVALID, "null argument");
+    requireDevice(dec->device);
+    prepareBatch(*dec, B, T, N);
+    dec->haveLengths = false;
+    decodeDevice(*dec, dEmissions, B, T, N, dLengths);
+  });
+}
+
+int flt_decode_batch(flt_decoder* dec, const float* emissions, int32_t B, int32_t T, int32_t N,
+                     const int32_t* lengths) {
+  return guarded([&] {
+    if (!dec || (!emissions && (long long)B * T > 0)) throw FltError(FLT_ERR_INVALID, "null argument");
+    requireDevice(dec->device);
+    flt_decoder& d = *dec;
+    for (int attempt = 0;; ++attempt) {
+      prepareBatch(d, B, T, N);
+      const int* dLen = nullptr;
+      if (lengths) {
+        for (int b = 0; b < B; ++b)
+          if (lengths[b] < 0 || lengths[b] > T) throw FltError(FLT_ERR_INVALID, "lengths[b] out of [0,T]");
+        d.dLengths.reserve(sizeof(int) * (size_t)std::max(B, 1));
+        rt::h2d(d.dLengths.p, lengths, sizeof(int) * B, d.stream);
+        dLen = d.dLengths.as<int>();
+      }
+      const bool onDevice = (long long)B * T == 0 || rt::isDevicePtr(emissions);
+      if (onDevice) {
+        decodeDevice(d, emissions, B, T, N, dLen);
+      } else {
+#if FLT_DEVICE_BUILD
+        // host emissions: stream them through two staging buffers so the PCIe copy of slice i+1
+        // overlaps the kernels of slice i
+        const long long perUtt = (long long)T * N * sizeof(float);
+        long long slice = std::max<long long>(1, (1LL << 30) / std::max<long long>(perUtt, 1));
+        slice = std::min<long long>(slice, B);
+        for (int i = 0; i < 2; ++i) d.staging[i].reserve((size_t)(slice * perUtt));
+        int k = 0;
+        for (long long b0 = 0; b0 < B; b0 += slice, k ^= 1) {
+          const int Bc = (int)std::min<long long>(slice, B - b0);
+          FLT_RT_TRY(cudaStreamWaitEvent(d.copyStream, d.evFree[k], 0));
+          FLT_RT_TRY(cudaMemcpyAsync(d.staging[k].p, emissions + b0 * T * N, (size_t)(Bc * perUtt),
+                                     cudaMemcpyHostToDevice, d.copyStream));
+          FLT_RT_TRY(cudaEventRecord(d.evCopied[k], d.copyStream));
+          FLT_RT_TRY(cudaStreamWaitEvent(d.stream, d.evCopied[k], 0));
+          runChunk(d, d.staging[k].as<float>(), Bc, T, N, dLen ? dLen + b0 : nullptr, b0);
+          FLT_RT_TRY(cudaEventRecord(d.evFree[k], d.stream));
+        }
+#else
+        decodeDevice(d, emissions, B, T, N, dLen);
+#endif
+      }
+      try {
+        checkStatus(d);
+        break;
+      } catch (const FltError& e) {
+        // the lexicon decoder's direct enumeration is data dependent: grow and redo the batch
+        if (std::string(e.what()) != "candidate capacity exceeded" || attempt >= 6) throw;
+        d.capBoost *= 4;
+        d.planN = -1;
+      }
+    }
+    d.haveLengths = lengths != nullptr;
+    if (lengths) d.lastLengths.assign(lengths, lengths + B);
+  });
+}
+
+int flt_decoder_synchronize(flt_decoder* dec) {
+  return guarded([&] {
+    if (!dec) throw FltError(FLT_ERR_INVALID, "null decoder");
+    rt::sync(dec->stream);
+  });
+}
+void* flt_decoder_stream(flt_decoder* dec) { return dec ? (void*)dec->stream : nullptr; }
+
+int flt_nbest_copy(flt_decoder* dec, int32_t nbest, int32_t* tokens, int32_t* words, double* scores,
+                   int32_t* counts) {
+  return guarded([&] {
+    if (!dec) throw FltError(FLT_ERR_INVALID, "null decoder");
+    flt_decoder& d = *dec;
+    if (nbest < 1 || nbest > d.nbest) throw FltError(FLT_ERR_INVALID, "nbest exceeds the decoder's nbest setting");
+    const int B = d.lastB, T = d.lastT, K = d.cfg.K;
+    if (B == 0) return;
+    checkStatus(d);
+    const size_t L = (size_t)T + 2;
+    if (nbest == d.nbest) {
+      if (tokens) rt::d2h(tokens, d.outTok.p, sizeof(int) * B * nbest * L, d.stream);
+      if (words) rt::d2h(words, d.outWord.p, sizeof(int) * B * nbest * L, d.stream);
+    } else {
+      for (int b = 0; b < B; ++b) {
+        if (tokens) rt::d2h(tokens + (size_t)b * nbest * L, d.outTok.as<int>() + (size_t)b * d.nbest * L,
+                            sizeof(int) * nbest * L, d.stream);
+        if (words) rt::d2h(words + (size_t)b * nbest * L, d.outWord.as<int>() + (size_t)b * d.nbest * L,
+                           sizeof(int) * nbest * L, d.stream);
+      }
+    }
+    if (scores) {
+      if (nbest == K) {
+        rt::d2h(scores, d.finScore.p, sizeof(double) * B * K * 3, d.stream);
+      } else {
+        for (int b = 0; b < B; ++b)
+          rt::d2h(scores + (size_t)b * nbest * 3, d.finScore.as<double>() + (size_t)b * K * 3,
+                  sizeof(double) * nbest * 3, d.stream);
+      }
+    }
+    if (counts) rt::d2h(counts, d.finCount.p, sizeof(int) * B, d.stream);
+    rt::sync(d.stream);
+  });
+}
+
+int flt_decoder_last_launches(const flt_decoder* dec, int32_t* out) {
+  return guarded([&] {
+    if (!dec || !out) throw FltError(FLT_ERR_INVALID, "null argument");
+    *out = dec->launches;
+  });
+}
+int flt_decoder_workspace_bytes(const flt_decoder* dec, int64_t* out) {
+  return guarded([&] {
+    if (!dec || !out) throw FltError(FLT_ERR_INVALID, "null argument");
+    int64_t t = 0;
+    for (const rt::DevBuf* b : {&dec->topTok, &dec->topVal, &dec->thr, &dec->hPar, &dec->hTok,
+                                &dec->hWord, &dec->finScore, &dec->finCount, &dec->status, &dec->ws,
+                                &dec->stateTab, &dec->outTok, &dec->outWord, &dec->staging[0],
+                                &dec->staging[1]})
+      t += (int64_t)b->cap;
+    *out = t;
+  });
+}
+
+int flt_topm_rows(const float* dEmissions, int64_t rows, int32_t N, int32_t M, int32_t* dTok,
+                  float* dVal, void* stream) {
+  return guarded([&] {
+    if (M < 1 || M > 2048 || M > N) throw FltError(FLT_ERR_INVALID, "need 1 <= M <= min(N, 2048)");
+    TopMCfg t{};
+    t.N = N;
+    t.M = M;
+    t.bst = N;
+    t.bias = nullptr;
+    t.capS = 2048;
+    t.P = std::max(kThreads, nextPow2(M));
+    t.stage = (size_t)N * 4 <= 100 * 1024;
+    TopMSmem ts;
+    const size_t smem = carveTopM(nullptr, t, ts);
+    TopMArgs a{};
+    a.emis = dEmissions;
+    a.rows = rows;
+    a.outTok = dTok;
+    a.outVal = dVal;
+    a.outThr = nullptr;
+    int gridMax = 4;
+#if FLT_DEVICE_BUILD
+    int dev = 0, sms = 148, occ = 1;
+    FLT_RT_TRY(cudaGetDevice(&dev));
+    FLT_RT_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    FLT_RT_TRY(cudaFuncSetAttribute(flt_k_topm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, flt_k_topm, kThreads, smem));
+    gridMax = std::max(1, occ) * sms * 8;
+#endif
+    if (rows > 0) launchTopM(t, a, (int)std::min<int64_t>(rows, gridMax), smem, (rt::Stream)stream);
+  });
+}
+
+} // extern "C"

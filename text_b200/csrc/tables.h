@@ -1,0 +1,110 @@
+// tables.h — flattened, read-only lookup tables the decode kernels gather from (HBM, L2-resident
+// at the benchmark sizes): the lexicon Trie as CSR arrays and the n-gram LM as per-order
+// open-addressing tables. Replaces, on the hot path, `TrieNode::children.find` / `labels` /
+// `maxScore` (decoder/Trie.h:39-54, decoder/LexiconDecoder.cpp:58-67,113) and
+// `KenLM::score` -> `lm::base::Model::BaseScore` (decoder/lm/KenLM.cpp:63-83).
+#pragma once
+#include "spmd.h"
+
+namespace flt {
+
+constexpr int kMaxOrder = 6;          // FL_TEXT_KENLM_MAX_ORDER, decoder/lm/CMakeLists.txt:3
+constexpr int kMaxCtx = kMaxOrder - 1;
+
+struct TrieDev {
+  int nNodes;
+  const int* childOff;    // [nNodes+1] CSR row offsets
+  const int* childTok;    // [nEdges]   token of each edge, ascending within a node
+  const int* childNode;   // [nEdges]   target node
+  const float* maxScore;  // [nNodes]   smeared score (TrieNode::maxScore)
+  const int* labelOff;    // [nNodes+1]
+  const int* labels;      // [nLabels]  word ids (TrieNode::labels, <= 6 per node)
+  const int* rootChild;   // [N]        node reached from the root by token n, or -1
+  int nRootLab;           // root children that carry labels (single-token words)
+  const int* rootLabTok;  // [nRootLab] their tokens
+};
+
+struct F2 {
+  float x, y; // (log10 prob, back-off)
+};
+
+struct LmDev {
+  int kind; // 0 = ZeroLM, 1 = n-gram
+  int order, vocab, bos, eos, nUsr;
+  const int* usr2lm;              // [nUsr] user word index -> LM vocabulary id (OOV -> 0 = <unk>)
+  const F2* uni;                  // [vocab]
+  const uint64_t* keys[kMaxOrder + 1]; // [n] -> open-addressing table of order n (n >= 2); 0 = empty
+  const F2* vals[kMaxOrder + 1];
+  uint32_t mask[kMaxOrder + 1];
+};
+
+// Key of an n-gram = chained 64-bit mix over its words in REVERSED order (most recent first), so
+// that growing the context by one older word extends the chain. KenLM's probing model likewise
+// keys n-grams by a 64-bit hash of the word ids; the oracle uses exact keys, so a collision here
+// would surface as a parity failure.
+FLT_HD uint64_t ngramChainStart(int w) { return mix64(0x9E3779B97F4A7C15ull + (uint64_t)(uint32_t)w); }
+FLT_HD uint64_t ngramChainExtend(uint64_t h, int w) {
+  return mix64(h * 0x100000001B3ull + (uint64_t)(uint32_t)w + 0x632BE59BD9B4E019ull);
+}
+FLT_HD uint64_t ngramFinalKey(uint64_t h) { return h == 0 ? 1 : h; }
+
+FLT_HD bool ngramFind(const LmDev& lm, int n, uint64_t chain, F2& out) {
+  const uint64_t key = ngramFinalKey(chain);
+  const uint32_t mask = lm.mask[n];
+  const uint64_t* keys = lm.keys[n];
+  if (!keys) return false;
+  uint32_t s = (uint32_t)(key >> 17) & mask;
+  for (;;) {
+    uint64_t k = keys[s];
+    if (k == key) {
+      out = lm.vals[n][s];
+      return true;
+    }
+    if (k == 0) return false;
+    s = (s + 1) & mask;
+  }
+}
+
+// p(w | ctx) in log10 as a float, ctx most-recent-first. Same evaluation order as KenLM's
+// FullScore: longest match grown one word at a time, then back-offs added from the shortest
+// unused context to the longest, all in float.
+FLT_HD float ngramScore(const LmDev& lm, const int* ctx, int nctx, int w) {
+  const int L = nctx < lm.order - 1 ? nctx : lm.order - 1;
+  float ret = lm.uni[w].x;
+  int matchLen = 1;
+  uint64_t h = ngramChainStart(w);
+  for (int k = 1; k <= L; ++k) {
+    h = ngramChainExtend(h, ctx[k - 1]);
+    F2 v;
+    if (!ngramFind(lm, k + 1, h, v)) break;
+    ret = v.x;
+    matchLen = k + 1;
+  }
+  if (matchLen - 1 < L) {
+    uint64_t g = 0;
+    for (int i = 0; i < L; ++i) {
+      g = i == 0 ? ngramChainStart(ctx[0]) : ngramChainExtend(g, ctx[i]);
+      if (i < matchLen - 1) continue;
+      if (i == 0) {
+        ret += lm.uni[ctx[0]].y;
+      } else {
+        F2 v;
+        if (ngramFind(lm, i + 1, g, v)) ret += v.y;
+      }
+    }
+  }
+  return ret;
+}
+
+// Context of the child state: (w, ctx...) truncated to order-1 words.
+FLT_HD int ngramAdvanceCtx(const LmDev& lm, const int* ctx, int nctx, int w, int* out) {
+  const int keep = lm.order - 1;
+  int n = 0;
+  if (keep > 0) {
+    out[n++] = w;
+    for (int i = 0; i < nctx && n < keep; ++i) out[n++] = ctx[i];
+  }
+  return n;
+}
+
+} // namespace flt
