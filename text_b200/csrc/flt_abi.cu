@@ -505,9 +505,9 @@ void planFor(flt_decoder& d, int N) {
   rt::sync(s);
 
   Ws w;
-  d.wsBytes = carveWs(nullptr, c, w);
+  d.wsBytes = (carveWs(nullptr, c, w) + 255) / 256 * 256;
   TopMSmem ts;
-  d.topmSmem = carveTopM(nullptr, t, ts);
+  d.topmSmem = (carveTopM(nullptr, t, ts) + 255) / 256 * 256;
   d.cfg = c;
   d.tcfg = t;
 #if FLT_DEVICE_BUILD
@@ -516,9 +516,9 @@ void planFor(flt_decoder& d, int N) {
   FLT_RT_TRY(cudaGetDeviceProperties(&prop, dev));
   d.numSMs = prop.multiProcessorCount;
   const size_t smemMax = prop.sharedMemPerBlockOptin;
-  FLT_RT_TRY(cudaFuncSetAttribute(flt_k_topm, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)std::min(d.topmSmem, smemMax)));
   if (d.topmSmem > smemMax) throw FltError(FLT_ERR_UNSUPPORTED, "N too large for the select kernel's shared memory");
+  FLT_RT_TRY(cudaFuncSetAttribute(flt_k_topm, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)std::max<size_t>(d.topmSmem, 48 * 1024)));
   int occ = 1;
   FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, flt_k_topm, kThreads, d.topmSmem));
   d.topmGridMax = std::max(1, occ) * d.numSMs;
@@ -526,15 +526,14 @@ void planFor(flt_decoder& d, int N) {
   d.cfg.capC = c.capC;
   int occ2 = 1;
   if (smemOk) {
-    FLT_RT_TRY(cudaFuncSetAttribute(flt_k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.wsBytes));
+    FLT_RT_TRY(cudaFuncSetAttribute(flt_k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)std::max<size_t>(d.wsBytes, 48 * 1024)));
     FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode, kThreads, d.wsBytes));
   } else {
     FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode, kThreads, 0));
     occ2 = std::min(occ2, 4);
   }
   d.gridMax = std::max(1, occ2) * d.numSMs;
-  d.wsBytes = (d.wsBytes + 255) / 256 * 256;
-  d.cfg.capP = c.capP;
   d.useSmemFlag = smemOk;
 #else
   d.gridMax = 4;
@@ -1015,7 +1014,7 @@ int flt_topm_rows(const float* dEmissions, int64_t rows, int32_t N, int32_t M, i
     t.P = std::max(kThreads, nextPow2(M));
     t.stage = (size_t)N * 4 <= 100 * 1024;
     TopMSmem ts;
-    const size_t smem = carveTopM(nullptr, t, ts);
+    const size_t smem = (carveTopM(nullptr, t, ts) + 255) / 256 * 256;
     TopMArgs a{};
     a.emis = dEmissions;
     a.rows = rows;
@@ -1027,7 +1026,8 @@ int flt_topm_rows(const float* dEmissions, int64_t rows, int32_t N, int32_t M, i
     int dev = 0, sms = 148, occ = 1;
     FLT_RT_TRY(cudaGetDevice(&dev));
     FLT_RT_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    FLT_RT_TRY(cudaFuncSetAttribute(flt_k_topm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FLT_RT_TRY(cudaFuncSetAttribute(flt_k_topm, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)std::max<size_t>(smem, 48 * 1024)));
     FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, flt_k_topm, kThreads, smem));
     gridMax = std::max(1, occ) * sms * 8;
 #endif
