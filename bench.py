@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — utterances/s of the decode hot path on synthetic [B,T,N] emissions.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # our CUDA path
+  python bench.py --impl reference [...]                          # the reference's CPU decoder
+  torchrun --nproc-per-node N bench.py --gpus N ...               # one rank per GPU, weak scaling
+
+A step = one decode of the whole per-GPU batch (token-beam select + beam step + n-best backtrace).
+`value` is timed with CUDA events on the decoder's stream with emissions already resident in HBM;
+`e2e` is the same batch through the C-ABI call with HOST (pinned) emissions, the PCIe copy and the
+n-best device->host copy inside the timed region. Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+PEAKS_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--workload", default="lexfree", choices=["lexfree", "lexicon"])
+    p.add_argument("--batch", type=int, default=256, help="utterances per GPU")
+    p.add_argument("--frames", type=int, default=1000)
+    p.add_argument("--tokens", type=int, default=10000)
+    p.add_argument("--beam", type=int, default=0, help="0 = 50 (lexfree) / 100 (lexicon)")
+    p.add_argument("--bst", type=int, default=0, help="beamSizeToken; 0 = N (token pruning off)")
+    p.add_argument("--threshold", type=float, default=1e9)
+    p.add_argument("--words", type=int, default=200000, help="lexicon size (lexicon workload)")
+    p.add_argument("--sigma", type=float, default=1.0)
+    p.add_argument("--nbest", type=int, default=0, help="0 = all final hypotheses (beam)")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-seconds", type=float, default=20.0)
+    return p.parse_args()
+
+
+def workload_name(a, beam, bst):
+    kind = "LexiconFreeDecoder" if a.workload == "lexfree" else f"LexiconDecoder {a.words}-word Trie"
+    return (f"{kind}, ZeroLM, CTC, N={a.tokens}, T={a.frames}, beam={beam}, beamSizeToken={bst}, "
+            f"batch={a.batch}/GPU")
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return PEAKS_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def build_spec(a, beam, bst):
+    from cases import spec_lexfree, spec_lexicon
+    from text_b200 import synth
+
+    N = a.tokens
+    if a.workload == "lexfree":
+        return spec_lexfree(N, beam, bst, a.threshold, sil=0, blank=N - 1)
+    sp = synth.lexicon(a.words, N, 2, 5, seed=7, exclude=(0, N - 1))
+    return spec_lexicon(N, beam, bst, sp, a.threshold, sil=0, blank=N - 1, unk=a.words)
+
+
+def cpu_leg(a, spec, sample_em, seconds, kind_pref=("ref", "ora")):
+    """Time the reference's decode() (or the oracle port) on all host threads over a bounded sample:
+    `sample_em` [P,Ts,N]; returns (utt/s extrapolated linearly in T, description)."""
+    from cases import Built
+    from oracle import pyoracle as po
+
+    kind = next((k for k in kind_pref if po.available(k)), None)
+    if kind is None:
+        po.build("ora")
+        kind = "ora"
+    O = po.Oracle(kind)
+    b = Built(O, spec)
+    threads = os.cpu_count() or 1
+    P, Ts, N = sample_em.shape
+    lex = spec["kind"] == "lexicon"
+    # calibrate on one utterance, then size the sample for ~`seconds`
+    t0 = time.perf_counter()
+    O.bench_mt(lex, spec["opt"], b.trie, b.lm, spec["sil"], spec["blank"], spec["unk"], sample_em[:1], 1, 0)
+    one = time.perf_counter() - t0
+    per_thread = max(1, min(int(seconds / max(one, 1e-3)), 16))
+    count = threads * per_thread
+    em = sample_em[np.arange(count) % P]
+    wall = O.bench_mt(lex, spec["opt"], b.trie, b.lm, spec["sil"], spec["blank"], spec["unk"], em,
+                      threads, 0)
+    b.close()
+    frac = Ts / float(a.frames)
+    ups = count / wall * frac
+    desc = (f"{count} utterances x first {Ts} of {a.frames} frames on {threads} threads "
+            f"({'unmodified reference compiled in place' if kind == 'ref' else 'oracle port'}); "
+            + ("full length" if Ts == a.frames else "extrapolated linearly in T"))
+    return ups, threads, ("reference" if kind == "ref" else "port"), desc, wall
+
+
+def sample_frames(a, bst):
+    # with token pruning off the reference allocates ~66 MB of LMState per frame:
+    # bound the CPU sample to a short prefix there
+    return a.frames if bst <= 256 else min(a.frames, 12)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from text_b200 import synth
+
+    beam = a.beam or (50 if a.workload == "lexfree" else 100)
+    bst = a.bst or a.tokens
+    spec = build_spec(a, beam, bst)
+    Ts = sample_frames(a, bst)
+    em = synth.emissions(4, Ts, a.tokens, seed=1234, sigma=a.sigma)
+    vals = []
+    for _ in range(a.warmup):
+        cpu_leg(a, spec, em, 1.0)
+    t_all = time.perf_counter()
+    for _ in range(a.steps):
+        ups, threads, kind, desc, wall = cpu_leg(a, spec, em, max(2.0, a.cpu_seconds / max(a.steps, 1)))
+        vals.append(ups)
+    v = float(np.mean(vals))
+    out = {"impl": "reference", "metric": "utterances/sec", "value": v, "unit": "utt/s",
+           "frames_per_s": v * a.frames, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+           "ms_per_step": (time.perf_counter() - t_all) / max(a.steps, 1) * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "config": {"workload": workload_name(a, beam, bst)},
+           "cpu_baseline": {"value": v, "unit": "utt/s", "cores": threads, "kind": kind, "sample": desc},
+           "e2e": {"value": v, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    from cases import Built, assert_same_nbest, has_ties
+    from flt_backend import FltBackend
+    from oracle import pyoracle as po
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    beam = a.beam or (50 if a.workload == "lexfree" else 100)
+    bst = a.bst or a.tokens
+    B, T, N = a.batch, a.frames, a.tokens
+    nbest = a.nbest or beam
+    spec = build_spec(a, beam, bst)
+    G = FltBackend("cuda")
+    G.api.device = local
+    built = Built(G, spec)
+    api, dec = G.api, built.dec
+    api.set_nbest(dec, nbest)
+
+    # synthetic emissions, generated where they are consumed
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    em = torch.empty((B, T, N), dtype=torch.float32, device=dev)
+    for b0 in range(0, B, 32):
+        z = torch.randn((min(32, B - b0), T, N), generator=gen, device=dev, dtype=torch.float32)
+        em[b0:b0 + z.shape[0]] = torch.log_softmax(z * a.sigma, dim=-1)
+    del z
+    torch.cuda.synchronize()
+
+    stream = torch.cuda.ExternalStream(api.stream(dec), device=dev)
+
+    def step():
+        api.decode_batch_async(dec, em.data_ptr(), B, T, N)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step()
+    api.synchronize(dec)
+    api.set_timing(dec, True)
+    clocks = ClockSampler(local)
+    clocks.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = {"token_select": 0.0, "beam_step": 0.0, "backtrace": 0.0}
+    launches = 0
+    ev0.record(stream)
+    for _ in range(a.steps):
+        step()
+        launches += api.last_launches(dec)
+    ev1.record(stream)
+    barrier()
+    api.synchronize(dec)
+    ms_total = ev0.elapsed_time(ev1)
+    # per-kernel device time of the LAST timed step (events recorded around each launch)
+    last = api.last_kernel_ms(dec)
+    api.set_timing(dec, False)
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / a.steps
+    value = world * B / (ms_step * 1e-3)
+    clk = clocks.summary()
+
+    # ---- e2e: host (pinned) emissions through the C-ABI, n-best copied back, wall clock
+    e2e = None
+    h2d = B * T * N * 4
+    d2h = B * nbest * (T + 2) * 4 * 2 + B * nbest * 3 * 8 + B * 4
+    if not a.no_e2e:
+        host = torch.empty((B, T, N), dtype=torch.float32, pin_memory=True)
+        host.copy_(em)
+        torch.cuda.synchronize()
+        res = None
+        for _ in range(min(a.warmup, 2)):
+            api.decode_batch_ptr(dec, host.data_ptr(), B, T, N)
+            res = api.nbest(dec, B, T, nbest)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            api.decode_batch_ptr(dec, host.data_ptr(), B, T, N)
+            res = api.nbest(dec, B, T, nbest)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": world * B * a.steps / dt, "unit": "utt/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": dt / a.steps * 1e3,
+               "note": "pinned host emissions -> flt_decode_batch (PCIe copy pipelined with the "
+                       "kernels) -> flt_nbest_copy; bound by the host link: "
+                       f"{h2d / (dt / a.steps) / 1e9:.1f} GB/s H2D achieved"}
+        del host
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- parity on a sample (outside the timed region): GPU n-best vs CPU oracle, same bits
+    P = 2
+    Tp = sample_frames(a, bst) if bst > 256 else T
+    Tp = min(Tp, 40) if bst > 256 else Tp
+    sub = em[:P, :Tp].contiguous().cpu().numpy()
+    got = G.decode_batch(dec, sub, nbest)
+    kind = "ref" if po.available("ref") else "ora"
+    O = po.Oracle(kind)
+    bo = Built(O, spec)
+    exact = ties = 0
+    for b in range(P):
+        ro = bo.decode(sub[b], nbest)
+        if has_ties(ro):
+            ties += 1
+            continue
+        try:
+            assert_same_nbest(ro, got[b], 1e-4)
+            exact += 1
+        except AssertionError:
+            pass
+    bo.close()
+    parity = {"utterances": P, "frames": Tp, "nbest": nbest, "exact_match": exact,
+              "excluded_for_ties": ties, "oracle": "reference" if kind == "ref" else "port",
+              "tolerance": "tokens/words bit-equal, scores abs 1e-4"}
+
+    # ---- roofline: per frame per utterance 4N + 12*beam algorithmic bytes
+    peak, peak_src = peaks()
+    bytes_per_utt = T * (4 * N + 12 * beam) + nbest * (T + 2) * 8 + nbest * 24
+    kernels = {}
+    alg = {"token_select": B * T * (4 * N + 8 * min(beam + 3, bst)),  # row read + list written
+           "beam_step": B * T * 12 * beam,                                  # back-pointer records
+           "backtrace": B * nbest * (T + 2) * 8}
+    for k, v in last.items():
+        if v["launches"]:
+            kernels[k] = {"ms": v["ms"], "launches": v["launches"], "algorithmic_bytes": alg[k],
+                          "achieved_gbs": alg[k] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None}
+    dom = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
+    roof = None
+    if dom:
+        ach = kernels[dom]["achieved_gbs"]
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "whole_step": {"achieved": (B * bytes_per_utt) / (ms_step * 1e-3) / 1e9,
+                               "frac": (B * bytes_per_utt) / (ms_step * 1e-3) / 1e9 / peak,
+                               "bytes_per_utterance": bytes_per_utt},
+                "step_latency_us_per_frame": kernels.get("beam_step", {}).get("ms", 0) * 1e3 / T
+                if "beam_step" in kernels else None}
+
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        Ts = sample_frames(a, bst)
+        sample = em[:4, :Ts].contiguous().cpu().numpy()
+        ups, threads, kind2, desc, _ = cpu_leg(a, spec, sample, a.cpu_seconds)
+        cpu = {"value": ups, "unit": "utt/s", "cores": threads, "kind": kind2, "sample": desc}
+
+    out = {"metric": "utterances/sec", "value": value, "unit": "utt/s", "frames_per_s": value * T,
+           "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic",
+           "config": {"workload": workload_name(a, beam, bst), "emissions": f"log_softmax({a.sigma}*N(0,1)) fp32",
+                      "nbest": nbest, "beamThreshold": a.threshold,
+                      "l2": f"inputs ({h2d / 1e9:.2f} GB/step/GPU) exceed L2 (126 MB); no flush needed"},
+           "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+           "gpu_launches": launches, "clocks": clk, "parity": parity,
+           "workspace_bytes": api.workspace_bytes(dec)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -126,6 +126,11 @@ int flt_nbest_copy(flt_decoder* dec, int32_t nbest, int32_t* tokens, int32_t* wo
 /* Introspection for benchmarks: kernels launched by the last flt_decode_batch* call, and device
  * bytes currently held by the decoder workspace. */
 int flt_decoder_last_launches(const flt_decoder* dec, int32_t* out);
+/* Per-kernel device time of the last flt_decode_batch* call, from CUDA events recorded on the
+ * decoder's stream around each launch (only while timing is on): ms3 / launches3 index
+ * 0 = token-beam select, 1 = beam step, 2 = n-best backtrace. Synchronises the stream. */
+int flt_decoder_set_timing(flt_decoder* dec, int32_t on);
+int flt_decoder_last_kernel_ms(flt_decoder* dec, float* ms3, int32_t* launches3);
 int flt_decoder_workspace_bytes(const flt_decoder* dec, int64_t* out);
 
 /* Stand-alone entry to the token-beam select kernel (decoder/LexiconFreeDecoder.cpp:39-51:

@@ -73,6 +73,8 @@ SYMBOLS = {
                                  C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "flt_decoder_last_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "flt_decoder_workspace_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "flt_decoder_set_timing": (C.c_int, [C.c_void_p, C.c_int32]),
+    "flt_decoder_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "flt_topm_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_void_p]),
 }
@@ -228,6 +230,16 @@ class Api:
         n = C.c_int32()
         self._ck(self.lib.flt_decoder_last_launches(dec, C.byref(n)))
         return n.value
+
+    def set_timing(self, dec, on=True):
+        self._ck(self.lib.flt_decoder_set_timing(dec, int(on)))
+
+    def last_kernel_ms(self, dec):
+        ms = (C.c_float * 3)()
+        n = (C.c_int32 * 3)()
+        self._ck(self.lib.flt_decoder_last_kernel_ms(dec, ms, n))
+        names = ("token_select", "beam_step", "backtrace")
+        return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(names)}
 
     def workspace_bytes(self, dec):
         n = C.c_int64()

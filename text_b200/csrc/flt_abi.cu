@@ -360,7 +360,13 @@ struct flt_decoder {
 #if FLT_DEVICE_BUILD
   cudaEvent_t evCopied[2]{}, evFree[2]{};
   int numSMs = 148;
+  std::vector<cudaEvent_t> evPool; // kernel timing: (start, stop) pairs, kind = index % 3
+  size_t evUsed = 0;
 #endif
+  bool timing = false;
+  std::vector<int> evKinds;
+  float kernelMs[3] = {0, 0, 0};
+  int kernelLaunches[3] = {0, 0, 0};
   // plan
   int planN = -1;
   DecCfg cfg{};
@@ -390,6 +396,7 @@ struct flt_decoder {
       if (evCopied[i]) cudaEventDestroy(evCopied[i]);
       if (evFree[i]) cudaEventDestroy(evFree[i]);
     }
+    for (cudaEvent_t e : evPool) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
     if (copyStream) cudaStreamDestroy(copyStream);
 #endif
@@ -547,6 +554,32 @@ void planFor(flt_decoder& d, int N) {
 
 namespace {
 
+struct KernelTimer { // records a CUDA-event pair around one launch when timing is on
+  flt_decoder& d;
+  int kind;
+  KernelTimer(flt_decoder& dd, int k) : d(dd), kind(k) {
+#if FLT_DEVICE_BUILD
+    if (!d.timing) return;
+    if (d.evUsed + 2 > d.evPool.size()) {
+      for (int i = 0; i < 2; ++i) {
+        cudaEvent_t e;
+        FLT_RT_TRY(cudaEventCreate(&e));
+        d.evPool.push_back(e);
+      }
+    }
+    FLT_RT_TRY(cudaEventRecord(d.evPool[d.evUsed], d.stream));
+#endif
+  }
+  ~KernelTimer() {
+#if FLT_DEVICE_BUILD
+    if (!d.timing) return;
+    cudaEventRecord(d.evPool[d.evUsed + 1], d.stream);
+    d.evUsed += 2;
+    d.evKinds.push_back(kind);
+#endif
+  }
+};
+
 // Run the three kernels over `Bc` utterances whose emissions are device-resident at dEmis, writing
 // n-best rows [outBase, outBase+Bc) of the decoder's output buffers.
 void runChunk(flt_decoder& d, const float* dEmis, int Bc, int T, int N, const int* dLen,
@@ -572,6 +605,7 @@ void runChunk(flt_decoder& d, const float* dEmis, int Bc, int T, int N, const in
     ta.outThr = c.setAll ? nullptr : d.thr.as<float>();
     const int grid = (int)std::min<long long>(rows, d.topmGridMax * 8LL);
     if (rows > 0) {
+      KernelTimer kt(d, 0);
       launchTopM(d.tcfg, ta, grid, d.topmSmem, s);
       d.launches++;
     }
@@ -602,8 +636,11 @@ void runChunk(flt_decoder& d, const float* dEmis, int Bc, int T, int N, const in
     a.wsGlobal = d.ws.as<char>();
     a.wsStride = (long long)d.wsBytes;
   }
-  launchDecode(c, a, grid, d.useSmemFlag ? d.wsBytes : 0, s);
-  d.launches++;
+  {
+    KernelTimer kt(d, 1);
+    launchDecode(c, a, grid, d.useSmemFlag ? d.wsBytes : 0, s);
+    d.launches++;
+  }
   BacktraceArgs b{};
   b.hParent = a.hParent;
   b.hTok = a.hTok;
@@ -616,8 +653,11 @@ void runChunk(flt_decoder& d, const float* dEmis, int Bc, int T, int N, const in
   b.nbest = d.nbest;
   b.outTok = d.outTok.as<int>() + outBase * d.nbest * (T + 2);
   b.outWord = d.outWord.as<int>() + outBase * d.nbest * (T + 2);
-  launchBacktrace(b, s);
-  d.launches++;
+  {
+    KernelTimer kt(d, 2);
+    launchBacktrace(b, s);
+    d.launches++;
+  }
 }
 
 void prepareBatch(flt_decoder& d, int B, int T, int N) {
@@ -632,6 +672,10 @@ void prepareBatch(flt_decoder& d, int B, int T, int N) {
   d.lastB = B;
   d.lastT = T;
   d.launches = 0;
+#if FLT_DEVICE_BUILD
+  d.evUsed = 0;
+#endif
+  d.evKinds.clear();
 }
 
 // device-resident emissions: whole batch in slices that bound the history / list buffers
@@ -986,6 +1030,30 @@ int flt_decoder_last_launches(const flt_decoder* dec, int32_t* out) {
   return guarded([&] {
     if (!dec || !out) throw FltError(FLT_ERR_INVALID, "null argument");
     *out = dec->launches;
+  });
+}
+int flt_decoder_set_timing(flt_decoder* dec, int32_t on) {
+  return guarded([&] {
+    if (!dec) throw FltError(FLT_ERR_INVALID, "null decoder");
+    dec->timing = on != 0;
+  });
+}
+int flt_decoder_last_kernel_ms(flt_decoder* dec, float* ms3, int32_t* launches3) {
+  return guarded([&] {
+    if (!dec || !ms3) throw FltError(FLT_ERR_INVALID, "null argument");
+    for (int k = 0; k < 3; ++k) {
+      ms3[k] = 0;
+      if (launches3) launches3[k] = 0;
+    }
+#if FLT_DEVICE_BUILD
+    rt::sync(dec->stream);
+    for (size_t i = 0; i < dec->evKinds.size(); ++i) {
+      float ms = 0;
+      FLT_RT_TRY(cudaEventElapsedTime(&ms, dec->evPool[2 * i], dec->evPool[2 * i + 1]));
+      ms3[dec->evKinds[i]] += ms;
+      if (launches3) launches3[dec->evKinds[i]]++;
+    }
+#endif
   });
 }
 int flt_decoder_workspace_bytes(const flt_decoder* dec, int64_t* out) {
