@@ -7,7 +7,7 @@
 //   candidatesAdd / candidatesStore Utils.h:131-225   (threshold filter, key merge, top-K)
 //   decodeEnd                       LexiconFreeDecoder.cpp:127-158, LexiconDecoder.cpp:231-274
 //   getAllHypothesis                Utils.h:229-266
-//   LMState::child identity         lm/LM.h:24-49 (here: an interned id per (parent id, label))
+//   LMState::child identity         lm/LM.h:24-49
 //
 // It is NOT a translation of those loops. The reference proposes beam x beamSizeToken candidates
 // per frame and sorts them; here the candidate set is cut down *exactly* before anything is
@@ -20,8 +20,16 @@
 //     top-K if r*(j-2) <= K. Only those cells are generated (K ln K instead of K*N);
 //   * everything else (trie children of non-root rows, stay / blank, word ends) is enumerated
 //     directly from the CSR trie.
-// Candidates are then merged by exact key in a CTA-private hash table, the K best groups are
-// found with a radix select on order-preserving 64-bit keys, and survivors are ranked.
+// Candidates are merged by key in a CTA-private hash table, the K best groups are found with a
+// radix select on order-preserving 64-bit keys, and survivors are ranked.
+//
+// LM-state identity. The reference identifies an LM state by the address of a node in a child
+// tree rooted at start() (lm/LM.h:24-49), i.e. by the sequence of labels that led to it. Here a
+// state carries a 128-bit fingerprint of that label sequence (two independent 64-bit chains,
+// extended with one multiply-mix per label): equal sequences give equal fingerprints at any time,
+// with no table, no atomics and no per-utterance reset. Two different sequences collide with
+// probability 2^-128 per pair.
+//
 // Arithmetic follows the reference's evaluation order (FP64 accumulators, FP32 sub-expressions,
 // no FMA contraction: this file is compiled with -fmad=false).
 #pragma once
@@ -30,7 +38,23 @@
 
 namespace flt {
 
+typedef unsigned long long u64;
+
 /* ------------------------------------------------------------------ configuration ---------- */
+// Byte offsets of every workspace array from the CTA's workspace base. Computed once on the host
+// (planFor) and passed in the kernel parameters, i.e. read from the constant bank.
+struct Lay {
+  int beamD[2], beamFp[2], beamI[2];
+  int rowHash, rowI;
+  int candScore, candKey, candI;
+  int mh, rep, surv, skey, pos;
+  int hist, sc, red;
+  int list[2];
+  int spec;
+  int wideOff;
+  int total;
+};
+
 struct DecCfg {
   int lexicon;   // 0 = LexiconFreeDecoder, 1 = LexiconDecoder
   int K;         // beamSize
@@ -43,16 +67,18 @@ struct DecCfg {
   int M;          // entries per frame in the token list produced by the select kernel
   int Mwide;      // columns the wide enumeration may use (<= M)
   int wideRanked; // 1 = wide rows use the ranked list; 0 = they enumerate their children directly
+  int listInSmem; // the frame's token list is prefetched into the workspace (M <= 2 * threads)
   int capC;       // candidate capacity
   int capH;       // merge table slots (pow2 >= 2*capC)
   int capRH;      // row table slots (pow2 >= 2*K)
-  int capP;       // pow2 >= K (sort scratch)
-  const int* wideOff; // [K+1]: wideOff[r] = sum_{q=1..r} J_q, J_q = min(Mwide, K/q + 3)
+  int capP;       // pow2 >= K
+  const int* wideOff; // [K+1]: wideOff[r] = sum_{q=1..r} J_q, J_q = min(Mwide, K/q + 3 (+slack))
+  Lay lay;
   TrieDev trie;
   LmDev lm;
 };
 
-/* Per-utterance arguments of one decode launch. */
+/* Per-launch arguments. */
 struct BatchArgs {
   const float* emis; // [B,T,N]
   int B, T;
@@ -65,456 +91,472 @@ struct BatchArgs {
   int* hWord;           // null for the lexicon-free decoder
   double* finScore;     // [B, K, 3]
   int* finCount;        // [B]
-  int* status;          // [B] bit0 = candidate overflow, bit1 = state table overflow
+  int* status;          // [B] bit0 = candidate overflow
   char* wsGlobal;       // per-CTA workspace slabs (used when the workspace does not fit smem)
   long long wsStride;
-  unsigned long long* stateTab; // per-CTA LM-state intern tables
-  long long stateCap;           // slots per table (pow2)
-  int useSmem;
 };
 
-/* ------------------------------------------------------------------ workspace ---------- */
+/* ------------------------------------------------------------------ workspace views ---------- */
 struct Beam {
-  double* score;
-  double* am;
-  double* lm;
-  int* sid;   // interned LM-state id (0 = the start state)
-  int* spid;  // (parent id, label) that names this state: the exact, time-invariant identity
-  int* slab;
-  int* lex;   // trie node (0 = root); always 0 for the lexicon-free decoder
-  int* tok;
-  int* pb;    // prevBlank
-  int* nctx;  // n-gram context length
-  int* ctx;   // [K, kMaxCtx] LM vocabulary ids, most recent first
+  double* d;  // [3][K] score, emittingModelScore, lmScore
+  u64* fp;    // [2][K] LM-state fingerprint
+  int* iv;    // [4][K] lex, tok, prevBlank, nctx; then ctx [K][kMaxCtx]
+  int K;
+  FLT_DEV double& score(int i) const { return d[i]; }
+  FLT_DEV double& am(int i) const { return d[K + i]; }
+  FLT_DEV double& lm(int i) const { return d[2 * K + i]; }
+  FLT_DEV u64& fpA(int i) const { return fp[i]; }
+  FLT_DEV u64& fpB(int i) const { return fp[K + i]; }
+  FLT_DEV int& lex(int i) const { return iv[i]; }
+  FLT_DEV int& tok(int i) const { return iv[K + i]; }
+  FLT_DEV int& pb(int i) const { return iv[2 * K + i]; }
+  FLT_DEV int& nctx(int i) const { return iv[3 * K + i]; }
+  FLT_DEV int* ctx(int i) const { return iv + 4 * K + i * kMaxCtx; }
 };
 
-enum { // ws.sc[] scalars
-  SC_NH = 0, SC_NCAND, SC_NREP, SC_NSEL, SC_NROWS, SC_NARROW_ITEMS, SC_WIDE_ITEMS, SC_OVF,
-  SC_BIN, SC_NEED, SC_BINCOUNT, SC_TIES, SC_COUNT
-};
-enum { // ws.sq[] 64-bit scalars
-  SQ_BEST = 0, SQ_MIN, SQ_PREFIX, SQ_COUNT
-};
 constexpr int CF_PB = 1, CF_NEW = 2, CF_ALIVE = 4, CF_FINISH = 8;
 constexpr int kIntMax = 0x7FFFFFFF;
 
+struct Cand {
+  double* sc; // [capC]
+  u64* key;   // [2][capC] 128-bit merge key: (LM state, lex, token, prevBlank)
+  int* iv;    // [6][capC] parent<<4|flags, token, word, lex, lm delta (float bits), e (float bits)
+  int cap;
+  FLT_DEV double& score(int x) const { return sc[x]; }
+  FLT_DEV u64& keyA(int x) const { return key[x]; }
+  FLT_DEV u64& keyB(int x) const { return key[cap + x]; }
+  FLT_DEV int& parflag(int x) const { return iv[x]; }
+  FLT_DEV int par(int x) const { return iv[x] >> 4; }
+  FLT_DEV int flags(int x) const { return iv[x] & 15; }
+  FLT_DEV int& tok(int x) const { return iv[cap + x]; }
+  FLT_DEV int& word(int x) const { return iv[2 * cap + x]; }
+  FLT_DEV int& lex(int x) const { return iv[3 * cap + x]; }
+  FLT_DEV float& lmd(int x) const { return ((float*)iv)[4 * cap + x]; }
+  FLT_DEV float& ce(int x) const { return ((float*)iv)[5 * cap + x]; }
+};
+
+struct Rows {
+  int* hash; // [capRH]
+  int* iv;
+  int K;
+  FLT_DEV int& rowOf(int i) const { return iv[i]; }
+  FLT_DEV int& m2(int i) const { return iv[K + i]; }
+  FLT_DEV int* rank() const { return iv + 2 * K; }             // [K+1]
+  FLT_DEV int* rankTmp() const { return iv + 3 * K + 1; }      // [K+1]
+  FLT_DEV int& leaderOfRank(int r) const { return iv[4 * K + 2 + r]; }
+  FLT_DEV int* deg() const { return iv + 5 * K + 2; }          // [K+1]
+  FLT_DEV int* degTmp() const { return iv + 6 * K + 3; }       // [K+1]
+};
+constexpr int kRowsInts = 7; // K-sized int arrays (+ slack) behind Rows::iv
+
+enum { // ws.sc[] scalars
+  SC_NH = 0, SC_NCAND, SC_NREP, SC_NSEL, SC_NROWS, SC_OVF, SC_BIN, SC_NEED, SC_BINCOUNT, SC_NICE,
+  SC_COUNT
+};
+
+// The workspace is addressed as base + constant-bank offset on every access (no pointer table in
+// local memory; with the shared-memory base the compiler emits LDS/STS with immediate offsets).
 struct Ws {
-  Beam beam[2];
-  // rows
-  int* rowHash;      // [capRH]
-  int* rowOf;        // [K] leader of the row of hyp i (wide hyps)
-  int* m2;           // [K] second-best member of the row led by i
-  int* rank;         // [K] scan scratch / row rank
-  int* rankTmp;      // [K]
-  int* leaderOfRank; // [K]
-  int* deg;          // [K+1] narrow items per hyp (scan)
-  int* degTmp;       // [K+1]
-  // candidates
-  double* cscore;
-  int* cpar;
-  int* ctok;
-  int* cword;
-  int* clex;
-  int* cflag;
-  int* clab;
-  float* clmd;
-  float* ce;
-  int* mh;   // [capH] merge table: candidate index of the group's best member, -1 empty
-  int* rep;  // [capC] group representatives
-  int* surv; // [capP] selected, then sorted
-  int* survTmp;
-  int* hist; // [256]
-  int* sc;
-  unsigned long long* sq;
-  unsigned long long* red; // [64] CTA-reduction scratch
+  char* base;
+  const DecCfg* c;
+  FLT_DEV Beam beam(int b) const {
+    const Lay& L = c->lay;
+    return Beam{(double*)(base + L.beamD[b]), (u64*)(base + L.beamFp[b]), (int*)(base + L.beamI[b]), c->K};
+  }
+  FLT_DEV Rows rows() const {
+    return Rows{(int*)(base + c->lay.rowHash), (int*)(base + c->lay.rowI), c->K};
+  }
+  FLT_DEV Cand cand() const {
+    const Lay& L = c->lay;
+    return Cand{(double*)(base + L.candScore), (u64*)(base + L.candKey), (int*)(base + L.candI), c->capC};
+  }
+  FLT_DEV int* mh() const { return (int*)(base + c->lay.mh); }       // [capH] merge table
+  FLT_DEV int* rep() const { return (int*)(base + c->lay.rep); }     // [capC] group representatives
+  FLT_DEV int* surv() const { return (int*)(base + c->lay.surv); }   // [2][capP] selected / ranked
+  FLT_DEV u64* skey() const { return (u64*)(base + c->lay.skey); }   // [capP] ordered score keys
+  FLT_DEV int* pos() const { return (int*)(base + c->lay.pos); }     // [capP] rank counters
+  FLT_DEV int* hist() const { return (int*)(base + c->lay.hist); }   // [256]
+  FLT_DEV int* sc() const { return (int*)(base + c->lay.sc); }
+  FLT_DEV u64* red() const { return (u64*)(base + c->lay.red); }     // [64]
+  FLT_DEV int* listTok(int b) const { return (int*)(base + c->lay.list[b]); } // [M] token list
+  FLT_DEV float* listVal(int b) const { return (float*)(base + c->lay.list[b] + 4 * c->M); }
+  FLT_DEV float* spec() const { return (float*)(base + c->lay.spec); } // [K+2] e[own], e[blank], e[sil]
+  FLT_DEV int* wideOff() const { return (int*)(base + c->lay.wideOff); } // [K+1]
 };
 
 FLT_HD size_t alignUp(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// Carve the workspace out of `base` (nullptr => just compute the size).
-FLT_HD size_t carveWs(char* base, const DecCfg& c, Ws& w) {
+FLT_HD void makeLayout(DecCfg& c) {
   size_t off = 0;
   auto take = [&](size_t bytes) {
-    char* p = base ? base + off : nullptr;
+    const size_t o = off;
     off = alignUp(off + bytes, 16);
-    return p;
+    return (int)o;
   };
   const int K = c.K;
+  Lay& L = c.lay;
   for (int b = 0; b < 2; ++b) {
-    Beam& B = w.beam[b];
-    B.score = (double*)take(sizeof(double) * K);
-    B.am = (double*)take(sizeof(double) * K);
-    B.lm = (double*)take(sizeof(double) * K);
-    B.sid = (int*)take(sizeof(int) * K);
-    B.spid = (int*)take(sizeof(int) * K);
-    B.slab = (int*)take(sizeof(int) * K);
-    B.lex = (int*)take(sizeof(int) * K);
-    B.tok = (int*)take(sizeof(int) * K);
-    B.pb = (int*)take(sizeof(int) * K);
-    B.nctx = (int*)take(sizeof(int) * K);
-    B.ctx = (int*)take(sizeof(int) * K * (c.lm.kind ? kMaxCtx : 0));
+    L.beamD[b] = take(sizeof(double) * 3 * K);
+    L.beamFp[b] = take(sizeof(u64) * 2 * K);
+    L.beamI[b] = take(sizeof(int) * (4 * K + (c.lm.kind ? K * kMaxCtx : 0)));
   }
-  w.rowHash = (int*)take(sizeof(int) * c.capRH);
-  w.rowOf = (int*)take(sizeof(int) * K);
-  w.m2 = (int*)take(sizeof(int) * K);
-  w.rank = (int*)take(sizeof(int) * (K + 1));
-  w.rankTmp = (int*)take(sizeof(int) * (K + 1));
-  w.leaderOfRank = (int*)take(sizeof(int) * K);
-  w.deg = (int*)take(sizeof(int) * (K + 1));
-  w.degTmp = (int*)take(sizeof(int) * (K + 1));
-  w.cscore = (double*)take(sizeof(double) * c.capC);
-  w.cpar = (int*)take(sizeof(int) * c.capC);
-  w.ctok = (int*)take(sizeof(int) * c.capC);
-  w.cword = (int*)take(sizeof(int) * c.capC);
-  w.clex = (int*)take(sizeof(int) * c.capC);
-  w.cflag = (int*)take(sizeof(int) * c.capC);
-  w.clab = (int*)take(sizeof(int) * c.capC);
-  w.clmd = (float*)take(sizeof(float) * c.capC);
-  w.ce = (float*)take(sizeof(float) * c.capC);
-  w.mh = (int*)take(sizeof(int) * c.capH);
-  w.rep = (int*)take(sizeof(int) * c.capC);
-  w.surv = (int*)take(sizeof(int) * c.capP);
-  w.survTmp = (int*)take(sizeof(int) * c.capP);
-  w.hist = (int*)take(sizeof(int) * 256);
-  w.sc = (int*)take(sizeof(int) * SC_COUNT);
-  w.sq = (unsigned long long*)take(sizeof(unsigned long long) * SQ_COUNT);
-  w.red = (unsigned long long*)take(sizeof(unsigned long long) * 64);
-  return off;
+  L.rowHash = take(sizeof(int) * c.capRH);
+  L.rowI = take(sizeof(int) * (kRowsInts * K + 8));
+  L.candScore = take(sizeof(double) * c.capC);
+  L.candKey = take(sizeof(u64) * 2 * c.capC);
+  L.candI = take(sizeof(int) * 6 * c.capC);
+  L.mh = take(sizeof(int) * c.capH);
+  L.rep = take(sizeof(int) * c.capC);
+  L.surv = take(sizeof(int) * 2 * c.capP);
+  L.skey = take(sizeof(u64) * c.capP);
+  L.pos = take(sizeof(int) * c.capP);
+  L.hist = take(sizeof(int) * 256);
+  L.sc = take(sizeof(int) * SC_COUNT);
+  L.red = take(sizeof(u64) * 64);
+  for (int b = 0; b < 2; ++b) L.list[b] = take(c.listInSmem ? 8 * (size_t)c.M : 0);
+  L.spec = take(sizeof(float) * (K + 2));
+  L.wideOff = take(sizeof(int) * (K + 1));
+  L.total = (int)off;
 }
 
 FLT_HD double negInf() { return bitsF64(0xFFF0000000000000ull); }
-FLT_HD double keyToDouble(unsigned long long key) { // inverse of orderedKey64
+FLT_HD double keyToDouble(u64 key) { // inverse of orderedKey64
   return bitsF64((key >> 63) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key);
 }
 
+/* ------------------------------------------------------------------ LM-state fingerprints ---- */
+FLT_HD void fpRoot(u64& a, u64& b) {
+  a = 0x243F6A8885A308D3ull;
+  b = 0x13198A2E03707344ull;
+}
+FLT_HD void fpChild(u64 pa, u64 pb, int label, u64& a, u64& b) {
+  const u64 l = (u64)(uint32_t)label;
+  a = mix64(pa * 0x9E3779B97F4A7C15ull + l + 0x632BE59BD9B4E019ull);
+  b = mix64(pb * 0xC2B2AE3D27D4EB4Full + l * 0x165667B19E3779F9ull + 0x27D4EB2F165667C5ull);
+}
+FLT_HD void candKeyOf(u64 sa, u64 sb, int lex, int tok, int pbFlag, u64& ka, u64& kb) {
+  const u64 p = ((u64)(uint32_t)lex << 32) | ((u64)(uint32_t)tok << 1) | (u64)(pbFlag ? 1 : 0);
+  ka = mix64(sa ^ mix64(p + 0x9E3779B97F4A7C15ull));
+  kb = mix64(sb + p * 0xD6E8FEB86659FD93ull);
+}
+
 /* ------------------------------------------------------------------ CTA collectives ---------- */
-// max over the CTA of a 64-bit key; every thread gets the result.
-FLT_DEV unsigned long long ctaMax64(const Cta& cta, unsigned long long v, unsigned long long* red) {
+// max and min over the CTA of 64-bit keys; every thread gets both.
+FLT_DEV void ctaMaxMin64(const Cta& cta, u64& vmax, u64& vmin, u64* red) {
 #if FLT_DEVICE_BUILD
   for (int o = 16; o > 0; o >>= 1) {
-    unsigned long long u = __shfl_xor_sync(0xffffffffu, v, o);
-    v = u > v ? u : v;
+    const u64 u = __shfl_xor_sync(0xffffffffu, vmax, o);
+    const u64 l = __shfl_xor_sync(0xffffffffu, vmin, o);
+    vmax = u > vmax ? u : vmax;
+    vmin = l < vmin ? l : vmin;
   }
   const int warp = cta.tid >> 5, lane = cta.tid & 31, nw = (cta.nthr + 31) >> 5;
   cta.sync(); // red[] may still be read from a previous call
-  if (lane == 0) red[warp] = v;
+  if (lane == 0) {
+    red[warp] = vmax;
+    red[32 + warp] = vmin;
+  }
   cta.sync();
-  unsigned long long r = red[0];
-  for (int i = 1; i < nw; ++i) r = red[i] > r ? red[i] : r;
-  return r;
+  u64 r = red[0], q = red[32];
+  for (int i = 1; i < nw; ++i) {
+    r = red[i] > r ? red[i] : r;
+    q = red[32 + i] < q ? red[32 + i] : q;
+  }
+  vmax = r;
+  vmin = q;
 #else
   (void)cta;
   (void)red;
+#endif
+}
+FLT_DEV u64 ctaMax64(const Cta& cta, u64 v, u64* red) {
+  u64 mn = ~0ull;
+  ctaMaxMin64(cta, v, mn, red);
   return v;
+}
+
+// Exclusive prefix sum of a[0..n) in place; a[n] receives the total. tmp has >= 64 ints.
+// Each thread scans a contiguous slice, slices are combined with a shuffle scan (2 barriers).
+FLT_DEV void ctaExclusiveScan(const Cta& cta, int* a, int* tmp, int n) {
+#if FLT_DEVICE_BUILD
+  const int per = (n + cta.nthr - 1) / cta.nthr;
+  const int lo = cta.tid * per, hi = lo + per < n ? lo + per : n;
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += a[i];
+  int incl = sum;
+  const int lane = cta.tid & 31, warp = cta.tid >> 5, nw = (cta.nthr + 31) >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) tmp[warp] = incl;
+  cta.sync();
+  int base = 0;
+  for (int wI = 0; wI < warp; ++wI) base += tmp[wI];
+  int total = 0;
+  for (int wI = 0; wI < nw; ++wI) total += tmp[wI];
+  int run = base + incl - sum;
+  for (int i = lo; i < hi; ++i) {
+    const int v = a[i];
+    a[i] = run;
+    run += v;
+  }
+  if (cta.tid == 0) a[n] = total;
+  cta.sync();
+#else
+  (void)tmp;
+  int run = 0;
+  for (int i = 0; i < n; ++i) {
+    const int v = a[i];
+    a[i] = run;
+    run += v;
+  }
+  a[n] = run;
+  (void)cta;
 #endif
 }
 
-// Exclusive prefix sum of a[0..n) in place; a[n] receives the total. tmp has n+1 entries.
-FLT_DEV void ctaExclusiveScan(const Cta& cta, int* a, int* tmp, int n) {
-  // Hillis-Steele inclusive scan with ping-pong, then shift.
-  int* src = a;
-  int* dst = tmp;
-  for (int d = 1; d < n; d <<= 1) {
-    for (int i = cta.tid; i < n; i += cta.nthr) dst[i] = src[i] + (i >= d ? src[i - d] : 0);
-    cta.sync();
-    int* t = src;
-    src = dst;
-    dst = t;
-  }
-  // src holds the inclusive scan; write exclusive into dst then copy back if needed
-  for (int i = cta.tid; i <= n; i += cta.nthr) dst[i] = i == 0 ? 0 : src[i - 1];
-  cta.sync();
-  if (dst != a) {
-    for (int i = cta.tid; i <= n; i += cta.nthr) a[i] = dst[i];
-    cta.sync();
-  }
-}
-
-// largest r in [0, n) with off[r] <= x, for a non-decreasing off[0..n]
+// largest r in [0, n) with off[r] <= x, for a non-decreasing off[0..n)
 FLT_DEV int searchOffsets(const int* off, int n, int x) {
   int lo = 0, hi = n - 1;
   while (lo < hi) {
-    int mid = (lo + hi + 1) >> 1;
+    const int mid = (lo + hi + 1) >> 1;
     if (off[mid] <= x) lo = mid;
     else hi = mid - 1;
   }
   return lo;
 }
 
-/* ------------------------------------------------------------------ LM-state interning ---------- */
-// find-or-insert (parent id, label) in the CTA's open-addressing table; the id is slot+1
-// (0 is the start state). Returns -1 when the table is full.
-FLT_DEV int internState(unsigned long long* tab, long long cap, int pid, int label) {
-  const unsigned long long key = ((unsigned long long)(unsigned)pid << 32) | (unsigned)label;
-  const unsigned long long kEmpty = ~0ull;
-  unsigned long long s = mix64(key) & (unsigned long long)(cap - 1);
-  for (long long probes = 0; probes < cap; ++probes) {
-    unsigned long long cur = tab[s];
-    if (cur == key) return (int)s + 1;
-    if (cur == kEmpty) {
-      unsigned long long old = atomCAS64(&tab[s], kEmpty, key);
-      if (old == kEmpty || old == key) return (int)s + 1;
-    }
-    s = (s + 1) & (unsigned long long)(cap - 1);
-  }
-  return -1;
-}
-
 /* ------------------------------------------------------------------ candidates ---------- */
-FLT_DEV void putCand(Ws& w, int slot, double score, int par, int tok, int word, int lex, int flags,
-                     float lmd, int lab, float ev) {
-  w.cscore[slot] = score;
-  w.cpar[slot] = par;
-  w.ctok[slot] = tok;
-  w.cword[slot] = word;
-  w.clex[slot] = lex;
-  w.cflag[slot] = flags | CF_ALIVE;
-  w.clmd[slot] = lmd;
-  w.clab[slot] = lab;
-  w.ce[slot] = ev;
+// label that names the candidate's new LM state: token (lexicon-free), word (lexicon), -1 (finish)
+FLT_DEV int candLabel(const DecCfg& c, const Cand& cd, int x) {
+  if (cd.flags(x) & CF_FINISH) return -1;
+  return c.lexicon ? cd.word(x) : cd.tok(x);
 }
 
-// exact identity of the candidate's LM state as a (parent id, label) pair
-FLT_DEV void candState(const Ws& w, const Beam& cur, int c, int& pid, int& lab) {
-  const int p = w.cpar[c];
-  if (w.cflag[c] & CF_NEW) {
-    pid = cur.sid[p];
-    lab = w.clab[c];
-  } else {
-    pid = cur.spid[p];
-    lab = cur.slab[p];
+FLT_DEV void putCand(const DecCfg& c, const Ws& w, const Beam& cur, int slot, double score, int par,
+                     int tok, int word, int lex, int flags, float lmd, float ev) {
+  const Cand cd = w.cand();
+  cd.score(slot) = score;
+  cd.parflag(slot) = (par << 4) | flags | CF_ALIVE;
+  cd.tok(slot) = tok;
+  cd.word(slot) = word;
+  cd.lex(slot) = lex;
+  cd.lmd(slot) = lmd;
+  cd.ce(slot) = ev;
+  u64 sa = cur.fpA(par), sb = cur.fpB(par);
+  if (flags & CF_NEW) {
+    const int label = (flags & CF_FINISH) ? -1 : (c.lexicon ? word : tok);
+    fpChild(sa, sb, label, sa, sb);
   }
-}
-
-FLT_DEV bool candKeyEq(const Ws& w, const Beam& cur, int a, int b) {
-  if (w.ctok[a] != w.ctok[b] || w.clex[a] != w.clex[b]) return false;
-  if ((w.cflag[a] ^ w.cflag[b]) & CF_PB) return false;
-  int pa, la, pb_, lb;
-  candState(w, cur, a, pa, la);
-  candState(w, cur, b, pb_, lb);
-  return pa == pb_ && la == lb;
+  candKeyOf(sa, sb, lex, tok, flags & CF_PB, cd.keyA(slot), cd.keyB(slot));
 }
 
 // deterministic total order used wherever the reference leaves ties to libstdc++ internals:
-// higher score first, then lower parent rank, token, word, lexicon node.
-FLT_DEV bool candBetter(const Ws& w, int a, int b) {
-  const double sa = w.cscore[a], sb = w.cscore[b];
+// higher score first, then lower parent rank, token, word, lexicon node, prevBlank.
+FLT_DEV bool candBetter(const Cand& cd, int a, int b) {
+  const double sa = cd.score(a), sb = cd.score(b);
   if (sa != sb) return sa > sb;
-  if (w.cpar[a] != w.cpar[b]) return w.cpar[a] < w.cpar[b];
-  if (w.ctok[a] != w.ctok[b]) return w.ctok[a] < w.ctok[b];
-  if (w.cword[a] != w.cword[b]) return w.cword[a] < w.cword[b];
-  if (w.clex[a] != w.clex[b]) return w.clex[a] < w.clex[b];
-  return (w.cflag[a] & CF_PB) < (w.cflag[b] & CF_PB);
-}
-
-FLT_DEV uint32_t candKeyHash(const Ws& w, const Beam& cur, int c) {
-  int pid, lab;
-  candState(w, cur, c, pid, lab);
-  uint64_t h = ((uint64_t)(uint32_t)pid << 32) | (uint32_t)lab;
-  h = mix64(h) ^ (((uint64_t)(uint32_t)w.clex[c] << 32) | ((uint32_t)w.ctok[c] << 1) |
-                  (uint32_t)(w.cflag[c] & CF_PB));
-  return (uint32_t)mix64(h);
-}
-
-/* token-set membership for tokens that are not taken from the ranked list */
-FLT_DEV bool inTokenSet(const DecCfg& c, const float* e, int n, float thrVal, const int* topTok,
-                        int listLen) {
-  if (c.setAll) return true;
-  const float v = e[n];
-  if (v > thrVal) return true;
-  if (v < thrVal) return false;
-  for (int j = 0; j < listLen; ++j) // equal to the cut value: membership = presence in the list
-    if (topTok[j] == n) return true;
-  return false;
+  if (cd.par(a) != cd.par(b)) return cd.par(a) < cd.par(b);
+  if (cd.tok(a) != cd.tok(b)) return cd.tok(a) < cd.tok(b);
+  if (cd.word(a) != cd.word(b)) return cd.word(a) < cd.word(b);
+  if (cd.lex(a) != cd.lex(b)) return cd.lex(a) < cd.lex(b);
+  return (cd.flags(a) & CF_PB) < (cd.flags(b) & CF_PB);
 }
 
 /* ------------------------------------------------------------------ the frame step ---------- */
 struct FrameIn {
-  const float* e;      // emission row [N]
-  const int* topTok;   // [M] ranked tokens (may be null when unused)
+  const float* e;      // emission row [N] (global)
+  const int* topTok;   // [M] ranked tokens (workspace copy when listInSmem, else global)
   const float* topVal; // [M]
   int listLen;         // valid entries in the list
   float thrVal;        // cut value of the token set (unused when setAll)
   int first;           // global frame 0 (ASG transitions are skipped, LexiconDecoder.cpp:70-73)
+  int listIsSet;       // the list holds the whole token set (lexicon-free, beamSizeToken < N)
   int* hParent;        // history row to write (frame t+1), [K]
   int* hTok;
   int* hWord;
 };
 
+/* token-set membership for tokens that are not taken from the ranked list */
+FLT_DEV bool inTokenSetV(const DecCfg& c, const FrameIn& f, int n, float v) {
+  if (c.setAll) return true;
+  if (v > f.thrVal) return true;
+  if (v < f.thrVal) return false;
+  if (!f.listIsSet) return true; // lexicon decoder: ties at the cut are taken (documented)
+  for (int j = 0; j < f.listLen; ++j) // equal to the cut value: membership = presence in the list
+    if (f.topTok[j] == n) return true;
+  return false;
+}
+
 // Phase R: group wide hypotheses into rows (same LM state; lexicon: also lex == root).
-FLT_DEV void phaseRows(const Cta& cta, const DecCfg& c, Ws& w, const Beam& cur, int nH) {
-  for (int s = cta.tid; s < c.capRH; s += cta.nthr) w.rowHash[s] = -1;
+FLT_DEV void phaseRows(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, int nH) {
+  const Rows R = w.rows();
+  for (int s = cta.tid; s < c.capRH; s += cta.nthr) R.hash[s] = -1;
   for (int i = cta.tid; i < nH; i += cta.nthr) {
-    w.m2[i] = kIntMax;
-    w.rowOf[i] = -1;
+    R.m2(i) = kIntMax;
+    R.rowOf(i) = -1;
   }
   cta.sync();
   const uint32_t mask = (uint32_t)c.capRH - 1;
   for (int i = cta.tid; i < nH; i += cta.nthr) {
-    if (c.lexicon && cur.lex[i] != 0) continue;
-    uint32_t s = (uint32_t)mix64((uint64_t)(uint32_t)cur.sid[i]) & mask;
+    if (c.lexicon && cur.lex(i) != 0) continue;
+    const u64 fa = cur.fpA(i), fb = cur.fpB(i);
+    uint32_t s = (uint32_t)fa & mask;
     for (;;) {
-      int old = atomCAS(&w.rowHash[s], -1, i);
+      const int old = atomCAS(&R.hash[s], -1, i);
       if (old == -1) break;
-      if (cur.sid[old] == cur.sid[i]) {
-        atomMin(&w.rowHash[s], i);
+      if (cur.fpA(old) == fa && cur.fpB(old) == fb) {
+        atomMin(&R.hash[s], i);
         break;
       }
       s = (s + 1) & mask;
     }
   }
   cta.sync();
+  int* rank = R.rank();
   for (int i = cta.tid; i < nH; i += cta.nthr) {
     int isLeader = 0;
-    if (!(c.lexicon && cur.lex[i] != 0)) {
-      uint32_t s = (uint32_t)mix64((uint64_t)(uint32_t)cur.sid[i]) & mask;
+    if (!(c.lexicon && cur.lex(i) != 0)) {
+      const u64 fa = cur.fpA(i), fb = cur.fpB(i);
+      uint32_t s = (uint32_t)fa & mask;
       for (;;) {
-        int occ = w.rowHash[s];
-        if (cur.sid[occ] == cur.sid[i]) {
-          w.rowOf[i] = occ;
+        const int occ = R.hash[s];
+        if (cur.fpA(occ) == fa && cur.fpB(occ) == fb) {
+          R.rowOf(i) = occ;
           isLeader = occ == i;
-          if (!isLeader) atomMin(&w.m2[occ], i);
+          if (!isLeader) atomMin(&R.m2(occ), i);
           break;
         }
         s = (s + 1) & mask;
       }
     }
-    w.rank[i] = isLeader;
+    rank[i] = isLeader;
   }
   cta.sync();
-  ctaExclusiveScan(cta, w.rank, w.rankTmp, nH); // rank[i] = leaders before i; rank[nH] = rows
+  ctaExclusiveScan(cta, rank, R.rankTmp(), nH); // rank[i] = leaders before i; rank[nH] = rows
   for (int i = cta.tid; i < nH; i += cta.nthr)
-    if (w.rowOf[i] == i) w.leaderOfRank[w.rank[i]] = i;
-  if (cta.tid == 0) w.sc[SC_NROWS] = w.rank[nH];
+    if (R.rowOf(i) == i) R.leaderOfRank(rank[i]) = i;
+  if (cta.tid == 0) w.sc()[SC_NROWS] = rank[nH];
   cta.sync();
 }
 
 FLT_DEV bool newTokenEligible(const DecCfg& c, const Beam& cur, int p, int n) {
-  if (c.lexicon) return !c.ctc || cur.pb[p] || n != cur.tok[p]; // LexiconDecoder.cpp:89-90
-  if (c.ctc) return n != cur.tok[p] || cur.pb[p];                // LexiconFreeDecoder.cpp:69-71
-  return n != cur.tok[p];
+  if (c.lexicon) return !c.ctc || cur.pb(p) || n != cur.tok(p); // LexiconDecoder.cpp:89-90
+  if (c.ctc) return n != cur.tok(p) || cur.pb(p);                // LexiconFreeDecoder.cpp:69-71
+  return n != cur.tok(p);
 }
 
-FLT_DEV double transAdd(const DecCfg& c, const FrameIn& f, int n, int prevTok) {
-  // returns the double `emittingModelScore` of the reference for token n after prevTok
-  double am = (double)f.e[n];
+// the reference's double `emittingModelScore` for an emission value ev of token n after prevTok
+FLT_DEV double amOf(const DecCfg& c, const FrameIn& f, float ev, int n, int prevTok) {
+  double am = (double)ev;
   if (!c.ctc && !f.first && c.trans) am += (double)c.trans[(size_t)n * c.N + prevTok];
   return am;
 }
 
+// new-token expansion of the row led by hypothesis i with token n (value ev)
+FLT_DEV void emitRowToken(const DecCfg& c, const Ws& w, const Beam& cur, int i, int n, float ev,
+                          int slot, double& best) {
+  int p = i;
+  if (!newTokenEligible(c, cur, p, n)) {
+    p = w.rows().m2(i);
+    if (p == kIntMax) return;
+  }
+  if (!c.lexicon) {
+    // LexiconFreeDecoder.cpp:64-85 with ZeroLM: score = prev + e (+sil) + lmWeight * 0
+    double score = cur.score(p) + (double)ev;
+    if (n == c.sil) score += c.silScore;
+    score = score + c.lmWeight * (double)0.0f;
+    putCand(c, w, cur, slot, score, p, n, -1, 0, CF_NEW, 0.0f, ev);
+    if (score > best) best = score;
+  } else {
+    // LexiconDecoder.cpp:62-110, prevLex == root, CTC (ranked mode excludes ASG)
+    const int child = c.trie.rootChild[n];
+    if (child < 0 || c.trie.childOff[child + 1] == c.trie.childOff[child]) return;
+    double score = cur.score(p) + (double)ev;
+    if (n == c.sil) score += c.silScore;
+    const float d = c.trie.maxScore[child] - 0.0f;
+    score = score + c.lmWeight * (double)d;
+    putCand(c, w, cur, slot, score, p, n, -1, child, 0, d, ev);
+    if (score > best) best = score;
+  }
+}
+
 // one wide cell: row led by hypothesis i, list column j
-FLT_DEV void emitWide(const DecCfg& c, Ws& w, const Beam& cur, const FrameIn& f, int i, int j,
+FLT_DEV void emitWide(const DecCfg& c, const Ws& w, const Beam& cur, const FrameIn& f, int i, int j,
                       int slot, double& best) {
-  w.cflag[slot] = 0;
+  w.cand().parflag(slot) = 0;
   if (j >= f.listLen) return;
   const int n = f.topTok[j];
   if (n < 0) return;                 // short list (fewer eligible tokens than columns)
   if (c.ctc && n == c.blank) return; // blank is never a new token
   if (n == c.sil && c.silScore > 0) return; // boosted sil is not rank-dominated: emitSilCell
-  int p = i;
-  if (!newTokenEligible(c, cur, p, n)) {
-    p = w.m2[i];
-    if (p == kIntMax) return;
-  }
-  const float ev = f.topVal[j];
-  if (!c.lexicon) {
-    // LexiconFreeDecoder.cpp:64-85 with ZeroLM: score = prev + e (+sil) + lmWeight * 0
-    double score = cur.score[p] + (double)ev;
-    if (n == c.sil) score += c.silScore;
-    score = score + c.lmWeight * (double)0.0f;
-    putCand(w, slot, score, p, n, -1, 0, CF_NEW, 0.0f, n, ev);
-    if (score > best) best = score;
-  } else {
-    // LexiconDecoder.cpp:62-110, prevLex == root, CTC (ranked mode excludes ASG)
-    const int child = c.trie.rootChild[n];
-    double score = cur.score[p] + (double)ev;
-    if (n == c.sil) score += c.silScore;
-    const float d = c.trie.maxScore[child] - 0.0f;
-    score = score + c.lmWeight * (double)d;
-    putCand(w, slot, score, p, n, -1, child, 0, d, -1, ev);
-    if (score > best) best = score;
-  }
+  emitRowToken(c, w, cur, i, n, f.topVal[j], slot, best);
 }
 
 // With silScore > 0 the sil expansion of a wide row is not dominated by the cells left of it in
 // the ranked list, so every row proposes it explicitly (slot given by the caller).
-FLT_DEV void emitSilCell(const DecCfg& c, Ws& w, const Beam& cur, const FrameIn& f, int i, int slot,
-                         double& best) {
-  w.cflag[slot] = 0;
-  if (!(c.silScore > 0) || w.rowOf[i] != i) return;
+FLT_DEV void emitSilCell(const DecCfg& c, const Ws& w, const Beam& cur, const FrameIn& f, int i,
+                         int slot, double& best) {
+  w.cand().parflag(slot) = 0;
+  if (!(c.silScore > 0) || w.rows().rowOf(i) != i) return;
   const int n = c.sil;
   if (n < 0 || n >= c.N || (c.ctc && n == c.blank)) return;
-  if (!inTokenSet(c, f.e, n, f.thrVal, f.topTok, f.listLen)) return;
-  int p = i;
-  if (!newTokenEligible(c, cur, p, n)) {
-    p = w.m2[i];
-    if (p == kIntMax) return;
-  }
-  const float ev = f.e[n];
-  if (!c.lexicon) {
-    double score = cur.score[p] + (double)ev;
-    score += c.silScore;
-    score = score + c.lmWeight * (double)0.0f;
-    putCand(w, slot, score, p, n, -1, 0, CF_NEW, 0.0f, n, ev);
-    if (score > best) best = score;
-  } else {
-    const int child = c.trie.rootChild[n];
-    if (child < 0 || c.trie.childOff[child + 1] == c.trie.childOff[child]) return;
-    double score = cur.score[p] + (double)ev;
-    score += c.silScore;
-    const float d = c.trie.maxScore[child] - 0.0f;
-    score = score + c.lmWeight * (double)d;
-    putCand(w, slot, score, p, n, -1, child, 0, d, -1, ev);
-    if (score > best) best = score;
-  }
+  const float ev = w.spec()[c.K + 1];
+  if (!inTokenSetV(c, f, n, ev)) return;
+  emitRowToken(c, w, cur, i, n, ev, slot, best);
+}
+
+// token whose emission hypothesis i needs for its stay / repeat candidate
+FLT_DEV int ownToken(const DecCfg& c, const Beam& cur, int i) {
+  return (c.lexicon && cur.lex(i) == 0) ? c.sil : cur.tok(i);
 }
 
 // stay / repeat and blank candidates of hypothesis i (slots base, base+1)
-FLT_DEV void emitSpecials(const DecCfg& c, Ws& w, const Beam& cur, const FrameIn& f, int i, int base,
-                          double& best) {
-  w.cflag[base] = 0;
-  w.cflag[base + 1] = 0;
+FLT_DEV void emitSpecials(const DecCfg& c, const Ws& w, const Beam& cur, const FrameIn& f, int i,
+                          int base, double& best) {
+  w.cand().parflag(base) = 0;
+  w.cand().parflag(base + 1) = 0;
+  const float eOwn = w.spec()[i], eBlank = w.spec()[c.K];
   if (!c.lexicon) {
     // repeat (third branch, LexiconFreeDecoder.cpp:98-110): n == prevIdx and not a new token
-    const int n = cur.tok[i];
-    const bool isRepeat = c.ctc ? (!cur.pb[i] && n != c.blank) : true;
-    if (isRepeat && n >= 0 && n < c.N && inTokenSet(c, f.e, n, f.thrVal, f.topTok, f.listLen)) {
-      double score = cur.score[i] + (double)f.e[n];
+    const int n = cur.tok(i);
+    const bool isRepeat = c.ctc ? (!cur.pb(i) && n != c.blank) : true;
+    if (isRepeat && n >= 0 && n < c.N && inTokenSetV(c, f, n, eOwn)) {
+      double score = cur.score(i) + (double)eOwn;
       if (n == c.sil) score += c.silScore;
-      putCand(w, base, score, i, n, -1, 0, 0, 0.0f, -1, f.e[n]);
+      putCand(c, w, cur, base, score, i, n, -1, 0, 0, 0.0f, eOwn);
       if (score > best) best = score;
     }
-    if (c.ctc && c.blank >= 0 && c.blank < c.N &&
-        inTokenSet(c, f.e, c.blank, f.thrVal, f.topTok, f.listLen)) {
+    if (c.ctc && inTokenSetV(c, f, c.blank, eBlank)) {
       const int n = c.blank;
-      double score = cur.score[i] + (double)f.e[n];
+      double score = cur.score(i) + (double)eBlank;
       if (n == c.sil) score += c.silScore;
-      putCand(w, base + 1, score, i, n, -1, 0, CF_PB, 0.0f, -1, f.e[n]);
+      putCand(c, w, cur, base + 1, score, i, n, -1, 0, CF_PB, 0.0f, eBlank);
       if (score > best) best = score;
     }
   } else {
-    const int lex = cur.lex[i];
-    if (!c.ctc || !cur.pb[i] || lex == 0) { // (2) same node, LexiconDecoder.cpp:167-194
-      const int n = lex == 0 ? c.sil : cur.tok[i];
-      const double am = transAdd(c, f, n, cur.tok[i]);
-      double score = cur.score[i] + am;
+    const int lex = cur.lex(i);
+    if (!c.ctc || !cur.pb(i) || lex == 0) { // (2) same node, LexiconDecoder.cpp:167-194
+      const int n = lex == 0 ? c.sil : cur.tok(i);
+      const double am = amOf(c, f, eOwn, n, cur.tok(i));
+      double score = cur.score(i) + am;
       if (n == c.sil) score += c.silScore;
-      putCand(w, base, score, i, n, -1, lex, 0, 0.0f, -1, f.e[n]);
+      putCand(c, w, cur, base, score, i, n, -1, lex, 0, 0.0f, eOwn);
       if (score > best) best = score;
     }
     if (c.ctc) { // (3) blank, LexiconDecoder.cpp:196-213
-      const int n = c.blank;
-      double score = cur.score[i] + (double)f.e[n];
-      putCand(w, base + 1, score, i, n, -1, lex, CF_PB, 0.0f, -1, f.e[n]);
+      const double score = cur.score(i) + (double)eBlank;
+      putCand(c, w, cur, base + 1, score, i, c.blank, -1, lex, CF_PB, 0.0f, eBlank);
       if (score > best) best = score;
     }
   }
 }
 
-FLT_DEV int allocCand(const DecCfg& c, Ws& w) {
-  int s = atomAdd(&w.sc[SC_NCAND], 1);
+FLT_DEV int allocCand(const DecCfg& c, const Ws& w) {
+  const int s = atomAdd(&w.sc()[SC_NCAND], 1);
   if (s >= c.capC) {
-    w.sc[SC_OVF] = 1;
+    w.sc()[SC_OVF] = 1;
     return -1;
   }
   return s;
@@ -522,37 +564,36 @@ FLT_DEV int allocCand(const DecCfg& c, Ws& w) {
 
 FLT_DEV float lmWordScore(const DecCfg& c, const Beam& cur, int p, int usrIdx) {
   if (c.lm.kind == 0) return 0.0f;
-  const int wlm = c.lm.usr2lm[usrIdx];
-  return ngramScore(c.lm, cur.ctx + (size_t)p * kMaxCtx, cur.nctx[p], wlm);
+  return ngramScore(c.lm, cur.ctx(p), cur.nctx(p), c.lm.usr2lm[usrIdx]);
 }
 
 // one trie edge of hypothesis i: child node `child` reached by token n (LexiconDecoder.cpp:62-164)
-FLT_DEV void emitEdge(const DecCfg& c, Ws& w, const Beam& cur, const FrameIn& f, int i, int n,
+FLT_DEV void emitEdge(const DecCfg& c, const Ws& w, const Beam& cur, const FrameIn& f, int i, int n,
                       int child, bool labelsOnly, double& best) {
-  if (!inTokenSet(c, f.e, n, f.thrVal, f.topTok, f.listLen)) return;
-  const TrieDev& t = c.trie;
-  const int lex = cur.lex[i];
-  const float lexMax = lex == 0 ? 0.0f : t.maxScore[lex];
-  const double am = transAdd(c, f, n, cur.tok[i]);
-  double score = cur.score[i] + am;
-  if (n == c.sil) score += c.silScore;
   const float ev = f.e[n];
+  if (!inTokenSetV(c, f, n, ev)) return;
+  const TrieDev& t = c.trie;
+  const int lex = cur.lex(i);
+  const float lexMax = lex == 0 ? 0.0f : t.maxScore[lex];
+  const double am = amOf(c, f, ev, n, cur.tok(i));
+  double score = cur.score(i) + am;
+  if (n == c.sil) score += c.silScore;
   const bool hasKids = t.childOff[child + 1] > t.childOff[child];
   if (!labelsOnly && hasKids && newTokenEligible(c, cur, i, n)) {
     const float d = t.maxScore[child] - lexMax;
     const double s = score + c.lmWeight * (double)d;
     const int slot = allocCand(c, w);
-    if (slot >= 0) putCand(w, slot, s, i, n, -1, child, 0, d, -1, ev);
+    if (slot >= 0) putCand(c, w, cur, slot, s, i, n, -1, child, 0, d, ev);
     if (s > best) best = s;
   }
   const int l0 = t.labelOff[child], l1 = t.labelOff[child + 1];
-  if (!(lex == 0 && cur.tok[i] == n)) { // LexiconDecoder.cpp:114-122
+  if (!(lex == 0 && cur.tok(i) == n)) { // LexiconDecoder.cpp:114-122
     for (int l = l0; l < l1; ++l) {
       const int label = t.labels[l];
       const float d = lmWordScore(c, cur, i, label) - lexMax;
       const double s = score + c.lmWeight * (double)d + c.wordScore;
       const int slot = allocCand(c, w);
-      if (slot >= 0) putCand(w, slot, s, i, n, label, 0, CF_NEW, d, label, ev);
+      if (slot >= 0) putCand(c, w, cur, slot, s, i, n, label, 0, CF_NEW, d, ev);
       if (s > best) best = s;
     }
   }
@@ -560,36 +601,37 @@ FLT_DEV void emitEdge(const DecCfg& c, Ws& w, const Beam& cur, const FrameIn& f,
     const float d = lmWordScore(c, cur, i, c.unk) - lexMax;
     const double s = score + c.lmWeight * (double)d + c.unkScore;
     const int slot = allocCand(c, w);
-    if (slot >= 0) putCand(w, slot, s, i, n, c.unk, 0, CF_NEW, d, c.unk, ev);
+    if (slot >= 0) putCand(c, w, cur, slot, s, i, n, c.unk, 0, CF_NEW, d, ev);
     if (s > best) best = s;
   }
 }
 
 // Phase M: merge candidates with equal (LM state, lex, token, prevBlank) keeping the best
-// (Utils.h:168-198, max-merge). Representatives are collected into w.rep.
-FLT_DEV void phaseMerge(const Cta& cta, const DecCfg& c, Ws& w, const Beam& cur, int nCand,
-                        double thrScore) {
-  for (int s = cta.tid; s < c.capH; s += cta.nthr) w.mh[s] = -1;
-  if (cta.tid == 0) w.sc[SC_NREP] = 0;
+// (Utils.h:168-198, max-merge). Representatives are collected into w.rep().
+FLT_DEV void phaseMerge(const Cta& cta, const DecCfg& c, const Ws& w, int nCand, double thrScore) {
+  const Cand cd = w.cand();
+  for (int s = cta.tid; s < c.capH; s += cta.nthr) w.mh()[s] = -1;
+  if (cta.tid == 0) w.sc()[SC_NREP] = 0;
   cta.sync();
   const uint32_t mask = (uint32_t)c.capH - 1;
   for (int x = cta.tid; x < nCand; x += cta.nthr) {
-    if (!(w.cflag[x] & CF_ALIVE)) continue;
-    if (!(w.cscore[x] >= thrScore)) { // Utils.h:161-165
-      w.cflag[x] &= ~CF_ALIVE;
+    if (!(cd.parflag(x) & CF_ALIVE)) continue;
+    if (!(cd.score(x) >= thrScore)) { // Utils.h:161-165
+      cd.parflag(x) &= ~CF_ALIVE;
       continue;
     }
-    uint32_t s = candKeyHash(w, cur, x) & mask;
+    const u64 ka = cd.keyA(x), kb = cd.keyB(x);
+    uint32_t s = (uint32_t)ka & mask;
     for (;;) {
-      int occ = w.mh[s];
+      int occ = w.mh()[s];
       if (occ == -1) {
-        occ = atomCAS(&w.mh[s], -1, x);
+        occ = atomCAS(&w.mh()[s], -1, x);
         if (occ == -1) break;
       }
-      if (candKeyEq(w, cur, occ, x)) {
+      if (cd.keyA(occ) == ka && cd.keyB(occ) == kb) {
         // same group: keep the better of the two in the slot
-        while (candBetter(w, x, occ)) {
-          int old = atomCAS(&w.mh[s], occ, x);
+        while (candBetter(cd, x, occ)) {
+          const int old = atomCAS(&w.mh()[s], occ, x);
           if (old == occ) break;
           occ = old;
         }
@@ -600,22 +642,22 @@ FLT_DEV void phaseMerge(const Cta& cta, const DecCfg& c, Ws& w, const Beam& cur,
   }
   cta.sync();
   for (int s = cta.tid; s < c.capH; s += cta.nthr) {
-    const int x = w.mh[s];
-    if (x >= 0) w.rep[atomAdd(&w.sc[SC_NREP], 1)] = x;
+    const int x = w.mh()[s];
+    if (x >= 0) w.rep()[atomAdd(&w.sc()[SC_NREP], 1)] = x;
   }
   cta.sync();
 }
 
 // find, scanning bins from 255 down, the bin where the running count reaches `need`
-FLT_DEV void findCutBin(const Cta& cta, Ws& w, int need) {
+FLT_DEV void findCutBin(const Cta& cta, const Ws& w, int need) {
 #if FLT_DEVICE_BUILD
   if (cta.tid < 32) {
     const int lane = cta.tid;
     int part = 0;
-    for (int k = 0; k < 8; ++k) part += w.hist[255 - (lane * 8 + k)];
+    for (int k = 0; k < 8; ++k) part += w.hist()[255 - (lane * 8 + k)];
     int incl = part;
     for (int o = 1; o < 32; o <<= 1) {
-      int u = __shfl_up_sync(0xffffffffu, incl, o);
+      const int u = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += u;
     }
     const int excl = incl - part;
@@ -623,11 +665,11 @@ FLT_DEV void findCutBin(const Cta& cta, Ws& w, int need) {
       int cum = excl;
       for (int k = 0; k < 8; ++k) {
         const int b = 255 - (lane * 8 + k);
-        const int h = w.hist[b];
+        const int h = w.hist()[b];
         if (cum + h >= need) {
-          w.sc[SC_BIN] = b;
-          w.sc[SC_NEED] = need - cum;
-          w.sc[SC_BINCOUNT] = h;
+          w.sc()[SC_BIN] = b;
+          w.sc()[SC_NEED] = need - cum;
+          w.sc()[SC_BINCOUNT] = h;
           break;
         }
         cum += h;
@@ -638,11 +680,11 @@ FLT_DEV void findCutBin(const Cta& cta, Ws& w, int need) {
   if (cta.tid == 0) {
     int cum = 0;
     for (int b = 255; b >= 0; --b) {
-      const int h = w.hist[b];
+      const int h = w.hist()[b];
       if (cum + h >= need) {
-        w.sc[SC_BIN] = b;
-        w.sc[SC_NEED] = need - cum;
-        w.sc[SC_BINCOUNT] = h;
+        w.sc()[SC_BIN] = b;
+        w.sc()[SC_NEED] = need - cum;
+        w.sc()[SC_BINCOUNT] = h;
         break;
       }
       cum += h;
@@ -651,47 +693,49 @@ FLT_DEV void findCutBin(const Cta& cta, Ws& w, int need) {
 #endif
 }
 
-// Phase Sel: choose the min(nRep, K) best representatives (Utils.h:200-220) into w.surv, then
-// rank them (score descending, deterministic ties). Returns the number selected.
-FLT_DEV int phaseSelect(const Cta& cta, const DecCfg& c, Ws& w, int nRep) {
+// Phase Sel: choose the min(nRep, K) best representatives (Utils.h:200-220) and rank them (score
+// descending, deterministic ties) into w.surv()[capP..]. Returns the number selected.
+FLT_DEV int phaseSelect(const Cta& cta, const DecCfg& c, const Ws& w, int nRep) {
+  const Cand cd = w.cand();
   const int K = c.K;
+  int* surv = w.surv();
+  int* ranked = w.surv() + c.capP;
   int nSel;
   if (nRep <= K) {
-    for (int r = cta.tid; r < nRep; r += cta.nthr) w.surv[r] = w.rep[r];
+    for (int r = cta.tid; r < nRep; r += cta.nthr) surv[r] = w.rep()[r];
     nSel = nRep;
     cta.sync();
   } else {
     // radix select on key - minKey, most significant differing byte first
-    unsigned long long lmax = 0, lmin = ~0ull;
+    u64 kmax = 0, kmin = ~0ull;
     for (int r = cta.tid; r < nRep; r += cta.nthr) {
-      const unsigned long long k = orderedKey64(w.cscore[w.rep[r]]);
-      lmax = k > lmax ? k : lmax;
-      lmin = k < lmin ? k : lmin;
+      const u64 k = orderedKey64(cd.score(w.rep()[r]));
+      kmax = k > kmax ? k : kmax;
+      kmin = k < kmin ? k : kmin;
     }
-    const unsigned long long kmax = ctaMax64(cta, lmax, w.red);
-    const unsigned long long kmin = ~ctaMax64(cta, ~lmin, w.red);
-    const unsigned long long range = kmax - kmin;
+    ctaMaxMin64(cta, kmax, kmin, w.red());
+    const u64 range = kmax - kmin;
     int shift = 0;
     while (shift < 56 && (range >> shift) > 255ull) shift += 8;
     int need = K;
-    unsigned long long prefix = 0; // bits above the current digit, already fixed
+    u64 prefix = 0; // digits above the current one, already fixed
     bool wholeBin = false;
-    if (cta.tid == 0) w.sc[SC_NSEL] = 0;
+    if (cta.tid == 0) w.sc()[SC_NSEL] = 0;
     for (;;) {
-      for (int b = cta.tid; b < 256; b += cta.nthr) w.hist[b] = 0;
+      for (int b = cta.tid; b < 256; b += cta.nthr) w.hist()[b] = 0;
       cta.sync();
       for (int r = cta.tid; r < nRep; r += cta.nthr) {
-        const unsigned long long k = orderedKey64(w.cscore[w.rep[r]]) - kmin;
+        const u64 k = orderedKey64(cd.score(w.rep()[r])) - kmin;
         if (shift >= 56 || (k >> (shift + 8)) == (prefix >> (shift + 8)))
-          atomAdd(&w.hist[(int)((k >> shift) & 255ull)], 1);
+          atomAdd(&w.hist()[(int)((k >> shift) & 255ull)], 1);
       }
       cta.sync();
       findCutBin(cta, w, need);
       cta.sync();
-      const int bin = w.sc[SC_BIN];
-      need = w.sc[SC_NEED];
-      const int binCount = w.sc[SC_BINCOUNT];
-      prefix |= (unsigned long long)bin << shift;
+      const int bin = w.sc()[SC_BIN];
+      need = w.sc()[SC_NEED];
+      const int binCount = w.sc()[SC_BINCOUNT];
+      prefix |= (u64)bin << shift;
       if (binCount == need) {
         wholeBin = true;
         break;
@@ -702,158 +746,184 @@ FLT_DEV int phaseSelect(const Cta& cta, const DecCfg& c, Ws& w, int nRep) {
     // keys strictly above the cut digit-prefix are selected; the cut bin is selected entirely
     // (wholeBin) or resolved among equals below.
     for (int r = cta.tid; r < nRep; r += cta.nthr) {
-      const int x = w.rep[r];
-      const unsigned long long k = (orderedKey64(w.cscore[x]) - kmin) >> shift;
-      const unsigned long long p = prefix >> shift;
-      if (k > p || (wholeBin && k == p)) w.surv[atomAdd(&w.sc[SC_NSEL], 1)] = x;
+      const int x = w.rep()[r];
+      const u64 k = (orderedKey64(cd.score(x)) - kmin) >> shift;
+      const u64 p = prefix >> shift;
+      if (k > p || (wholeBin && k == p)) surv[atomAdd(&w.sc()[SC_NSEL], 1)] = x;
     }
     cta.sync();
     if (!wholeBin) {
       // rare: pick `need` of the equal-score groups by the deterministic order
       if (cta.tid == 0) {
-        int n = w.sc[SC_NSEL];
+        const int n0 = w.sc()[SC_NSEL];
+        int n = n0;
         for (int q = 0; q < need; ++q) {
           int bestX = -1;
           for (int r = 0; r < nRep; ++r) {
-            const int x = w.rep[r];
-            if (((orderedKey64(w.cscore[x]) - kmin) >> shift) != (prefix >> shift)) continue;
+            const int x = w.rep()[r];
+            if (((orderedKey64(cd.score(x)) - kmin) >> shift) != (prefix >> shift)) continue;
             bool taken = false;
-            for (int z = w.sc[SC_NSEL]; z < n; ++z) taken |= w.surv[z] == x;
+            for (int z = n0; z < n; ++z) taken |= surv[z] == x;
             if (taken) continue;
-            if (bestX < 0 || candBetter(w, x, bestX)) bestX = x;
+            if (bestX < 0 || candBetter(cd, x, bestX)) bestX = x;
           }
-          w.surv[n++] = bestX;
+          surv[n++] = bestX;
         }
-        w.sc[SC_NSEL] = n;
+        w.sc()[SC_NSEL] = n;
       }
       cta.sync();
     }
-    nSel = w.sc[SC_NSEL];
+    nSel = w.sc()[SC_NSEL];
   }
-  // rank by counting (nSel <= K): position = number of strictly better survivors
+  // rank by counting, all threads: thread (a, part) counts the survivors of its slice that beat a
   for (int a = cta.tid; a < nSel; a += cta.nthr) {
-    const int x = w.surv[a];
-    int pos = 0;
-    for (int b = 0; b < nSel; ++b) pos += candBetter(w, w.surv[b], x) ? 1 : 0;
-    w.survTmp[pos] = x;
+    w.skey()[a] = orderedKey64(cd.score(surv[a]));
+    w.pos()[a] = 0;
   }
+  cta.sync();
+  if (nSel > 0) {
+    const int parts = nSel >= cta.nthr ? 1 : cta.nthr / nSel;
+    const int slice = (nSel + parts - 1) / parts;
+    for (int t = cta.tid; t < nSel * parts; t += cta.nthr) {
+      const int a = t % nSel, part = t / nSel;
+      const int lo = part * slice, hi = lo + slice < nSel ? lo + slice : nSel;
+      const u64 ka = w.skey()[a];
+      const int xa = surv[a];
+      int cnt = 0;
+      for (int b = lo; b < hi; ++b) {
+        const u64 kb = w.skey()[b];
+        cnt += (kb > ka || (kb == ka && b != a && candBetter(cd, surv[b], xa))) ? 1 : 0;
+      }
+      if (cnt) atomAdd(&w.pos()[a], cnt);
+    }
+  }
+  cta.sync();
+  for (int a = cta.tid; a < nSel; a += cta.nthr) ranked[w.pos()[a]] = surv[a];
   cta.sync();
   return nSel;
 }
 
-// Phase F: materialise the new beam from the ranked survivors (in w.survTmp), intern new LM
-// states, write the back-pointer records.
-FLT_DEV void phaseFinalize(const Cta& cta, const DecCfg& c, Ws& w, const Beam& cur, Beam& nxt,
-                           const FrameIn& f, int nSel, unsigned long long* stateTab,
-                           long long stateCap, int* status) {
+// Phase F: materialise the new beam from the ranked survivors, extend the LM-state fingerprints
+// and n-gram contexts, write the back-pointer records.
+FLT_DEV void phaseFinalize(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur,
+                           const Beam& nxt, const FrameIn& f, int nSel) {
+  const Cand cd = w.cand();
+  const int* ranked = w.surv() + c.capP;
   for (int q = cta.tid; q < nSel; q += cta.nthr) {
-    const int x = w.survTmp[q];
-    const int p = w.cpar[x];
-    const int fl = w.cflag[x];
-    const int n = w.ctok[x];
-    nxt.score[q] = w.cscore[x];
+    const int x = ranked[q];
+    const int p = cd.par(x);
+    const int fl = cd.flags(x);
+    const int n = cd.tok(x);
+    nxt.score(q) = cd.score(x);
     if (fl & CF_FINISH) {
-      nxt.am[q] = cur.am[p];
+      nxt.am(q) = cur.am(p);
     } else {
-      double am = (double)w.ce[x];
-      if (!c.ctc && !f.first && c.trans) am += (double)c.trans[(size_t)n * c.N + cur.tok[p]];
-      nxt.am[q] = cur.am[p] + am;
+      nxt.am(q) = cur.am(p) + amOf(c, f, cd.ce(x), n, cur.tok(p));
     }
-    nxt.lm[q] = cur.lm[p] + (double)w.clmd[x];
-    nxt.lex[q] = w.clex[x];
-    nxt.tok[q] = n;
-    nxt.pb[q] = (fl & CF_PB) ? 1 : 0;
+    nxt.lm(q) = cur.lm(p) + (double)cd.lmd(x);
+    nxt.lex(q) = cd.lex(x);
+    nxt.tok(q) = n;
+    nxt.pb(q) = (fl & CF_PB) ? 1 : 0;
     if (fl & CF_NEW) {
-      const int lab = w.clab[x];
-      // final states (decodeEnd) are never expanded again: no id needed
-      int id = (fl & CF_FINISH) ? 0 : internState(stateTab, stateCap, cur.sid[p], lab);
-      if (id < 0) {
-        *status |= 2;
-        id = 0;
-      }
-      nxt.sid[q] = id;
-      nxt.spid[q] = cur.sid[p];
-      nxt.slab[q] = lab;
+      const int lab = candLabel(c, cd, x);
+      fpChild(cur.fpA(p), cur.fpB(p), lab, nxt.fpA(q), nxt.fpB(q));
       if (c.lm.kind) {
         const int wlm = lab < 0 ? c.lm.eos : c.lm.usr2lm[lab];
-        nxt.nctx[q] = ngramAdvanceCtx(c.lm, cur.ctx + (size_t)p * kMaxCtx, cur.nctx[p], wlm,
-                                      nxt.ctx + (size_t)q * kMaxCtx);
+        nxt.nctx(q) = ngramAdvanceCtx(c.lm, cur.ctx(p), cur.nctx(p), wlm, nxt.ctx(q));
       }
     } else {
-      nxt.sid[q] = cur.sid[p];
-      nxt.spid[q] = cur.spid[p];
-      nxt.slab[q] = cur.slab[p];
+      nxt.fpA(q) = cur.fpA(p);
+      nxt.fpB(q) = cur.fpB(p);
       if (c.lm.kind) {
-        nxt.nctx[q] = cur.nctx[p];
-        for (int k = 0; k < cur.nctx[p]; ++k)
-          nxt.ctx[(size_t)q * kMaxCtx + k] = cur.ctx[(size_t)p * kMaxCtx + k];
+        const int nc = cur.nctx(p);
+        nxt.nctx(q) = nc;
+        for (int k = 0; k < nc; ++k) nxt.ctx(q)[k] = cur.ctx(p)[k];
       }
     }
     f.hParent[q] = p;
     f.hTok[q] = n;
-    if (f.hWord) f.hWord[q] = w.cword[x];
+    if (f.hWord) f.hWord[q] = cd.word(x);
   }
-  if (cta.tid == 0) w.sc[SC_NH] = nSel;
+  if (cta.tid == 0) w.sc()[SC_NH] = nSel;
   cta.sync();
 }
 
 // One frame: cur -> nxt. All threads of the CTA call this with identical arguments.
-FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, Ws& w, const Beam& cur, Beam& nxt,
-                       const FrameIn& f, unsigned long long* stateTab, long long stateCap,
-                       int* status) {
-  const int nH = w.sc[SC_NH];
+FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur,
+                       const Beam& nxt, const FrameIn& f, int* status) {
+  const int nH = w.sc()[SC_NH];
   if (nH == 0) return; // the beam died (Utils.h:155-158): every later frame is empty
   double best = negInf();
-  const int K = c.K;
+
+  // issue the scattered emission reads now; they are consumed after the row grouping
+  float eOwn = 0.0f, eBlank = 0.0f, eSil = 0.0f;
+  if (cta.tid < nH) {
+    const int n = ownToken(c, cur, cta.tid);
+    if (n >= 0 && n < c.N) eOwn = f.e[n];
+  }
+  if (cta.tid == cta.nthr - 1) {
+    if (c.ctc) eBlank = f.e[c.blank];
+    eSil = f.e[c.sil];
+  }
 
   int wideItems = 0;
   if (c.wideRanked) {
     phaseRows(cta, c, w, cur, nH);
-    wideItems = c.wideOff[w.sc[SC_NROWS]];
+    wideItems = w.wideOff()[w.sc()[SC_NROWS]];
+  }
+  if (cta.tid < nH) w.spec()[cta.tid] = eOwn;
+  for (int i = cta.tid + cta.nthr; i < nH; i += cta.nthr) { // beams wider than the CTA
+    const int n = ownToken(c, cur, i);
+    w.spec()[i] = (n >= 0 && n < c.N) ? f.e[n] : 0.0f;
+  }
+  if (cta.tid == cta.nthr - 1) {
+    w.spec()[c.K] = eBlank;
+    w.spec()[c.K + 1] = eSil;
   }
   const int specBase = wideItems;
   const int narrowBase = specBase + 3 * nH;
   if (cta.tid == 0) {
-    w.sc[SC_NCAND] = narrowBase;
-    w.sc[SC_OVF] = narrowBase > c.capC ? 1 : 0;
+    w.sc()[SC_NCAND] = narrowBase;
+    w.sc()[SC_OVF] = 0;
   }
+  cta.sync();
   if (narrowBase > c.capC) { // cannot happen with a correctly sized capC; fail the utterance
-    cta.sync();
     if (cta.tid == 0) {
       *status |= 1;
-      w.sc[SC_NH] = 0;
+      w.sc()[SC_NH] = 0;
     }
     cta.sync();
     return;
   }
   // wide cells
   if (c.wideRanked) {
-    const int nRows = w.sc[SC_NROWS];
+    const int nRows = w.sc()[SC_NROWS];
     for (int x = cta.tid; x < wideItems; x += cta.nthr) {
-      const int r = searchOffsets(c.wideOff, nRows + 1, x); // row rank r (0-based)
-      emitWide(c, w, cur, f, w.leaderOfRank[r], x - c.wideOff[r], x, best);
+      const int r = searchOffsets(w.wideOff(), nRows + 1, x); // row rank r (0-based)
+      emitWide(c, w, cur, f, w.rows().leaderOfRank(r), x - w.wideOff()[r], x, best);
     }
   }
   // stay / repeat / blank
   for (int i = cta.tid; i < nH; i += cta.nthr) {
     emitSpecials(c, w, cur, f, i, specBase + 3 * i, best);
     if (c.wideRanked) emitSilCell(c, w, cur, f, i, specBase + 3 * i + 2, best);
-    else w.cflag[specBase + 3 * i + 2] = 0;
+    else w.cand().parflag(specBase + 3 * i + 2) = 0;
   }
   // trie edges
   if (c.lexicon) {
     const TrieDev& t = c.trie;
+    int* deg = w.rows().deg();
     for (int i = cta.tid; i < nH; i += cta.nthr) {
-      const int lex = cur.lex[i];
-      w.deg[i] = (c.wideRanked && lex == 0) ? t.nRootLab : t.childOff[lex + 1] - t.childOff[lex];
+      const int lex = cur.lex(i);
+      deg[i] = (c.wideRanked && lex == 0) ? t.nRootLab : t.childOff[lex + 1] - t.childOff[lex];
     }
     cta.sync();
-    ctaExclusiveScan(cta, w.deg, w.degTmp, nH);
-    const int items = w.deg[nH];
+    ctaExclusiveScan(cta, deg, w.rows().degTmp(), nH);
+    const int items = deg[nH];
     for (int x = cta.tid; x < items; x += cta.nthr) {
-      const int i = searchOffsets(w.deg, nH + 1, x);
-      const int k = x - w.deg[i];
-      const int lex = cur.lex[i];
+      const int i = searchOffsets(deg, nH + 1, x);
+      const int k = x - deg[i];
+      const int lex = cur.lex(i);
       if (c.wideRanked && lex == 0) {
         const int n = t.rootLabTok[k];
         emitEdge(c, w, cur, f, i, n, t.rootChild[n], true, best);
@@ -863,115 +933,152 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, Ws& w, const Beam& cur, 
       }
     }
   }
-  const unsigned long long bestKey = ctaMax64(cta, orderedKey64(best), w.red);
-  cta.sync();
-  int nCand = w.sc[SC_NCAND];
-  if (w.sc[SC_OVF]) {
+  const u64 bestKey = ctaMax64(cta, orderedKey64(best), w.red());
+  int nCand = w.sc()[SC_NCAND];
+  if (w.sc()[SC_OVF]) {
     if (cta.tid == 0) *status |= 1;
     nCand = nCand < c.capC ? nCand : c.capC;
   }
   // candidatesBestScore_ - beamThreshold (LexiconDecoder.cpp:217-224)
   const double thrScore = keyToDouble(bestKey) - c.beamThreshold;
-  phaseMerge(cta, c, w, cur, nCand, thrScore);
-  const int nRep = w.sc[SC_NREP];
-  const int nSel = phaseSelect(cta, c, w, nRep);
-  phaseFinalize(cta, c, w, cur, nxt, f, nSel, stateTab, stateCap, status);
-  (void)K;
+  phaseMerge(cta, c, w, nCand, thrScore);
+  const int nSel = phaseSelect(cta, c, w, w.sc()[SC_NREP]);
+  phaseFinalize(cta, c, w, cur, nxt, f, nSel);
 }
 
 // decodeEnd (LexiconFreeDecoder.cpp:127-158, LexiconDecoder.cpp:231-274) as one more "frame".
-FLT_DEV void finishStep(const Cta& cta, const DecCfg& c, Ws& w, const Beam& cur, Beam& nxt,
-                        const FrameIn& f, unsigned long long* stateTab, long long stateCap,
-                        int* status) {
-  const int nH = w.sc[SC_NH];
+FLT_DEV void finishStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur,
+                        const Beam& nxt, const FrameIn& f) {
+  const int nH = w.sc()[SC_NH];
   if (nH == 0) return;
-  if (cta.tid == 0) w.sc[SC_TIES] = 0;
+  if (cta.tid == 0) w.sc()[SC_NICE] = 0;
   cta.sync();
   if (c.lexicon) {
     for (int i = cta.tid; i < nH; i += cta.nthr)
-      if (cur.lex[i] == 0) w.sc[SC_TIES] = 1; // "nice ending" exists (benign same-value race)
+      if (cur.lex(i) == 0) w.sc()[SC_NICE] = 1; // "nice ending" exists (benign same-value race)
     cta.sync();
   }
-  const bool nice = c.lexicon && w.sc[SC_TIES] != 0;
+  const bool nice = c.lexicon && w.sc()[SC_NICE] != 0;
   double best = negInf();
   for (int i = cta.tid; i < nH; i += cta.nthr) {
-    w.cflag[i] = 0;
-    if (nice && cur.lex[i] != 0) continue;
+    w.cand().parflag(i) = 0;
+    if (nice && cur.lex(i) != 0) continue;
     float ls = 0.0f;
     int flags = CF_FINISH;
-    if (c.lm.kind) { // KenLM::finish: score </s>, state = child(-1)
-      ls = ngramScore(c.lm, cur.ctx + (size_t)i * kMaxCtx, cur.nctx[i], c.lm.eos);
+    if (c.lm.kind) { // KenLM::finish: score </s>, state = child(-1); ZeroLM: same state, 0
+      ls = ngramScore(c.lm, cur.ctx(i), cur.nctx(i), c.lm.eos);
       flags |= CF_NEW;
     }
-    const double score = cur.score[i] + c.lmWeight * (double)ls;
-    putCand(w, i, score, i, c.sil, -1, cur.lex[i], flags, ls, -1, 0.0f);
+    const double score = cur.score(i) + c.lmWeight * (double)ls;
+    putCand(c, w, cur, i, score, i, c.sil, -1, cur.lex(i), flags, ls, 0.0f);
     if (score > best) best = score;
   }
-  const unsigned long long bestKey = ctaMax64(cta, orderedKey64(best), w.red);
-  cta.sync();
-  phaseMerge(cta, c, w, cur, nH, keyToDouble(bestKey) - c.beamThreshold);
-  const int nSel = phaseSelect(cta, c, w, w.sc[SC_NREP]);
-  phaseFinalize(cta, c, w, cur, nxt, f, nSel, stateTab, stateCap, status);
+  const u64 bestKey = ctaMax64(cta, orderedKey64(best), w.red());
+  phaseMerge(cta, c, w, nH, keyToDouble(bestKey) - c.beamThreshold);
+  const int nSel = phaseSelect(cta, c, w, w.sc()[SC_NREP]);
+  phaseFinalize(cta, c, w, cur, nxt, f, nSel);
 }
 
 /* ------------------------------------------------------------------ whole-utterance driver ---- */
-// One CTA decodes utterances bid, bid+nblk, ... start to finish.
-FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char* smem) {
-  Ws w;
-  char* base = a.useSmem ? smem : a.wsGlobal + (long long)cta.bid * a.wsStride;
-  carveWs(base, c, w);
-  unsigned long long* stateTab = a.stateTab + (long long)cta.bid * a.stateCap;
+// One CTA decodes utterances bid, bid+nblk, ... start to finish. `base` is the CTA's workspace:
+// shared memory or a global slab.
+FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char* base) {
+  const Ws w{base, &c};
   const int K = c.K;
+  for (int i = cta.tid; i <= K; i += cta.nthr) w.wideOff()[i] = c.wideOff[i];
   for (int b = cta.bid; b < a.B; b += cta.nblk) {
     const int len = a.lengths ? a.lengths[b] : a.T;
-    // reset the LM-state table and seed the beam (decodeBegin, LexiconDecoder.cpp:21-30)
-    for (long long s = cta.tid; s < a.stateCap; s += cta.nthr) stateTab[s] = ~0ull;
     int curIdx = 0;
-    if (cta.tid == 0) {
-      Beam& B0 = w.beam[0];
-      B0.score[0] = 0.0;
-      B0.am[0] = 0.0;
-      B0.lm[0] = 0.0;
-      B0.sid[0] = 0;
-      B0.spid[0] = -1;
-      B0.slab[0] = -1;
-      B0.lex[0] = 0;
-      B0.tok[0] = c.sil;
-      B0.pb[0] = 0;
-      B0.nctx[0] = 0;
+    cta.sync(); // previous utterance fully retired
+    if (cta.tid == 0) { // decodeBegin (LexiconDecoder.cpp:21-30)
+      const Beam B0 = w.beam(0);
+      B0.score(0) = 0.0;
+      B0.am(0) = 0.0;
+      B0.lm(0) = 0.0;
+      fpRoot(B0.fpA(0), B0.fpB(0));
+      B0.lex(0) = 0;
+      B0.tok(0) = c.sil;
+      B0.pb(0) = 0;
+      B0.nctx(0) = 0;
       if (c.lm.kind && c.lm.order > 1) {
-        B0.ctx[0] = c.lm.bos;
-        B0.nctx[0] = 1;
+        B0.ctx(0)[0] = c.lm.bos;
+        B0.nctx(0) = 1;
       }
-      w.sc[SC_NH] = 1;
+      w.sc()[SC_NH] = 1;
       a.status[b] = 0;
-      int* hp = a.hParent + ((long long)b * (a.T + 2)) * K;
-      hp[0] = -1;
-      a.hTok[((long long)b * (a.T + 2)) * K] = c.sil;
-      if (a.hWord) a.hWord[((long long)b * (a.T + 2)) * K] = -1;
+      const long long h0 = ((long long)b * (a.T + 2)) * K;
+      a.hParent[h0] = -1;
+      a.hTok[h0] = c.sil;
+      if (a.hWord) a.hWord[h0] = -1;
+    }
+    // token list of frame 0 into the workspace
+    const long long row0 = (long long)b * a.T;
+    if (c.listInSmem && len > 0) {
+      for (int j = cta.tid; j < c.M; j += cta.nthr) {
+        w.listTok(0)[j] = a.topTok[row0 * c.M + j];
+        w.listVal(0)[j] = a.topVal[row0 * c.M + j];
+      }
     }
     cta.sync();
     for (int t = 0; t < len; ++t) {
+      const long long row = row0 + t;
+      // prefetch the next frame's list into registers (<= 2 entries per thread, listInSmem)
+      int pfTok[2] = {-1, -1};
+      float pfVal[2] = {0.0f, 0.0f};
+      const bool pf = c.listInSmem && t + 1 < len;
+      if (pf) {
+#pragma unroll
+        for (int z = 0; z < 2; ++z) {
+          const int j = cta.tid + z * cta.nthr;
+          if (j < c.M) {
+            pfTok[z] = a.topTok[(row + 1) * c.M + j];
+            pfVal[z] = a.topVal[(row + 1) * c.M + j];
+          }
+        }
+      }
       FrameIn f;
-      const long long row = (long long)b * a.T + t;
       f.e = a.emis + row * c.N;
-      f.topTok = a.topTok ? a.topTok + row * c.M : nullptr;
-      f.topVal = a.topVal ? a.topVal + row * c.M : nullptr;
+      if (c.listInSmem) {
+        f.topTok = w.listTok(t & 1);
+        f.topVal = w.listVal(t & 1);
+      } else {
+        f.topTok = a.topTok ? a.topTok + row * c.M : nullptr;
+        f.topVal = a.topVal ? a.topVal + row * c.M : nullptr;
+      }
       f.listLen = c.M;
       f.thrVal = a.thrVal ? a.thrVal[row] : 0.0f;
       f.first = t == 0;
+      f.listIsSet = !c.lexicon;
       const long long h = ((long long)b * (a.T + 2) + (t + 1)) * K;
       f.hParent = a.hParent + h;
       f.hTok = a.hTok + h;
       f.hWord = a.hWord ? a.hWord + h : nullptr;
-      frameStep(cta, c, w, w.beam[curIdx], w.beam[curIdx ^ 1], f, stateTab, a.stateCap,
-                a.status + b);
-      if (w.sc[SC_NH] == 0) break;
+      frameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.status + b);
+      if (pf) {
+#if FLT_DEVICE_BUILD
+#pragma unroll
+        for (int z = 0; z < 2; ++z) {
+          const int j = cta.tid + z * cta.nthr;
+          if (j < c.M) {
+            w.listTok((t + 1) & 1)[j] = pfTok[z];
+            w.listVal((t + 1) & 1)[j] = pfVal[z];
+          }
+        }
+#else
+        (void)pfTok;
+        (void)pfVal;
+        for (int j = 0; j < c.M; ++j) { // model: the single thread copies the whole list
+          w.listTok((t + 1) & 1)[j] = a.topTok[(row + 1) * c.M + j];
+          w.listVal((t + 1) & 1)[j] = a.topVal[(row + 1) * c.M + j];
+        }
+#endif
+      }
+      if (w.sc()[SC_NH] == 0) break;
       curIdx ^= 1;
       cta.sync();
     }
     int nFin = 0;
-    if (w.sc[SC_NH] != 0) {
+    if (w.sc()[SC_NH] != 0) {
       FrameIn f;
       f.e = nullptr;
       f.topTok = nullptr;
@@ -979,25 +1086,24 @@ FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char
       f.listLen = 0;
       f.thrVal = 0.0f;
       f.first = 0;
+      f.listIsSet = 0;
       const long long h = ((long long)b * (a.T + 2) + (len + 1)) * K;
       f.hParent = a.hParent + h;
       f.hTok = a.hTok + h;
       f.hWord = a.hWord ? a.hWord + h : nullptr;
-      finishStep(cta, c, w, w.beam[curIdx], w.beam[curIdx ^ 1], f, stateTab, a.stateCap,
-                 a.status + b);
+      finishStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f);
       curIdx ^= 1;
-      nFin = w.sc[SC_NH];
+      nFin = w.sc()[SC_NH];
     }
     cta.sync();
-    const Beam& F = w.beam[curIdx];
+    const Beam F = w.beam(curIdx);
     for (int q = cta.tid; q < nFin; q += cta.nthr) {
       double* o = a.finScore + ((long long)b * K + q) * 3;
-      o[0] = F.score[q];
-      o[1] = F.am[q];
-      o[2] = F.lm[q];
+      o[0] = F.score(q);
+      o[1] = F.am(q);
+      o[2] = F.lm(q);
     }
     if (cta.tid == 0) a.finCount[b] = nFin;
-    cta.sync();
   }
 }
 

@@ -30,10 +30,16 @@ __global__ void __launch_bounds__(256) flt_k_topm(TopMCfg c, TopMArgs a) {
   Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
   topmCta(cta, c, a, smem);
 }
+// workspace in shared memory (the fast path: every access is an LDS/STS with constant-bank offsets)
 __global__ void __launch_bounds__(256) flt_k_decode(DecCfg c, BatchArgs a) {
   extern __shared__ __align__(16) char smem[];
   Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
   decodeCta(cta, c, a, smem);
+}
+// workspace in a global slab per CTA (beams / candidate sets too large for shared memory)
+__global__ void __launch_bounds__(256) flt_k_decode_gmem(DecCfg c, BatchArgs a) {
+  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
+  decodeCta(cta, c, a, a.wsGlobal + (long long)blockIdx.x * a.wsStride);
 }
 __global__ void flt_k_backtrace(BacktraceArgs a) {
   const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -72,15 +78,17 @@ void launchTopM(const TopMCfg& c, const TopMArgs& a, int grid, size_t smem, rt::
 }
 void launchDecode(const DecCfg& c, const BatchArgs& a, int grid, size_t smem, rt::Stream s) {
 #if FLT_DEVICE_BUILD
-  flt_k_decode<<<grid, kThreads, smem, s>>>(c, a);
+  if (smem) flt_k_decode<<<grid, kThreads, smem, s>>>(c, a);
+  else flt_k_decode_gmem<<<grid, kThreads, 0, s>>>(c, a);
   FLT_RT_TRY(cudaGetLastError());
 #else
-  std::vector<char> sm(smem + 16);
+  std::vector<char> sm(c.lay.total + 16);
   for (int b = 0; b < grid; ++b) {
     Cta cta{0, 1, b, grid};
     decodeCta(cta, c, a, sm.data());
   }
   (void)s;
+  (void)smem;
 #endif
 }
 void launchBacktrace(const BacktraceArgs& a, rt::Stream s) {
@@ -377,9 +385,8 @@ struct flt_decoder {
   std::vector<int> wideOffHost;
   rt::DevBuf dWideOff, dBias, dTrans;
   // batch buffers
-  rt::DevBuf topTok, topVal, thr, hPar, hTok, hWord, finScore, finCount, status, ws, stateTab,
-      outTok, outWord, dLengths, staging[2];
-  long long stateCap = 0;
+  rt::DevBuf topTok, topVal, thr, hPar, hTok, hWord, finScore, finCount, status, ws, outTok,
+      outWord, dLengths, staging[2];
   int lastB = 0, lastT = 0, launches = 0;
   int capBoost = 1; // candidate-capacity multiplier, grown after an overflow
   bool useSmemFlag = false;
@@ -388,8 +395,8 @@ struct flt_decoder {
 
   ~flt_decoder() {
     for (rt::DevBuf* b : {&dWideOff, &dBias, &dTrans, &topTok, &topVal, &thr, &hPar, &hTok, &hWord,
-                          &finScore, &finCount, &status, &ws, &stateTab, &outTok, &outWord,
-                          &dLengths, &staging[0], &staging[1]})
+                          &finScore, &finCount, &status, &ws, &outTok, &outWord, &dLengths,
+                          &staging[0], &staging[1]})
       b->release();
 #if FLT_DEVICE_BUILD
     for (int i = 0; i < 2; ++i) {
@@ -486,6 +493,7 @@ void planFor(flt_decoder& d, int N) {
   c.capH = nextPow2((int)std::min<long long>(2 * capC, 1LL << 27));
   c.capRH = nextPow2(2 * K);
   c.capP = nextPow2(K);
+  c.listInSmem = d.needTopM && c.M <= 2 * kThreads;
 
   rt::Stream s = d.stream;
   c.wideOff = upload(d.dWideOff, d.wideOffHost, s);
@@ -511,8 +519,8 @@ void planFor(flt_decoder& d, int N) {
   }
   rt::sync(s);
 
-  Ws w;
-  d.wsBytes = (carveWs(nullptr, c, w) + 255) / 256 * 256;
+  makeLayout(c);
+  d.wsBytes = ((size_t)c.lay.total + 255) / 256 * 256;
   TopMSmem ts;
   d.topmSmem = (carveTopM(nullptr, t, ts) + 255) / 256 * 256;
   d.cfg = c;
@@ -530,14 +538,13 @@ void planFor(flt_decoder& d, int N) {
   FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, flt_k_topm, kThreads, d.topmSmem));
   d.topmGridMax = std::max(1, occ) * d.numSMs;
   const bool smemOk = d.wsBytes <= std::min<size_t>(smemMax, 110 * 1024);
-  d.cfg.capC = c.capC;
   int occ2 = 1;
   if (smemOk) {
     FLT_RT_TRY(cudaFuncSetAttribute(flt_k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)std::max<size_t>(d.wsBytes, 48 * 1024)));
     FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode, kThreads, d.wsBytes));
   } else {
-    FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode, kThreads, 0));
+    FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode_gmem, kThreads, 0));
     occ2 = std::min(occ2, 4);
   }
   d.gridMax = std::max(1, occ2) * d.numSMs;
@@ -624,13 +631,6 @@ void runChunk(flt_decoder& d, const float* dEmis, int Bc, int T, int N, const in
   a.finCount = d.finCount.as<int>() + outBase;
   a.status = d.status.as<int>() + outBase;
   const int grid = std::max(1, std::min(Bc, d.gridMax));
-  long long cap = 64;
-  while (cap < 2LL * ((long long)K * (T + 1) + 2)) cap <<= 1;
-  d.stateCap = cap;
-  d.stateTab.reserve(sizeof(unsigned long long) * cap * grid);
-  a.stateTab = d.stateTab.as<unsigned long long>();
-  a.stateCap = cap;
-  a.useSmem = d.useSmemFlag ? 1 : 0;
   if (!d.useSmemFlag) {
     d.ws.reserve(d.wsBytes * grid);
     a.wsGlobal = d.ws.as<char>();
@@ -754,7 +754,6 @@ void checkStatus(flt_decoder& d) {
   rt::sync(d.stream);
   int bits = 0;
   for (int b = 0; b < d.lastB; ++b) bits |= st[b];
-  if (bits & 2) throw FltError(FLT_ERR_RUNTIME, "LM-state table overflow (internal sizing error)");
   if (bits & 1) throw FltError(FLT_ERR_RUNTIME, "candidate capacity exceeded");
 }
 
@@ -1062,8 +1061,7 @@ int flt_decoder_workspace_bytes(const flt_decoder* dec, int64_t* out) {
     int64_t t = 0;
     for (const rt::DevBuf* b : {&dec->topTok, &dec->topVal, &dec->thr, &dec->hPar, &dec->hTok,
                                 &dec->hWord, &dec->finScore, &dec->finCount, &dec->status, &dec->ws,
-                                &dec->stateTab, &dec->outTok, &dec->outWord, &dec->staging[0],
-                                &dec->staging[1]})
+                                &dec->outTok, &dec->outWord, &dec->staging[0], &dec->staging[1]})
       t += (int64_t)b->cap;
     *out = t;
   });
