@@ -1,0 +1,70 @@
+"""Kernel-level test of the token-beam select (K1) through flt_topm_rows: for every row the list
+must equal the reference's partial_sort result (decoder/LexiconFreeDecoder.cpp:39-51) under the
+deterministic tie rule (value descending, then token ascending) — including adversarial rows that
+defeat the chunk-maximum bound (sorted, constant, heavy ties, -inf) and shapes that take the generic
+path (N % 4 != 0, misaligned base pointer, M > 256)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def expected(rows, M):
+    N = rows.shape[1]
+    idx = np.lexsort((np.arange(N)[None, :].repeat(rows.shape[0], 0), -rows.astype(np.float64)), axis=1)
+    tok = idx[:, :M]
+    return tok, np.take_along_axis(rows, tok, axis=1)
+
+
+def make_rows(kind, R, N, rng):
+    if kind == "gauss":
+        return rng.standard_normal((R, N)).astype(np.float32)
+    if kind == "logsoftmax":
+        z = rng.standard_normal((R, N)).astype(np.float32)
+        return (z - np.log(np.exp(z).sum(1, keepdims=True))).astype(np.float32)
+    if kind == "ascending":
+        return np.tile(np.arange(N, dtype=np.float32), (R, 1))
+    if kind == "descending":
+        return np.tile(-np.arange(N, dtype=np.float32), (R, 1))
+    if kind == "constant":
+        return np.full((R, N), -3.25, np.float32)
+    if kind == "few_values":
+        return rng.integers(0, 4, size=(R, N)).astype(np.float32)
+    if kind == "neg_inf":
+        x = rng.standard_normal((R, N)).astype(np.float32)
+        x[:, ::3] = -np.inf
+        return x
+    raise ValueError(kind)
+
+
+CASES = [
+    # N, M, offset (floats)
+    (10000, 53, 0), (10000, 1, 0), (10000, 256, 0), (10000, 300, 0), (10240, 53, 0), (10244, 53, 0),
+    (9999, 53, 0), (10000, 53, 1), (5000, 103, 0), (29, 29, 0), (29, 5, 0), (64, 64, 0), (4096, 53, 0),
+    (4100, 53, 0),
+]
+
+
+@pytest.mark.parametrize("kind", ["gauss", "logsoftmax", "ascending", "descending", "constant",
+                                  "few_values", "neg_inf"])
+@pytest.mark.parametrize("N,M,offset", CASES)
+def test_topm_rows(kind, N, M, offset):
+    import torch
+
+    from text_b200 import capi
+
+    api = capi.Api()
+    rng = np.random.default_rng(N * 7 + M)
+    R = 37
+    rows = make_rows(kind, R, N, rng)
+    flat = torch.empty(R * N + offset + 8, dtype=torch.float32, device="cuda")
+    view = flat[offset:offset + R * N].view(R, N)
+    view.copy_(torch.from_numpy(rows))
+    tok = torch.full((R, M), -7, dtype=torch.int32, device="cuda")
+    val = torch.zeros((R, M), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    api.topm_rows(view.data_ptr(), R, N, M, tok.data_ptr(), val.data_ptr(), None)
+    torch.cuda.synchronize()
+    etok, eval_ = expected(rows, M)
+    np.testing.assert_array_equal(tok.cpu().numpy(), etok)
+    np.testing.assert_array_equal(val.cpu().numpy(), eval_)

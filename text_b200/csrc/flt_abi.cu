@@ -480,7 +480,9 @@ void planFor(flt_decoder& d, int N) {
                    "(beamSizeToken < N and > 2048, or beamSize > 2040 in ranked mode)");
   t.M = c.M;
   t.P = std::max(kThreads, nextPow2(want));
-  t.stage = (size_t)N * 4 <= 100 * 1024;
+  // register-resident fast path (alignment of the emission pointer is checked per launch)
+  t.fast = (N % 4 == 0) && N <= 4 * kFastVec * kThreads && want <= 256 && c.M <= 256;
+  t.stage = !t.fast && (size_t)N * 4 <= 100 * 1024;
   // wide offsets
   d.wideOffHost.assign(K + 1, 0);
   for (int r = 1; r <= K; ++r)
@@ -610,10 +612,12 @@ void runChunk(flt_decoder& d, const float* dEmis, int Bc, int T, int N, const in
     ta.outTok = d.topTok.as<int>();
     ta.outVal = d.topVal.as<float>();
     ta.outThr = c.setAll ? nullptr : d.thr.as<float>();
+    TopMCfg tc = d.tcfg;
+    if ((reinterpret_cast<uintptr_t>(dEmis) & 15) != 0) tc.fast = 0;
     const int grid = (int)std::min<long long>(rows, d.topmGridMax * 8LL);
     if (rows > 0) {
       KernelTimer kt(d, 0);
-      launchTopM(d.tcfg, ta, grid, d.topmSmem, s);
+      launchTopM(tc, ta, grid, d.topmSmem, s);
       d.launches++;
     }
     a.topTok = ta.outTok;
@@ -1078,7 +1082,9 @@ int flt_topm_rows(const float* dEmissions, int64_t rows, int32_t N, int32_t M, i
     t.bias = nullptr;
     t.capS = 2048;
     t.P = std::max(kThreads, nextPow2(M));
-    t.stage = (size_t)N * 4 <= 100 * 1024;
+    t.fast = (N % 4 == 0) && N <= 4 * kFastVec * kThreads && M <= 256 &&
+             (reinterpret_cast<uintptr_t>(dEmissions) & 15) == 0;
+    t.stage = !t.fast && (size_t)N * 4 <= 100 * 1024;
     TopMSmem ts;
     const size_t smem = (carveTopM(nullptr, t, ts) + 255) / 256 * 256;
     TopMArgs a{};

@@ -81,6 +81,6 @@ def src(f, n):
 
 
 print(f"kernel {name}: {tot_i:.0f} warp-instructions, {tot_s:.0f} samples")
-for key, (inst, samp, st) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+for key, (inst, samp, st) in sorted(agg.items(), key=lambda kv: -(kv[1][0] if os.environ.get("BY_INST") else kv[1][1]))[:top]:
     tops = ",".join(f"{k[6:]}:{v / max(samp, 1) * 100:.0f}%" for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:2])
     print(f"{samp / tot_s * 100:5.1f}% samp {inst / tot_i * 100:5.1f}% inst  {key[0]}:{key[1]:<4} [{tops}] {src(*key)}")
