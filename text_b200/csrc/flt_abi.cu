@@ -25,7 +25,7 @@ using namespace flt;
 
 /* =============================================================================== kernels ==== */
 #if FLT_DEVICE_BUILD
-__global__ void __launch_bounds__(256) flt_k_topm(TopMCfg c, TopMArgs a) {
+__global__ void __launch_bounds__(256, 3) flt_k_topm(TopMCfg c, TopMArgs a) {
   extern __shared__ __align__(16) char smem[];
   Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
   topmCta(cta, c, a, smem);

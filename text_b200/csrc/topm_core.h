@@ -74,6 +74,7 @@ struct TopMSmem {
   unsigned long long* sortBuf; // [max(P, capS)]
   int* cnt;                    // [4]
   unsigned long long* red;     // [64]
+  int* rankCnt;                // [capS] rank counters of the fast path (kept zero between rows)
 };
 
 FLT_HD size_t carveTopM(char* base, const TopMCfg& c, TopMSmem& s) {
@@ -87,6 +88,7 @@ FLT_HD size_t carveTopM(char* base, const TopMCfg& c, TopMSmem& s) {
   s.sortBuf = (unsigned long long*)take(sizeof(unsigned long long) * nbuf);
   s.red = (unsigned long long*)take(sizeof(unsigned long long) * 64);
   s.cnt = (int*)take(sizeof(int) * 4);
+  s.rankCnt = (int*)take(sizeof(int) * c.capS);
   s.row = (float*)take(c.stage ? sizeof(float) * c.N : 0);
   return off;
 }
@@ -217,7 +219,7 @@ FLT_DEV float warpSortDesc(float v, int lane) { // bitonic sort across the 32 la
 // descending (ns >= min(want, #valid)), and *nsOut = ns. Returns false if the survivors overflowed
 // capS (caller falls back to the generic path).
 FLT_DEV bool fastSelect(const Cta& cta, const TopMCfg& c, TopMSmem& s, const float (&keyv)[4 * kFastVec],
-                        int want, bool rawMode, int nvec, int* nsOut) {
+                        int want, int minExpected, int* nsOut) {
   const int lane = cta.tid & 31, warp = cta.tid >> 5, nw = cta.nthr >> 5;
   const float ninf = bitsF32(0xFF800000u);
   float m = ninf;
@@ -232,15 +234,12 @@ FLT_DEV bool fastSelect(const Cta& cta, const TopMCfg& c, TopMSmem& s, const flo
   cta.sync();
   float tau = tauS[0];
   for (int i = 1; i < nw; ++i) tau = fminf(tau, tauS[i]);
+  // -inf (padding, ineligible tokens) never passes: clamp the bound to the lowest finite float
+  tau = fmaxf(tau, bitsF32(0xFF7FFFFFu));
   // count, warp-scan, one atomic per warp, then write
-  // valid element: inside the row (raw emissions, where -inf is a legitimate value) or eligible
-  // (biased keys, where -inf marks a token that must never be listed)
-  auto ok = [&](int z) {
-    return keyv[z] >= tau && (rawMode ? ((z >> 2) * cta.nthr + cta.tid) < nvec : keyv[z] > ninf);
-  };
   int cntMine = 0;
 #pragma unroll
-  for (int z = 0; z < 4 * kFastVec; ++z) cntMine += ok(z) ? 1 : 0;
+  for (int z = 0; z < 4 * kFastVec; ++z) cntMine += keyv[z] >= tau ? 1 : 0;
   int incl = cntMine;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -251,27 +250,40 @@ FLT_DEV bool fastSelect(const Cta& cta, const TopMCfg& c, TopMSmem& s, const flo
   if (lane == 31) base = atomAdd(&s.cnt[0], incl);
   base = __shfl_sync(0xffffffffu, base, 31);
   int pos = base + incl - cntMine;
+  unsigned long long* src = s.sortBuf + c.capS;
   if (cntMine) {
 #pragma unroll
     for (int z = 0; z < 4 * kFastVec; ++z) {
-      if (ok(z)) {
+      if (keyv[z] >= tau) {
         // element index of register z: vector it = z/4 at float4 index it*nthr + tid
         const int idx = ((z >> 2) * cta.nthr + cta.tid) * 4 + (z & 3);
-        if (pos < c.capS) s.sortBuf[c.capS + pos] = topmKey(keyv[z], idx);
+        if (pos < c.capS) src[pos] = topmKey(keyv[z], idx);
         ++pos;
       }
     }
   }
   cta.sync();
   const int ns = s.cnt[0];
-  if (ns > c.capS) return false;
-  // rank by counting into sortBuf[0..ns)
-  const unsigned long long* src = s.sortBuf + c.capS;
+  // overflow, or a row that needs -inf entries to fill the list: generic path
+  if (ns > c.capS || ns < minExpected) return false;
+  // rank by counting, spread over the CTA: thread (a, part) counts its slice of the survivors
+  int* rankCnt = s.rankCnt; // zero on entry, re-zeroed below
+  if (ns > 0) {
+    const int parts = ns >= cta.nthr ? 1 : cta.nthr / ns;
+    const int slice = (ns + parts - 1) / parts;
+    for (int t = cta.tid; t < ns * parts; t += cta.nthr) {
+      const int a = t % ns, part = t / ns;
+      const int lo = part * slice, hi = lo + slice < ns ? lo + slice : ns;
+      const unsigned long long ka = src[a];
+      int cnt = 0;
+      for (int b = lo; b < hi; ++b) cnt += src[b] > ka ? 1 : 0;
+      if (cnt) atomAdd(&rankCnt[a], cnt);
+    }
+  }
+  cta.sync();
   for (int a = cta.tid; a < ns; a += cta.nthr) {
-    const unsigned long long ka = src[a];
-    int rank = 0;
-    for (int b = 0; b < ns; ++b) rank += src[b] > ka ? 1 : 0;
-    s.sortBuf[rank] = ka;
+    s.sortBuf[rankCnt[a]] = src[a];
+    rankCnt[a] = 0;
   }
   cta.sync();
   *nsOut = ns;
@@ -315,7 +327,10 @@ FLT_DEV bool topmRowFast(const Cta& cta, const TopMCfg& c, const TopMArgs& a, To
   }
   int ns = 0;
   const int want = restricted ? c.bst : c.M;
-  if (!fastSelect(cta, c, s, keyv, want, !(c.bias && !restricted), nvec, &ns)) return false;
+  // raw emissions: fewer survivors than min(want, N) means -inf values are needed -> generic path
+  const bool biased = c.bias && !restricted;
+  const int minExpected = biased ? 0 : (want < N ? want : N);
+  if (!fastSelect(cta, c, s, keyv, want, minExpected, &ns)) return false;
   int* ot = a.outTok + r * c.M;
   float* ov = a.outVal + r * c.M;
   if (!restricted) {
@@ -380,6 +395,8 @@ FLT_DEV void topmCta(const Cta& cta, const TopMCfg& c, const TopMArgs& a, char* 
   TopMSmem s;
   carveTopM(smem, c, s);
   const int N = c.N;
+  for (int i = cta.tid; i < c.capS; i += cta.nthr) s.rankCnt[i] = 0;
+  cta.sync();
   for (long long r = cta.bid; r < a.rows; r += cta.nblk) {
     const float* g = a.emis + r * N;
     const float* row = g;
