@@ -52,6 +52,9 @@ struct Lay {
   int list[2];
   int spec;
   int wideOff;
+  int itemRow;   // int16 [wideOff[K]]: row rank of each wide work item
+  int cslot;     // int [capC]: merge-table slot of each candidate
+  int gath;      // int [64]: members of the cut bin (one-warp finish of the radix select)
   int total;
 };
 
@@ -72,6 +75,7 @@ struct DecCfg {
   int capH;       // merge table slots (pow2 >= 2*capC)
   int capRH;      // row table slots (pow2 >= 2*K)
   int capP;       // pow2 >= K
+  int wideTotal;  // wideOff[K]
   const int* wideOff; // [K+1]: wideOff[r] = sum_{q=1..r} J_q, J_q = min(Mwide, K/q + 3 (+slack))
   Lay lay;
   TrieDev trie;
@@ -146,12 +150,14 @@ struct Rows {
   FLT_DEV int& leaderOfRank(int r) const { return iv[4 * K + 2 + r]; }
   FLT_DEV int* deg() const { return iv + 5 * K + 2; }          // [K+1]
   FLT_DEV int* degTmp() const { return iv + 6 * K + 3; }       // [K+1]
+  FLT_DEV int& slotOf(int i) const { return iv[7 * K + 4 + i]; } // row-table slot of hyp i
 };
-constexpr int kRowsInts = 7; // K-sized int arrays (+ slack) behind Rows::iv
+constexpr int kRowsInts = 8; // K-sized int arrays (+ slack) behind Rows::iv
 
 enum { // ws.sc[] scalars
   SC_NH = 0, SC_NCAND, SC_NREP, SC_NSEL, SC_NROWS, SC_OVF, SC_BIN, SC_NEED, SC_BINCOUNT, SC_NICE,
-  SC_COUNT
+  SC_NGATH, SC_OR_LO, SC_OR_HI, SC_AND_LO, SC_AND_HI, SC_WCNT /* 32 warp counters follow */,
+  SC_COUNT = SC_WCNT + 32
 };
 
 // The workspace is addressed as base + constant-bank offset on every access (no pointer table in
@@ -182,6 +188,10 @@ struct Ws {
   FLT_DEV float* listVal(int b) const { return (float*)(base + c->lay.list[b] + 4 * c->M); }
   FLT_DEV float* spec() const { return (float*)(base + c->lay.spec); } // [K+2] e[own], e[blank], e[sil]
   FLT_DEV int* wideOff() const { return (int*)(base + c->lay.wideOff); } // [K+1]
+  FLT_DEV short* itemRow() const { return (short*)(base + c->lay.itemRow); }
+  FLT_DEV int* cslot() const { return (int*)(base + c->lay.cslot); }
+  FLT_DEV int* gath() const { return (int*)(base + c->lay.gath); }
+  FLT_DEV u64* rkey() const { return (u64*)(base + c->lay.candKey); } // reps' score keys (reuses keyA)
 };
 
 FLT_HD size_t alignUp(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -216,6 +226,9 @@ FLT_HD void makeLayout(DecCfg& c) {
   for (int b = 0; b < 2; ++b) L.list[b] = take(c.listInSmem ? 8 * (size_t)c.M : 0);
   L.spec = take(sizeof(float) * (K + 2));
   L.wideOff = take(sizeof(int) * (K + 1));
+  L.itemRow = take(sizeof(short) * (c.wideTotal + 2));
+  L.cslot = take(sizeof(int) * c.capC);
+  L.gath = take(sizeof(int) * 64);
   L.total = (int)off;
 }
 
@@ -229,15 +242,44 @@ FLT_HD void fpRoot(u64& a, u64& b) {
   a = 0x243F6A8885A308D3ull;
   b = 0x13198A2E03707344ull;
 }
+// one 64-bit multiply + xor-shift per chain and label
 FLT_HD void fpChild(u64 pa, u64 pb, int label, u64& a, u64& b) {
   const u64 l = (u64)(uint32_t)label;
-  a = mix64(pa * 0x9E3779B97F4A7C15ull + l + 0x632BE59BD9B4E019ull);
-  b = mix64(pb * 0xC2B2AE3D27D4EB4Full + l * 0x165667B19E3779F9ull + 0x27D4EB2F165667C5ull);
+  u64 x = (pa ^ (l + 0x632BE59BD9B4E019ull)) * 0x9E3779B97F4A7C15ull;
+  u64 y = (pb + l * 0x165667B19E3779F9ull + 0x27D4EB2F165667C5ull) * 0xC2B2AE3D27D4EB4Full;
+  a = x ^ (x >> 32);
+  b = y ^ (y >> 29);
 }
 FLT_HD void candKeyOf(u64 sa, u64 sb, int lex, int tok, int pbFlag, u64& ka, u64& kb) {
   const u64 p = ((u64)(uint32_t)lex << 32) | ((u64)(uint32_t)tok << 1) | (u64)(pbFlag ? 1 : 0);
-  ka = mix64(sa ^ mix64(p + 0x9E3779B97F4A7C15ull));
-  kb = mix64(sb + p * 0xD6E8FEB86659FD93ull);
+  u64 x = (sa ^ p) * 0xD6E8FEB86659FD93ull;
+  u64 y = (sb + p) * 0xFF51AFD7ED558CCDull;
+  ka = x ^ (x >> 31);
+  kb = y ^ (y >> 30);
+}
+
+FLT_DEV int highBit64(u64 v) { // index of the most significant set bit (v != 0)
+#if FLT_DEVICE_BUILD
+  return 63 - __clzll((long long)v);
+#else
+  return 63 - __builtin_clzll(v);
+#endif
+}
+
+// warp-aggregated counter increment: one atomic per converged group of callers
+FLT_DEV int aggInc(int* ctr, int tid) {
+#if FLT_DEVICE_BUILD
+  const unsigned mask = __activemask();
+  const int lane = tid & 31;
+  const int leader = __ffs(mask) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(ctr, __popc(mask));
+  base = __shfl_sync(mask, base, leader);
+  return base + __popc(mask & ((1u << lane) - 1u));
+#else
+  (void)tid;
+  return (*ctr)++;
+#endif
 }
 
 /* ------------------------------------------------------------------ CTA collectives ---------- */
@@ -389,17 +431,18 @@ FLT_DEV bool inTokenSetV(const DecCfg& c, const FrameIn& f, int n, float v) {
   return false;
 }
 
-// Phase R: group wide hypotheses into rows (same LM state; lexicon: also lex == root).
-FLT_DEV void phaseRows(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, int nH) {
+// Phase R: group wide hypotheses into rows (same LM state; lexicon: also lex == root), find each
+// row's best and second-best member, and rank the rows by their best member. The row table is
+// empty on entry and left empty (each leader clears its own slot). Ends with a barrier.
+// `tail` runs between the last two barriers (used to publish per-frame scalars for free).
+template <class Tail>
+FLT_DEV void phaseRows(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, int nH, Tail tail) {
   const Rows R = w.rows();
-  for (int s = cta.tid; s < c.capRH; s += cta.nthr) R.hash[s] = -1;
+  int* sc = w.sc();
+  const uint32_t mask = (uint32_t)c.capRH - 1;
   for (int i = cta.tid; i < nH; i += cta.nthr) {
     R.m2(i) = kIntMax;
     R.rowOf(i) = -1;
-  }
-  cta.sync();
-  const uint32_t mask = (uint32_t)c.capRH - 1;
-  for (int i = cta.tid; i < nH; i += cta.nthr) {
     if (c.lexicon && cur.lex(i) != 0) continue;
     const u64 fa = cur.fpA(i), fb = cur.fpB(i);
     uint32_t s = (uint32_t)fa & mask;
@@ -412,32 +455,60 @@ FLT_DEV void phaseRows(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
       }
       s = (s + 1) & mask;
     }
+    R.slotOf(i) = (int)s;
   }
   cta.sync();
+  // leaders, second members, row ranks (hypotheses are sorted by score: rank = leaders before me)
+  const bool small = nH <= cta.nthr;
   int* rank = R.rank();
-  for (int i = cta.tid; i < nH; i += cta.nthr) {
-    int isLeader = 0;
-    if (!(c.lexicon && cur.lex(i) != 0)) {
-      const u64 fa = cur.fpA(i), fb = cur.fpB(i);
-      uint32_t s = (uint32_t)fa & mask;
-      for (;;) {
-        const int occ = R.hash[s];
-        if (cur.fpA(occ) == fa && cur.fpB(occ) == fb) {
-          R.rowOf(i) = occ;
-          isLeader = occ == i;
-          if (!isLeader) atomMin(&R.m2(occ), i);
-          break;
-        }
-        s = (s + 1) & mask;
-      }
+  int myRank = 0, isLeader = 0;
+  for (int i = cta.tid; i < (small ? cta.nthr : nH); i += cta.nthr) {
+    isLeader = 0;
+    if (i < nH && !(c.lexicon && cur.lex(i) != 0)) {
+      const int occ = R.hash[R.slotOf(i)];
+      R.rowOf(i) = occ;
+      isLeader = occ == i;
+      if (!isLeader) atomMin(&R.m2(occ), i);
     }
-    rank[i] = isLeader;
+#if FLT_DEVICE_BUILD
+    if (small) {
+      const unsigned bal = __ballot_sync(0xffffffffu, isLeader);
+      myRank = __popc(bal & ((1u << (cta.tid & 31)) - 1u));
+      if ((cta.tid & 31) == 0) sc[SC_WCNT + (cta.tid >> 5)] = __popc(bal);
+    } else
+#endif
+    {
+      if (i < nH) rank[i] = isLeader;
+    }
   }
   cta.sync();
-  ctaExclusiveScan(cta, rank, R.rankTmp(), nH); // rank[i] = leaders before i; rank[nH] = rows
-  for (int i = cta.tid; i < nH; i += cta.nthr)
-    if (R.rowOf(i) == i) R.leaderOfRank(rank[i]) = i;
-  if (cta.tid == 0) w.sc()[SC_NROWS] = rank[nH];
+#if FLT_DEVICE_BUILD
+  if (small) {
+    const int warp = cta.tid >> 5, nw = (cta.nthr + 31) >> 5;
+    int before = 0, total = 0;
+    for (int k = 0; k < nw; ++k) {
+      const int v = sc[SC_WCNT + k];
+      before += k < warp ? v : 0;
+      total += v;
+    }
+    if (isLeader) {
+      R.leaderOfRank(before + myRank) = cta.tid;
+      R.hash[R.slotOf(cta.tid)] = -1;
+    }
+    if (cta.tid == 0) sc[SC_NROWS] = total;
+  } else
+#endif
+  {
+    (void)myRank;
+    ctaExclusiveScan(cta, rank, R.rankTmp(), nH); // rank[i] = leaders before i; rank[nH] = rows
+    for (int i = cta.tid; i < nH; i += cta.nthr)
+      if (R.rowOf(i) == i) {
+        R.leaderOfRank(rank[i]) = i;
+        R.hash[R.slotOf(i)] = -1;
+      }
+    if (cta.tid == 0) sc[SC_NROWS] = rank[nH];
+  }
+  tail();
   cta.sync();
 }
 
@@ -607,31 +678,29 @@ FLT_DEV void emitEdge(const DecCfg& c, const Ws& w, const Beam& cur, const Frame
 }
 
 // Phase M: merge candidates with equal (LM state, lex, token, prevBlank) keeping the best
-// (Utils.h:168-198, max-merge). Representatives are collected into w.rep().
-FLT_DEV void phaseMerge(const Cta& cta, const DecCfg& c, const Ws& w, int nCand, double thrScore) {
+// (Utils.h:168-198, max-merge). The merge table is empty on entry; representatives (the group
+// maxima) are collected into rep[] with their order-preserving score keys in rkey[], and the
+// AND / OR of all keys is accumulated for the radix select. Two barriers.
+FLT_DEV void phaseMerge(const Cta& cta, const DecCfg& c, const Ws& w, int nCand) {
   const Cand cd = w.cand();
-  for (int s = cta.tid; s < c.capH; s += cta.nthr) w.mh()[s] = -1;
-  if (cta.tid == 0) w.sc()[SC_NREP] = 0;
-  cta.sync();
+  int* mh = w.mh();
+  int* cslot = w.cslot();
+  int* sc = w.sc();
   const uint32_t mask = (uint32_t)c.capH - 1;
   for (int x = cta.tid; x < nCand; x += cta.nthr) {
     if (!(cd.parflag(x) & CF_ALIVE)) continue;
-    if (!(cd.score(x) >= thrScore)) { // Utils.h:161-165
-      cd.parflag(x) &= ~CF_ALIVE;
-      continue;
-    }
     const u64 ka = cd.keyA(x), kb = cd.keyB(x);
     uint32_t s = (uint32_t)ka & mask;
     for (;;) {
-      int occ = w.mh()[s];
+      int occ = mh[s];
       if (occ == -1) {
-        occ = atomCAS(&w.mh()[s], -1, x);
+        occ = atomCAS(&mh[s], -1, x);
         if (occ == -1) break;
       }
       if (cd.keyA(occ) == ka && cd.keyB(occ) == kb) {
         // same group: keep the better of the two in the slot
         while (candBetter(cd, x, occ)) {
-          const int old = atomCAS(&w.mh()[s], occ, x);
+          const int old = atomCAS(&mh[s], occ, x);
           if (old == occ) break;
           occ = old;
         }
@@ -639,22 +708,60 @@ FLT_DEV void phaseMerge(const Cta& cta, const DecCfg& c, const Ws& w, int nCand,
       }
       s = (s + 1) & mask;
     }
+    cslot[x] = (int)s;
   }
   cta.sync();
-  for (int s = cta.tid; s < c.capH; s += cta.nthr) {
-    const int x = w.mh()[s];
-    if (x >= 0) w.rep()[atomAdd(&w.sc()[SC_NREP], 1)] = x;
+  u64* rkey = w.rkey();
+  int* rep = w.rep();
+  u64 orK = 0, andK = ~0ull;
+  for (int x = cta.tid; x < nCand; x += cta.nthr) {
+    if (!(cd.parflag(x) & CF_ALIVE)) continue;
+    if (mh[cslot[x]] != x) continue;
+    const int r = aggInc(&sc[SC_NREP], cta.tid);
+    const u64 k = orderedKey64(cd.score(x));
+    rep[r] = x;
+    rkey[r] = k; // keyA storage is free again: every insert finished at the barrier above
+    orK |= k;
+    andK &= k;
   }
+#if FLT_DEVICE_BUILD
+  {
+    const unsigned oLo = __reduce_or_sync(0xffffffffu, (unsigned)orK);
+    const unsigned oHi = __reduce_or_sync(0xffffffffu, (unsigned)(orK >> 32));
+    const unsigned aLo = __reduce_and_sync(0xffffffffu, (unsigned)andK);
+    const unsigned aHi = __reduce_and_sync(0xffffffffu, (unsigned)(andK >> 32));
+    if ((cta.tid & 31) == 0) {
+      atomicOr((unsigned*)&sc[SC_OR_LO], oLo);
+      atomicOr((unsigned*)&sc[SC_OR_HI], oHi);
+      atomicAnd((unsigned*)&sc[SC_AND_LO], aLo);
+      atomicAnd((unsigned*)&sc[SC_AND_HI], aHi);
+    }
+  }
+#else
+  sc[SC_OR_LO] |= (int)(unsigned)orK;
+  sc[SC_OR_HI] |= (int)(unsigned)(orK >> 32);
+  sc[SC_AND_LO] &= (int)(unsigned)andK;
+  sc[SC_AND_HI] &= (int)(unsigned)(andK >> 32);
+#endif
   cta.sync();
 }
 
-// find, scanning bins from 255 down, the bin where the running count reaches `need`
+// find, scanning bins from 255 down, the bin where the running count reaches `need`; the bins are
+// zeroed again as they are read (one warp)
 FLT_DEV void findCutBin(const Cta& cta, const Ws& w, int need) {
+  int* hist = w.hist();
+  int* sc = w.sc();
 #if FLT_DEVICE_BUILD
   if (cta.tid < 32) {
     const int lane = cta.tid;
+    int h[8];
     int part = 0;
-    for (int k = 0; k < 8; ++k) part += w.hist()[255 - (lane * 8 + k)];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      h[k] = hist[255 - (lane * 8 + k)];
+      hist[255 - (lane * 8 + k)] = 0;
+      part += h[k];
+    }
     int incl = part;
     for (int o = 1; o < 32; o <<= 1) {
       const int u = __shfl_up_sync(0xffffffffu, incl, o);
@@ -663,29 +770,29 @@ FLT_DEV void findCutBin(const Cta& cta, const Ws& w, int need) {
     const int excl = incl - part;
     if (excl < need && incl >= need) {
       int cum = excl;
+#pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const int b = 255 - (lane * 8 + k);
-        const int h = w.hist()[b];
-        if (cum + h >= need) {
-          w.sc()[SC_BIN] = b;
-          w.sc()[SC_NEED] = need - cum;
-          w.sc()[SC_BINCOUNT] = h;
-          break;
+        if (cum < need && cum + h[k] >= need) {
+          sc[SC_BIN] = 255 - (lane * 8 + k);
+          sc[SC_NEED] = need - cum;
+          sc[SC_BINCOUNT] = h[k];
         }
-        cum += h;
+        cum += h[k];
       }
     }
   }
 #else
   if (cta.tid == 0) {
     int cum = 0;
+    bool found = false;
     for (int b = 255; b >= 0; --b) {
-      const int h = w.hist()[b];
-      if (cum + h >= need) {
-        w.sc()[SC_BIN] = b;
-        w.sc()[SC_NEED] = need - cum;
-        w.sc()[SC_BINCOUNT] = h;
-        break;
+      const int h = hist[b];
+      hist[b] = 0;
+      if (!found && cum + h >= need) {
+        sc[SC_BIN] = b;
+        sc[SC_NEED] = need - cum;
+        sc[SC_BINCOUNT] = h;
+        found = true;
       }
       cum += h;
     }
@@ -693,167 +800,264 @@ FLT_DEV void findCutBin(const Cta& cta, const Ws& w, int need) {
 #endif
 }
 
-// Phase Sel: choose the min(nRep, K) best representatives (Utils.h:200-220) and rank them (score
-// descending, deterministic ties) into w.surv()[capP..]. Returns the number selected.
+// Phase Sel: choose the min(nRep, K) best representatives (Utils.h:200-220), rank them (score
+// descending, deterministic ties) into surv[capP..], and return how many there are.
+// Radix select on the score keys, most significant *varying* bit first (from the AND/OR of the
+// keys); a cut bin with <= 32 members is finished by one warp.
 FLT_DEV int phaseSelect(const Cta& cta, const DecCfg& c, const Ws& w, int nRep) {
   const Cand cd = w.cand();
   const int K = c.K;
+  int* sc = w.sc();
   int* surv = w.surv();
   int* ranked = w.surv() + c.capP;
+  const int* rep = w.rep();
+  const u64* rkey = w.rkey();
+  u64* skey = w.skey();
+  int* pos = w.pos();
+  int* hist = w.hist();
+  int* mh = w.mh();
+  const int* cslot = w.cslot();
   int nSel;
   if (nRep <= K) {
-    for (int r = cta.tid; r < nRep; r += cta.nthr) surv[r] = w.rep()[r];
+    for (int r = cta.tid; r < nRep; r += cta.nthr) {
+      const int x = rep[r];
+      surv[r] = x;
+      skey[r] = rkey[r];
+      pos[r] = 0;
+      mh[cslot[x]] = -1; // leave the merge table empty
+    }
     nSel = nRep;
     cta.sync();
   } else {
-    // radix select on key - minKey, most significant differing byte first
-    u64 kmax = 0, kmin = ~0ull;
-    for (int r = cta.tid; r < nRep; r += cta.nthr) {
-      const u64 k = orderedKey64(cd.score(w.rep()[r]));
-      kmax = k > kmax ? k : kmax;
-      kmin = k < kmin ? k : kmin;
-    }
-    ctaMaxMin64(cta, kmax, kmin, w.red());
-    const u64 range = kmax - kmin;
-    int shift = 0;
-    while (shift < 56 && (range >> shift) > 255ull) shift += 8;
+    const u64 orK = ((u64)(unsigned)sc[SC_OR_HI] << 32) | (unsigned)sc[SC_OR_LO];
+    const u64 andK = ((u64)(unsigned)sc[SC_AND_HI] << 32) | (unsigned)sc[SC_AND_LO];
+    const u64 vary = orK ^ andK; // bit positions on which the keys differ
+    const int top = vary ? highBit64(vary) : 0;
+    int shift = top >= 7 ? top - 7 : 0; // first digit = the 8 bits ending at the top varying bit
+    int width = top >= 7 ? 8 : top + 1;
     int need = K;
-    u64 prefix = 0; // digits above the current one, already fixed
-    bool wholeBin = false;
-    if (cta.tid == 0) w.sc()[SC_NSEL] = 0;
+    u64 hiMask = 0, hiVal = 0; // digits already fixed (bits above the current digit)
+    int mode = 0;              // 1 = whole cut bin selected, 2 = gathered bin resolved, 3 = ties
+    int cutDigit = 0;
     for (;;) {
-      for (int b = cta.tid; b < 256; b += cta.nthr) w.hist()[b] = 0;
-      cta.sync();
+      const u64 dmask = (1ull << width) - 1ull;
       for (int r = cta.tid; r < nRep; r += cta.nthr) {
-        const u64 k = orderedKey64(cd.score(w.rep()[r])) - kmin;
-        if (shift >= 56 || (k >> (shift + 8)) == (prefix >> (shift + 8)))
-          atomAdd(&w.hist()[(int)((k >> shift) & 255ull)], 1);
+        const u64 k = rkey[r];
+        if ((k & hiMask) == hiVal) atomAdd(&hist[(int)((k >> shift) & dmask)], 1);
       }
       cta.sync();
       findCutBin(cta, w, need);
       cta.sync();
-      const int bin = w.sc()[SC_BIN];
-      need = w.sc()[SC_NEED];
-      const int binCount = w.sc()[SC_BINCOUNT];
-      prefix |= (u64)bin << shift;
+      cutDigit = sc[SC_BIN];
+      need = sc[SC_NEED];
+      const int binCount = sc[SC_BINCOUNT];
       if (binCount == need) {
-        wholeBin = true;
+        mode = 1;
         break;
       }
-      if (shift == 0) break; // `need` of `binCount` identical keys: exact ties at the cut
-      shift -= 8;
+      if (binCount <= 32) {
+        mode = 2;
+        break;
+      }
+      if (shift == 0) {
+        mode = 3; // more than 32 identical keys straddle the cut
+        break;
+      }
+      hiMask |= dmask << shift;
+      hiVal |= (u64)cutDigit << shift;
+      width = shift >= 8 ? 8 : shift;
+      shift -= width;
     }
-    // keys strictly above the cut digit-prefix are selected; the cut bin is selected entirely
-    // (wholeBin) or resolved among equals below.
+    const u64 dmask = (1ull << width) - 1ull;
+    // selected outright: same fixed digits and a larger current digit, or (mode 1) the cut bin too
     for (int r = cta.tid; r < nRep; r += cta.nthr) {
-      const int x = w.rep()[r];
-      const u64 k = (orderedKey64(cd.score(x)) - kmin) >> shift;
-      const u64 p = prefix >> shift;
-      if (k > p || (wholeBin && k == p)) surv[atomAdd(&w.sc()[SC_NSEL], 1)] = x;
+      const u64 k = rkey[r];
+      const int x = rep[r];
+      mh[cslot[x]] = -1; // leave the merge table empty
+      bool sel = false;
+      if ((k & hiMask) != hiVal) {
+        sel = (k & hiMask) > hiVal;
+      } else {
+        const int dg = (int)((k >> shift) & dmask);
+        sel = dg > cutDigit || (mode == 1 && dg == cutDigit);
+        if (mode >= 2 && dg == cutDigit) w.gath()[aggInc(&sc[SC_NGATH], cta.tid) & 63] = r;
+      }
+      if (sel) {
+        const int a = aggInc(&sc[SC_NSEL], cta.tid);
+        surv[a] = x;
+        skey[a] = k;
+        pos[a] = 0;
+      }
     }
     cta.sync();
-    if (!wholeBin) {
-      // rare: pick `need` of the equal-score groups by the deterministic order
+    if (mode == 2) {
+      // one warp ranks the <= 32 members of the cut bin and keeps the best `need`
+#if FLT_DEVICE_BUILD
+      if (cta.tid < 32) {
+        const int ng = sc[SC_NGATH];
+        const int lane = cta.tid;
+        const int r = lane < ng ? w.gath()[lane] : -1;
+        const u64 k = r >= 0 ? rkey[r] : 0ull;
+        const int x = r >= 0 ? rep[r] : -1;
+        int better = 0;
+        for (int o = 0; o < ng; ++o) {
+          const u64 ko = __shfl_sync(0xffffffffu, k, o);
+          const int xo = __shfl_sync(0xffffffffu, x, o);
+          if (r >= 0 && o != lane) better += (ko > k || (ko == k && candBetter(cd, xo, x))) ? 1 : 0;
+        }
+        if (r >= 0 && better < need) {
+          const int a = aggInc(&sc[SC_NSEL], cta.tid);
+          surv[a] = x;
+          skey[a] = k;
+          pos[a] = 0;
+        }
+      }
+#else
       if (cta.tid == 0) {
-        const int n0 = w.sc()[SC_NSEL];
+        const int ng = sc[SC_NGATH];
+        for (int i = 0; i < ng; ++i) {
+          const int r = w.gath()[i];
+          int better = 0;
+          for (int o = 0; o < ng; ++o) {
+            const int ro = w.gath()[o];
+            if (o != i) better += (rkey[ro] > rkey[r] || (rkey[ro] == rkey[r] && candBetter(cd, rep[ro], rep[r]))) ? 1 : 0;
+          }
+          if (better < need) {
+            const int a = sc[SC_NSEL]++;
+            surv[a] = rep[r];
+            skey[a] = rkey[r];
+            pos[a] = 0;
+          }
+        }
+      }
+#endif
+      cta.sync();
+    } else if (mode == 3) {
+      // rare: `need` of many equal-score groups, by the deterministic order (one thread)
+      if (cta.tid == 0) {
+        const int n0 = sc[SC_NSEL];
         int n = n0;
         for (int q = 0; q < need; ++q) {
           int bestX = -1;
+          u64 bk = 0;
           for (int r = 0; r < nRep; ++r) {
-            const int x = w.rep()[r];
-            if (((orderedKey64(cd.score(x)) - kmin) >> shift) != (prefix >> shift)) continue;
+            const u64 k = rkey[r];
+            if ((k & hiMask) != hiVal || (int)((k >> shift) & dmask) != cutDigit) continue;
+            const int x = rep[r];
             bool taken = false;
             for (int z = n0; z < n; ++z) taken |= surv[z] == x;
             if (taken) continue;
-            if (bestX < 0 || candBetter(cd, x, bestX)) bestX = x;
+            if (bestX < 0 || candBetter(cd, x, bestX)) {
+              bestX = x;
+              bk = k;
+            }
           }
-          surv[n++] = bestX;
+          surv[n] = bestX;
+          skey[n] = bk;
+          pos[n] = 0;
+          ++n;
         }
-        w.sc()[SC_NSEL] = n;
+        sc[SC_NSEL] = n;
       }
       cta.sync();
     }
-    nSel = w.sc()[SC_NSEL];
+    nSel = sc[SC_NSEL];
   }
   // rank by counting, all threads: thread (a, part) counts the survivors of its slice that beat a
-  for (int a = cta.tid; a < nSel; a += cta.nthr) {
-    w.skey()[a] = orderedKey64(cd.score(surv[a]));
-    w.pos()[a] = 0;
-  }
-  cta.sync();
   if (nSel > 0) {
     const int parts = nSel >= cta.nthr ? 1 : cta.nthr / nSel;
     const int slice = (nSel + parts - 1) / parts;
     for (int t = cta.tid; t < nSel * parts; t += cta.nthr) {
       const int a = t % nSel, part = t / nSel;
       const int lo = part * slice, hi = lo + slice < nSel ? lo + slice : nSel;
-      const u64 ka = w.skey()[a];
+      const u64 ka = skey[a];
       const int xa = surv[a];
       int cnt = 0;
       for (int b = lo; b < hi; ++b) {
-        const u64 kb = w.skey()[b];
+        const u64 kb = skey[b];
         cnt += (kb > ka || (kb == ka && b != a && candBetter(cd, surv[b], xa))) ? 1 : 0;
       }
-      if (cnt) atomAdd(&w.pos()[a], cnt);
+      if (cnt) atomAdd(&pos[a], cnt);
     }
   }
   cta.sync();
-  for (int a = cta.tid; a < nSel; a += cta.nthr) ranked[w.pos()[a]] = surv[a];
+  for (int a = cta.tid; a < nSel; a += cta.nthr) ranked[pos[a]] = surv[a];
   cta.sync();
   return nSel;
 }
 
-// Phase F: materialise the new beam from the ranked survivors, extend the LM-state fingerprints
-// and n-gram contexts, write the back-pointer records.
+// Phase F: apply the beam threshold to the ranked survivors (Utils.h:161-165: keep score >=
+// best - beamThreshold; for a max-merge filtering after the merge keeps the same groups),
+// materialise the new beam, extend the LM-state fingerprints and n-gram contexts, write the
+// back-pointer records, and reset the per-frame scalars.
 FLT_DEV void phaseFinalize(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur,
                            const Beam& nxt, const FrameIn& f, int nSel) {
   const Cand cd = w.cand();
+  int* sc = w.sc();
   const int* ranked = w.surv() + c.capP;
-  for (int q = cta.tid; q < nSel; q += cta.nthr) {
-    const int x = ranked[q];
-    const int p = cd.par(x);
-    const int fl = cd.flags(x);
-    const int n = cd.tok(x);
-    nxt.score(q) = cd.score(x);
-    if (fl & CF_FINISH) {
-      nxt.am(q) = cur.am(p);
-    } else {
-      nxt.am(q) = cur.am(p) + amOf(c, f, cd.ce(x), n, cur.tok(p));
-    }
-    nxt.lm(q) = cur.lm(p) + (double)cd.lmd(x);
-    nxt.lex(q) = cd.lex(x);
-    nxt.tok(q) = n;
-    nxt.pb(q) = (fl & CF_PB) ? 1 : 0;
-    if (fl & CF_NEW) {
-      const int lab = candLabel(c, cd, x);
-      fpChild(cur.fpA(p), cur.fpB(p), lab, nxt.fpA(q), nxt.fpB(q));
-      if (c.lm.kind) {
-        const int wlm = lab < 0 ? c.lm.eos : c.lm.usr2lm[lab];
-        nxt.nctx(q) = ngramAdvanceCtx(c.lm, cur.ctx(p), cur.nctx(p), wlm, nxt.ctx(q));
+  if (nSel == 0) {
+    if (cta.tid == 0) sc[SC_NH] = 0;
+  } else {
+    // candidatesBestScore_ - beamThreshold (LexiconDecoder.cpp:217-224)
+    const double thrScore = cd.score(ranked[0]) - c.beamThreshold;
+    for (int q = cta.tid; q < nSel; q += cta.nthr) {
+      const int x = ranked[q];
+      const double score = cd.score(x);
+      if (!(score >= thrScore)) continue;
+      if (q + 1 == nSel || !(cd.score(ranked[q + 1]) >= thrScore)) sc[SC_NH] = q + 1;
+      const int p = cd.par(x);
+      const int fl = cd.flags(x);
+      const int n = cd.tok(x);
+      nxt.score(q) = score;
+      if (fl & CF_FINISH) {
+        nxt.am(q) = cur.am(p);
+      } else {
+        nxt.am(q) = cur.am(p) + amOf(c, f, cd.ce(x), n, cur.tok(p));
       }
-    } else {
-      nxt.fpA(q) = cur.fpA(p);
-      nxt.fpB(q) = cur.fpB(p);
-      if (c.lm.kind) {
-        const int nc = cur.nctx(p);
-        nxt.nctx(q) = nc;
-        for (int k = 0; k < nc; ++k) nxt.ctx(q)[k] = cur.ctx(p)[k];
+      nxt.lm(q) = cur.lm(p) + (double)cd.lmd(x);
+      nxt.lex(q) = cd.lex(x);
+      nxt.tok(q) = n;
+      nxt.pb(q) = (fl & CF_PB) ? 1 : 0;
+      if (fl & CF_NEW) {
+        const int lab = candLabel(c, cd, x);
+        fpChild(cur.fpA(p), cur.fpB(p), lab, nxt.fpA(q), nxt.fpB(q));
+        if (c.lm.kind) {
+          const int wlm = lab < 0 ? c.lm.eos : c.lm.usr2lm[lab];
+          nxt.nctx(q) = ngramAdvanceCtx(c.lm, cur.ctx(p), cur.nctx(p), wlm, nxt.ctx(q));
+        }
+      } else {
+        nxt.fpA(q) = cur.fpA(p);
+        nxt.fpB(q) = cur.fpB(p);
+        if (c.lm.kind) {
+          const int nc = cur.nctx(p);
+          nxt.nctx(q) = nc;
+          for (int k = 0; k < nc; ++k) nxt.ctx(q)[k] = cur.ctx(p)[k];
+        }
       }
+      f.hParent[q] = p;
+      f.hTok[q] = n;
+      if (f.hWord) f.hWord[q] = cd.word(x);
     }
-    f.hParent[q] = p;
-    f.hTok[q] = n;
-    if (f.hWord) f.hWord[q] = cd.word(x);
   }
-  if (cta.tid == 0) w.sc()[SC_NH] = nSel;
+  if (cta.tid == 0) { // scalars for the next frame's merge / select
+    sc[SC_NREP] = 0;
+    sc[SC_NSEL] = 0;
+    sc[SC_NGATH] = 0;
+    sc[SC_OR_LO] = 0;
+    sc[SC_OR_HI] = 0;
+    sc[SC_AND_LO] = -1;
+    sc[SC_AND_HI] = -1;
+  }
   cta.sync();
 }
 
 // One frame: cur -> nxt. All threads of the CTA call this with identical arguments.
 FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur,
                        const Beam& nxt, const FrameIn& f, int* status) {
-  const int nH = w.sc()[SC_NH];
+  int* sc = w.sc();
+  const int nH = sc[SC_NH];
   if (nH == 0) return; // the beam died (Utils.h:155-158): every later frame is empty
-  double best = negInf();
+  double best = negInf(); // (kept for emit helpers; the threshold uses the ranked best)
 
   // issue the scattered emission reads now; they are consumed after the row grouping
   float eOwn = 0.0f, eBlank = 0.0f, eSil = 0.0f;
@@ -865,42 +1069,45 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
     if (c.ctc) eBlank = f.e[c.blank];
     eSil = f.e[c.sil];
   }
-
+  float* spec = w.spec();
+  auto publish = [&]() {
+    if (cta.tid < nH) spec[cta.tid] = eOwn;
+    for (int i = cta.tid + cta.nthr; i < nH; i += cta.nthr) { // beams wider than the CTA
+      const int n = ownToken(c, cur, i);
+      spec[i] = (n >= 0 && n < c.N) ? f.e[n] : 0.0f;
+    }
+    if (cta.tid == cta.nthr - 1) {
+      spec[c.K] = eBlank;
+      spec[c.K + 1] = eSil;
+    }
+    if (cta.tid == 0) sc[SC_OVF] = 0;
+  };
   int wideItems = 0;
   if (c.wideRanked) {
-    phaseRows(cta, c, w, cur, nH);
-    wideItems = w.wideOff()[w.sc()[SC_NROWS]];
-  }
-  if (cta.tid < nH) w.spec()[cta.tid] = eOwn;
-  for (int i = cta.tid + cta.nthr; i < nH; i += cta.nthr) { // beams wider than the CTA
-    const int n = ownToken(c, cur, i);
-    w.spec()[i] = (n >= 0 && n < c.N) ? f.e[n] : 0.0f;
-  }
-  if (cta.tid == cta.nthr - 1) {
-    w.spec()[c.K] = eBlank;
-    w.spec()[c.K + 1] = eSil;
+    phaseRows(cta, c, w, cur, nH, publish);
+    wideItems = w.wideOff()[sc[SC_NROWS]];
+  } else {
+    publish();
+    cta.sync();
   }
   const int specBase = wideItems;
   const int narrowBase = specBase + 3 * nH;
-  if (cta.tid == 0) {
-    w.sc()[SC_NCAND] = narrowBase;
-    w.sc()[SC_OVF] = 0;
-  }
-  cta.sync();
   if (narrowBase > c.capC) { // cannot happen with a correctly sized capC; fail the utterance
+    cta.sync();
     if (cta.tid == 0) {
       *status |= 1;
-      w.sc()[SC_NH] = 0;
+      sc[SC_NH] = 0;
     }
     cta.sync();
     return;
   }
   // wide cells
   if (c.wideRanked) {
-    const int nRows = w.sc()[SC_NROWS];
+    const short* itemRow = w.itemRow();
+    const int* wideOff = w.wideOff();
     for (int x = cta.tid; x < wideItems; x += cta.nthr) {
-      const int r = searchOffsets(w.wideOff(), nRows + 1, x); // row rank r (0-based)
-      emitWide(c, w, cur, f, w.rows().leaderOfRank(r), x - w.wideOff()[r], x, best);
+      const int r = itemRow[x]; // row rank (0-based)
+      emitWide(c, w, cur, f, w.rows().leaderOfRank(r), x - wideOff[r], x, best);
     }
   }
   // stay / repeat / blank
@@ -910,6 +1117,7 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
     else w.cand().parflag(specBase + 3 * i + 2) = 0;
   }
   // trie edges
+  int nCand = narrowBase;
   if (c.lexicon) {
     const TrieDev& t = c.trie;
     int* deg = w.rows().deg();
@@ -917,6 +1125,7 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
       const int lex = cur.lex(i);
       deg[i] = (c.wideRanked && lex == 0) ? t.nRootLab : t.childOff[lex + 1] - t.childOff[lex];
     }
+    if (cta.tid == 0) sc[SC_NCAND] = narrowBase;
     cta.sync();
     ctaExclusiveScan(cta, deg, w.rows().degTmp(), nH);
     const int items = deg[nH];
@@ -932,34 +1141,35 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
         emitEdge(c, w, cur, f, i, t.childTok[e], t.childNode[e], false, best);
       }
     }
+    cta.sync();
+    nCand = sc[SC_NCAND];
+    if (sc[SC_OVF]) {
+      if (cta.tid == 0) *status |= 1;
+      nCand = nCand < c.capC ? nCand : c.capC;
+    }
+  } else {
+    cta.sync();
   }
-  const u64 bestKey = ctaMax64(cta, orderedKey64(best), w.red());
-  int nCand = w.sc()[SC_NCAND];
-  if (w.sc()[SC_OVF]) {
-    if (cta.tid == 0) *status |= 1;
-    nCand = nCand < c.capC ? nCand : c.capC;
-  }
-  // candidatesBestScore_ - beamThreshold (LexiconDecoder.cpp:217-224)
-  const double thrScore = keyToDouble(bestKey) - c.beamThreshold;
-  phaseMerge(cta, c, w, nCand, thrScore);
-  const int nSel = phaseSelect(cta, c, w, w.sc()[SC_NREP]);
+  (void)best;
+  phaseMerge(cta, c, w, nCand);
+  const int nSel = phaseSelect(cta, c, w, sc[SC_NREP]);
   phaseFinalize(cta, c, w, cur, nxt, f, nSel);
 }
 
 // decodeEnd (LexiconFreeDecoder.cpp:127-158, LexiconDecoder.cpp:231-274) as one more "frame".
 FLT_DEV void finishStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur,
                         const Beam& nxt, const FrameIn& f) {
-  const int nH = w.sc()[SC_NH];
+  int* sc = w.sc();
+  const int nH = sc[SC_NH];
   if (nH == 0) return;
-  if (cta.tid == 0) w.sc()[SC_NICE] = 0;
+  if (cta.tid == 0) sc[SC_NICE] = 0;
   cta.sync();
   if (c.lexicon) {
     for (int i = cta.tid; i < nH; i += cta.nthr)
-      if (cur.lex(i) == 0) w.sc()[SC_NICE] = 1; // "nice ending" exists (benign same-value race)
+      if (cur.lex(i) == 0) sc[SC_NICE] = 1; // "nice ending" exists (benign same-value race)
     cta.sync();
   }
-  const bool nice = c.lexicon && w.sc()[SC_NICE] != 0;
-  double best = negInf();
+  const bool nice = c.lexicon && sc[SC_NICE] != 0;
   for (int i = cta.tid; i < nH; i += cta.nthr) {
     w.cand().parflag(i) = 0;
     if (nice && cur.lex(i) != 0) continue;
@@ -971,11 +1181,10 @@ FLT_DEV void finishStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam
     }
     const double score = cur.score(i) + c.lmWeight * (double)ls;
     putCand(c, w, cur, i, score, i, c.sil, -1, cur.lex(i), flags, ls, 0.0f);
-    if (score > best) best = score;
   }
-  const u64 bestKey = ctaMax64(cta, orderedKey64(best), w.red());
-  phaseMerge(cta, c, w, nH, keyToDouble(bestKey) - c.beamThreshold);
-  const int nSel = phaseSelect(cta, c, w, w.sc()[SC_NREP]);
+  cta.sync();
+  phaseMerge(cta, c, w, nH);
+  const int nSel = phaseSelect(cta, c, w, sc[SC_NREP]);
   phaseFinalize(cta, c, w, cur, nxt, f, nSel);
 }
 
@@ -986,6 +1195,21 @@ FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char
   const Ws w{base, &c};
   const int K = c.K;
   for (int i = cta.tid; i <= K; i += cta.nthr) w.wideOff()[i] = c.wideOff[i];
+  for (int i = cta.tid; i < c.capRH; i += cta.nthr) w.rows().hash[i] = -1; // kept empty by its users
+  for (int i = cta.tid; i < c.capH; i += cta.nthr) w.mh()[i] = -1;
+  for (int i = cta.tid; i < 256; i += cta.nthr) w.hist()[i] = 0;
+  if (cta.tid == 0) {
+    int* sc = w.sc();
+    sc[SC_NREP] = 0;
+    sc[SC_NSEL] = 0;
+    sc[SC_NGATH] = 0;
+    sc[SC_OR_LO] = 0;
+    sc[SC_OR_HI] = 0;
+    sc[SC_AND_LO] = -1;
+    sc[SC_AND_HI] = -1;
+  }
+  for (int r = cta.tid; r < K; r += cta.nthr) // row rank of every wide work item
+    for (int x = c.wideOff[r]; x < c.wideOff[r + 1]; ++x) w.itemRow()[x] = (short)r;
   for (int b = cta.bid; b < a.B; b += cta.nblk) {
     const int len = a.lengths ? a.lengths[b] : a.T;
     int curIdx = 0;

@@ -433,6 +433,7 @@ void planFor(flt_decoder& d, int N) {
   c.unk = d.unk;
   if (o.beamSize < 1) throw FltError(FLT_ERR_INVALID, "beamSize must be >= 1");
   if (o.beamSizeToken < 1) throw FltError(FLT_ERR_INVALID, "beamSizeToken must be >= 1");
+  if (!(o.beamThreshold >= 0)) throw FltError(FLT_ERR_INVALID, "beamThreshold must be >= 0");
   if (o.criterionType != FLT_CRITERION_CTC && o.criterionType != FLT_CRITERION_ASG)
     throw FltError(FLT_ERR_UNSUPPORTED, "criterion type must be ASG or CTC for these decoders");
   if (o.logAdd)
@@ -495,6 +496,7 @@ void planFor(flt_decoder& d, int N) {
   c.capH = nextPow2((int)std::min<long long>(2 * capC, 1LL << 27));
   c.capRH = nextPow2(2 * K);
   c.capP = nextPow2(K);
+  c.wideTotal = c.wideRanked ? d.wideOffHost[K] : 0;
   c.listInSmem = d.needTopM && c.M <= 2 * kThreads;
 
   rt::Stream s = d.stream;
