@@ -243,6 +243,7 @@ def run_ours(a):
     ms_total = ev0.elapsed_time(ev1)
     # per-kernel device time of the LAST timed step (events recorded around each launch)
     last = api.last_kernel_ms(dec)
+    work = api.last_stats(dec)
     api.set_timing(dec, False)
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
@@ -349,7 +350,7 @@ def run_ours(a):
            "config": {"workload": workload_name(a, beam, bst), "emissions": f"log_softmax({a.sigma}*N(0,1)) fp32",
                       "nbest": nbest, "beamThreshold": a.threshold,
                       "l2": f"inputs ({h2d / 1e9:.2f} GB/step/GPU) exceed L2 (126 MB); no flush needed"},
-           "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+           "roofline": roof, "kernels": kernels, "beam_step_work": work, "cpu_baseline": cpu, "e2e": e2e,
            "gpu_launches": launches, "clocks": clk, "parity": parity,
            "workspace_bytes": api.workspace_bytes(dec)}
     print(json.dumps(out))

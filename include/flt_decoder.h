@@ -131,6 +131,9 @@ int flt_decoder_last_launches(const flt_decoder* dec, int32_t* out);
  * 0 = token-beam select, 1 = beam step, 2 = n-best backtrace. Synchronises the stream. */
 int flt_decoder_set_timing(flt_decoder* dec, int32_t on);
 int flt_decoder_last_kernel_ms(flt_decoder* dec, float* ms3, int32_t* launches3);
+/* Beam-step work counters of the last call (collected while timing is on), summed over frames:
+ * out4 = {frames stepped, candidates materialised, merge groups, survivors}. */
+int flt_decoder_last_stats(flt_decoder* dec, uint64_t* out4);
 int flt_decoder_workspace_bytes(const flt_decoder* dec, int64_t* out);
 
 /* Stand-alone entry to the token-beam select kernel (decoder/LexiconFreeDecoder.cpp:39-51:

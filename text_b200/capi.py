@@ -75,6 +75,7 @@ SYMBOLS = {
     "flt_decoder_workspace_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "flt_decoder_set_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "flt_decoder_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "flt_decoder_last_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "flt_topm_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_void_p]),
 }
@@ -240,6 +241,13 @@ class Api:
         self._ck(self.lib.flt_decoder_last_kernel_ms(dec, ms, n))
         names = ("token_select", "beam_step", "backtrace")
         return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(names)}
+
+    def last_stats(self, dec):
+        v = (C.c_uint64 * 4)()
+        self._ck(self.lib.flt_decoder_last_stats(dec, v))
+        frames = max(int(v[0]), 1)
+        return dict(frames=int(v[0]), candidates_per_frame=v[1] / frames, groups_per_frame=v[2] / frames,
+                    survivors_per_frame=v[3] / frames)
 
     def workspace_bytes(self, dec):
         n = C.c_int64()

@@ -76,6 +76,9 @@ struct DecCfg {
   int capRH;      // row table slots (pow2 >= 2*K)
   int capP;       // pow2 >= K
   int wideTotal;  // wideOff[K]
+  int nTau;       // pruning rectangles: rows 1..tauA[k] x columns 0..tauCol[k] hold >= K regular cells
+  int tauA[16];
+  int tauCol[16];
   const int* wideOff; // [K+1]: wideOff[r] = sum_{q=1..r} J_q, J_q = min(Mwide, K/q + 3 (+slack))
   Lay lay;
   TrieDev trie;
@@ -98,6 +101,7 @@ struct BatchArgs {
   int* status;          // [B] bit0 = candidate overflow
   char* wsGlobal;       // per-CTA workspace slabs (used when the workspace does not fit smem)
   long long wsStride;
+  unsigned long long* stats; // optional [4]: frames, candidates, merge groups, survivors (sums)
 };
 
 /* ------------------------------------------------------------------ workspace views ---------- */
@@ -525,9 +529,19 @@ FLT_DEV double amOf(const DecCfg& c, const FrameIn& f, float ev, int n, int prev
   return am;
 }
 
+// slot for a candidate that survived the pruning bound (compact: only live candidates are stored)
+FLT_DEV int allocCand(const Cta& cta, const DecCfg& c, const Ws& w) {
+  const int s = aggInc(&w.sc()[SC_NCAND], cta.tid);
+  if (s >= c.capC) {
+    w.sc()[SC_OVF] = 1;
+    return -1;
+  }
+  return s;
+}
+
 // new-token expansion of the row led by hypothesis i with token n (value ev)
-FLT_DEV void emitRowToken(const DecCfg& c, const Ws& w, const Beam& cur, int i, int n, float ev,
-                          int slot, double& best) {
+FLT_DEV void emitRowToken(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, int i, int n,
+                          float ev, double tau) {
   int p = i;
   if (!newTokenEligible(c, cur, p, n)) {
     p = w.rows().m2(i);
@@ -538,8 +552,9 @@ FLT_DEV void emitRowToken(const DecCfg& c, const Ws& w, const Beam& cur, int i, 
     double score = cur.score(p) + (double)ev;
     if (n == c.sil) score += c.silScore;
     score = score + c.lmWeight * (double)0.0f;
-    putCand(c, w, cur, slot, score, p, n, -1, 0, CF_NEW, 0.0f, ev);
-    if (score > best) best = score;
+    if (score < tau) return;
+    const int slot = allocCand(cta, c, w);
+    if (slot >= 0) putCand(c, w, cur, slot, score, p, n, -1, 0, CF_NEW, 0.0f, ev);
   } else {
     // LexiconDecoder.cpp:62-110, prevLex == root, CTC (ranked mode excludes ASG)
     const int child = c.trie.rootChild[n];
@@ -548,34 +563,33 @@ FLT_DEV void emitRowToken(const DecCfg& c, const Ws& w, const Beam& cur, int i, 
     if (n == c.sil) score += c.silScore;
     const float d = c.trie.maxScore[child] - 0.0f;
     score = score + c.lmWeight * (double)d;
-    putCand(c, w, cur, slot, score, p, n, -1, child, 0, d, ev);
-    if (score > best) best = score;
+    if (score < tau) return;
+    const int slot = allocCand(cta, c, w);
+    if (slot >= 0) putCand(c, w, cur, slot, score, p, n, -1, child, 0, d, ev);
   }
 }
 
 // one wide cell: row led by hypothesis i, list column j
-FLT_DEV void emitWide(const DecCfg& c, const Ws& w, const Beam& cur, const FrameIn& f, int i, int j,
-                      int slot, double& best) {
-  w.cand().parflag(slot) = 0;
+FLT_DEV void emitWide(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, const FrameIn& f,
+                      int i, int j, double tau) {
   if (j >= f.listLen) return;
   const int n = f.topTok[j];
   if (n < 0) return;                 // short list (fewer eligible tokens than columns)
   if (c.ctc && n == c.blank) return; // blank is never a new token
   if (n == c.sil && c.silScore > 0) return; // boosted sil is not rank-dominated: emitSilCell
-  emitRowToken(c, w, cur, i, n, f.topVal[j], slot, best);
+  emitRowToken(cta, c, w, cur, i, n, f.topVal[j], tau);
 }
 
 // With silScore > 0 the sil expansion of a wide row is not dominated by the cells left of it in
-// the ranked list, so every row proposes it explicitly (slot given by the caller).
-FLT_DEV void emitSilCell(const DecCfg& c, const Ws& w, const Beam& cur, const FrameIn& f, int i,
-                         int slot, double& best) {
-  w.cand().parflag(slot) = 0;
+// the ranked list, so every row proposes it explicitly.
+FLT_DEV void emitSilCell(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur,
+                         const FrameIn& f, int i, double tau) {
   if (!(c.silScore > 0) || w.rows().rowOf(i) != i) return;
   const int n = c.sil;
   if (n < 0 || n >= c.N || (c.ctc && n == c.blank)) return;
   const float ev = w.spec()[c.K + 1];
   if (!inTokenSetV(c, f, n, ev)) return;
-  emitRowToken(c, w, cur, i, n, ev, slot, best);
+  emitRowToken(cta, c, w, cur, i, n, ev, tau);
 }
 
 // token whose emission hypothesis i needs for its stay / repeat candidate
@@ -583,11 +597,9 @@ FLT_DEV int ownToken(const DecCfg& c, const Beam& cur, int i) {
   return (c.lexicon && cur.lex(i) == 0) ? c.sil : cur.tok(i);
 }
 
-// stay / repeat and blank candidates of hypothesis i (slots base, base+1)
-FLT_DEV void emitSpecials(const DecCfg& c, const Ws& w, const Beam& cur, const FrameIn& f, int i,
-                          int base, double& best) {
-  w.cand().parflag(base) = 0;
-  w.cand().parflag(base + 1) = 0;
+// stay / repeat and blank candidates of hypothesis i
+FLT_DEV void emitSpecials(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur,
+                          const FrameIn& f, int i, double tau) {
   const float eOwn = w.spec()[i], eBlank = w.spec()[c.K];
   if (!c.lexicon) {
     // repeat (third branch, LexiconFreeDecoder.cpp:98-110): n == prevIdx and not a new token
@@ -596,15 +608,19 @@ FLT_DEV void emitSpecials(const DecCfg& c, const Ws& w, const Beam& cur, const F
     if (isRepeat && n >= 0 && n < c.N && inTokenSetV(c, f, n, eOwn)) {
       double score = cur.score(i) + (double)eOwn;
       if (n == c.sil) score += c.silScore;
-      putCand(c, w, cur, base, score, i, n, -1, 0, 0, 0.0f, eOwn);
-      if (score > best) best = score;
+      if (!(score < tau)) {
+        const int slot = allocCand(cta, c, w);
+        if (slot >= 0) putCand(c, w, cur, slot, score, i, n, -1, 0, 0, 0.0f, eOwn);
+      }
     }
     if (c.ctc && inTokenSetV(c, f, c.blank, eBlank)) {
       const int n = c.blank;
       double score = cur.score(i) + (double)eBlank;
       if (n == c.sil) score += c.silScore;
-      putCand(c, w, cur, base + 1, score, i, n, -1, 0, CF_PB, 0.0f, eBlank);
-      if (score > best) best = score;
+      if (!(score < tau)) {
+        const int slot = allocCand(cta, c, w);
+        if (slot >= 0) putCand(c, w, cur, slot, score, i, n, -1, 0, CF_PB, 0.0f, eBlank);
+      }
     }
   } else {
     const int lex = cur.lex(i);
@@ -613,24 +629,19 @@ FLT_DEV void emitSpecials(const DecCfg& c, const Ws& w, const Beam& cur, const F
       const double am = amOf(c, f, eOwn, n, cur.tok(i));
       double score = cur.score(i) + am;
       if (n == c.sil) score += c.silScore;
-      putCand(c, w, cur, base, score, i, n, -1, lex, 0, 0.0f, eOwn);
-      if (score > best) best = score;
+      if (!(score < tau)) {
+        const int slot = allocCand(cta, c, w);
+        if (slot >= 0) putCand(c, w, cur, slot, score, i, n, -1, lex, 0, 0.0f, eOwn);
+      }
     }
     if (c.ctc) { // (3) blank, LexiconDecoder.cpp:196-213
       const double score = cur.score(i) + (double)eBlank;
-      putCand(c, w, cur, base + 1, score, i, c.blank, -1, lex, CF_PB, 0.0f, eBlank);
-      if (score > best) best = score;
+      if (!(score < tau)) {
+        const int slot = allocCand(cta, c, w);
+        if (slot >= 0) putCand(c, w, cur, slot, score, i, c.blank, -1, lex, CF_PB, 0.0f, eBlank);
+      }
     }
   }
-}
-
-FLT_DEV int allocCand(const DecCfg& c, const Ws& w) {
-  const int s = atomAdd(&w.sc()[SC_NCAND], 1);
-  if (s >= c.capC) {
-    w.sc()[SC_OVF] = 1;
-    return -1;
-  }
-  return s;
 }
 
 FLT_DEV float lmWordScore(const DecCfg& c, const Beam& cur, int p, int usrIdx) {
@@ -639,8 +650,8 @@ FLT_DEV float lmWordScore(const DecCfg& c, const Beam& cur, int p, int usrIdx) {
 }
 
 // one trie edge of hypothesis i: child node `child` reached by token n (LexiconDecoder.cpp:62-164)
-FLT_DEV void emitEdge(const DecCfg& c, const Ws& w, const Beam& cur, const FrameIn& f, int i, int n,
-                      int child, bool labelsOnly, double& best) {
+FLT_DEV void emitEdge(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, const FrameIn& f,
+                      int i, int n, int child, bool labelsOnly, double tau) {
   const float ev = f.e[n];
   if (!inTokenSetV(c, f, n, ev)) return;
   const TrieDev& t = c.trie;
@@ -653,9 +664,10 @@ FLT_DEV void emitEdge(const DecCfg& c, const Ws& w, const Beam& cur, const Frame
   if (!labelsOnly && hasKids && newTokenEligible(c, cur, i, n)) {
     const float d = t.maxScore[child] - lexMax;
     const double s = score + c.lmWeight * (double)d;
-    const int slot = allocCand(c, w);
-    if (slot >= 0) putCand(c, w, cur, slot, s, i, n, -1, child, 0, d, ev);
-    if (s > best) best = s;
+    if (!(s < tau)) {
+      const int slot = allocCand(cta, c, w);
+      if (slot >= 0) putCand(c, w, cur, slot, s, i, n, -1, child, 0, d, ev);
+    }
   }
   const int l0 = t.labelOff[child], l1 = t.labelOff[child + 1];
   if (!(lex == 0 && cur.tok(i) == n)) { // LexiconDecoder.cpp:114-122
@@ -663,17 +675,18 @@ FLT_DEV void emitEdge(const DecCfg& c, const Ws& w, const Beam& cur, const Frame
       const int label = t.labels[l];
       const float d = lmWordScore(c, cur, i, label) - lexMax;
       const double s = score + c.lmWeight * (double)d + c.wordScore;
-      const int slot = allocCand(c, w);
+      if (s < tau) continue;
+      const int slot = allocCand(cta, c, w);
       if (slot >= 0) putCand(c, w, cur, slot, s, i, n, label, 0, CF_NEW, d, ev);
-      if (s > best) best = s;
     }
   }
   if (l0 == l1 && c.hasUnk) { // LexiconDecoder.cpp:145-164
     const float d = lmWordScore(c, cur, i, c.unk) - lexMax;
     const double s = score + c.lmWeight * (double)d + c.unkScore;
-    const int slot = allocCand(c, w);
-    if (slot >= 0) putCand(c, w, cur, slot, s, i, n, c.unk, 0, CF_NEW, d, ev);
-    if (s > best) best = s;
+    if (!(s < tau)) {
+      const int slot = allocCand(cta, c, w);
+      if (slot >= 0) putCand(c, w, cur, slot, s, i, n, c.unk, 0, CF_NEW, d, ev);
+    }
   }
 }
 
@@ -1053,11 +1066,10 @@ FLT_DEV void phaseFinalize(const Cta& cta, const DecCfg& c, const Ws& w, const B
 
 // One frame: cur -> nxt. All threads of the CTA call this with identical arguments.
 FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur,
-                       const Beam& nxt, const FrameIn& f, int* status) {
+                       const Beam& nxt, const FrameIn& f, int* status, unsigned long long* stats) {
   int* sc = w.sc();
   const int nH = sc[SC_NH];
   if (nH == 0) return; // the beam died (Utils.h:155-158): every later frame is empty
-  double best = negInf(); // (kept for emit helpers; the threshold uses the ranked best)
 
   // issue the scattered emission reads now; they are consumed after the row grouping
   float eOwn = 0.0f, eBlank = 0.0f, eSil = 0.0f;
@@ -1080,7 +1092,10 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
       spec[c.K] = eBlank;
       spec[c.K + 1] = eSil;
     }
-    if (cta.tid == 0) sc[SC_OVF] = 0;
+    if (cta.tid == 0) {
+      sc[SC_OVF] = 0;
+      sc[SC_NCAND] = 0;
+    }
   };
   int wideItems = 0;
   if (c.wideRanked) {
@@ -1090,16 +1105,21 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
     publish();
     cta.sync();
   }
-  const int specBase = wideItems;
-  const int narrowBase = specBase + 3 * nH;
-  if (narrowBase > c.capC) { // cannot happen with a correctly sized capC; fail the utterance
-    cta.sync();
-    if (cta.tid == 0) {
-      *status |= 1;
-      sc[SC_NH] = 0;
+  // Pruning bound (exact): any rectangle rows 1..a x columns 0..col of the (row rank x ranked
+  // token) grid holds >= a*(col-2) >= K regular cells, i.e. K distinct merge groups, each scoring
+  // at least fl(s + e_col) where s bounds the a-th row's best member from below. A candidate below
+  // the best such corner can never be among the K best groups. Lexicon-free rows have at most two
+  // members, so the a-th row's leader is one of the first 2a-1 hypotheses.
+  double tau = negInf();
+  if (c.wideRanked && !c.lexicon) {
+    for (int k = 0; k < c.nTau; ++k) {
+      const int i = 2 * c.tauA[k] - 2, col = c.tauCol[k];
+      if (i < nH && col < f.listLen && f.topTok[col] >= 0) {
+        const double corner = cur.score(i) + (double)f.topVal[col] + c.lmWeight * (double)0.0f;
+        tau = corner > tau ? corner : tau;
+      }
     }
-    cta.sync();
-    return;
+    if (c.silScore < 0) tau += c.silScore; // keeps the bound valid if a counted cell is the sil one
   }
   // wide cells
   if (c.wideRanked) {
@@ -1107,17 +1127,15 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
     const int* wideOff = w.wideOff();
     for (int x = cta.tid; x < wideItems; x += cta.nthr) {
       const int r = itemRow[x]; // row rank (0-based)
-      emitWide(c, w, cur, f, w.rows().leaderOfRank(r), x - wideOff[r], x, best);
+      emitWide(cta, c, w, cur, f, w.rows().leaderOfRank(r), x - wideOff[r], tau);
     }
   }
   // stay / repeat / blank
   for (int i = cta.tid; i < nH; i += cta.nthr) {
-    emitSpecials(c, w, cur, f, i, specBase + 3 * i, best);
-    if (c.wideRanked) emitSilCell(c, w, cur, f, i, specBase + 3 * i + 2, best);
-    else w.cand().parflag(specBase + 3 * i + 2) = 0;
+    emitSpecials(cta, c, w, cur, f, i, tau);
+    if (c.wideRanked) emitSilCell(cta, c, w, cur, f, i, tau);
   }
   // trie edges
-  int nCand = narrowBase;
   if (c.lexicon) {
     const TrieDev& t = c.trie;
     int* deg = w.rows().deg();
@@ -1125,7 +1143,6 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
       const int lex = cur.lex(i);
       deg[i] = (c.wideRanked && lex == 0) ? t.nRootLab : t.childOff[lex + 1] - t.childOff[lex];
     }
-    if (cta.tid == 0) sc[SC_NCAND] = narrowBase;
     cta.sync();
     ctaExclusiveScan(cta, deg, w.rows().degTmp(), nH);
     const int items = deg[nH];
@@ -1135,24 +1152,32 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
       const int lex = cur.lex(i);
       if (c.wideRanked && lex == 0) {
         const int n = t.rootLabTok[k];
-        emitEdge(c, w, cur, f, i, n, t.rootChild[n], true, best);
+        emitEdge(cta, c, w, cur, f, i, n, t.rootChild[n], true, tau);
       } else {
         const int e = t.childOff[lex] + k;
-        emitEdge(c, w, cur, f, i, t.childTok[e], t.childNode[e], false, best);
+        emitEdge(cta, c, w, cur, f, i, t.childTok[e], t.childNode[e], false, tau);
       }
     }
-    cta.sync();
-    nCand = sc[SC_NCAND];
-    if (sc[SC_OVF]) {
-      if (cta.tid == 0) *status |= 1;
-      nCand = nCand < c.capC ? nCand : c.capC;
-    }
-  } else {
-    cta.sync();
   }
-  (void)best;
+  cta.sync();
+  int nCand = sc[SC_NCAND];
+  if (sc[SC_OVF]) {
+    if (cta.tid == 0) *status |= 1;
+    nCand = nCand < c.capC ? nCand : c.capC;
+  }
   phaseMerge(cta, c, w, nCand);
-  const int nSel = phaseSelect(cta, c, w, sc[SC_NREP]);
+  const int nRep = sc[SC_NREP];
+  const int nSel = phaseSelect(cta, c, w, nRep);
+#if FLT_DEVICE_BUILD
+  if (stats && cta.tid == 0) {
+    atomicAdd(stats + 0, 1ull);
+    atomicAdd(stats + 1, (unsigned long long)nCand);
+    atomicAdd(stats + 2, (unsigned long long)nRep);
+    atomicAdd(stats + 3, (unsigned long long)nSel);
+  }
+#else
+  (void)stats;
+#endif
   phaseFinalize(cta, c, w, cur, nxt, f, nSel);
 }
 
@@ -1277,7 +1302,7 @@ FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char
       f.hParent = a.hParent + h;
       f.hTok = a.hTok + h;
       f.hWord = a.hWord ? a.hWord + h : nullptr;
-      frameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.status + b);
+      frameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.status + b, a.stats);
       if (pf) {
 #if FLT_DEVICE_BUILD
 #pragma unroll

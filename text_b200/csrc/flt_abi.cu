@@ -59,7 +59,15 @@ struct FltError : std::runtime_error {
   FltError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
 };
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 256; // token-select kernel
+int decThreads() {            // beam-step kernel (tunable for experiments)
+  static int t = [] {
+    const char* e = getenv("FLT_DEC_THREADS");
+    int v = e ? atoi(e) : 256;
+    return (v == 64 || v == 128 || v == 256) ? v : 256;
+  }();
+  return t;
+}
 constexpr int kTrieMaxLabel = 6; // decoder/Trie.h:19
 
 /* ------------------------------------------------------------------ launches ---------- */
@@ -78,8 +86,8 @@ void launchTopM(const TopMCfg& c, const TopMArgs& a, int grid, size_t smem, rt::
 }
 void launchDecode(const DecCfg& c, const BatchArgs& a, int grid, size_t smem, rt::Stream s) {
 #if FLT_DEVICE_BUILD
-  if (smem) flt_k_decode<<<grid, kThreads, smem, s>>>(c, a);
-  else flt_k_decode_gmem<<<grid, kThreads, 0, s>>>(c, a);
+  if (smem) flt_k_decode<<<grid, decThreads(), smem, s>>>(c, a);
+  else flt_k_decode_gmem<<<grid, decThreads(), 0, s>>>(c, a);
   FLT_RT_TRY(cudaGetLastError());
 #else
   std::vector<char> sm(c.lay.total + 16);
@@ -386,7 +394,7 @@ struct flt_decoder {
   rt::DevBuf dWideOff, dBias, dTrans;
   // batch buffers
   rt::DevBuf topTok, topVal, thr, hPar, hTok, hWord, finScore, finCount, status, ws, outTok,
-      outWord, dLengths, staging[2];
+      outWord, dLengths, staging[2], dStats;
   int lastB = 0, lastT = 0, launches = 0;
   int capBoost = 1; // candidate-capacity multiplier, grown after an overflow
   bool useSmemFlag = false;
@@ -396,7 +404,7 @@ struct flt_decoder {
   ~flt_decoder() {
     for (rt::DevBuf* b : {&dWideOff, &dBias, &dTrans, &topTok, &topVal, &thr, &hPar, &hTok, &hWord,
                           &finScore, &finCount, &status, &ws, &outTok, &outWord, &dLengths,
-                          &staging[0], &staging[1]})
+                          &staging[0], &staging[1], &dStats})
       b->release();
 #if FLT_DEVICE_BUILD
     for (int i = 0; i < 2; ++i) {
@@ -497,7 +505,21 @@ void planFor(flt_decoder& d, int N) {
   c.capRH = nextPow2(2 * K);
   c.capP = nextPow2(K);
   c.wideTotal = c.wideRanked ? d.wideOffHost[K] : 0;
-  c.listInSmem = d.needTopM && c.M <= 2 * kThreads;
+  // pruning rectangles (beam_core.h frameStep): a rows x (ceil(K/a)+3) columns
+  c.nTau = 0;
+  if (c.wideRanked && !d.lexicon) {
+    const int as[16] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 32, 40, 48, 64};
+    for (int k = 0; k < 16; ++k) {
+      const int a = as[k];
+      const int col = (K + a - 1) / a + 2;
+      if (2 * a - 2 < K && col < c.Mwide) {
+        c.tauA[c.nTau] = a;
+        c.tauCol[c.nTau] = col;
+        c.nTau++;
+      }
+    }
+  }
+  c.listInSmem = d.needTopM && c.M <= 2 * decThreads();
 
   rt::Stream s = d.stream;
   c.wideOff = upload(d.dWideOff, d.wideOffHost, s);
@@ -546,9 +568,9 @@ void planFor(flt_decoder& d, int N) {
   if (smemOk) {
     FLT_RT_TRY(cudaFuncSetAttribute(flt_k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)std::max<size_t>(d.wsBytes, 48 * 1024)));
-    FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode, kThreads, d.wsBytes));
+    FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode, decThreads(), d.wsBytes));
   } else {
-    FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode_gmem, kThreads, 0));
+    FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode_gmem, decThreads(), 0));
     occ2 = std::min(occ2, 4);
   }
   d.gridMax = std::max(1, occ2) * d.numSMs;
@@ -637,6 +659,7 @@ void runChunk(flt_decoder& d, const float* dEmis, int Bc, int T, int N, const in
   a.finCount = d.finCount.as<int>() + outBase;
   a.status = d.status.as<int>() + outBase;
   const int grid = std::max(1, std::min(Bc, d.gridMax));
+  a.stats = d.timing ? d.dStats.as<unsigned long long>() : nullptr;
   if (!d.useSmemFlag) {
     d.ws.reserve(d.wsBytes * grid);
     a.wsGlobal = d.ws.as<char>();
@@ -678,6 +701,10 @@ void prepareBatch(flt_decoder& d, int B, int T, int N) {
   d.lastB = B;
   d.lastT = T;
   d.launches = 0;
+  if (d.timing) {
+    d.dStats.reserve(sizeof(unsigned long long) * 4);
+    rt::devZero(d.dStats.p, sizeof(unsigned long long) * 4, d.stream);
+  }
 #if FLT_DEVICE_BUILD
   d.evUsed = 0;
 #endif
@@ -1059,6 +1086,15 @@ int flt_decoder_last_kernel_ms(flt_decoder* dec, float* ms3, int32_t* launches3)
       if (launches3) launches3[dec->evKinds[i]]++;
     }
 #endif
+  });
+}
+int flt_decoder_last_stats(flt_decoder* dec, uint64_t* out4) {
+  return guarded([&] {
+    if (!dec || !out4) throw FltError(FLT_ERR_INVALID, "null argument");
+    for (int k = 0; k < 4; ++k) out4[k] = 0;
+    if (!dec->dStats.p) return;
+    rt::d2h(out4, dec->dStats.p, sizeof(uint64_t) * 4, dec->stream);
+    rt::sync(dec->stream);
   });
 }
 int flt_decoder_workspace_bytes(const flt_decoder* dec, int64_t* out) {
