@@ -61,6 +61,10 @@ typedef struct {
 
 ORA_DECLARE(ref)
 ORA_DECLARE(ora)
+/* restatement only: events during the current utterance whose outcome the reference leaves to
+ * libstdc++ internals (equal scores inside a merge group, at the beam cut, at the token-beam cut).
+ * Tests exclude such utterances from bit-exact comparison. */
+long ora_tie_events(void* dec);
 
 #ifdef __cplusplus
 }

@@ -249,6 +249,10 @@ struct ODecoder {
   double best = kNegInf;
   std::vector<int> order;
   bool failed = false;
+  // Tie detector (test infrastructure): events since begin() where the reference's result is left
+  // to libstdc++ internals - equal-score members of one merge group (which parent survives),
+  // equal scores straddling the beam cut (nth_element), equal emissions at the token-beam cut.
+  long tieEvents = 0;
 
   void add(const Hyp& h) { // Utils.h:131-144
     if (h.score >= best) best = h.score;
@@ -273,6 +277,7 @@ struct ODecoder {
       if (cmpKey(cur, head) != 0) {
         order[n++] = order[i];
       } else {
+        if (cur.score == head.score && !opt.logAdd) ++tieEvents;
         double mx = std::max(head.score, cur.score);
         if (opt.logAdd) {
           double mn = std::min(head.score, cur.score);
@@ -290,6 +295,7 @@ struct ODecoder {
       return a < b;
     });
     int fin = std::min(n, (int)opt.beamSize);
+    if (fin < n && cands[order[fin - 1]].score == cands[order[fin]].score) ++tieEvents;
     for (int i = 0; i < fin; ++i) out.push_back(cands[order[i]]);
   }
 
@@ -310,6 +316,7 @@ struct ODecoder {
     nDecoded = nPruned = 0;
     begun = true;
     failed = false;
+    tieEvents = 0;
   }
 
   void selectTokens(const float* e, int N, std::vector<int>& idx) { // *Decoder.cpp "partial_sort"
@@ -318,6 +325,10 @@ struct ODecoder {
     if (N > opt.beamSizeToken) {
       std::partial_sort(idx.begin(), idx.begin() + opt.beamSizeToken, idx.end(),
                         [&](int l, int r) { return e[l] != e[r] ? e[l] > e[r] : l < r; });
+      float cut = e[idx[opt.beamSizeToken - 1]];
+      int atCut = 0;
+      for (int i = 0; i < N; ++i) atCut += e[i] == cut;
+      if (atCut > 1) ++tieEvents;
       idx.resize(opt.beamSizeToken);
     }
   }
@@ -719,6 +730,7 @@ void ora_decode_step(void* dec, const float* emis, int T, int N) {
 }
 void ora_decode_end(void* dec) { ((ODecoder*)dec)->end(); }
 void ora_prune(void* dec, int lookBack) { ((ODecoder*)dec)->prune(lookBack); }
+long ora_tie_events(void* dec) { return ((ODecoder*)dec)->tieEvents; }
 int ora_n_hypothesis(void* dec) {
   auto* d = (ODecoder*)dec;
   return (int)d->hyp[d->nDecoded - d->nPruned].size();

@@ -105,6 +105,8 @@ class Oracle:
            [C.c_int, C.POINTER(Options), vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, fp, C.c_int,
             C.c_int, C.c_int, C.c_int, C.c_int])
         fn("last_error", C.c_char_p, [])
+        if kind == "ora":
+            fn("tie_events", C.c_long, [vp])
 
     def _err(self):
         return self._last_error().decode()
@@ -184,6 +186,10 @@ class Oracle:
             raise RuntimeError(self._err())
         n = min(n, max_hyp)
         return dict(n=n, scores=scores[:n], tokens=tokens[:n], words=words[:n])
+
+    def tie_events(self, dec):
+        """restatement only: implementation-defined tie events during the last decode"""
+        return int(self._tie_events(dec))
 
     def decode_begin(self, dec):
         self._decode_begin(dec)
