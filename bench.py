@@ -231,7 +231,6 @@ def run_ours(a):
     clocks.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kms = {"token_select": 0.0, "beam_step": 0.0, "backtrace": 0.0}
     launches = 0
     ev0.record(stream)
     for _ in range(a.steps):
@@ -319,7 +318,10 @@ def run_ours(a):
     kernels = {}
     alg = {"token_select": B * T * (4 * N + 8 * min(beam + 3, bst)),  # row read + list written
            "beam_step": B * T * 12 * beam,                                  # back-pointer records
-           "backtrace": B * nbest * (T + 2) * 8}
+           "backtrace": B * nbest * (T + 2) * 8,
+           # fused select + step: the whole per-frame figure of SURVEY.md §8d (row read once +
+           # one back-pointer record per surviving hypothesis)
+           "fused_select_step": B * T * (4 * N + 12 * beam)}
     for k, v in last.items():
         if v["launches"]:
             kernels[k] = {"ms": v["ms"], "launches": v["launches"], "algorithmic_bytes": alg[k],
@@ -333,8 +335,8 @@ def run_ours(a):
                 "whole_step": {"achieved": (B * bytes_per_utt) / (ms_step * 1e-3) / 1e9,
                                "frac": (B * bytes_per_utt) / (ms_step * 1e-3) / 1e9 / peak,
                                "bytes_per_utterance": bytes_per_utt},
-                "step_latency_us_per_frame": kernels.get("beam_step", {}).get("ms", 0) * 1e3 / T
-                if "beam_step" in kernels else None}
+                "step_latency_us_per_frame": next((kernels[k]["ms"] * 1e3 / T for k in
+                                                   ("fused_select_step", "beam_step") if k in kernels), None)}
 
     cpu = None
     if world == 1 and not a.no_cpu_baseline:

@@ -127,10 +127,11 @@ int flt_nbest_copy(flt_decoder* dec, int32_t nbest, int32_t* tokens, int32_t* wo
  * bytes currently held by the decoder workspace. */
 int flt_decoder_last_launches(const flt_decoder* dec, int32_t* out);
 /* Per-kernel device time of the last flt_decode_batch* call, from CUDA events recorded on the
- * decoder's stream around each launch (only while timing is on): ms3 / launches3 index
- * 0 = token-beam select, 1 = beam step, 2 = n-best backtrace. Synchronises the stream. */
+ * decoder's stream around each launch (only while timing is on): ms4 / launches4 index
+ * 0 = token-beam select, 1 = beam step, 2 = n-best backtrace, 3 = fused select + step.
+ * Synchronises the stream. */
 int flt_decoder_set_timing(flt_decoder* dec, int32_t on);
-int flt_decoder_last_kernel_ms(flt_decoder* dec, float* ms3, int32_t* launches3);
+int flt_decoder_last_kernel_ms(flt_decoder* dec, float* ms4, int32_t* launches4);
 /* Beam-step work counters of the last call (collected while timing is on), summed over frames:
  * out4 = {frames stepped, candidates materialised, merge groups, survivors}. */
 int flt_decoder_last_stats(flt_decoder* dec, uint64_t* out4);

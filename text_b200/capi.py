@@ -236,10 +236,10 @@ class Api:
         self._ck(self.lib.flt_decoder_set_timing(dec, int(on)))
 
     def last_kernel_ms(self, dec):
-        ms = (C.c_float * 3)()
-        n = (C.c_int32 * 3)()
+        ms = (C.c_float * 4)()
+        n = (C.c_int32 * 4)()
         self._ck(self.lib.flt_decoder_last_kernel_ms(dec, ms, n))
-        names = ("token_select", "beam_step", "backtrace")
+        names = ("token_select", "beam_step", "backtrace", "fused_select_step")
         return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(names)}
 
     def last_stats(self, dec):

@@ -55,6 +55,8 @@ struct Lay {
   int itemRow;   // int16 [wideOff[K]]: row rank of each wide work item
   int cslot;     // int [capC]: merge-table slot of each candidate
   int gath;      // int [64]: members of the cut bin (one-warp finish of the radix select)
+  // lexicon-free fast step (beam_lf.h)
+  int lfSlotB, lfSlotOf, lfCbin;
   int total;
 };
 
@@ -76,6 +78,8 @@ struct DecCfg {
   int capRH;      // row table slots (pow2 >= 2*K)
   int capP;       // pow2 >= K
   int wideTotal;  // wideOff[K]
+  int lfFast;     // 1 = lexicon-free fast step (beam_lf.h): cells indexed by hypothesis, no merge table
+  int lfBins;     // histogram bins of its select (pow2, multiple of 32)
   int nTau;       // pruning rectangles: rows 1..tauA[k] x columns 0..tauCol[k] hold >= K regular cells
   int tauA[16];
   int tauCol[16];
@@ -107,7 +111,7 @@ struct BatchArgs {
 /* ------------------------------------------------------------------ workspace views ---------- */
 struct Beam {
   double* d;  // [3][K] score, emittingModelScore, lmScore
-  u64* fp;    // [2][K] LM-state fingerprint
+  u64* fp;    // [2][K] LM-state fingerprint (+ [2][K] fingerprint of the parent state, beam_lf.h)
   int* iv;    // [4][K] lex, tok, prevBlank, nctx; then ctx [K][kMaxCtx]
   int K;
   FLT_DEV double& score(int i) const { return d[i]; }
@@ -115,6 +119,8 @@ struct Beam {
   FLT_DEV double& lm(int i) const { return d[2 * K + i]; }
   FLT_DEV u64& fpA(int i) const { return fp[i]; }
   FLT_DEV u64& fpB(int i) const { return fp[K + i]; }
+  FLT_DEV u64& pfpA(int i) const { return fp[2 * K + i]; }
+  FLT_DEV u64& pfpB(int i) const { return fp[3 * K + i]; }
   FLT_DEV int& lex(int i) const { return iv[i]; }
   FLT_DEV int& tok(int i) const { return iv[K + i]; }
   FLT_DEV int& pb(int i) const { return iv[2 * K + i]; }
@@ -128,7 +134,7 @@ constexpr int kIntMax = 0x7FFFFFFF;
 struct Cand {
   double* sc; // [capC]
   u64* key;   // [2][capC] 128-bit merge key: (LM state, lex, token, prevBlank)
-  int* iv;    // [6][capC] parent<<4|flags, token, word, lex, lm delta (float bits), e (float bits)
+  int* iv;    // [6][capC] parent<<4|flags, token, e (float bits), word, lex, lm delta (float bits)
   int cap;
   FLT_DEV double& score(int x) const { return sc[x]; }
   FLT_DEV u64& keyA(int x) const { return key[x]; }
@@ -137,10 +143,10 @@ struct Cand {
   FLT_DEV int par(int x) const { return iv[x] >> 4; }
   FLT_DEV int flags(int x) const { return iv[x] & 15; }
   FLT_DEV int& tok(int x) const { return iv[cap + x]; }
-  FLT_DEV int& word(int x) const { return iv[2 * cap + x]; }
-  FLT_DEV int& lex(int x) const { return iv[3 * cap + x]; }
-  FLT_DEV float& lmd(int x) const { return ((float*)iv)[4 * cap + x]; }
-  FLT_DEV float& ce(int x) const { return ((float*)iv)[5 * cap + x]; }
+  FLT_DEV float& ce(int x) const { return ((float*)iv)[2 * cap + x]; }
+  FLT_DEV int& word(int x) const { return iv[3 * cap + x]; }
+  FLT_DEV int& lex(int x) const { return iv[4 * cap + x]; }
+  FLT_DEV float& lmd(int x) const { return ((float*)iv)[5 * cap + x]; }
 };
 
 struct Rows {
@@ -209,30 +215,34 @@ FLT_HD void makeLayout(DecCfg& c) {
   };
   const int K = c.K;
   Lay& L = c.lay;
+  const bool lf = c.lfFast != 0;
   for (int b = 0; b < 2; ++b) {
     L.beamD[b] = take(sizeof(double) * 3 * K);
-    L.beamFp[b] = take(sizeof(u64) * 2 * K);
+    L.beamFp[b] = take(sizeof(u64) * (lf ? 4 : 2) * K);
     L.beamI[b] = take(sizeof(int) * (4 * K + (c.lm.kind ? K * kMaxCtx : 0)));
   }
   L.rowHash = take(sizeof(int) * c.capRH);
-  L.rowI = take(sizeof(int) * (kRowsInts * K + 8));
+  L.rowI = take(lf ? 0 : sizeof(int) * (kRowsInts * K + 8));
   L.candScore = take(sizeof(double) * c.capC);
-  L.candKey = take(sizeof(u64) * 2 * c.capC);
-  L.candI = take(sizeof(int) * 6 * c.capC);
-  L.mh = take(sizeof(int) * c.capH);
+  L.candKey = take(sizeof(u64) * (lf ? 1 : 2) * c.capC);
+  L.candI = take(sizeof(int) * (lf ? 3 : 6) * c.capC);
+  L.mh = take(lf ? 0 : sizeof(int) * c.capH);
   L.rep = take(sizeof(int) * c.capC);
   L.surv = take(sizeof(int) * 2 * c.capP);
-  L.skey = take(sizeof(u64) * c.capP);
-  L.pos = take(sizeof(int) * c.capP);
-  L.hist = take(sizeof(int) * 256);
+  L.skey = take(lf ? 0 : sizeof(u64) * c.capP);
+  L.pos = take(lf ? 0 : sizeof(int) * c.capP);
+  L.hist = take(sizeof(int) * (lf && c.lfBins > 256 ? c.lfBins : 256));
   L.sc = take(sizeof(int) * SC_COUNT);
   L.red = take(sizeof(u64) * 64);
   for (int b = 0; b < 2; ++b) L.list[b] = take(c.listInSmem ? 8 * (size_t)c.M : 0);
   L.spec = take(sizeof(float) * (K + 2));
   L.wideOff = take(sizeof(int) * (K + 1));
   L.itemRow = take(sizeof(short) * (c.wideTotal + 2));
-  L.cslot = take(sizeof(int) * c.capC);
+  L.cslot = take(lf ? 0 : sizeof(int) * c.capC);
   L.gath = take(sizeof(int) * 64);
+  L.lfSlotB = take(lf ? sizeof(int) * c.capRH : 0);
+  L.lfSlotOf = take(lf ? sizeof(int) * K : 0);
+  L.lfCbin = take(lf ? sizeof(unsigned short) * c.capC : 0);
   L.total = (int)off;
 }
 
@@ -419,6 +429,7 @@ struct FrameIn {
   float thrVal;        // cut value of the token set (unused when setAll)
   int first;           // global frame 0 (ASG transitions are skipped, LexiconDecoder.cpp:70-73)
   int listIsSet;       // the list holds the whole token set (lexicon-free, beamSizeToken < N)
+  int specReady;       // spec[] already holds this frame's gathered emissions (fused kernel)
   int* hParent;        // history row to write (frame t+1), [K]
   int* hTok;
   int* hWord;
@@ -1214,15 +1225,27 @@ FLT_DEV void finishStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam
 }
 
 /* ------------------------------------------------------------------ whole-utterance driver ---- */
+// lexicon-free fast step, beam_lf.h
+FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur,
+                         const Beam& nxt, const FrameIn& f, unsigned long long* stats);
+FLT_DEV void lfFinish(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, const Beam& nxt,
+                      const FrameIn& f);
+
 // One CTA decodes utterances bid, bid+nblk, ... start to finish. `base` is the CTA's workspace:
 // shared memory or a global slab.
-FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char* base) {
-  const Ws w{base, &c};
+// workspace tables that persist over the CTA's utterances (kept clean by their users)
+FLT_DEV void ctaInitWorkspace(const Cta& cta, const DecCfg& c, const Ws& w, char* base) {
   const int K = c.K;
   for (int i = cta.tid; i <= K; i += cta.nthr) w.wideOff()[i] = c.wideOff[i];
-  for (int i = cta.tid; i < c.capRH; i += cta.nthr) w.rows().hash[i] = -1; // kept empty by its users
-  for (int i = cta.tid; i < c.capH; i += cta.nthr) w.mh()[i] = -1;
-  for (int i = cta.tid; i < 256; i += cta.nthr) w.hist()[i] = 0;
+  for (int i = cta.tid; i < c.capRH; i += cta.nthr) w.rows().hash[i] = -1;
+  if (c.lfFast) {
+    int* slotB = (int*)(base + c.lay.lfSlotB);
+    for (int i = cta.tid; i < c.capRH; i += cta.nthr) slotB[i] = -1;
+    for (int i = cta.tid; i < c.lfBins; i += cta.nthr) w.hist()[i] = 0;
+  } else {
+    for (int i = cta.tid; i < c.capH; i += cta.nthr) w.mh()[i] = -1;
+    for (int i = cta.tid; i < 256; i += cta.nthr) w.hist()[i] = 0;
+  }
   if (cta.tid == 0) {
     int* sc = w.sc();
     sc[SC_NREP] = 0;
@@ -1235,31 +1258,75 @@ FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char
   }
   for (int r = cta.tid; r < K; r += cta.nthr) // row rank of every wide work item
     for (int x = c.wideOff[r]; x < c.wideOff[r + 1]; ++x) w.itemRow()[x] = (short)r;
+}
+
+// decodeBegin (LexiconDecoder.cpp:21-30, LexiconFreeDecoder.cpp:20-28): one thread seeds beam 0
+FLT_DEV void seedUtterance(const DecCfg& c, const Ws& w, const BatchArgs& a, int b) {
+  const int K = c.K;
+  const Beam B0 = w.beam(0);
+  B0.score(0) = 0.0;
+  B0.am(0) = 0.0;
+  B0.lm(0) = 0.0;
+  fpRoot(B0.fpA(0), B0.fpB(0));
+  if (c.lfFast) { // the root state has no parent: a fingerprint no state carries
+    B0.pfpA(0) = 0;
+    B0.pfpB(0) = 0;
+  }
+  B0.lex(0) = 0;
+  B0.tok(0) = c.sil;
+  B0.pb(0) = 0;
+  B0.nctx(0) = 0;
+  if (c.lm.kind && c.lm.order > 1) {
+    B0.ctx(0)[0] = c.lm.bos;
+    B0.nctx(0) = 1;
+  }
+  w.sc()[SC_NH] = 1;
+  a.status[b] = 0;
+  const long long h0 = ((long long)b * (a.T + 2)) * K;
+  a.hParent[h0] = -1;
+  a.hTok[h0] = c.sil;
+  if (a.hWord) a.hWord[h0] = -1;
+}
+
+// the three scores of every final hypothesis and their count
+FLT_DEV void writeFinals(const Cta& cta, const DecCfg& c, const Ws& w, const BatchArgs& a, int b,
+                         int curIdx, int nFin) {
+  const Beam F = w.beam(curIdx);
+  for (int q = cta.tid; q < nFin; q += cta.nthr) {
+    double* o = a.finScore + ((long long)b * c.K + q) * 3;
+    o[0] = F.score(q);
+    o[1] = F.am(q);
+    o[2] = F.lm(q);
+  }
+  if (cta.tid == 0) a.finCount[b] = nFin;
+}
+
+FLT_DEV FrameIn finishFrameIn(const DecCfg& c, const BatchArgs& a, int b, int len) {
+  FrameIn f;
+  f.e = nullptr;
+  f.topTok = nullptr;
+  f.topVal = nullptr;
+  f.listLen = 0;
+  f.thrVal = 0.0f;
+  f.first = 0;
+  f.listIsSet = 0;
+  f.specReady = 0;
+  const long long h = ((long long)b * (a.T + 2) + (len + 1)) * c.K;
+  f.hParent = a.hParent + h;
+  f.hTok = a.hTok + h;
+  f.hWord = a.hWord ? a.hWord + h : nullptr;
+  return f;
+}
+
+FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char* base) {
+  const Ws w{base, &c};
+  const int K = c.K;
+  ctaInitWorkspace(cta, c, w, base);
   for (int b = cta.bid; b < a.B; b += cta.nblk) {
     const int len = a.lengths ? a.lengths[b] : a.T;
     int curIdx = 0;
     cta.sync(); // previous utterance fully retired
-    if (cta.tid == 0) { // decodeBegin (LexiconDecoder.cpp:21-30)
-      const Beam B0 = w.beam(0);
-      B0.score(0) = 0.0;
-      B0.am(0) = 0.0;
-      B0.lm(0) = 0.0;
-      fpRoot(B0.fpA(0), B0.fpB(0));
-      B0.lex(0) = 0;
-      B0.tok(0) = c.sil;
-      B0.pb(0) = 0;
-      B0.nctx(0) = 0;
-      if (c.lm.kind && c.lm.order > 1) {
-        B0.ctx(0)[0] = c.lm.bos;
-        B0.nctx(0) = 1;
-      }
-      w.sc()[SC_NH] = 1;
-      a.status[b] = 0;
-      const long long h0 = ((long long)b * (a.T + 2)) * K;
-      a.hParent[h0] = -1;
-      a.hTok[h0] = c.sil;
-      if (a.hWord) a.hWord[h0] = -1;
-    }
+    if (cta.tid == 0) seedUtterance(c, w, a, b);
     // token list of frame 0 into the workspace
     const long long row0 = (long long)b * a.T;
     if (c.listInSmem && len > 0) {
@@ -1298,11 +1365,13 @@ FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char
       f.thrVal = a.thrVal ? a.thrVal[row] : 0.0f;
       f.first = t == 0;
       f.listIsSet = !c.lexicon;
+      f.specReady = 0;
       const long long h = ((long long)b * (a.T + 2) + (t + 1)) * K;
       f.hParent = a.hParent + h;
       f.hTok = a.hTok + h;
       f.hWord = a.hWord ? a.hWord + h : nullptr;
-      frameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.status + b, a.stats);
+      if (c.lfFast) lfFrameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.stats);
+      else frameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.status + b, a.stats);
       if (pf) {
 #if FLT_DEVICE_BUILD
 #pragma unroll
@@ -1328,31 +1397,14 @@ FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char
     }
     int nFin = 0;
     if (w.sc()[SC_NH] != 0) {
-      FrameIn f;
-      f.e = nullptr;
-      f.topTok = nullptr;
-      f.topVal = nullptr;
-      f.listLen = 0;
-      f.thrVal = 0.0f;
-      f.first = 0;
-      f.listIsSet = 0;
-      const long long h = ((long long)b * (a.T + 2) + (len + 1)) * K;
-      f.hParent = a.hParent + h;
-      f.hTok = a.hTok + h;
-      f.hWord = a.hWord ? a.hWord + h : nullptr;
-      finishStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f);
+      const FrameIn f = finishFrameIn(c, a, b, len);
+      if (c.lfFast) lfFinish(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f);
+      else finishStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f);
       curIdx ^= 1;
       nFin = w.sc()[SC_NH];
     }
     cta.sync();
-    const Beam F = w.beam(curIdx);
-    for (int q = cta.tid; q < nFin; q += cta.nthr) {
-      double* o = a.finScore + ((long long)b * K + q) * 3;
-      o[0] = F.score(q);
-      o[1] = F.am(q);
-      o[2] = F.lm(q);
-    }
-    if (cta.tid == 0) a.finCount[b] = nFin;
+    writeFinals(cta, c, w, a, b, curIdx, nFin);
   }
 }
 

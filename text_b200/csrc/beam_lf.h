@@ -1,0 +1,488 @@
+// beam_lf.h — the lexicon-free frame step (LexiconFreeDecoder + ZeroLM, max-merge), written for
+// latency: five CTA barriers per frame, no allocation atomics, no merge table, no radix passes.
+//
+// Replaces LexiconFreeDecoder::decodeStep's expansion (decoder/LexiconFreeDecoder.cpp:53-112) and
+// candidatesStore (decoder/Utils.h:146-225) for one frame; decodeEnd (LexiconFreeDecoder.cpp:127-158)
+// is lfFinish below. Same exact-pruning argument as beam_core.h, restated in hypothesis-index
+// space so that no row ranking is needed:
+//
+//   * The beam is sorted by score (index = rank). Hypotheses sharing an LM state form a row; a row
+//     of this decoder has at most two members, (S, x, prevBlank=0) and (S, blank, prevBlank=1).
+//     Hypotheses 0..i therefore span >= i/2+1 rows whose best member scores >= score(i), and the
+//     new-token candidate of hypothesis i with the j-th ranked token is dominated by
+//     (i/2+1)*(j-1) distinct merge groups: it is generated only if (i/2+1)*(j-2) <= K.
+//   * Merge groups (decoder/Utils.h:176-198, max-merge) are resolved where candidates are
+//     generated, so every materialised candidate is a distinct group:
+//       - same row, same new token / blank: only the better (lower-index) eligible member emits;
+//       - new token n from state S vs the repeat of a hypothesis already in child(S, n): both
+//         sides look the other up in a table of the beam's LM-state fingerprints and only the
+//         winner (higher score, then lower parent index) emits.
+//   * Top-K: candidate scores lie in [tau, U] (tau = corner bound, U = best hypothesis + row
+//     maximum); a monotone linear map sends them to NB bins and a per-warp suffix scan of the
+//     histogram gives every candidate the number of candidates in higher bins. Candidates with
+//     fewer than K above them (the top-K plus the rest of the cut bin) are ranked exactly by
+//     counting among themselves; rank < K = survivor, placed at ranked[rank]. Crowded bins only
+//     lengthen that list, they never change the result.
+#pragma once
+#include "beam_core.h"
+
+namespace flt {
+
+struct LfTab { // fingerprint -> row members
+  int* a;      // [capRH] first member (claims the slot), -1 = empty
+  int* b;      // [capRH] second member or -1
+  int* slotOf; // [K] slot of hypothesis i
+  uint32_t mask;
+};
+
+FLT_DEV LfTab lfTab(const Ws& w) {
+  const Lay& L = w.c->lay;
+  return LfTab{(int*)(w.base + L.rowHash), (int*)(w.base + L.lfSlotB), (int*)(w.base + L.lfSlotOf),
+               (uint32_t)w.c->capRH - 1};
+}
+FLT_DEV unsigned short* lfCbin(const Ws& w) { return (unsigned short*)(w.base + w.c->lay.lfCbin); }
+
+// new-token test of hypothesis p for token n (LexiconFreeDecoder.cpp:69-71)
+FLT_DEV bool lfEligible(const DecCfg& c, const Beam& cur, int p, int n) {
+  if (c.ctc) return n != c.blank && (n != cur.tok(p) || cur.pb(p));
+  return n != cur.tok(p);
+}
+
+// row members of the LM state with fingerprint (xa, xb); false if the state is not in the beam
+FLT_DEV bool lfProbe(const LfTab& t, const Beam& cur, u64 xa, u64 xb, int& ma, int& mb) {
+  uint32_t s = (uint32_t)xa & t.mask;
+  for (;;) {
+    const int a = t.a[s];
+    if (a < 0) return false;
+    if (cur.fpA(a) == xa && cur.fpB(a) == xb) {
+      ma = a;
+      mb = t.b[s];
+      return true;
+    }
+    s = (s + 1) & t.mask;
+  }
+}
+
+// deterministic order of two candidates: higher score, lower parent, lower token, prevBlank
+FLT_DEV bool lfBetter(const Cand& cd, int a, int b) {
+  const double sa = cd.score(a), sb = cd.score(b);
+  if (sa != sb) return sa > sb;
+  if (cd.par(a) != cd.par(b)) return cd.par(a) < cd.par(b);
+  if (cd.tok(a) != cd.tok(b)) return cd.tok(a) < cd.tok(b);
+  return (cd.flags(a) & CF_PB) < (cd.flags(b) & CF_PB);
+}
+
+// candidate score of hypothesis p taking token n with emission ev (LexiconFreeDecoder.cpp:64-67,
+// :75 with ZeroLM's 0.0f; transitions only enter emittingModelScore, :59-63)
+FLT_DEV double lfScore(const DecCfg& c, const Beam& cur, int p, int n, float ev, bool isNew) {
+  double score = cur.score(p) + (double)ev;
+  if (n == c.sil) score += c.silScore;
+  if (isNew) score = score + c.lmWeight * (double)0.0f;
+  return score;
+}
+
+// new-token candidate of hypothesis i with token n: true if it is to be materialised
+FLT_DEV bool lfCell(const DecCfg& c, const Beam& cur, const LfTab& t, int i, int n, float ev,
+                    double tau, double& score) {
+  if (!lfEligible(c, cur, i, n)) return false;
+  const int s = t.slotOf[i];
+  const int a = t.a[s], b = t.b[s];
+  const int partner = a == i ? b : a;
+  if (partner >= 0 && partner < i && lfEligible(c, cur, partner, n)) return false; // the better member emits
+  score = lfScore(c, cur, i, n, ev, true);
+  if (score < tau) return false;
+  // a hypothesis already in the child state whose repeat has the same key (child(S,n), n, 0)
+  u64 ca, cb;
+  fpChild(cur.fpA(i), cur.fpB(i), n, ca, cb);
+  int ma = -1, mb = -1;
+  if (lfProbe(t, cur, ca, cb, ma, mb)) {
+    int m = -1;
+    if (cur.tok(ma) == n && !cur.pb(ma)) m = ma;
+    else if (mb >= 0 && cur.tok(mb) == n && !cur.pb(mb)) m = mb;
+    if (m >= 0) {
+      const double sm = lfScore(c, cur, m, n, ev, false);
+      if (sm > score || (sm == score && m < i)) return false; // the repeat wins the merge
+    }
+  }
+  return true;
+}
+
+// repeat candidate of hypothesis i (LexiconFreeDecoder.cpp:98-110)
+FLT_DEV bool lfRepeat(const DecCfg& c, const Beam& cur, const LfTab& t, const FrameIn& f, int i,
+                      float eOwn, double tau, double& score) {
+  const int n = cur.tok(i);
+  const bool isRepeat = c.ctc ? (!cur.pb(i) && n != c.blank) : true;
+  if (!(isRepeat && n >= 0 && n < c.N && inTokenSetV(c, f, n, eOwn))) return false;
+  score = lfScore(c, cur, i, n, eOwn, false);
+  if (score < tau) return false;
+  // new token n from the parent state merges into the same key
+  int ma = -1, mb = -1;
+  if (lfProbe(t, cur, cur.pfpA(i), cur.pfpB(i), ma, mb)) {
+    int p = -1;
+    if (lfEligible(c, cur, ma, n)) p = ma;
+    if (mb >= 0 && lfEligible(c, cur, mb, n) && (p < 0 || mb < p)) p = mb;
+    if (p >= 0) {
+      const double sp = lfScore(c, cur, p, n, eOwn, true);
+      if (sp > score || (sp == score && p < i)) return false;
+    }
+  }
+  return true;
+}
+
+// blank candidate of hypothesis i (LexiconFreeDecoder.cpp:86-97): the better member of a row emits
+FLT_DEV bool lfBlank(const DecCfg& c, const Beam& cur, const LfTab& t, const FrameIn& f, int i,
+                     float eBlank, double tau, double& score) {
+  if (!c.ctc) return false;
+  const int s = t.slotOf[i];
+  const int a = t.a[s], b = t.b[s];
+  const int partner = a == i ? b : a;
+  if (partner >= 0 && partner < i) return false;
+  if (!inTokenSetV(c, f, c.blank, eBlank)) return false;
+  score = lfScore(c, cur, i, c.blank, eBlank, false);
+  return !(score < tau);
+}
+
+// e[own token] of every hypothesis, e[blank], e[sil] of one emission row -> spec[]
+FLT_DEV void lfGatherSpec(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& beam, int nH,
+                          const float* row) {
+  float* spec = w.spec();
+  for (int i = cta.tid; i < nH; i += cta.nthr) {
+    const int n = beam.tok(i);
+    spec[i] = (n >= 0 && n < c.N) ? row[n] : 0.0f;
+  }
+  if (cta.tid == cta.nthr - 1) {
+    spec[c.K] = c.ctc ? row[c.blank] : 0.0f;
+    spec[c.K + 1] = row[c.sil];
+  }
+}
+
+// Work items of a frame: [0, wideItems) = cells (hypothesis, ranked column); then nH repeat items,
+// nH blank items and (silScore > 0 only) nH sil cells. Item x owns candidate slot x.
+FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur,
+                         const Beam& nxt, const FrameIn& f, unsigned long long* stats) {
+  int* sc = w.sc();
+  const int nH = sc[SC_NH];
+  if (nH == 0) return; // the beam died (Utils.h:155-158)
+  const int K = c.K;
+  const LfTab t = lfTab(w);
+  const Cand cd = w.cand();
+  float* spec = w.spec();
+  int* hist = w.hist();
+  const int NB = c.lfBins;
+
+  // scattered emission reads, published for the threads that own the special items (the fused
+  // kernel has already gathered them from the staged row: f.specReady)
+  if (!f.specReady) lfGatherSpec(cta, c, w, cur, nH, f.e);
+  // (1) fingerprint table of the beam
+  for (int i = cta.tid; i < nH; i += cta.nthr) {
+    const u64 fa = cur.fpA(i), fb = cur.fpB(i);
+    uint32_t s = (uint32_t)fa & t.mask;
+    for (;;) {
+      const int old = atomCAS(&t.a[s], -1, i);
+      if (old == -1) break;
+      if (cur.fpA(old) == fa && cur.fpB(old) == fb) {
+        t.b[s] = i; // a row has at most two members
+        break;
+      }
+      s = (s + 1) & t.mask;
+    }
+    t.slotOf[i] = (int)s;
+  }
+
+  // corner bound (beam_core.h frameStep): lanes 0..nTau-1 of every warp take one rectangle each
+  double tau = negInf();
+  {
+#if FLT_DEVICE_BUILD
+    const int lane = cta.tid & 31;
+    if (lane < c.nTau) {
+      const int i = 2 * c.tauA[lane] - 2, col = c.tauCol[lane];
+      if (i < nH && col < f.listLen && f.topTok[col] >= 0)
+        tau = cur.score(i) + (double)f.topVal[col] + c.lmWeight * (double)0.0f;
+    }
+    for (int o = 8; o > 0; o >>= 1) { // nTau <= 16
+      const double u = __shfl_xor_sync(0xffffffffu, tau, o);
+      tau = u > tau ? u : tau;
+    }
+    tau = __shfl_sync(0xffffffffu, tau, 0); // lanes 0..15 hold the maximum
+#else
+    for (int k = 0; k < c.nTau; ++k) {
+      const int i = 2 * c.tauA[k] - 2, col = c.tauCol[k];
+      if (i < nH && col < f.listLen && f.topTok[col] >= 0) {
+        const double corner = cur.score(i) + (double)f.topVal[col] + c.lmWeight * (double)0.0f;
+        tau = corner > tau ? corner : tau;
+      }
+    }
+#endif
+    if (c.silScore < 0) tau += c.silScore; // keeps the bound valid if a counted cell is the sil one
+  }
+  // candidate scores lie in [tau, upper]: monotone linear map to NB bins
+  const float eTop = (f.listLen > 0 && f.topTok[0] >= 0) ? f.topVal[0] : 0.0f;
+  double upper = cur.score(0) + (double)eTop;
+  if (c.silScore > 0) upper += c.silScore;
+  const double range = upper - tau;
+  const bool binned = range > 0.0 && range < 1e300; // finite, non-degenerate
+  const double scale = binned ? (double)NB / range : 0.0;
+  cta.sync(); // ---- B1
+
+  // (2) candidates, each in the slot of its work item, and the histogram of their scores
+  const short* itemRow = w.itemRow();
+  const int* wideOff = w.wideOff();
+  const int wideItems = wideOff[nH];
+  const int nKinds = c.silScore > 0 ? 3 : 2;
+  const int items = wideItems + nKinds * nH;
+  unsigned short* cbin = lfCbin(w);
+  for (int x = cta.tid; x < items; x += cta.nthr) {
+    bool alive = false;
+    double score = 0.0;
+    int par = 0, tok = 0, flags = 0;
+    float ev = 0.0f;
+    if (x < wideItems) {
+      par = itemRow[x];
+      const int j = x - wideOff[par];
+      if (j < f.listLen) {
+        tok = f.topTok[j];
+        ev = f.topVal[j];
+        flags = CF_NEW;
+        // a boosted sil is not rank-dominated: every hypothesis proposes it as a special item
+        if (tok >= 0 && !(tok == c.sil && c.silScore > 0)) alive = lfCell(c, cur, t, par, tok, ev, tau, score);
+      }
+    } else {
+      const int y = x - wideItems;
+      const int kind = (y >= nH ? 1 : 0) + (y >= 2 * nH ? 1 : 0);
+      par = y - kind * nH;
+      if (kind == 0) {
+        tok = cur.tok(par);
+        ev = spec[par];
+        alive = lfRepeat(c, cur, t, f, par, ev, tau, score);
+      } else if (kind == 1) {
+        tok = c.blank;
+        ev = spec[K];
+        flags = CF_PB;
+        alive = lfBlank(c, cur, t, f, par, ev, tau, score);
+      } else {
+        tok = c.sil;
+        ev = spec[K + 1];
+        flags = CF_NEW;
+        if (inTokenSetV(c, f, tok, ev)) alive = lfCell(c, cur, t, par, tok, ev, tau, score);
+      }
+    }
+    if (alive) {
+      int bin = 0;
+      if (binned) {
+        const double pos = (score - tau) * scale;
+        bin = pos >= (double)(NB - 1) ? NB - 1 : (int)pos;
+        bin = bin < 0 ? 0 : bin;
+        atomAdd(&hist[bin], 1);
+      }
+      cbin[x] = (unsigned short)bin;
+      cd.score(x) = score;
+      cd.parflag(x) = (par << 4) | flags | CF_ALIVE;
+      cd.tok(x) = tok;
+      cd.ce(x) = ev;
+    } else {
+      cd.parflag(x) = 0;
+    }
+  }
+  cta.sync(); // ---- B2
+
+  // (3) cut bin = lowest bin with fewer than K candidates in higher bins; every warp finds it for
+  // itself (lane L owns NB/32 consecutive bins). Candidates at or above it are "relevant".
+  int cut = 0;
+  if (binned) {
+#if FLT_DEVICE_BUILD
+    const int lane = cta.tid & 31;
+    const int per = NB >> 5;
+    int own = 0;
+    for (int k = 0; k < per; ++k) own += hist[lane * per + k];
+    int suf = own; // inclusive suffix over lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_down_sync(0xffffffffu, suf, o);
+      if (lane + o < 32) suf += u;
+    }
+    int ab = suf - own; // candidates in bins of higher lanes
+    const unsigned qual = __ballot_sync(0xffffffffu, ab < K);
+    const int src = __ffs(qual) - 1; // lowest lane whose top bin qualifies (lane 31 always does)
+    int local = 0;
+    if (lane == src) {
+      for (int k = per - 1; k >= 0; --k) {
+        if (ab < K) local = lane * per + k;
+        ab += hist[lane * per + k];
+      }
+    }
+    cut = __shfl_sync(0xffffffffu, local, src);
+#else
+    int ab = 0;
+    for (int bn = NB - 1; bn >= 0; --bn) {
+      if (ab < K) cut = bn;
+      ab += hist[bn];
+    }
+#endif
+  }
+  int* list = w.rep();  // [capC] relevant candidates
+  u64* lkey = w.rkey(); // [capC] their ordered score keys
+  for (int x0 = 0; x0 < items; x0 += cta.nthr) { // warp-uniform trip count
+    const int x = x0 + cta.tid;
+    const bool rel = x < items && (cd.parflag(x) & CF_ALIVE) && (int)cbin[x] >= cut;
+#if FLT_DEVICE_BUILD
+    const unsigned m = __ballot_sync(0xffffffffu, rel); // one counter update per warp
+    if (m == 0) continue;
+    const int lane = cta.tid & 31;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&sc[SC_NSEL], __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (rel) {
+      const int q = base + __popc(m & ((1u << lane) - 1u));
+      list[q] = x;
+      lkey[q] = orderedKey64(cd.score(x));
+    }
+#else
+    if (rel) {
+      const int q = sc[SC_NSEL]++;
+      list[q] = x;
+      lkey[q] = orderedKey64(cd.score(x));
+    }
+#endif
+  }
+  cta.sync(); // ---- B3
+  const int nL = sc[SC_NSEL];
+  const int nSel = nL < K ? nL : K;
+  if (binned)
+    for (int bn = cta.tid; bn < NB; bn += cta.nthr) hist[bn] = 0;
+  // (4) exact ranks among the relevant candidates by counting: `parts` adjacent lanes share one
+  // candidate and split the list between them
+  int* ranked = w.surv() + c.capP;
+  {
+    int lg = 0;
+    while (lg < 5 && (nL << (lg + 1)) <= cta.nthr) ++lg;
+    const int parts = 1 << lg;
+    const int per = cta.nthr >> lg; // candidates per sweep
+    const int part = cta.tid & (parts - 1);
+    for (int a0 = 0; a0 < nL; a0 += per) {
+      const int qa = a0 + (cta.tid >> lg);
+      int cnt = 0;
+      int xa = -1;
+      if (qa < nL) {
+        xa = list[qa];
+        const u64 ka = lkey[qa];
+#pragma unroll 4
+        for (int qb = part; qb < nL; qb += parts) {
+          const u64 kb = lkey[qb];
+          cnt += kb > ka ? 1 : 0;
+          if (kb == ka && qb != qa && lfBetter(cd, list[qb], xa)) ++cnt; // equal scores: rare
+        }
+      }
+#if FLT_DEVICE_BUILD
+      for (int o = 1; o < parts; o <<= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+#endif
+      if (xa >= 0 && part == 0 && cnt < K) ranked[cnt] = xa;
+    }
+  }
+  cta.sync(); // ---- B4
+#if FLT_DEVICE_BUILD
+  if (stats && cta.tid == 0) {
+    atomicAdd(stats + 0, 1ull);
+    atomicAdd(stats + 1, (unsigned long long)items);
+    atomicAdd(stats + 2, (unsigned long long)nL); // candidates ranked exactly
+    atomicAdd(stats + 3, (unsigned long long)nSel);
+  }
+#else
+  (void)stats;
+#endif
+
+  // (5) the new beam (Utils.h:161-165 threshold against the best, then the K best in rank order)
+  if (cta.tid == 0) sc[SC_NSEL] = 0;
+  for (int i = cta.tid; i < nH; i += cta.nthr) { // leave the fingerprint table empty
+    const int s = t.slotOf[i];
+    t.a[s] = -1;
+    t.b[s] = -1;
+  }
+  if (nSel == 0) {
+    if (cta.tid == 0) sc[SC_NH] = 0;
+  } else {
+    const double thrScore = cd.score(ranked[0]) - c.beamThreshold;
+    for (int q = cta.tid; q < nSel; q += cta.nthr) {
+      const int x = ranked[q];
+      const double score = cd.score(x);
+      if (!(score >= thrScore)) continue;
+      if (q + 1 == nSel || !(cd.score(ranked[q + 1]) >= thrScore)) sc[SC_NH] = q + 1;
+      const int p = cd.par(x);
+      const int fl = cd.flags(x);
+      const int n = cd.tok(x);
+      nxt.score(q) = score;
+      nxt.am(q) = cur.am(p) + amOf(c, f, cd.ce(x), n, cur.tok(p));
+      nxt.lm(q) = cur.lm(p) + (double)0.0f;
+      nxt.lex(q) = 0;
+      nxt.tok(q) = n;
+      nxt.pb(q) = (fl & CF_PB) ? 1 : 0;
+      if (fl & CF_NEW) {
+        fpChild(cur.fpA(p), cur.fpB(p), n, nxt.fpA(q), nxt.fpB(q));
+        nxt.pfpA(q) = cur.fpA(p);
+        nxt.pfpB(q) = cur.fpB(p);
+      } else {
+        nxt.fpA(q) = cur.fpA(p);
+        nxt.fpB(q) = cur.fpB(p);
+        nxt.pfpA(q) = cur.pfpA(p);
+        nxt.pfpB(q) = cur.pfpB(p);
+      }
+      f.hParent[q] = p;
+      f.hTok[q] = n;
+    }
+  }
+  cta.sync(); // ---- B5
+}
+
+// decodeEnd (LexiconFreeDecoder.cpp:127-158) with ZeroLM: finish() returns the same state and 0,
+// every hypothesis proposes (state, sil, prevBlank=0); the two members of a row merge (max).
+// The beam is already sorted, so the survivors keep their order.
+FLT_DEV void lfFinish(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, const Beam& nxt,
+                      const FrameIn& f) {
+  int* sc = w.sc();
+  const int nH = sc[SC_NH];
+  if (nH == 0) return;
+  const LfTab t = lfTab(w);
+  int* keep = w.surv(); // [capP] flags
+  for (int i = cta.tid; i < nH; i += cta.nthr) {
+    const u64 fa = cur.fpA(i), fb = cur.fpB(i);
+    uint32_t s = (uint32_t)fa & t.mask;
+    for (;;) {
+      const int old = atomCAS(&t.a[s], -1, i);
+      if (old == -1) break;
+      if (cur.fpA(old) == fa && cur.fpB(old) == fb) {
+        t.b[s] = i;
+        break;
+      }
+      s = (s + 1) & t.mask;
+    }
+    t.slotOf[i] = (int)s;
+  }
+  cta.sync();
+  const double best = cur.score(0) + c.lmWeight * (double)0.0f;
+  for (int i = cta.tid; i < nH; i += cta.nthr) {
+    const int s = t.slotOf[i];
+    const int a = t.a[s], b = t.b[s];
+    const int partner = a == i ? b : a;
+    const double score = cur.score(i) + c.lmWeight * (double)0.0f;
+    keep[i] = !(partner >= 0 && partner < i) && score >= best - c.beamThreshold;
+  }
+  cta.sync();
+  for (int i = cta.tid; i < nH; i += cta.nthr) {
+    const int s = t.slotOf[i];
+    t.a[s] = -1;
+    t.b[s] = -1;
+    int q = 0;
+    for (int j = 0; j < i; ++j) q += keep[j];
+    if (keep[i]) {
+      nxt.score(q) = cur.score(i) + c.lmWeight * (double)0.0f;
+      nxt.am(q) = cur.am(i);
+      nxt.lm(q) = cur.lm(i) + (double)0.0f;
+      f.hParent[q] = i;
+      f.hTok[q] = c.sil;
+    }
+    if (i == nH - 1) sc[SC_NH] = q + keep[i];
+  }
+  cta.sync();
+}
+
+} // namespace flt

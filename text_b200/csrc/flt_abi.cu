@@ -19,7 +19,9 @@
 
 #include "runtime.h"
 #include "beam_core.h"
+#include "beam_lf.h"
 #include "topm_core.h"
+#include "fused_core.h"
 
 using namespace flt;
 
@@ -36,10 +38,23 @@ __global__ void __launch_bounds__(256) flt_k_decode(DecCfg c, BatchArgs a) {
   Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
   decodeCta(cta, c, a, smem);
 }
+// same, 512 threads per utterance (two CTAs per SM): small batches leave SMs under-occupied
+__global__ void __launch_bounds__(512, 2) flt_k_decode512(DecCfg c, BatchArgs a) {
+  extern __shared__ __align__(16) char smem[];
+  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
+  decodeCta(cta, c, a, smem);
+}
 // workspace in a global slab per CTA (beams / candidate sets too large for shared memory)
 __global__ void __launch_bounds__(256) flt_k_decode_gmem(DecCfg c, BatchArgs a) {
   Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
   decodeCta(cta, c, a, a.wsGlobal + (long long)blockIdx.x * a.wsStride);
+}
+// token-beam select + beam step fused: 8 consumer + 4 producer warps per utterance (fused_core.h)
+__global__ void __launch_bounds__(kFusedConsumers + kFusedProducers, 2)
+    flt_k_fused(DecCfg c, TopMCfg tc, FuseLay fl, BatchArgs a) {
+  extern __shared__ __align__(128) char smem[];
+  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
+  fusedCta(cta, c, tc, fl, a, smem);
 }
 __global__ void flt_k_backtrace(BacktraceArgs a) {
   const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -64,7 +79,7 @@ int decThreads() {            // beam-step kernel (tunable for experiments)
   static int t = [] {
     const char* e = getenv("FLT_DEC_THREADS");
     int v = e ? atoi(e) : 256;
-    return (v == 64 || v == 128 || v == 256) ? v : 256;
+    return (v == 64 || v == 128 || v == 256 || v == 512) ? v : 256;
   }();
   return t;
 }
@@ -86,7 +101,8 @@ void launchTopM(const TopMCfg& c, const TopMArgs& a, int grid, size_t smem, rt::
 }
 void launchDecode(const DecCfg& c, const BatchArgs& a, int grid, size_t smem, rt::Stream s) {
 #if FLT_DEVICE_BUILD
-  if (smem) flt_k_decode<<<grid, decThreads(), smem, s>>>(c, a);
+  if (smem && decThreads() == 512) flt_k_decode512<<<grid, 512, smem, s>>>(c, a);
+  else if (smem) flt_k_decode<<<grid, decThreads(), smem, s>>>(c, a);
   else flt_k_decode_gmem<<<grid, decThreads(), 0, s>>>(c, a);
   FLT_RT_TRY(cudaGetLastError());
 #else
@@ -97,6 +113,20 @@ void launchDecode(const DecCfg& c, const BatchArgs& a, int grid, size_t smem, rt
   }
   (void)s;
   (void)smem;
+#endif
+}
+void launchFused(const DecCfg& c, const TopMCfg& tc, const FuseLay& fl, const BatchArgs& a, int grid,
+                 rt::Stream s) {
+#if FLT_DEVICE_BUILD
+  flt_k_fused<<<grid, kFusedConsumers + kFusedProducers, fl.total, s>>>(c, tc, fl, a);
+  FLT_RT_TRY(cudaGetLastError());
+#else
+  std::vector<char> sm(fl.total + 128);
+  for (int b = 0; b < grid; ++b) {
+    Cta cta{0, 1, b, grid};
+    fusedCta(cta, c, tc, fl, a, sm.data());
+  }
+  (void)s;
 #endif
 }
 void launchBacktrace(const BacktraceArgs& a, rt::Stream s) {
@@ -381,13 +411,15 @@ struct flt_decoder {
 #endif
   bool timing = false;
   std::vector<int> evKinds;
-  float kernelMs[3] = {0, 0, 0};
-  int kernelLaunches[3] = {0, 0, 0};
   // plan
   int planN = -1;
   DecCfg cfg{};
   TopMCfg tcfg{};
   bool needTopM = false;
+  bool fused = false; // select + step in one kernel (fused_core.h)
+  TopMCfg ftcfg{};
+  FuseLay flay{};
+  int fusedGridMax = 1;
   size_t wsBytes = 0, topmSmem = 0;
   int gridMax = 1, topmGridMax = 1;
   std::vector<int> wideOffHost;
@@ -492,10 +524,16 @@ void planFor(flt_decoder& d, int N) {
   // register-resident fast path (alignment of the emission pointer is checked per launch)
   t.fast = (N % 4 == 0) && N <= 4 * kFastVec * kThreads && want <= 256 && c.M <= 256;
   t.stage = !t.fast && (size_t)N * 4 <= 100 * 1024;
+  // lexicon-free fast step (beam_lf.h): ZeroLM max-merge, candidate indices fit 16 bits
+  c.lfFast = !d.lexicon && d.lm->kind == 0 && !o.logAdd && K <= 256 && !getenv("FLT_NO_LF");
+  c.lfBins = std::min(1024, std::max(256, nextPow2(4 * K)));
   // wide offsets
   d.wideOffHost.assign(K + 1, 0);
-  for (int r = 1; r <= K; ++r)
-    d.wideOffHost[r] = d.wideOffHost[r - 1] + std::min(c.Mwide, K / r + 3 + (d.lexicon ? 2 : 0));
+  for (int r = 1; r <= K; ++r) {
+    // fast step: item row = hypothesis index r-1, which spans >= (r-1)/2+1 rows
+    const int rows = c.lfFast ? (r - 1) / 2 + 1 : r;
+    d.wideOffHost[r] = d.wideOffHost[r - 1] + std::min(c.Mwide, K / rows + 3 + (d.lexicon ? 2 : 0));
+  }
   const long long narrowBudget = d.lexicon ? std::max<long long>(4096, 24LL * K) : 0;
   long long capC = (long long)(c.wideRanked ? d.wideOffHost[K] : 0) + 3LL * K + narrowBudget * d.capBoost;
   capC = (capC + 63) / 64 * 64;
@@ -551,6 +589,37 @@ void planFor(flt_decoder& d, int N) {
   d.topmSmem = (carveTopM(nullptr, t, ts) + 255) / 256 * 256;
   d.cfg = c;
   d.tcfg = t;
+  // fused select + step: the row stage, the producer scratch and the consumer workspace share the
+  // CTA's shared memory; two CTAs per SM need <= 113 KB each
+  d.fused = false;
+  if (c.lfFast && !getenv("FLT_NO_FUSED") && N % 4 == 0 && want <= 32 * (kFusedProducers / 32) &&
+      decThreads() == 256) {
+    TopMCfg ft = t;
+    ft.P = std::max(kFusedProducers, nextPow2(want));
+    ft.capS = 512;
+    ft.fast = 1;
+    ft.stage = 0;
+    ft.bias = nullptr;
+    FuseLay fl{};
+    size_t off = 0;
+    auto take = [&](size_t bytes, size_t align) {
+      off = (off + align - 1) / align * align;
+      const size_t o = off;
+      off += bytes;
+      return (int)o;
+    };
+    fl.ws = take(c.lay.total, 16);
+    TopMSmem ts2;
+    fl.prod = take(carveTopM(nullptr, ft, ts2), 16);
+    fl.row = take((size_t)N * 4, 128);
+    for (int k = 0; k < 2; ++k) fl.list[k] = take(8 * (size_t)c.M, 16);
+    for (int k = 0; k < 2; ++k) fl.thr[k] = take(4, 4);
+    fl.mbar = take(8 * MB_COUNT, 8);
+    fl.total = (int)((off + 127) / 128 * 128);
+    d.ftcfg = ft;
+    d.flay = fl;
+    d.fused = fl.total <= 113 * 1024;
+  }
 #if FLT_DEVICE_BUILD
   int dev = d.device;
   cudaDeviceProp prop;
@@ -568,16 +637,34 @@ void planFor(flt_decoder& d, int N) {
   if (smemOk) {
     FLT_RT_TRY(cudaFuncSetAttribute(flt_k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)std::max<size_t>(d.wsBytes, 48 * 1024)));
-    FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode, decThreads(), d.wsBytes));
+    FLT_RT_TRY(cudaFuncSetAttribute(flt_k_decode512, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)std::max<size_t>(d.wsBytes, 48 * 1024)));
+    if (decThreads() == 512)
+      FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode512, 512, d.wsBytes));
+    else
+      FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode, decThreads(), d.wsBytes));
   } else {
     FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode_gmem, decThreads(), 0));
     occ2 = std::min(occ2, 4);
   }
   d.gridMax = std::max(1, occ2) * d.numSMs;
   d.useSmemFlag = smemOk;
+  if (d.fused) {
+    if ((size_t)d.flay.total > smemMax) {
+      d.fused = false;
+    } else {
+      FLT_RT_TRY(cudaFuncSetAttribute(flt_k_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      std::max(d.flay.total, 48 * 1024)));
+      int occ3 = 1;
+      FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &occ3, flt_k_fused, kFusedConsumers + kFusedProducers, d.flay.total));
+      d.fusedGridMax = std::max(1, occ3) * d.numSMs;
+    }
+  }
 #else
   d.gridMax = 4;
   d.topmGridMax = 4;
+  d.fusedGridMax = 3;
   d.useSmemFlag = true;
 #endif
   d.planN = N;
@@ -626,7 +713,8 @@ void runChunk(flt_decoder& d, const float* dEmis, int Bc, int T, int N, const in
   a.B = Bc;
   a.T = T;
   a.lengths = dLen;
-  if (d.needTopM) {
+  const bool fused = d.fused && (reinterpret_cast<uintptr_t>(dEmis) & 15) == 0;
+  if (d.needTopM && !fused) {
     d.topTok.reserve(sizeof(int) * rows * c.M);
     d.topVal.reserve(sizeof(float) * rows * c.M);
     if (!c.setAll) d.thr.reserve(sizeof(float) * rows);
@@ -658,14 +746,18 @@ void runChunk(flt_decoder& d, const float* dEmis, int Bc, int T, int N, const in
   a.finScore = d.finScore.as<double>() + outBase * K * 3;
   a.finCount = d.finCount.as<int>() + outBase;
   a.status = d.status.as<int>() + outBase;
-  const int grid = std::max(1, std::min(Bc, d.gridMax));
+  const int grid = std::max(1, std::min(Bc, fused ? d.fusedGridMax : d.gridMax));
   a.stats = d.timing ? d.dStats.as<unsigned long long>() : nullptr;
-  if (!d.useSmemFlag) {
-    d.ws.reserve(d.wsBytes * grid);
-    a.wsGlobal = d.ws.as<char>();
-    a.wsStride = (long long)d.wsBytes;
-  }
-  {
+  if (fused) {
+    KernelTimer kt(d, 3);
+    launchFused(c, d.ftcfg, d.flay, a, grid, s);
+    d.launches++;
+  } else {
+    if (!d.useSmemFlag) {
+      d.ws.reserve(d.wsBytes * grid);
+      a.wsGlobal = d.ws.as<char>();
+      a.wsStride = (long long)d.wsBytes;
+    }
     KernelTimer kt(d, 1);
     launchDecode(c, a, grid, d.useSmemFlag ? d.wsBytes : 0, s);
     d.launches++;
@@ -716,7 +808,8 @@ void decodeDevice(flt_decoder& d, const float* dEmis, int B, int T, int N, const
   const long long perUtt = (long long)(T + 2) * d.cfg.K * 12 + (long long)T * d.cfg.M * 8 + 64;
   long long slice = std::max<long long>(1, (8LL << 30) / perUtt);
   slice = std::min<long long>(slice, B);
-  if (slice >= d.gridMax) slice = slice / d.gridMax * d.gridMax; // whole waves
+  const int gm = d.fused ? d.fusedGridMax : d.gridMax;
+  if (slice >= gm) slice = slice / gm * gm; // whole waves
   for (long long b0 = 0; b0 < B; b0 += slice) {
     const int Bc = (int)std::min<long long>(slice, B - b0);
     runChunk(d, dEmis + b0 * T * N, Bc, T, N, dLen ? dLen + b0 : nullptr, b0);
@@ -1073,7 +1166,7 @@ int flt_decoder_set_timing(flt_decoder* dec, int32_t on) {
 int flt_decoder_last_kernel_ms(flt_decoder* dec, float* ms3, int32_t* launches3) {
   return guarded([&] {
     if (!dec || !ms3) throw FltError(FLT_ERR_INVALID, "null argument");
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < 4; ++k) {
       ms3[k] = 0;
       if (launches3) launches3[k] = 0;
     }

@@ -32,9 +32,11 @@ struct Cta {
   int nthr; // threads per CTA
   int bid;  // CTA index
   int nblk; // CTAs in the grid
+  int bar = 0; // 0 = the whole CTA (__syncthreads); else a named barrier over this role's nthr threads
   FLT_DEV void sync() const {
 #if FLT_DEVICE_BUILD
-    __syncthreads();
+    if (bar == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthr) : "memory");
 #endif
   }
 };
