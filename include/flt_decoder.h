@@ -133,8 +133,10 @@ int flt_decoder_last_launches(const flt_decoder* dec, int32_t* out);
 int flt_decoder_set_timing(flt_decoder* dec, int32_t on);
 int flt_decoder_last_kernel_ms(flt_decoder* dec, float* ms4, int32_t* launches4);
 /* Beam-step work counters of the last call (collected while timing is on), summed over frames:
- * out4 = {frames stepped, candidates materialised, merge groups, survivors}. */
-int flt_decoder_last_stats(flt_decoder* dec, uint64_t* out4);
+ * out16[0..3] = {frames stepped, work items, live candidates (merge groups), survivors};
+ * out16[4..10] = SM cycles thread 0 of the lexicon-free step spent in each phase (hash insert,
+ * emit, scan, rank, new beam, wait for the producers, hand-over + emission gather); rest 0. */
+int flt_decoder_last_stats(flt_decoder* dec, uint64_t* out16);
 int flt_decoder_workspace_bytes(const flt_decoder* dec, int64_t* out);
 
 /* Stand-alone entry to the token-beam select kernel (decoder/LexiconFreeDecoder.cpp:39-51:

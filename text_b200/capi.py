@@ -243,11 +243,15 @@ class Api:
         return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(names)}
 
     def last_stats(self, dec):
-        v = (C.c_uint64 * 4)()
+        v = (C.c_uint64 * 16)()
         self._ck(self.lib.flt_decoder_last_stats(dec, v))
         frames = max(int(v[0]), 1)
-        return dict(frames=int(v[0]), candidates_per_frame=v[1] / frames, groups_per_frame=v[2] / frames,
-                    survivors_per_frame=v[3] / frames)
+        out = dict(frames=int(v[0]), candidates_per_frame=v[1] / frames, groups_per_frame=v[2] / frames,
+                   survivors_per_frame=v[3] / frames)
+        if any(v[4:11]):
+            names = ("insert", "emit", "scan", "rank", "new_beam", "wait_list", "handover_gather")
+            out["phase_cycles_per_frame"] = {n: round(v[4 + i] / frames, 1) for i, n in enumerate(names)}
+        return out
 
     def workspace_bytes(self, dec):
         n = C.c_int64()

@@ -56,7 +56,7 @@ struct Lay {
   int cslot;     // int [capC]: merge-table slot of each candidate
   int gath;      // int [64]: members of the cut bin (one-warp finish of the radix select)
   // lexicon-free fast step (beam_lf.h)
-  int lfSlotB, lfSlotOf, lfCbin;
+  int lfSlotB, lfSlotOf, lfCbin, lfAbove;
   int total;
 };
 
@@ -242,7 +242,8 @@ FLT_HD void makeLayout(DecCfg& c) {
   L.gath = take(sizeof(int) * 64);
   L.lfSlotB = take(lf ? sizeof(int) * c.capRH : 0);
   L.lfSlotOf = take(lf ? sizeof(int) * K : 0);
-  L.lfCbin = take(lf ? sizeof(unsigned short) * c.capC : 0);
+  L.lfCbin = take(lf ? sizeof(unsigned short) * 2 * c.capC : 0); // bin, arrival order in the bin
+  L.lfAbove = take(lf ? sizeof(unsigned short) * 16 * c.lfBins : 0); // one copy per warp (<= 16)
   L.total = (int)off;
 }
 

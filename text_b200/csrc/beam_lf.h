@@ -20,9 +20,9 @@
 //   * Top-K: candidate scores lie in [tau, U] (tau = corner bound, U = best hypothesis + row
 //     maximum); a monotone linear map sends them to NB bins and a per-warp suffix scan of the
 //     histogram gives every candidate the number of candidates in higher bins. Candidates with
-//     fewer than K above them (the top-K plus the rest of the cut bin) are ranked exactly by
-//     counting among themselves; rank < K = survivor, placed at ranked[rank]. Crowded bins only
-//     lengthen that list, they never change the result.
+//     fewer than K above them (the top-K plus the rest of the cut bin) get their exact rank by
+//     comparing with the other members of their own bin; rank < K = survivor, placed at
+//     ranked[rank]. Crowded bins only lengthen those comparisons, they never change the result.
 #pragma once
 #include "beam_core.h"
 
@@ -156,6 +156,30 @@ FLT_DEV void lfGatherSpec(const Cta& cta, const DecCfg& c, const Ws& w, const Be
   }
 }
 
+// phase timing for the benchmark (thread 0, only while the decoder's timing is on): cycles spent
+// up to each barrier exit, summed over frames into stats[4 + phase]
+struct LfPhaseClock {
+  unsigned long long* stats;
+  long long t0;
+  FLT_DEV void start(const Cta& cta, unsigned long long* st) {
+    stats = cta.tid == 0 ? st : nullptr;
+#if FLT_DEVICE_BUILD
+    if (stats) t0 = clock64();
+#endif
+  }
+  FLT_DEV void mark(int phase) {
+#if FLT_DEVICE_BUILD
+    if (stats) {
+      const long long t1 = clock64();
+      atomicAdd(stats + 4 + phase, (unsigned long long)(t1 - t0));
+      t0 = t1;
+    }
+#else
+    (void)phase;
+#endif
+  }
+};
+
 // Work items of a frame: [0, wideItems) = cells (hypothesis, ranked column); then nH repeat items,
 // nH blank items and (silScore > 0 only) nH sil cells. Item x owns candidate slot x.
 FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur,
@@ -163,6 +187,8 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
   int* sc = w.sc();
   const int nH = sc[SC_NH];
   if (nH == 0) return; // the beam died (Utils.h:155-158)
+  LfPhaseClock pc;
+  pc.start(cta, stats);
   const int K = c.K;
   const LfTab t = lfTab(w);
   const Cand cd = w.cand();
@@ -223,6 +249,7 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
   const bool binned = range > 0.0 && range < 1e300; // finite, non-degenerate
   const double scale = binned ? (double)NB / range : 0.0;
   cta.sync(); // ---- B1
+  pc.mark(0);
 
   // (2) candidates, each in the slot of its work item, and the histogram of their scores
   const short* itemRow = w.itemRow();
@@ -231,6 +258,7 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
   const int nKinds = c.silScore > 0 ? 3 : 2;
   const int items = wideItems + nKinds * nH;
   unsigned short* cbin = lfCbin(w);
+  unsigned short* cslot = cbin + c.capC;
   for (int x = cta.tid; x < items; x += cta.nthr) {
     bool alive = false;
     double score = 0.0;
@@ -272,9 +300,9 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
         const double pos = (score - tau) * scale;
         bin = pos >= (double)(NB - 1) ? NB - 1 : (int)pos;
         bin = bin < 0 ? 0 : bin;
-        atomAdd(&hist[bin], 1);
       }
       cbin[x] = (unsigned short)bin;
+      cslot[x] = (unsigned short)atomAdd(&hist[bin], 1); // arrival order inside the bin
       cd.score(x) = score;
       cd.parflag(x) = (par << 4) | flags | CF_ALIVE;
       cd.tok(x) = tok;
@@ -284,94 +312,115 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
     }
   }
   cta.sync(); // ---- B2
+  pc.mark(1);
 
-  // (3) cut bin = lowest bin with fewer than K candidates in higher bins; every warp finds it for
-  // itself (lane L owns NB/32 consecutive bins). Candidates at or above it are "relevant".
-  int cut = 0;
-  if (binned) {
-#if FLT_DEVICE_BUILD
-    const int lane = cta.tid & 31;
-    const int per = NB >> 5;
-    int own = 0;
-    for (int k = 0; k < per; ++k) own += hist[lane * per + k];
-    int suf = own; // inclusive suffix over lanes
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int u = __shfl_down_sync(0xffffffffu, suf, o);
-      if (lane + o < 32) suf += u;
-    }
-    int ab = suf - own; // candidates in bins of higher lanes
-    const unsigned qual = __ballot_sync(0xffffffffu, ab < K);
-    const int src = __ffs(qual) - 1; // lowest lane whose top bin qualifies (lane 31 always does)
-    int local = 0;
-    if (lane == src) {
-      for (int k = per - 1; k >= 0; --k) {
-        if (ab < K) local = lane * per + k;
-        ab += hist[lane * per + k];
-      }
-    }
-    cut = __shfl_sync(0xffffffffu, local, src);
-#else
-    int ab = 0;
-    for (int bn = NB - 1; bn >= 0; --bn) {
-      if (ab < K) cut = bn;
-      ab += hist[bn];
-    }
-#endif
-  }
+  // (3) above[bin] = candidates in higher bins, from a suffix scan of the histogram that every
+  // warp does for itself into a private copy (lane L owns NB/32 consecutive bins). Candidates with
+  // above < K (the K best and the rest of the cut bin) are "relevant" and go to list position
+  // above[bin] + arrival order: the list is grouped by bin, best bins first, with no further atomics.
   int* list = w.rep();  // [capC] relevant candidates
   u64* lkey = w.rkey(); // [capC] their ordered score keys
-  for (int x0 = 0; x0 < items; x0 += cta.nthr) { // warp-uniform trip count
-    const int x = x0 + cta.tid;
-    const bool rel = x < items && (cd.parflag(x) & CF_ALIVE) && (int)cbin[x] >= cut;
+  int total = 0;        // live candidates of the frame
+  int nRel = 0;         // relevant ones (list length)
 #if FLT_DEVICE_BUILD
-    const unsigned m = __ballot_sync(0xffffffffu, rel); // one counter update per warp
-    if (m == 0) continue;
+  unsigned short* above = (unsigned short*)(w.base + c.lay.lfAbove) + (cta.tid >> 5) * NB;
+  {
     const int lane = cta.tid & 31;
-    const int leader = __ffs(m) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(&sc[SC_NSEL], __popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (rel) {
-      const int q = base + __popc(m & ((1u << lane) - 1u));
-      list[q] = x;
-      lkey[q] = orderedKey64(cd.score(x));
+    if (NB == 256) {
+      const int4 lo = *(const int4*)(hist + lane * 8), hi = *(const int4*)(hist + lane * 8 + 4);
+      const int h[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      const int own = ((h[0] + h[1]) + (h[2] + h[3])) + ((h[4] + h[5]) + (h[6] + h[7]));
+      int suf = own; // inclusive suffix over lanes
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_down_sync(0xffffffffu, suf, o);
+        if (lane + o < 32) suf += u;
+      }
+      total = __shfl_sync(0xffffffffu, suf, 0);
+      int ab = suf - own; // candidates in bins of higher lanes
+      unsigned short av[8];
+      int rel = 0;
+#pragma unroll
+      for (int k = 7; k >= 0; --k) {
+        av[k] = (unsigned short)(ab > 65535 ? 65535 : ab);
+        rel += ab < K ? h[k] : 0;
+        ab += h[k];
+      }
+      nRel = __reduce_add_sync(0xffffffffu, rel);
+      uint4 pk;
+      pk.x = av[0] | ((unsigned)av[1] << 16);
+      pk.y = av[2] | ((unsigned)av[3] << 16);
+      pk.z = av[4] | ((unsigned)av[5] << 16);
+      pk.w = av[6] | ((unsigned)av[7] << 16);
+      *(uint4*)(above + lane * 8) = pk;
+    } else {
+      const int per = NB >> 5;
+      int own = 0;
+      for (int k = 0; k < per; ++k) own += hist[lane * per + k];
+      int suf = own;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_down_sync(0xffffffffu, suf, o);
+        if (lane + o < 32) suf += u;
+      }
+      total = __shfl_sync(0xffffffffu, suf, 0);
+      int ab = suf - own;
+      int rel = 0;
+      for (int k = per - 1; k >= 0; --k) {
+        const int hk = hist[lane * per + k];
+        above[lane * per + k] = (unsigned short)(ab > 65535 ? 65535 : ab);
+        rel += ab < K ? hk : 0;
+        ab += hk;
+      }
+      nRel = __reduce_add_sync(0xffffffffu, rel);
     }
+    __syncwarp();
+  }
 #else
-    if (rel) {
-      const int q = sc[SC_NSEL]++;
-      list[q] = x;
-      lkey[q] = orderedKey64(cd.score(x));
-    }
+  unsigned short* above = (unsigned short*)(w.base + c.lay.lfAbove);
+  for (int bn = NB - 1; bn >= 0; --bn) {
+    above[bn] = (unsigned short)(total > 65535 ? 65535 : total);
+    if (total < K) nRel += hist[bn];
+    total += hist[bn];
+  }
 #endif
+  const int nSel = total < K ? total : K;
+  for (int x = cta.tid; x < items; x += cta.nthr) {
+    if (!(cd.parflag(x) & CF_ALIVE)) continue;
+    const int ab = above[cbin[x]];
+    if (ab >= K) continue; // K candidates score strictly higher
+    const int q = ab + cslot[x];
+    list[q] = x;
+    lkey[q] = orderedKey64(cd.score(x));
   }
   cta.sync(); // ---- B3
-  const int nL = sc[SC_NSEL];
-  const int nSel = nL < K ? nL : K;
-  if (binned)
-    for (int bn = cta.tid; bn < NB; bn += cta.nthr) hist[bn] = 0;
-  // (4) exact ranks among the relevant candidates by counting: `parts` adjacent lanes share one
-  // candidate and split the list between them
+  pc.mark(2);
+  // (4) exact ranks among the nRel relevant candidates by counting: `parts` adjacent lanes share
+  // one candidate and split the list between them (equal scores: the lower work item first)
   int* ranked = w.surv() + c.capP;
   {
     int lg = 0;
-    while (lg < 5 && (nL << (lg + 1)) <= cta.nthr) ++lg;
+    while (lg < 5 && (nRel << (lg + 1)) <= cta.nthr) ++lg;
     const int parts = 1 << lg;
     const int per = cta.nthr >> lg; // candidates per sweep
     const int part = cta.tid & (parts - 1);
-    for (int a0 = 0; a0 < nL; a0 += per) {
+    for (int a0 = 0; a0 < nRel; a0 += per) {
       const int qa = a0 + (cta.tid >> lg);
       int cnt = 0;
       int xa = -1;
-      if (qa < nL) {
+      if (qa < nRel) {
         xa = list[qa];
         const u64 ka = lkey[qa];
+        bool tie = false;
 #pragma unroll 4
-        for (int qb = part; qb < nL; qb += parts) {
+        for (int qb = part; qb < nRel; qb += parts) {
           const u64 kb = lkey[qb];
           cnt += kb > ka ? 1 : 0;
-          if (kb == ka && qb != qa && lfBetter(cd, list[qb], xa)) ++cnt; // equal scores: rare
+          tie |= kb == ka;
         }
+        if (tie) // some key equals ka (always true for the lane that meets qb == qa): settle by item
+          for (int qb = part; qb < nRel; qb += parts)
+            if (lkey[qb] == ka && list[qb] < xa) ++cnt;
       }
 #if FLT_DEVICE_BUILD
       for (int o = 1; o < parts; o <<= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -380,11 +429,14 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
     }
   }
   cta.sync(); // ---- B4
+  pc.mark(3);
+  for (int bn = cta.tid; bn < NB; bn += cta.nthr) hist[bn] = 0;
+  const int nL = total;
 #if FLT_DEVICE_BUILD
   if (stats && cta.tid == 0) {
     atomicAdd(stats + 0, 1ull);
     atomicAdd(stats + 1, (unsigned long long)items);
-    atomicAdd(stats + 2, (unsigned long long)nL); // candidates ranked exactly
+    atomicAdd(stats + 2, (unsigned long long)nL); // live candidates
     atomicAdd(stats + 3, (unsigned long long)nSel);
   }
 #else
@@ -392,7 +444,6 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
 #endif
 
   // (5) the new beam (Utils.h:161-165 threshold against the best, then the K best in rank order)
-  if (cta.tid == 0) sc[SC_NSEL] = 0;
   for (int i = cta.tid; i < nH; i += cta.nthr) { // leave the fingerprint table empty
     const int s = t.slotOf[i];
     t.a[s] = -1;
@@ -431,6 +482,7 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
     }
   }
   cta.sync(); // ---- B5
+  pc.mark(4);
 }
 
 // decodeEnd (LexiconFreeDecoder.cpp:127-158) with ZeroLM: finish() returns the same state and 0,

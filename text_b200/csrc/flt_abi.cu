@@ -540,7 +540,7 @@ void planFor(flt_decoder& d, int N) {
   if (capC > (1LL << 26)) throw FltError(FLT_ERR_RUNTIME, "candidate capacity exceeded");
   c.capC = (int)capC;
   c.capH = nextPow2((int)std::min<long long>(2 * capC, 1LL << 27));
-  c.capRH = nextPow2(2 * K);
+  c.capRH = nextPow2((c.lfFast ? 8 : 2) * K); // fast step: sparse table, probes mostly end at once
   c.capP = nextPow2(K);
   c.wideTotal = c.wideRanked ? d.wideOffHost[K] : 0;
   // pruning rectangles (beam_core.h frameStep): a rows x (ceil(K/a)+3) columns
@@ -596,7 +596,8 @@ void planFor(flt_decoder& d, int N) {
       decThreads() == 256) {
     TopMCfg ft = t;
     ft.P = std::max(kFusedProducers, nextPow2(want));
-    ft.capS = 512;
+    ft.capS = kProdCap;
+    ft.extra = 2 * kProdBins;
     ft.fast = 1;
     ft.stage = 0;
     ft.bias = nullptr;
@@ -794,8 +795,8 @@ void prepareBatch(flt_decoder& d, int B, int T, int N) {
   d.lastT = T;
   d.launches = 0;
   if (d.timing) {
-    d.dStats.reserve(sizeof(unsigned long long) * 4);
-    rt::devZero(d.dStats.p, sizeof(unsigned long long) * 4, d.stream);
+    d.dStats.reserve(sizeof(unsigned long long) * 16);
+    rt::devZero(d.dStats.p, sizeof(unsigned long long) * 16, d.stream);
   }
 #if FLT_DEVICE_BUILD
   d.evUsed = 0;
@@ -1184,9 +1185,9 @@ int flt_decoder_last_kernel_ms(flt_decoder* dec, float* ms3, int32_t* launches3)
 int flt_decoder_last_stats(flt_decoder* dec, uint64_t* out4) {
   return guarded([&] {
     if (!dec || !out4) throw FltError(FLT_ERR_INVALID, "null argument");
-    for (int k = 0; k < 4; ++k) out4[k] = 0;
+    for (int k = 0; k < 16; ++k) out4[k] = 0;
     if (!dec->dStats.p) return;
-    rt::d2h(out4, dec->dStats.p, sizeof(uint64_t) * 4, dec->stream);
+    rt::d2h(out4, dec->dStats.p, sizeof(uint64_t) * 16, dec->stream);
     rt::sync(dec->stream);
   });
 }

@@ -3,19 +3,18 @@
 // One CTA per utterance: 8 consumer warps run the serial frame loop (beam_lf.h), 4 producer warps
 // run ahead of them over the emission rows:
 //
-//   producer, row r:   wait(rowFree)  -> one thread: cp.async.bulk (TMA, 1-D) row r HBM -> smem stage,
-//                      completion on the rowFull mbarrier -> all producer warps: select the ranked
-//                      token list of row r from the staged row (two passes over shared memory)
-//                      -> wait(listFree[r&1]) -> write list slot r&1 -> arrive(listReady[r&1])
-//   consumer, frame t: wait(listReady[t&1]) -> frame step with list t and the emissions gathered
-//                      for its own tokens -> arrive(listFree[t&1]) -> wait(rowFull, row t+1)
-//                      -> gather e[t+1][own tokens / blank / sil] of the NEW beam from the staged
-//                      row -> arrive(rowFree)
+//   producer, row r:   wait(rowFull: the TMA bulk copy of row r into the shared-memory stage)
+//                      -> pass 1 over the stage (per-thread maxima) -> the stage is free: one thread
+//                      issues cp.async.bulk for row r+1, which streams in behind the rest of the
+//                      select -> bound -> pass 2 (filter) re-reads row r from L2 -> survivors are
+//                      ranked with a small histogram -> wait(listFree[r&1]) -> write list slot r&1
+//                      -> arrive(listReady[r&1])
+//   consumer, frame t: wait(listReady[t&1]) -> frame step with list t (its handful of per-hypothesis
+//                      emission gathers hit L2: the row was just streamed) -> arrive(listFree[t&1])
 //
-// so that every emission row is read from HBM exactly once (4N bytes per frame, the §8d figure),
-// the scattered per-hypothesis emission gathers become shared-memory reads, no token list ever
-// goes through HBM, and the bandwidth-bound select is hidden behind the latency-bound step.
-// While the consumers step frame t the producers load and select row t+1.
+// so that every emission row is read from HBM exactly once (4N bytes per frame, the §8d figure), no
+// token list ever goes through HBM, and the bandwidth-bound select is hidden behind the
+// latency-bound step: the producers run up to two rows ahead of the consumers.
 //
 // Replaces decoder/LexiconFreeDecoder.cpp:39-51 (partial_sort per frame) and :53-125 (decodeStep)
 // together; same results as the two-kernel path (flt_k_topm + flt_k_decode), which remains for
@@ -36,11 +35,11 @@ struct FuseLay {       // byte offsets from the CTA's shared-memory base
   int row;             // staged emission row [N] fp32, 16-byte aligned
   int list[2];         // token list ring: int tok[M], float val[M]
   int thr[2];          // cut value of the token set per ring slot
-  int mbar;            // 6 mbarriers: rowFull, rowFree, listReady[2], listFree[2]
+  int mbar;            // 5 mbarriers: rowFull, listReady[2], listFree[2]
   int total;
 };
 
-enum { MB_ROW_FULL = 0, MB_ROW_FREE, MB_LIST_READY0, MB_LIST_READY1, MB_LIST_FREE0, MB_LIST_FREE1, MB_COUNT };
+enum { MB_ROW_FULL = 0, MB_LIST_READY0, MB_LIST_READY1, MB_LIST_FREE0, MB_LIST_FREE1, MB_COUNT };
 
 /* ------------------------------------------------------------------ mbarrier / bulk copy ------ */
 #if FLT_DEVICE_BUILD
@@ -55,6 +54,23 @@ FLT_DEV void mbarArriveExpectTx(u64* b, uint32_t bytes) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smemU32(b)),
                "r"(bytes)
                : "memory");
+}
+// producer-side wait: the producers run ahead and mostly wait for the consumers; back off so the
+// polling does not take issue slots from the latency-critical consumer warps
+FLT_DEV void mbarWaitRelaxed(u64* b, uint32_t parity) {
+  const uint32_t addr = smemU32(b);
+  for (;;) {
+    uint32_t done = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(128);
+  }
 }
 FLT_DEV void mbarWait(u64* b, uint32_t parity) {
   const uint32_t addr = smemU32(b);
@@ -79,102 +95,219 @@ FLT_DEV void bulkLoad(void* dst, const void* src, uint32_t bytes, u64* b) {
 FLT_DEV void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
 
-/* ------------------------------------------------------------------ producer: select from smem - */
-// Ranked list of one staged row: M entries (token, value) by value descending (ties: lower token),
-// -1 / 0 past the number of valid entries; *outThr = value of the beamSizeToken-th largest when the
-// token set is restricted. No bias (lexicon-free decoder).
-FLT_DEV void topmRowStaged(const Cta& p, const TopMCfg& c, TopMSmem& s, const float* row, int* outTok,
-                           float* outVal, float* outThr) {
+/* ------------------------------------------------------------------ producer: select ---------- */
+constexpr int kProdBins = 128; // histogram bins of the survivor ranking (4 per lane)
+constexpr int kProdCap = 512;  // survivor capacity (TopMCfg::capS of the fused producer)
+
+// Running guess of the select bound, carried from row to row by the producer (uniform over its
+// threads). A row is filtered in ONE pass over the staged copy against `g`; if at least `want`
+// elements pass, the result is exact (every element >= the want-th largest was collected). The
+// guess follows the previous row's exact want-th value minus a margin that adapts to how many
+// elements passed. A miss (too few / too many survivors) costs one exact two-pass select from L2.
+struct ProdGuess {
+  float g;      // bound to try on the next row; +inf = none yet
+  float margin; // fraction of (row maximum - want-th value) the guess sits below the want-th value
+};
+
+#if FLT_DEVICE_BUILD
+// collect every element >= bound of the row at r4 (shared or global) into sv[] (unordered keys);
+// returns this thread's maximum
+FLT_DEV float prodFilter(const Cta& p, const TopMCfg& c, TopMSmem& s, const float4* r4, float bound,
+                         unsigned long long* sv) {
+  const int nvec = c.N >> 2;
+  float top = bitsF32(0xFF800000u);
+#pragma unroll 4
+  for (int v = p.tid; v < nvec; v += p.nthr) {
+    const float4 x = r4[v];
+    const float mx = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+    top = fmaxf(top, mx);
+    if (mx >= bound) {
+      if (x.x >= bound) {
+        const int pos = atomAdd(&s.cnt[0], 1);
+        if (pos < c.capS) sv[pos] = topmKey(x.x, v * 4 + 0);
+      }
+      if (x.y >= bound) {
+        const int pos = atomAdd(&s.cnt[0], 1);
+        if (pos < c.capS) sv[pos] = topmKey(x.y, v * 4 + 1);
+      }
+      if (x.z >= bound) {
+        const int pos = atomAdd(&s.cnt[0], 1);
+        if (pos < c.capS) sv[pos] = topmKey(x.z, v * 4 + 2);
+      }
+      if (x.w >= bound) {
+        const int pos = atomAdd(&s.cnt[0], 1);
+        if (pos < c.capS) sv[pos] = topmKey(x.w, v * 4 + 3);
+      }
+    }
+  }
+  return top;
+}
+#endif
+
+// Ranked list of one row: M entries (token, value) by value descending (ties: lower token), -1 / 0
+// past the number of valid entries; *outThr = value of the beamSizeToken-th largest when the token
+// set is restricted. No bias (lexicon-free decoder).
+//   `row` is the shared-memory stage (TMA-filled), `grow` the same row in global memory (L2).
+//   stageFree() is called as soon as every thread is done with the stage, so that the next row's
+//   bulk copy overlaps the rest of the select; beforeWrite() is called before the outputs are
+//   written (the caller waits there for the ring slot to be free).
+template <class StageFree, class BeforeWrite>
+FLT_DEV void topmRowStaged(const Cta& p, const TopMCfg& c, TopMSmem& s, ProdGuess& pg, const float* row,
+                           const float* grow, int* outTok, float* outVal, float* outThr,
+                           StageFree stageFree, BeforeWrite beforeWrite) {
   const int N = c.N;
   const bool restricted = c.bst < N;
   const int want = restricted ? c.bst : c.M;
   bool done = false;
 #if FLT_DEVICE_BUILD
   if (c.fast) {
-    // two passes over the staged row: per-thread maxima -> bound, then filter against the bound
     const int lane = p.tid & 31, warp = p.tid >> 5, nw = p.nthr >> 5;
-    const int nvec = N >> 2;
-    const float4* r4 = (const float4*)row;
+    // scratch: sortBuf [0,capS) survivors grouped by bin | [capS,2capS) survivors as collected;
+    // red: per-warp bounds / maxima; rankCnt: histogram [kProdBins], above [kProdBins] per warp is
+    // kept in registers, survivor (bin, slot) [2][capS] u16
+    float* bnd = (float*)s.red;          // [nw] per-warp bound, [32 + nw] per-warp maximum
+    int* hist = s.rankCnt;               // [kProdBins] zero on entry, re-zeroed below
+    int* above = s.rankCnt + kProdBins;  // [kProdBins]
+    unsigned short* sbin = (unsigned short*)(s.rankCnt + 2 * kProdBins); // [2][capS]
+    unsigned long long* sv = s.sortBuf + c.capS;
+    const int minExpected = want < N ? want : N;
     const float ninf = bitsF32(0xFF800000u);
-    float m = ninf;
-    for (int v = p.tid; v < nvec; v += p.nthr) {
-      const float4 x = r4[v];
-      m = fmaxf(m, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
-    }
-    const float sorted = warpSortDesc(m, lane);
-    const int r = (want + nw - 1) / nw; // every warp certifies r elements >= its r-th largest maximum
-    const float tw = __shfl_sync(0xffffffffu, sorted, r - 1);
-    float* tauS = (float*)s.red;
-    if (lane == 0) tauS[warp] = tw;
-    if (p.tid == 0) s.cnt[0] = 0;
-    p.sync();
-    float tau = tauS[0];
-    for (int i = 1; i < nw; ++i) tau = fminf(tau, tauS[i]);
-    tau = fmaxf(tau, bitsF32(0xFF7FFFFFu)); // -inf never passes
-    int cntMine = 0;
-    for (int v = p.tid; v < nvec; v += p.nthr) {
-      const float4 x = r4[v];
-      cntMine += (x.x >= tau ? 1 : 0) + (x.y >= tau ? 1 : 0) + (x.z >= tau ? 1 : 0) + (x.w >= tau ? 1 : 0);
-    }
-    int incl = cntMine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int u = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += u;
-    }
-    int base = 0;
-    if (lane == 31) base = atomAdd(&s.cnt[0], incl);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    int pos = base + incl - cntMine;
-    unsigned long long* src = s.sortBuf + c.capS;
-    if (cntMine) {
+    // ---- one pass over the stage against the running guess
+    float bound = pg.g;
+    float top = prodFilter(p, c, s, (const float4*)row, bound, sv);
+    p.sync(); // every thread is done reading the stage
+    stageFree();
+    int ns = s.cnt[0];
+    if (!(ns >= minExpected && ns <= c.capS && ns <= 2 * p.nthr)) {
+      // ---- miss: exact bound from the per-thread maxima (pass 1), then filter again (pass 2), L2
+      p.sync(); // everyone has read cnt[0]
+      const float4* g4 = (const float4*)grow;
+      const int nvec = N >> 2;
+      float m = ninf;
+#pragma unroll 4
       for (int v = p.tid; v < nvec; v += p.nthr) {
-        const float4 x = r4[v];
-        const float e4[4] = {x.x, x.y, x.z, x.w};
+        const float4 x = __ldg(g4 + v);
+        m = fmaxf(m, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
+      }
+      const float sorted = warpSortDesc(m, lane);
+      const int r = (want + nw - 1) / nw; // every warp certifies r elements >= its r-th largest maximum
+      const float tw = __shfl_sync(0xffffffffu, sorted, r - 1);
+      if (lane == 0) bnd[warp] = tw;
+      if (p.tid == 0) s.cnt[0] = 0;
+      p.sync();
+      bound = bnd[0];
+      for (int i = 1; i < nw; ++i) bound = fminf(bound, bnd[i]);
+      bound = fmaxf(bound, bitsF32(0xFF7FFFFFu)); // -inf never passes
+      p.sync(); // bnd[] is reused below
+      top = prodFilter(p, c, s, g4, bound, sv);
+      p.sync();
+      ns = s.cnt[0];
+    }
+    if (ns >= minExpected && ns <= c.capS && ns <= 2 * p.nthr) {
+      // ---- rank the survivors: linear histogram over [bound, row maximum], exact order inside bins
+      {
+        const unsigned tk = __reduce_max_sync(0xffffffffu, orderedKey32(top));
+        if (lane == 0) bnd[32 + warp] = orderedKey32Inv(tk);
+      }
+      p.sync();
+      top = bnd[32];
+      for (int i = 1; i < nw; ++i) top = fmaxf(top, bnd[32 + i]);
+      const float range = top - bound;
+      const float scale = (range > 0.0f && range < 3.0e38f) ? (float)kProdBins / range : 0.0f;
+      unsigned long long mine[2];
+      int myBin[2], mySlot[2];
 #pragma unroll
-        for (int z = 0; z < 4; ++z) {
-          if (e4[z] >= tau) {
-            if (pos < c.capS) src[pos] = topmKey(e4[z], v * 4 + z);
-            ++pos;
-          }
+      for (int z = 0; z < 2; ++z) {
+        const int a = p.tid + z * p.nthr;
+        myBin[z] = -1;
+        if (a < ns) {
+          mine[z] = sv[a];
+          int bin = (int)((topmKeyVal(mine[z]) - bound) * scale);
+          bin = bin > kProdBins - 1 ? kProdBins - 1 : (bin < 0 ? 0 : bin);
+          myBin[z] = bin;
+          mySlot[z] = atomAdd(&hist[bin], 1);
         }
       }
+      p.sync();
+      { // above[bin] = survivors in higher bins; every warp scans, warp 0 publishes
+        const int4 h4 = *(const int4*)(hist + lane * 4);
+        const int own = (h4.x + h4.y) + (h4.z + h4.w);
+        int suf = own;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u = __shfl_down_sync(0xffffffffu, suf, o);
+          if (lane + o < 32) suf += u;
+        }
+        int4 a4;
+        int ab = suf - own;
+        a4.w = ab;
+        ab += h4.w;
+        a4.z = ab;
+        ab += h4.z;
+        a4.y = ab;
+        ab += h4.y;
+        a4.x = ab;
+        if (warp == 0) *(int4*)(above + lane * 4) = a4;
+      }
+      p.sync();
+      // survivors grouped by bin (best bins first); only those that can rank < want are placed
+#pragma unroll
+      for (int z = 0; z < 2; ++z)
+        if (myBin[z] >= 0) {
+          const int ab = above[myBin[z]];
+          if (ab < want) s.sortBuf[ab + mySlot[z]] = mine[z];
+          else myBin[z] = -1;
+        }
+      p.sync();
+      beforeWrite();
+#pragma unroll
+      for (int z = 0; z < 2; ++z)
+        if (myBin[z] >= 0) {
+          const int ab = above[myBin[z]];
+          const int cnt = hist[myBin[z]];
+          int rr = ab;
+          for (int k = 0; k < cnt; ++k) rr += s.sortBuf[ab + k] > mine[z] ? 1 : 0;
+          if (rr < want) {
+            outTok[rr] = topmKeyTok(mine[z]);
+            outVal[rr] = topmKeyVal(mine[z]);
+            if (rr == want - 1) {
+              s.cnt[1] = (int)f32Bits(topmKeyVal(mine[z])); // the exact want-th value
+              if (restricted) *outThr = topmKeyVal(mine[z]);
+            }
+          }
+        }
+      p.sync();
+      for (int bn = p.tid; bn < kProdBins; bn += p.nthr) hist[bn] = 0;
+      if (p.tid == 0) s.cnt[0] = 0;
+      // next row's guess: below this row's want-th value by a margin that tracks the survivor count
+      const float wth = bitsF32((uint32_t)s.cnt[1]);
+      if (ns > 3 * want) pg.margin *= 0.8f;
+      else if (ns < want + want / 2) pg.margin *= 1.25f;
+      pg.margin = fminf(fmaxf(pg.margin, 0.02f), 4.0f);
+      pg.g = wth - pg.margin * (top - wth);
+      p.sync();
+      return;
     }
+    // adversarial row (ties en masse, -inf padding): generic path below
+    for (int bn = p.tid; bn < kProdBins; bn += p.nthr) hist[bn] = 0;
+    if (p.tid == 0) s.cnt[0] = 0;
+    pg.g = bitsF32(0x7F800000u);
     p.sync();
-    const int ns = s.cnt[0];
-    const int minExpected = want < N ? want : N;
-    if (ns <= c.capS && ns >= minExpected) {
-      int* rankCnt = s.rankCnt; // zero on entry, re-zeroed below
-      const int parts = ns >= p.nthr ? 1 : p.nthr / ns;
-      const int slice = (ns + parts - 1) / parts;
-      for (int t = p.tid; t < ns * parts; t += p.nthr) {
-        const int a = t % ns, part = t / ns;
-        const int lo = part * slice, hi = lo + slice < ns ? lo + slice : ns;
-        const unsigned long long ka = src[a];
-        int cnt = 0;
-        for (int b = lo; b < hi; ++b) cnt += src[b] > ka ? 1 : 0;
-        if (cnt) atomAdd(&rankCnt[a], cnt);
-      }
-      p.sync();
-      for (int a = p.tid; a < ns; a += p.nthr) {
-        s.sortBuf[rankCnt[a]] = src[a];
-        rankCnt[a] = 0;
-      }
-      for (int a = ns + p.tid; a < want; a += p.nthr) s.sortBuf[a] = 0ull;
-      p.sync();
-      done = true;
-    } else {
-      p.sync(); // everyone has read cnt[0] before the generic path reuses it
-    }
   }
+#else
+  stageFree();
+  (void)row;
+  (void)pg;
 #endif
-  if (!done) topmSelect(p, c, s, N, want, [&](int i) { return topmKey(row[i], i); });
+  if (!done) topmSelect(p, c, s, N, want, [&](int i) { return topmKey(grow[i], i); });
+  beforeWrite();
   if (restricted && p.tid == 0) *outThr = topmKeyVal(s.sortBuf[c.bst - 1]);
   for (int j = p.tid; j < c.M; j += p.nthr) {
     const unsigned long long k = j < want ? s.sortBuf[j] : 0ull;
     outTok[j] = k ? topmKeyTok(k) : -1;
     outVal[j] = k ? topmKeyVal(k) : 0.0f;
   }
+  if (p.tid == 0) s.cnt[0] = 0; // the single-pass filter of the next row counts from zero
   p.sync();
 }
 
@@ -199,7 +332,7 @@ FLT_DEV FrameIn fusedFrameIn(const DecCfg& c, const BatchArgs& a, const FusedVie
   f.thrVal = c.setAll ? 0.0f : *v.thr(slot);
   f.first = t == 0;
   f.listIsSet = 1;
-  f.specReady = 1;
+  f.specReady = 0; // the per-hypothesis emissions are gathered from L2 at the start of the step
   const long long h = ((long long)b * (a.T + 2) + (t + 1)) * c.K;
   f.hParent = a.hParent + h;
   f.hTok = a.hTok + h;
@@ -215,8 +348,8 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
   const Ws w{smem + fl.ws, &c};
   TopMSmem ps;
   carveTopM(smem + fl.prod, tc, ps);
-  const uint32_t rowBytes = (uint32_t)c.N * 4u;
 #if FLT_DEVICE_BUILD
+  const uint32_t rowBytes = (uint32_t)c.N * 4u;
   if (whole.tid == 0) {
     for (int k = 0; k < MB_COUNT; ++k) mbarInit(v.mbar(k), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -226,25 +359,47 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
   if (!isConsumer) {
     /* ---------------- producer warps ---------------- */
     const Cta p{whole.tid - kFusedConsumers, kFusedProducers, whole.bid, whole.nblk, 2};
-    for (int i = p.tid; i < tc.capS; i += p.nthr) ps.rankCnt[i] = 0;
+    for (int i = p.tid; i < 2 * kProdBins + tc.capS; i += p.nthr) ps.rankCnt[i] = 0;
+    if (p.tid < 4) ps.cnt[p.tid] = 0;
     p.sync();
-    uint32_t r = 0; // rows staged so far by this CTA
-    for (int b = whole.bid; b < a.B; b += whole.nblk) {
-      const int len = a.lengths ? a.lengths[b] : a.T;
-      const float* g = a.emis + (long long)b * a.T * c.N;
-      for (int t = 0; t < len; ++t, ++r) {
-        mbarWait(v.mbar(MB_ROW_FREE), (r + 1) & 1); // the consumers gathered from the previous row
-        if (p.tid == 0) {
-          fenceProxyAsync();
-          mbarArriveExpectTx(v.mbar(MB_ROW_FULL), rowBytes);
-          bulkLoad(v.row(), g + (long long)t * c.N, rowBytes, v.mbar(MB_ROW_FULL));
-        }
-        mbarWait(v.mbar(MB_ROW_FULL), r & 1);
-        const int slot = (int)(r & 1);
-        mbarWait(v.mbar(MB_LIST_FREE0 + slot), ((r >> 1) + 1) & 1);
-        topmRowStaged(p, tc, ps, v.row(), v.listTok(slot), v.listVal(slot, c.M), v.thr(slot));
-        if (p.tid == 0) mbarArrive(v.mbar(MB_LIST_READY0 + slot));
+    ProdGuess pg{bitsF32(0x7F800000u), 0.25f};
+    // rows of this CTA in order: (b, t) for b = bid, bid + nblk, ...; `r` counts them
+    uint32_t r = 0;
+    int nb = whole.bid, nt = 0; // the next row to stage
+    auto advance = [&](int& b, int& t) { // first row with t < len at or after (b, t); b >= B when none
+      while (b < a.B) {
+        const int len = a.lengths ? a.lengths[b] : a.T;
+        if (t < len) return;
+        b += whole.nblk;
+        t = 0;
       }
+    };
+    advance(nb, nt);
+    if (nb < a.B && p.tid == 0) { // prime the stage
+      mbarArriveExpectTx(v.mbar(MB_ROW_FULL), rowBytes);
+      bulkLoad(v.row(), a.emis + ((long long)nb * a.T + nt) * c.N, rowBytes, v.mbar(MB_ROW_FULL));
+    }
+    while (nb < a.B) {
+      const int b = nb, t = nt;
+      nt = t + 1;
+      advance(nb, nt); // (nb, nt) = the row after (b, t)
+      const float* grow = a.emis + ((long long)b * a.T + t) * c.N;
+      mbarWait(v.mbar(MB_ROW_FULL), r & 1);
+      const int slot = (int)(r & 1);
+      const bool hasNext = nb < a.B;
+      const float* gnext = hasNext ? a.emis + ((long long)nb * a.T + nt) * c.N : nullptr;
+      topmRowStaged(
+          p, tc, ps, pg, v.row(), grow, v.listTok(slot), v.listVal(slot, c.M), v.thr(slot),
+          [&]() {
+            if (hasNext && p.tid == 0) { // the stage is free: stream the next row in behind the select
+              fenceProxyAsync();
+              mbarArriveExpectTx(v.mbar(MB_ROW_FULL), rowBytes);
+              bulkLoad(v.row(), gnext, rowBytes, v.mbar(MB_ROW_FULL));
+            }
+          },
+          [&]() { mbarWaitRelaxed(v.mbar(MB_LIST_FREE0 + slot), ((r >> 1) + 1) & 1); });
+      if (p.tid == 0) mbarArrive(v.mbar(MB_LIST_READY0 + slot));
+      ++r;
     }
     return;
   }
@@ -252,13 +407,7 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
   const Cta cta{whole.tid, kFusedConsumers, whole.bid, whole.nblk, 1};
 #else
   const Cta cta = whole;
-  for (int i = 0; i < tc.capS; ++i) ps.rankCnt[i] = 0;
-  auto produce = [&](int b, int t, int slot) { // host model: the producer's work for row (b, t), inline
-    const float* gp = a.emis + ((long long)b * a.T + t) * c.N;
-    float* row = v.row();
-    for (int i = 0; i < c.N; ++i) row[i] = gp[i];
-    topmRowStaged(cta, tc, ps, row, v.listTok(slot), v.listVal(slot, c.M), v.thr(slot));
-  };
+  for (int i = 0; i < 2 * kProdBins + tc.capS; ++i) ps.rankCnt[i] = 0;
 #endif
   ctaInitWorkspace(cta, c, w, smem + fl.ws);
   uint32_t g = 0; // frames consumed so far by this CTA (same sequence as the producer's r)
@@ -269,40 +418,25 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
     if (cta.tid == 0) seedUtterance(c, w, a, b);
     cta.sync();
     for (int t = 0; t < len; ++t, ++g) {
-      if (t == 0) { // emissions of the seed hypothesis from row 0
+      const int slot = (int)(g & 1); // ring slot = running row count & 1, on both sides
+      LfPhaseClock oc; // time spent waiting for the producers
+      oc.start(cta, a.stats);
 #if FLT_DEVICE_BUILD
-        mbarWait(v.mbar(MB_ROW_FULL), g & 1);
+      mbarWait(v.mbar(MB_LIST_READY0 + slot), (g >> 1) & 1);
 #else
-        produce(b, 0, (int)(g & 1));
-#endif
-        lfGatherSpec(cta, c, w, w.beam(curIdx), w.sc()[SC_NH], v.row());
-        cta.sync();
-#if FLT_DEVICE_BUILD
-        if (cta.tid == 0) mbarArrive(v.mbar(MB_ROW_FREE));
-#endif
+      { // host model: the producer's work for row (b, t), inline
+        const float* grow = a.emis + ((long long)b * a.T + t) * c.N;
+        ProdGuess pg{0.0f, 0.0f};
+        topmRowStaged(cta, tc, ps, pg, grow, grow, v.listTok(slot), v.listVal(slot, c.M), v.thr(slot), [] {}, [] {});
       }
-#if FLT_DEVICE_BUILD
-      mbarWait(v.mbar(MB_LIST_READY0 + (g & 1)), (g >> 1) & 1);
 #endif
-      // ring slot = running row count & 1, on both sides
-      const FrameIn f = fusedFrameIn(c, a, v, b, t, (int)(g & 1));
+      oc.mark(5);
+      const FrameIn f = fusedFrameIn(c, a, v, b, t, slot);
       lfFrameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.stats); // ends with a barrier
       curIdx ^= 1;
 #if FLT_DEVICE_BUILD
-      if (cta.tid == 0) mbarArrive(v.mbar(MB_LIST_FREE0 + (g & 1)));
+      if (cta.tid == 0) mbarArrive(v.mbar(MB_LIST_FREE0 + slot));
 #endif
-      if (t + 1 < len) { // emissions of the new beam from row t+1
-#if FLT_DEVICE_BUILD
-        mbarWait(v.mbar(MB_ROW_FULL), (g + 1) & 1);
-#else
-        produce(b, t + 1, (int)((g + 1) & 1));
-#endif
-        lfGatherSpec(cta, c, w, w.beam(curIdx), w.sc()[SC_NH], v.row());
-        cta.sync();
-#if FLT_DEVICE_BUILD
-        if (cta.tid == 0) mbarArrive(v.mbar(MB_ROW_FREE));
-#endif
-      }
     }
     int nFin = 0;
     if (w.sc()[SC_NH] != 0) {

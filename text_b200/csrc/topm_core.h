@@ -31,6 +31,7 @@ struct TopMCfg {
   int capS;       // survivor capacity (pow2)
   int stage;      // 1 = stage the row in shared memory
   int fast;       // 1 = register-resident fast path applies (see fastSelect)
+  int extra;      // extra ints behind rankCnt (scratch of the fused producer, fused_core.h)
 };
 
 struct TopMArgs {
@@ -88,7 +89,7 @@ FLT_HD size_t carveTopM(char* base, const TopMCfg& c, TopMSmem& s) {
   s.sortBuf = (unsigned long long*)take(sizeof(unsigned long long) * nbuf);
   s.red = (unsigned long long*)take(sizeof(unsigned long long) * 64);
   s.cnt = (int*)take(sizeof(int) * 4);
-  s.rankCnt = (int*)take(sizeof(int) * c.capS);
+  s.rankCnt = (int*)take(sizeof(int) * (c.capS + c.extra));
   s.row = (float*)take(c.stage ? sizeof(float) * c.N : 0);
   return off;
 }
