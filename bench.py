@@ -330,8 +330,21 @@ def run_ours(a):
     roof = None
     if dom:
         ach = kernels[dom]["achieved_gbs"]
+        # DRAM bytes per launch of this kernel from the committed ncu --set full capture of the
+        # same workload (profiles/traffic.json), else null
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tj = json.load(f)
+            ent = tj.get({"fused_select_step": "flt_k_fused", "token_select": "flt_k_topm",
+                          "beam_step": "flt_k_decode"}.get(dom, dom))
+            if ent and ent["workload"] == workload_name(a, beam, bst):
+                traffic = ent["dram_bytes_per_launch"] / max(kernels[dom]["launches"], 1) * 1.0
+        except Exception:
+            traffic = None
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"] / max(kernels[dom]["launches"], 1),
                 "whole_step": {"achieved": (B * bytes_per_utt) / (ms_step * 1e-3) / 1e9,
                                "frac": (B * bytes_per_utt) / (ms_step * 1e-3) / 1e9 / peak,
                                "bytes_per_utterance": bytes_per_utt},

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libflt_decoder.so")
+LIB_PATH = os.environ.get("FLT_LIB") or os.path.join(_HERE, "lib", "libflt_decoder.so")
 
 OK, ERR_INVALID, ERR_OUT_OF_RANGE, ERR_RUNTIME, ERR_CUDA, ERR_UNSUPPORTED = range(6)
 CRITERION_ASG, CRITERION_CTC = 0, 1
@@ -251,6 +251,7 @@ class Api:
         if any(v[4:11]):
             names = ("insert", "emit", "scan", "rank", "new_beam", "wait_list", "handover_gather")
             out["phase_cycles_per_frame"] = {n: round(v[4 + i] / frames, 1) for i, n in enumerate(names)}
+            out["select_guess_misses"] = int(v[11])
         return out
 
     def workspace_bytes(self, dec):

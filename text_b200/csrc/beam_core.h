@@ -430,7 +430,8 @@ struct FrameIn {
   float thrVal;        // cut value of the token set (unused when setAll)
   int first;           // global frame 0 (ASG transitions are skipped, LexiconDecoder.cpp:70-73)
   int listIsSet;       // the list holds the whole token set (lexicon-free, beamSizeToken < N)
-  int specReady;       // spec[] already holds this frame's gathered emissions (fused kernel)
+  int specReady;       // spec[] already holds this frame's gathered emissions
+  const float* eNext;  // next frame's emission row or null (beam_lf.h prefetches its gathers)
   int* hParent;        // history row to write (frame t+1), [K]
   int* hTok;
   int* hWord;
@@ -1227,8 +1228,12 @@ FLT_DEV void finishStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam
 
 /* ------------------------------------------------------------------ whole-utterance driver ---- */
 // lexicon-free fast step, beam_lf.h
+struct LfCarry { // emissions of the NEXT frame, loaded while the current one retires (registers)
+  float eOwn, eBlank, eSil;
+  int valid;
+};
 FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur,
-                         const Beam& nxt, const FrameIn& f, unsigned long long* stats);
+                         const Beam& nxt, const FrameIn& f, unsigned long long* stats, LfCarry& carry);
 FLT_DEV void lfFinish(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, const Beam& nxt,
                       const FrameIn& f);
 
@@ -1312,6 +1317,7 @@ FLT_DEV FrameIn finishFrameIn(const DecCfg& c, const BatchArgs& a, int b, int le
   f.first = 0;
   f.listIsSet = 0;
   f.specReady = 0;
+  f.eNext = nullptr;
   const long long h = ((long long)b * (a.T + 2) + (len + 1)) * c.K;
   f.hParent = a.hParent + h;
   f.hTok = a.hTok + h;
@@ -1328,6 +1334,7 @@ FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char
     int curIdx = 0;
     cta.sync(); // previous utterance fully retired
     if (cta.tid == 0) seedUtterance(c, w, a, b);
+    LfCarry carry{0.0f, 0.0f, 0.0f, 0};
     // token list of frame 0 into the workspace
     const long long row0 = (long long)b * a.T;
     if (c.listInSmem && len > 0) {
@@ -1367,11 +1374,12 @@ FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char
       f.first = t == 0;
       f.listIsSet = !c.lexicon;
       f.specReady = 0;
+      f.eNext = t + 1 < len ? f.e + c.N : nullptr;
       const long long h = ((long long)b * (a.T + 2) + (t + 1)) * K;
       f.hParent = a.hParent + h;
       f.hTok = a.hTok + h;
       f.hWord = a.hWord ? a.hWord + h : nullptr;
-      if (c.lfFast) lfFrameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.stats);
+      if (c.lfFast) lfFrameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.stats, carry);
       else frameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.status + b, a.stats);
       if (pf) {
 #if FLT_DEVICE_BUILD

@@ -183,7 +183,7 @@ struct LfPhaseClock {
 // Work items of a frame: [0, wideItems) = cells (hypothesis, ranked column); then nH repeat items,
 // nH blank items and (silScore > 0 only) nH sil cells. Item x owns candidate slot x.
 FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur,
-                         const Beam& nxt, const FrameIn& f, unsigned long long* stats) {
+                         const Beam& nxt, const FrameIn& f, unsigned long long* stats, LfCarry& carry) {
   int* sc = w.sc();
   const int nH = sc[SC_NH];
   if (nH == 0) return; // the beam died (Utils.h:155-158)
@@ -198,7 +198,19 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
 
   // scattered emission reads, published for the threads that own the special items (the fused
   // kernel has already gathered them from the staged row: f.specReady)
-  if (!f.specReady) lfGatherSpec(cta, c, w, cur, nH, f.e);
+  if (carry.valid) { // loaded while the previous frame retired
+    if (cta.tid < nH) spec[cta.tid] = carry.eOwn;
+    for (int i = cta.tid + cta.nthr; i < nH; i += cta.nthr) { // beams wider than the CTA
+      const int n = cur.tok(i);
+      spec[i] = (n >= 0 && n < c.N) ? f.e[n] : 0.0f;
+    }
+    if (cta.tid == cta.nthr - 1) {
+      spec[K] = carry.eBlank;
+      spec[K + 1] = carry.eSil;
+    }
+  } else if (!f.specReady) {
+    lfGatherSpec(cta, c, w, cur, nH, f.e);
+  }
   // (1) fingerprint table of the beam
   for (int i = cta.tid; i < nH; i += cta.nthr) {
     const u64 fa = cur.fpA(i), fb = cur.fpB(i);
@@ -245,9 +257,11 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
   const float eTop = (f.listLen > 0 && f.topTok[0] >= 0) ? f.topVal[0] : 0.0f;
   double upper = cur.score(0) + (double)eTop;
   if (c.silScore > 0) upper += c.silScore;
-  const double range = upper - tau;
-  const bool binned = range > 0.0 && range < 1e300; // finite, non-degenerate
-  const double scale = binned ? (double)NB / range : 0.0;
+  // (double -> float conversion, the float subtraction of a constant and the multiplication by a
+  // positive constant are all monotone, so bins never invert the score order)
+  const float rangeF = (float)(upper - tau);
+  const bool binned = rangeF > 0.0f && rangeF < 3.0e38f; // finite, non-degenerate
+  const float scaleF = binned ? (float)NB / rangeF : 0.0f;
   cta.sync(); // ---- B1
   pc.mark(0);
 
@@ -297,8 +311,8 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
     if (alive) {
       int bin = 0;
       if (binned) {
-        const double pos = (score - tau) * scale;
-        bin = pos >= (double)(NB - 1) ? NB - 1 : (int)pos;
+        const float pos = (float)(score - tau) * scaleF;
+        bin = pos >= (float)(NB - 1) ? NB - 1 : (int)pos;
         bin = bin < 0 ? 0 : bin;
       }
       cbin[x] = (unsigned short)bin;
@@ -416,9 +430,9 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
         for (int qb = part; qb < nRel; qb += parts) {
           const u64 kb = lkey[qb];
           cnt += kb > ka ? 1 : 0;
-          tie |= kb == ka;
+          tie |= (kb == ka) & (qb != qa);
         }
-        if (tie) // some key equals ka (always true for the lane that meets qb == qa): settle by item
+        if (tie) // another candidate with exactly this score: settle by work item (rare)
           for (int qb = part; qb < nRel; qb += parts)
             if (lkey[qb] == ka && list[qb] < xa) ++cnt;
       }
@@ -479,7 +493,15 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
       }
       f.hParent[q] = p;
       f.hTok[q] = n;
+      // the emission this hypothesis needs in the next frame: issue the (L2 / HBM) load now, it
+      // lands while the barrier and the next frame's first phase run
+      if (q == cta.tid && f.eNext && n >= 0 && n < c.N) carry.eOwn = f.eNext[n];
     }
+  }
+  carry.valid = f.eNext != nullptr;
+  if (f.eNext && cta.tid == cta.nthr - 1) {
+    carry.eBlank = c.ctc ? f.eNext[c.blank] : 0.0f;
+    carry.eSil = f.eNext[c.sil];
   }
   cta.sync(); // ---- B5
   pc.mark(4);

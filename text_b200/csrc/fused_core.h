@@ -26,8 +26,11 @@
 
 namespace flt {
 
-constexpr int kFusedConsumers = 256; // threads (warps 0..7)
-constexpr int kFusedProducers = 128; // threads (warps 8..11)
+#ifndef FLT_FUSED_CONSUMERS
+#define FLT_FUSED_CONSUMERS 256
+#endif
+constexpr int kFusedConsumers = FLT_FUSED_CONSUMERS; // threads (the first warps of the CTA)
+constexpr int kFusedProducers = 128; // threads (the last 4 warps)
 
 struct FuseLay {       // byte offsets from the CTA's shared-memory base
   int ws;              // consumer workspace (DecCfg::lay)
@@ -121,21 +124,23 @@ FLT_DEV float prodFilter(const Cta& p, const TopMCfg& c, TopMSmem& s, const floa
     const float4 x = r4[v];
     const float mx = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
     top = fmaxf(top, mx);
-    if (mx >= bound) {
-      if (x.x >= bound) {
-        const int pos = atomAdd(&s.cnt[0], 1);
+    if (mx >= bound) { // rare: ~1.5 x want elements of the row
+      const unsigned m4 = (x.x >= bound ? 1u : 0u) | (x.y >= bound ? 2u : 0u) | (x.z >= bound ? 4u : 0u) |
+                          (x.w >= bound ? 8u : 0u);
+      int pos = atomAdd(&s.cnt[0], __popc(m4));
+      if (m4 & 1u) {
         if (pos < c.capS) sv[pos] = topmKey(x.x, v * 4 + 0);
+        ++pos;
       }
-      if (x.y >= bound) {
-        const int pos = atomAdd(&s.cnt[0], 1);
+      if (m4 & 2u) {
         if (pos < c.capS) sv[pos] = topmKey(x.y, v * 4 + 1);
+        ++pos;
       }
-      if (x.z >= bound) {
-        const int pos = atomAdd(&s.cnt[0], 1);
+      if (m4 & 4u) {
         if (pos < c.capS) sv[pos] = topmKey(x.z, v * 4 + 2);
+        ++pos;
       }
-      if (x.w >= bound) {
-        const int pos = atomAdd(&s.cnt[0], 1);
+      if (m4 & 8u) {
         if (pos < c.capS) sv[pos] = topmKey(x.w, v * 4 + 3);
       }
     }
@@ -152,7 +157,8 @@ FLT_DEV float prodFilter(const Cta& p, const TopMCfg& c, TopMSmem& s, const floa
 //   bulk copy overlaps the rest of the select; beforeWrite() is called before the outputs are
 //   written (the caller waits there for the ring slot to be free).
 template <class StageFree, class BeforeWrite>
-FLT_DEV void topmRowStaged(const Cta& p, const TopMCfg& c, TopMSmem& s, ProdGuess& pg, const float* row,
+FLT_DEV void topmRowStaged(const Cta& p, const TopMCfg& c, TopMSmem& s, ProdGuess& pg,
+                           unsigned long long* stats, const float* row,
                            const float* grow, int* outTok, float* outVal, float* outThr,
                            StageFree stageFree, BeforeWrite beforeWrite) {
   const int N = c.N;
@@ -180,6 +186,7 @@ FLT_DEV void topmRowStaged(const Cta& p, const TopMCfg& c, TopMSmem& s, ProdGues
     int ns = s.cnt[0];
     if (!(ns >= minExpected && ns <= c.capS && ns <= 2 * p.nthr)) {
       // ---- miss: exact bound from the per-thread maxima (pass 1), then filter again (pass 2), L2
+      if (stats && p.tid == 0) atomicAdd(stats + 11, 1ull);
       p.sync(); // everyone has read cnt[0]
       const float4* g4 = (const float4*)grow;
       const int nvec = N >> 2;
@@ -281,8 +288,8 @@ FLT_DEV void topmRowStaged(const Cta& p, const TopMCfg& c, TopMSmem& s, ProdGues
       if (p.tid == 0) s.cnt[0] = 0;
       // next row's guess: below this row's want-th value by a margin that tracks the survivor count
       const float wth = bitsF32((uint32_t)s.cnt[1]);
-      if (ns > 3 * want) pg.margin *= 0.8f;
-      else if (ns < want + want / 2) pg.margin *= 1.25f;
+      if (ns > want + (3 * want) / 4) pg.margin *= 0.85f;
+      else if (ns < want + want / 4) pg.margin *= 1.25f;
       pg.margin = fminf(fmaxf(pg.margin, 0.02f), 4.0f);
       pg.g = wth - pg.margin * (top - wth);
       p.sync();
@@ -298,6 +305,7 @@ FLT_DEV void topmRowStaged(const Cta& p, const TopMCfg& c, TopMSmem& s, ProdGues
   stageFree();
   (void)row;
   (void)pg;
+  (void)stats;
 #endif
   if (!done) topmSelect(p, c, s, N, want, [&](int i) { return topmKey(grow[i], i); });
   beforeWrite();
@@ -332,7 +340,8 @@ FLT_DEV FrameIn fusedFrameIn(const DecCfg& c, const BatchArgs& a, const FusedVie
   f.thrVal = c.setAll ? 0.0f : *v.thr(slot);
   f.first = t == 0;
   f.listIsSet = 1;
-  f.specReady = 0; // the per-hypothesis emissions are gathered from L2 at the start of the step
+  f.specReady = 0; // the per-hypothesis emissions come from L2 (the row was just streamed)
+  f.eNext = nullptr; // set by the caller
   const long long h = ((long long)b * (a.T + 2) + (t + 1)) * c.K;
   f.hParent = a.hParent + h;
   f.hTok = a.hTok + h;
@@ -389,7 +398,7 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
       const bool hasNext = nb < a.B;
       const float* gnext = hasNext ? a.emis + ((long long)nb * a.T + nt) * c.N : nullptr;
       topmRowStaged(
-          p, tc, ps, pg, v.row(), grow, v.listTok(slot), v.listVal(slot, c.M), v.thr(slot),
+          p, tc, ps, pg, a.stats, v.row(), grow, v.listTok(slot), v.listVal(slot, c.M), v.thr(slot),
           [&]() {
             if (hasNext && p.tid == 0) { // the stage is free: stream the next row in behind the select
               fenceProxyAsync();
@@ -416,6 +425,7 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
     int curIdx = 0;
     cta.sync(); // previous utterance fully retired
     if (cta.tid == 0) seedUtterance(c, w, a, b);
+    LfCarry carry{0.0f, 0.0f, 0.0f, 0};
     cta.sync();
     for (int t = 0; t < len; ++t, ++g) {
       const int slot = (int)(g & 1); // ring slot = running row count & 1, on both sides
@@ -427,12 +437,13 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
       { // host model: the producer's work for row (b, t), inline
         const float* grow = a.emis + ((long long)b * a.T + t) * c.N;
         ProdGuess pg{0.0f, 0.0f};
-        topmRowStaged(cta, tc, ps, pg, grow, grow, v.listTok(slot), v.listVal(slot, c.M), v.thr(slot), [] {}, [] {});
+        topmRowStaged(cta, tc, ps, pg, nullptr, grow, grow, v.listTok(slot), v.listVal(slot, c.M), v.thr(slot), [] {}, [] {});
       }
 #endif
       oc.mark(5);
-      const FrameIn f = fusedFrameIn(c, a, v, b, t, slot);
-      lfFrameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.stats); // ends with a barrier
+      FrameIn f = fusedFrameIn(c, a, v, b, t, slot);
+      f.eNext = t + 1 < len ? f.e + c.N : nullptr;
+      lfFrameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.stats, carry); // ends with a barrier
       curIdx ^= 1;
 #if FLT_DEVICE_BUILD
       if (cta.tid == 0) mbarArrive(v.mbar(MB_LIST_FREE0 + slot));
