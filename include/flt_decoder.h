@@ -123,6 +123,13 @@ void* flt_decoder_stream(flt_decoder* dec);
 int flt_nbest_copy(flt_decoder* dec, int32_t nbest, int32_t* tokens, int32_t* words,
                    double* scores, int32_t* counts);
 
+/* Device addresses of the last batch's n-best buffers (valid until the next flt_decode_batch* call
+ * on this decoder; synchronise the decoder's stream before reading them from another stream):
+ * tokens / words [B, nbestSetting, T+2] int32, scores [B, beamSize, 3] fp64, counts [B] int32.
+ * For device-side consumers, e.g. the NCCL gather of n-best blocks across GPUs. */
+int flt_nbest_device_ptrs(flt_decoder* dec, int32_t** tokens, int32_t** words, double** scores,
+                          int32_t** counts);
+
 /* Introspection for benchmarks: kernels launched by the last flt_decode_batch* call, and device
  * bytes currently held by the decoder workspace. */
 int flt_decoder_last_launches(const flt_decoder* dec, int32_t* out);

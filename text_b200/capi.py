@@ -71,6 +71,8 @@ SYMBOLS = {
     "flt_decoder_stream": (C.c_void_p, [C.c_void_p]),
     "flt_nbest_copy": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                  C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+    "flt_nbest_device_ptrs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "flt_decoder_last_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "flt_decoder_workspace_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "flt_decoder_set_timing": (C.c_int, [C.c_void_p, C.c_int32]),
@@ -226,6 +228,23 @@ class Api:
         self._ck(self.lib.flt_nbest_copy(dec, nbest, _i32p(tokens), _i32p(words),
                                          scores.ctypes.data_as(C.POINTER(C.c_double)), _i32p(counts)))
         return dict(tokens=tokens, words=words, scores=scores, counts=counts)
+
+    def nbest_device(self, dec, B, T, nbest, K):
+        """The last batch's n-best buffers as torch CUDA tensors that alias the decoder's memory
+        (no copy): tokens / words [B,nbest,T+2] int32, scores [B,K,3] f64, counts [B] int32."""
+        import torch
+
+        p = [C.c_void_p() for _ in range(4)]
+        self._ck(self.lib.flt_nbest_device_ptrs(dec, *[C.byref(x) for x in p]))
+
+        class _Cai:
+            def __init__(self, ptr, shape, typestr):
+                self.__cuda_array_interface__ = dict(shape=shape, typestr=typestr, data=(ptr, False), version=3)
+
+        dev = torch.device("cuda", self.device)
+        mk = lambda ptr, shape, ts: torch.as_tensor(_Cai(ptr.value, shape, ts), device=dev)
+        return dict(tokens=mk(p[0], (B, nbest, T + 2), "<i4"), words=mk(p[1], (B, nbest, T + 2), "<i4"),
+                    scores=mk(p[2], (B, K, 3), "<f8"), counts=mk(p[3], (B,), "<i4"))
 
     def last_launches(self, dec):
         n = C.c_int32()

@@ -1152,6 +1152,17 @@ int flt_nbest_copy(flt_decoder* dec, int32_t nbest, int32_t* tokens, int32_t* wo
   });
 }
 
+int flt_nbest_device_ptrs(flt_decoder* dec, int32_t** tokens, int32_t** words, double** scores,
+                          int32_t** counts) {
+  return guarded([&] {
+    if (!dec) throw FltError(FLT_ERR_INVALID, "null decoder");
+    if (tokens) *tokens = dec->outTok.as<int32_t>();
+    if (words) *words = dec->outWord.as<int32_t>();
+    if (scores) *scores = dec->finScore.as<double>();
+    if (counts) *counts = dec->finCount.as<int32_t>();
+  });
+}
+
 int flt_decoder_last_launches(const flt_decoder* dec, int32_t* out) {
   return guarded([&] {
     if (!dec || !out) throw FltError(FLT_ERR_INVALID, "null argument");

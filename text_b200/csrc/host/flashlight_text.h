@@ -1,0 +1,444 @@
+// flashlight_text.h — C++17 mirror of flashlight/text's decoder-path classes over the C-ABI of the
+// B200 decode path (include/flt_decoder.h). Header-only; link with text_b200/lib/libflt_decoder.so.
+//
+// Same namespace, class names, constructor signatures, method names and exception types as the
+// reference, so that code written against
+//   flashlight/lib/text/decoder/Decoder.h:16-74            CriterionType, Decoder
+//   flashlight/lib/text/decoder/Utils.h:30-39              DecodeResult
+//   flashlight/lib/text/decoder/LexiconDecoder.h:21-31,115-157     LexiconDecoderOptions, LexiconDecoder
+//   flashlight/lib/text/decoder/LexiconFreeDecoder.h:20-28,100-139 LexiconFreeDecoderOptions, LexiconFreeDecoder
+//   flashlight/lib/text/decoder/Trie.h:21-92               SmearingMode, TrieNode, Trie
+//   flashlight/lib/text/decoder/lm/LM.h:21-85, lm/ZeroLM.h, lm/KenLM.h:52-67
+//   flashlight/lib/text/dictionary/Dictionary.h:23-66      Dictionary (only what KenLM's ctor needs)
+// compiles unchanged for the decode path. All decoding runs on the GPU; there is no CPU decoder
+// behind these classes (constructing a decoder without a CUDA device throws std::runtime_error).
+//
+// Additive: Decoder::decodeBatch (B utterances in one call) and LexiconDecoder/LexiconFreeDecoder
+// ::setNbest. Differences, all loud:
+//   * LM objects other than ZeroLM / KenLM (ARPA file) cannot be used by the decoders
+//     (std::invalid_argument): a user-defined LM::score cannot run on the device.
+//   * Online use: decodeBegin / decodeStep(chunk) / decodeEnd buffer the chunks and decode at
+//     decodeEnd; getBestHypothesis / prune before decodeEnd throw std::runtime_error.
+//   * TrieNode objects returned by insert / search are value snapshots (children not populated).
+#pragma once
+#include <cmath>
+#include <cstdlib>
+#include <limits>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "../../../include/flt_decoder.h"
+
+namespace fl {
+namespace lib {
+namespace text {
+
+namespace detail {
+inline void check(int code) {
+  if (code == FLT_OK) return;
+  const std::string msg = flt_last_error();
+  switch (code) {
+    case FLT_ERR_INVALID: throw std::invalid_argument(msg);
+    case FLT_ERR_OUT_OF_RANGE: throw std::out_of_range(msg);
+    default: throw std::runtime_error(msg);
+  }
+}
+inline int deviceOrdinal() {
+  const char* e = std::getenv("FLT_DEVICE");
+  return e ? std::atoi(e) : 0;
+}
+} // namespace detail
+
+/* ------------------------------------------------------------------ Decoder.h / Utils.h ------ */
+enum class CriterionType { ASG = 0, CTC = 1, S2S = 2 };
+
+struct DecodeResult {
+  double score;
+  double emittingModelScore;
+  double lmScore;
+  std::vector<int> words;
+  std::vector<int> tokens;
+  explicit DecodeResult(int length = 0)
+      : score(0), emittingModelScore(0), lmScore(0), words(length, -1), tokens(length, -1) {}
+};
+
+/* ------------------------------------------------------------------ Dictionary (subset) ------ */
+class Dictionary {
+ public:
+  Dictionary() = default;
+  explicit Dictionary(const std::vector<std::string>& tkns) {
+    for (const auto& t : tkns) addEntry(t);
+  }
+  size_t entrySize() const { return entry2idx_.size(); }
+  size_t indexSize() const { return idx2entry_.size(); }
+  void addEntry(const std::string& entry, int idx) {
+    if (entry2idx_.count(entry)) throw std::invalid_argument("Duplicate entry name in dictionary '" + entry + "'");
+    entry2idx_[entry] = idx;
+    if (!idx2entry_.count(idx)) idx2entry_[idx] = entry;
+  }
+  void addEntry(const std::string& entry) {
+    int idx = (int)idx2entry_.size();
+    while (idx2entry_.count(idx)) ++idx;
+    addEntry(entry, idx);
+  }
+  std::string getEntry(int idx) const {
+    auto it = idx2entry_.find(idx);
+    if (it == idx2entry_.end()) throw std::invalid_argument("Unknown index in dictionary '" + std::to_string(idx) + "'");
+    return it->second;
+  }
+  int getIndex(const std::string& entry) const {
+    auto it = entry2idx_.find(entry);
+    if (it == entry2idx_.end()) {
+      if (defaultIndex_ < 0) throw std::invalid_argument("Unknown entry in dictionary: '" + entry + "'");
+      return defaultIndex_;
+    }
+    return it->second;
+  }
+  bool contains(const std::string& entry) const { return entry2idx_.count(entry) > 0; }
+  void setDefaultIndex(int idx) { defaultIndex_ = idx; }
+
+ private:
+  std::unordered_map<std::string, int> entry2idx_;
+  std::unordered_map<int, std::string> idx2entry_;
+  int defaultIndex_ = -1;
+};
+
+/* ------------------------------------------------------------------ Trie.h ------------------ */
+constexpr int kTrieMaxLabel = 6;
+enum class SmearingMode { NONE = 0, MAX = 1, LOGADD = 2 };
+
+struct TrieNode {
+  explicit TrieNode(int idx) : idx(idx), maxScore(0) {
+    labels.reserve(kTrieMaxLabel);
+    scores.reserve(kTrieMaxLabel);
+  }
+  std::unordered_map<int, std::shared_ptr<TrieNode>> children; // not populated by this mirror
+  int idx;
+  std::vector<int> labels;
+  std::vector<float> scores;
+  float maxScore;
+};
+using TrieNodePtr = std::shared_ptr<TrieNode>;
+
+class Trie {
+ public:
+  Trie(int maxChildren, int rootIdx) : maxChildren_(maxChildren), root_(std::make_shared<TrieNode>(rootIdx)) {
+    detail::check(flt_trie_create(maxChildren, rootIdx, &h_));
+  }
+  ~Trie() { flt_trie_destroy(h_); }
+  Trie(const Trie&) = delete;
+  Trie& operator=(const Trie&) = delete;
+
+  const TrieNode* getRoot() const { return root_.get(); }
+
+  // Trie.cpp:26-48 (throws std::out_of_range on a token index outside [0, maxChildren))
+  TrieNodePtr insert(const std::vector<int>& indices, int label, float score) {
+    detail::check(flt_trie_insert(h_, indices.data(), (int)indices.size(), label, score));
+    return search(indices);
+  }
+  // Trie.cpp:50-64 (nullptr when the path does not exist)
+  TrieNodePtr search(const std::vector<int>& indices) {
+    int found = 0, nLabels = 0, labels[kTrieMaxLabel];
+    float maxScore = 0, scores[kTrieMaxLabel];
+    detail::check(flt_trie_search(h_, indices.data(), (int)indices.size(), &found, &maxScore, &nLabels, labels, scores));
+    if (!found) return nullptr;
+    auto node = std::make_shared<TrieNode>(indices.empty() ? root_->idx : indices.back());
+    node->labels.assign(labels, labels + nLabels);
+    node->scores.assign(scores, scores + nLabels);
+    node->maxScore = maxScore;
+    return node;
+  }
+  // Trie.cpp:79-101
+  void smear(const SmearingMode smearMode) { detail::check(flt_trie_smear(h_, (int)smearMode)); }
+
+  flt_trie* handle() const { return h_; }
+
+ private:
+  int maxChildren_;
+  TrieNodePtr root_;
+  flt_trie* h_ = nullptr;
+};
+using TriePtr = std::shared_ptr<Trie>;
+
+/* ------------------------------------------------------------------ lm/LM.h ------------------ */
+struct LMState {
+  std::unordered_map<int, std::shared_ptr<LMState>> children;
+  std::vector<int> history; // labels from the start state (this mirror's host-side scoring)
+
+  template <typename T>
+  std::shared_ptr<T> child(int usrIdx) {
+    auto s = children.find(usrIdx);
+    if (s == children.end()) {
+      auto state = std::make_shared<T>();
+      state->history = history;
+      state->history.push_back(usrIdx);
+      children[usrIdx] = state;
+      return state;
+    }
+    return std::static_pointer_cast<T>(s->second);
+  }
+  // lm/LM.h:37-49: pointer order, throws on null
+  int compare(const std::shared_ptr<LMState>& state) const {
+    LMState* inState = state.get();
+    if (!inState) throw std::runtime_error("a state is null");
+    if (this == inState) return 0;
+    return this < inState ? -1 : 1;
+  }
+};
+using LMStatePtr = std::shared_ptr<LMState>;
+
+class LM {
+ public:
+  virtual ~LM() = default;
+  virtual LMStatePtr start(bool startWithNothing) = 0;
+  virtual std::pair<LMStatePtr, float> score(const LMStatePtr& state, const int usrTokenIdx) = 0;
+  virtual std::pair<LMStatePtr, float> finish(const LMStatePtr& state) = 0;
+  virtual void updateCache(std::vector<LMStatePtr> /*stateIdices*/) {}
+  // device-resident model behind this LM, or nullptr (user-defined LMs cannot decode on the device)
+  virtual const flt_lm* handle() const { return nullptr; }
+
+ protected:
+  std::vector<int> usrToLmIdxMap_;
+};
+using LMPtr = std::shared_ptr<LM>;
+
+// lm/ZeroLM.cpp:14-26
+class ZeroLM : public LM {
+ public:
+  ZeroLM() { detail::check(flt_lm_zero_create(&h_)); }
+  ~ZeroLM() override { flt_lm_destroy(h_); }
+  LMStatePtr start(bool /*startWithNothing*/) override { return std::make_shared<LMState>(); }
+  std::pair<LMStatePtr, float> score(const LMStatePtr& state, const int usrTokenIdx) override {
+    return std::make_pair(state->child<LMState>(usrTokenIdx), 0.0f);
+  }
+  std::pair<LMStatePtr, float> finish(const LMStatePtr& state) override { return std::make_pair(state, 0.0f); }
+  const flt_lm* handle() const override { return h_; }
+
+ private:
+  flt_lm* h_ = nullptr;
+};
+using ZeroLMPtr = std::shared_ptr<ZeroLM>;
+
+// lm/KenLM.cpp:32-83 for ARPA files: log10 scores, OOV -> <unk>, start = <s> context, finish = </s>
+struct KenLMState : LMState {};
+class KenLM : public LM {
+ public:
+  KenLM(const std::string& path, const Dictionary& usrTknDict) {
+    const int n = (int)usrTknDict.indexSize();
+    std::vector<std::string> words(n);
+    std::vector<const char*> ptrs(n);
+    for (int i = 0; i < n; ++i) {
+      words[i] = usrTknDict.getEntry(i);
+      ptrs[i] = words[i].c_str();
+    }
+    detail::check(flt_lm_ngram_load_arpa(path.c_str(), ptrs.data(), n, &h_));
+  }
+  ~KenLM() override { flt_lm_destroy(h_); }
+  LMStatePtr start(bool startWithNothing) override {
+    if (startWithNothing) throw std::runtime_error("[KenLM] start(true) (null context) is not supported by the device model");
+    return std::make_shared<KenLMState>();
+  }
+  std::pair<LMStatePtr, float> score(const LMStatePtr& state, const int usrTokenIdx) override {
+    auto out = state->child<KenLMState>(usrTokenIdx);
+    std::vector<float> s(out->history.size());
+    detail::check(flt_lm_score_seq(h_, out->history.data(), (int)out->history.size(), 0, s.data()));
+    return std::make_pair(std::static_pointer_cast<LMState>(out), s.back());
+  }
+  std::pair<LMStatePtr, float> finish(const LMStatePtr& state) override {
+    auto out = state->child<KenLMState>(-1);
+    std::vector<float> s(state->history.size() + 1);
+    detail::check(flt_lm_score_seq(h_, state->history.data(), (int)state->history.size(), 1, s.data()));
+    return std::make_pair(std::static_pointer_cast<LMState>(out), s.back());
+  }
+  const flt_lm* handle() const override { return h_; }
+
+ private:
+  flt_lm* h_ = nullptr;
+};
+using KenLMPtr = std::shared_ptr<KenLM>;
+
+/* ------------------------------------------------------------------ options ------------------ */
+struct LexiconDecoderOptions {
+  int beamSize;
+  int beamSizeToken;
+  double beamThreshold;
+  double lmWeight;
+  double wordScore;
+  double unkScore;
+  double silScore;
+  bool logAdd;
+  CriterionType criterionType;
+};
+struct LexiconFreeDecoderOptions {
+  int beamSize;
+  int beamSizeToken;
+  double beamThreshold;
+  double lmWeight;
+  double silScore;
+  bool logAdd;
+  CriterionType criterionType;
+};
+
+/* ------------------------------------------------------------------ Decoder ------------------ */
+class Decoder {
+ public:
+  Decoder() = default;
+  virtual ~Decoder() { flt_decoder_destroy(h_); }
+  Decoder(const Decoder&) = delete;
+  Decoder& operator=(const Decoder&) = delete;
+
+  virtual void decodeBegin() {
+    buffer_.clear();
+    bufT_ = 0;
+    bufN_ = 0;
+    final_.clear();
+    ended_ = false;
+  }
+  // chunks are buffered; the device decodes at decodeEnd (see the header comment)
+  virtual void decodeStep(const float* emissions, int T, int N) {
+    if (bufT_ > 0 && N != bufN_) throw std::invalid_argument("decodeStep: N changed between chunks");
+    bufN_ = N;
+    buffer_.insert(buffer_.end(), emissions, emissions + (size_t)T * N);
+    bufT_ += T;
+    ended_ = false;
+  }
+  virtual void decodeEnd() {
+    auto all = decodeBatch(buffer_.data(), 1, bufT_, bufN_ > 0 ? bufN_ : 1);
+    final_ = std::move(all[0]);
+    ended_ = true;
+  }
+  // Decoder.h:51-57
+  virtual std::vector<DecodeResult> decode(const float* emissions, int T, int N) {
+    auto all = decodeBatch(emissions, 1, T, N);
+    final_ = all[0];
+    bufT_ = T;
+    ended_ = true;
+    return std::move(all[0]);
+  }
+  virtual void prune(int /*lookBack*/ = 0) {
+    if (!ended_) throw std::runtime_error("prune() before decodeEnd() is not supported on the device path yet");
+  }
+  virtual int nDecodedFramesInBuffer() const { return bufT_ + (ended_ ? 1 : 0); }
+  virtual DecodeResult getBestHypothesis(int lookBack = 0) const {
+    if (!ended_ || lookBack != 0)
+      throw std::runtime_error("getBestHypothesis() with lookBack or before decodeEnd() is not supported on the device path yet");
+    return final_.empty() ? DecodeResult() : final_[0];
+  }
+  virtual std::vector<DecodeResult> getAllFinalHypothesis() const { return final_; }
+  int nHypothesis() const { return (int)final_.size(); }
+
+  // B utterances at once. emissions: row-major [B,T,N] fp32, host or device memory; lengths
+  // (host, optional): valid frames per utterance; nbest <= beamSize hypotheses are materialised
+  // per utterance (-1: all). result[b] is sorted by score, best first (Utils.h:252-266).
+  std::vector<std::vector<DecodeResult>> decodeBatch(const float* emissions, int B, int T, int N,
+                                                      const int* lengths = nullptr, int nbest = -1) {
+    const int K = beamSize();
+    const int nb = nbest < 0 ? K : (nbest < K ? nbest : K);
+    detail::check(flt_decoder_set_nbest(h_, nb > 0 ? nb : 1));
+    detail::check(flt_decode_batch(h_, emissions, B, T, N, lengths));
+    const size_t L = (size_t)T + 2;
+    std::vector<int32_t> tok((size_t)B * nb * L), wrd((size_t)B * nb * L), cnt(B);
+    std::vector<double> sc((size_t)B * nb * 3);
+    if (B > 0 && nb > 0) detail::check(flt_nbest_copy(h_, nb, tok.data(), wrd.data(), sc.data(), cnt.data()));
+    std::vector<std::vector<DecodeResult>> out(B);
+    for (int b = 0; b < B; ++b) {
+      const int n = cnt[b] < nb ? cnt[b] : nb;
+      const int len = (lengths ? lengths[b] : T) + 2;
+      out[b].reserve(n);
+      for (int r = 0; r < n; ++r) {
+        DecodeResult d(len);
+        const size_t o = ((size_t)b * nb + r);
+        d.score = sc[o * 3 + 0];
+        d.emittingModelScore = sc[o * 3 + 1];
+        d.lmScore = sc[o * 3 + 2];
+        for (int i = 0; i < len; ++i) {
+          d.tokens[i] = tok[o * L + i];
+          d.words[i] = wrd[o * L + i];
+        }
+        out[b].push_back(std::move(d));
+      }
+    }
+    return out;
+  }
+  flt_decoder* handle() const { return h_; }
+
+ protected:
+  virtual int beamSize() const = 0;
+  flt_decoder* h_ = nullptr;
+  std::vector<float> buffer_;
+  int bufT_ = 0, bufN_ = 0;
+  std::vector<DecodeResult> final_;
+  bool ended_ = false;
+};
+
+namespace detail {
+inline const flt_lm* deviceLM(const LMPtr& lm) {
+  if (!lm) throw std::invalid_argument("null LM");
+  const flt_lm* h = lm->handle();
+  if (!h)
+    throw std::invalid_argument(
+        "this LM has no device model: only ZeroLM and KenLM (ARPA) can decode on the GPU; "
+        "user-defined LM::score cannot run there");
+  return h;
+}
+} // namespace detail
+
+// LexiconDecoder.h:115-157
+class LexiconDecoder : public Decoder {
+ public:
+  LexiconDecoder(LexiconDecoderOptions opt, const TriePtr& lexicon, const LMPtr& lm, const int sil,
+                 const int blank, const int unk, const std::vector<float>& transitions, const bool isLmToken)
+      : opt_(std::move(opt)), lexicon_(lexicon), lm_(lm), sil_(sil), blank_(blank), unk_(unk),
+        transitions_(transitions), isLmToken_(isLmToken) {
+    if (!lexicon) throw std::invalid_argument("null lexicon");
+    flt_options o{opt_.beamSize, opt_.beamSizeToken, opt_.beamThreshold, opt_.lmWeight, opt_.wordScore,
+                  opt_.unkScore, opt_.silScore, opt_.logAdd ? 1 : 0, (int)opt_.criterionType};
+    detail::check(flt_decoder_create_lexicon(&o, lexicon->handle(), detail::deviceLM(lm), sil, blank, unk,
+                                             transitions_.data(), (int64_t)transitions_.size(),
+                                             isLmToken ? 1 : 0, detail::deviceOrdinal(), &h_));
+  }
+  const LexiconDecoderOptions& getOptions() const { return opt_; }
+
+ protected:
+  int beamSize() const override { return opt_.beamSize; }
+  LexiconDecoderOptions opt_;
+  TriePtr lexicon_;
+  LMPtr lm_;
+  int sil_, blank_, unk_;
+  std::vector<float> transitions_;
+  bool isLmToken_;
+};
+
+// LexiconFreeDecoder.h:100-139
+class LexiconFreeDecoder : public Decoder {
+ public:
+  LexiconFreeDecoder(LexiconFreeDecoderOptions opt, const LMPtr& lm, const int sil, const int blank,
+                     const std::vector<float>& transitions)
+      : opt_(std::move(opt)), lm_(lm), sil_(sil), blank_(blank), transitions_(transitions) {
+    flt_options o{opt_.beamSize, opt_.beamSizeToken, opt_.beamThreshold, opt_.lmWeight, 0.0,
+                  -std::numeric_limits<double>::infinity(), opt_.silScore, opt_.logAdd ? 1 : 0,
+                  (int)opt_.criterionType};
+    detail::check(flt_decoder_create_lexfree(&o, detail::deviceLM(lm), sil, blank, transitions_.data(),
+                                             (int64_t)transitions_.size(), detail::deviceOrdinal(), &h_));
+  }
+  const LMPtr& getLMPtr() const { return lm_; }
+  int getSilIdx() const { return sil_; }
+  int getBlankIdx() const { return blank_; }
+  const LexiconFreeDecoderOptions& getOptions() const { return opt_; }
+  const std::vector<float>& getTransitions() const { return transitions_; }
+
+ protected:
+  int beamSize() const override { return opt_.beamSize; }
+  LexiconFreeDecoderOptions opt_;
+  LMPtr lm_;
+  int sil_, blank_;
+  std::vector<float> transitions_;
+};
+
+} // namespace text
+} // namespace lib
+} // namespace fl
