@@ -78,6 +78,7 @@ struct DecCfg {
   int capRH;      // row table slots (pow2 >= 2*K)
   int capP;       // pow2 >= K
   int wideTotal;  // wideOff[K]
+  int prune2;     // 1 = two-pass histogram pruning of the candidates (lexicon decoder)
   int lfFast;     // 1 = lexicon-free fast step (beam_lf.h): cells indexed by hypothesis, no merge table
   int lfBins;     // histogram bins of its select (pow2, multiple of 32)
   int nTau;       // pruning rectangles: rows 1..tauA[k] x columns 0..tauCol[k] hold >= K regular cells
@@ -166,7 +167,9 @@ constexpr int kRowsInts = 8; // K-sized int arrays (+ slack) behind Rows::iv
 
 enum { // ws.sc[] scalars
   SC_NH = 0, SC_NCAND, SC_NREP, SC_NSEL, SC_NROWS, SC_OVF, SC_BIN, SC_NEED, SC_BINCOUNT, SC_NICE,
-  SC_NGATH, SC_OR_LO, SC_OR_HI, SC_AND_LO, SC_AND_HI, SC_WCNT /* 32 warp counters follow */,
+  SC_NGATH, SC_OR_LO, SC_OR_HI, SC_AND_LO, SC_AND_HI,
+  SC_PMODE, SC_PCUT, SC_PLO_LO, SC_PLO_HI, SC_PSCALE, // two-pass candidate pruning (frameStep)
+  SC_WCNT /* 32 warp counters follow */,
   SC_COUNT = SC_WCNT + 32
 };
 
@@ -542,8 +545,28 @@ FLT_DEV double amOf(const DecCfg& c, const FrameIn& f, float ev, int n, int prev
   return am;
 }
 
+// Two-pass pruning (lexicon decoder): pass 1 only histograms the candidate scores (mode 1), pass 2
+// materialises the candidates whose bin is at or above the cut (mode 2). The map score -> bin is
+// monotone, so everything left out scores no higher than anything kept; frameStep verifies that
+// the kept set holds >= K merge groups (else it repeats the frame without the cut).
+constexpr int kPruneBins = 256;
+FLT_DEV int pruneBin(const int* sc, double score) {
+  const double lo = bitsF64(((u64)(unsigned)sc[SC_PLO_HI] << 32) | (unsigned)sc[SC_PLO_LO]);
+  const float pos = (float)(score - lo) * bitsF32((uint32_t)sc[SC_PSCALE]);
+  return pos >= (float)(kPruneBins - 1) ? kPruneBins - 1 : (pos > 0.0f ? (int)pos : 0);
+}
+
 // slot for a candidate that survived the pruning bound (compact: only live candidates are stored)
-FLT_DEV int allocCand(const Cta& cta, const DecCfg& c, const Ws& w) {
+FLT_DEV int allocCand(const Cta& cta, const DecCfg& c, const Ws& w, double score) {
+  const int mode = w.sc()[SC_PMODE];
+  if (mode) {
+    const int bin = pruneBin(w.sc(), score);
+    if (mode == 1) {
+      atomAdd(&w.hist()[bin], 1);
+      return -1;
+    }
+    if (bin < w.sc()[SC_PCUT]) return -1;
+  }
   const int s = aggInc(&w.sc()[SC_NCAND], cta.tid);
   if (s >= c.capC) {
     w.sc()[SC_OVF] = 1;
@@ -566,7 +589,7 @@ FLT_DEV void emitRowToken(const Cta& cta, const DecCfg& c, const Ws& w, const Be
     if (n == c.sil) score += c.silScore;
     score = score + c.lmWeight * (double)0.0f;
     if (score < tau) return;
-    const int slot = allocCand(cta, c, w);
+    const int slot = allocCand(cta, c, w, score);
     if (slot >= 0) putCand(c, w, cur, slot, score, p, n, -1, 0, CF_NEW, 0.0f, ev);
   } else {
     // LexiconDecoder.cpp:62-110, prevLex == root, CTC (ranked mode excludes ASG)
@@ -577,7 +600,7 @@ FLT_DEV void emitRowToken(const Cta& cta, const DecCfg& c, const Ws& w, const Be
     const float d = c.trie.maxScore[child] - 0.0f;
     score = score + c.lmWeight * (double)d;
     if (score < tau) return;
-    const int slot = allocCand(cta, c, w);
+    const int slot = allocCand(cta, c, w, score);
     if (slot >= 0) putCand(c, w, cur, slot, score, p, n, -1, child, 0, d, ev);
   }
 }
@@ -622,7 +645,7 @@ FLT_DEV void emitSpecials(const Cta& cta, const DecCfg& c, const Ws& w, const Be
       double score = cur.score(i) + (double)eOwn;
       if (n == c.sil) score += c.silScore;
       if (!(score < tau)) {
-        const int slot = allocCand(cta, c, w);
+        const int slot = allocCand(cta, c, w, score);
         if (slot >= 0) putCand(c, w, cur, slot, score, i, n, -1, 0, 0, 0.0f, eOwn);
       }
     }
@@ -631,7 +654,7 @@ FLT_DEV void emitSpecials(const Cta& cta, const DecCfg& c, const Ws& w, const Be
       double score = cur.score(i) + (double)eBlank;
       if (n == c.sil) score += c.silScore;
       if (!(score < tau)) {
-        const int slot = allocCand(cta, c, w);
+        const int slot = allocCand(cta, c, w, score);
         if (slot >= 0) putCand(c, w, cur, slot, score, i, n, -1, 0, CF_PB, 0.0f, eBlank);
       }
     }
@@ -643,14 +666,14 @@ FLT_DEV void emitSpecials(const Cta& cta, const DecCfg& c, const Ws& w, const Be
       double score = cur.score(i) + am;
       if (n == c.sil) score += c.silScore;
       if (!(score < tau)) {
-        const int slot = allocCand(cta, c, w);
+        const int slot = allocCand(cta, c, w, score);
         if (slot >= 0) putCand(c, w, cur, slot, score, i, n, -1, lex, 0, 0.0f, eOwn);
       }
     }
     if (c.ctc) { // (3) blank, LexiconDecoder.cpp:196-213
       const double score = cur.score(i) + (double)eBlank;
       if (!(score < tau)) {
-        const int slot = allocCand(cta, c, w);
+        const int slot = allocCand(cta, c, w, score);
         if (slot >= 0) putCand(c, w, cur, slot, score, i, c.blank, -1, lex, CF_PB, 0.0f, eBlank);
       }
     }
@@ -678,7 +701,7 @@ FLT_DEV void emitEdge(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& 
     const float d = t.maxScore[child] - lexMax;
     const double s = score + c.lmWeight * (double)d;
     if (!(s < tau)) {
-      const int slot = allocCand(cta, c, w);
+      const int slot = allocCand(cta, c, w, s);
       if (slot >= 0) putCand(c, w, cur, slot, s, i, n, -1, child, 0, d, ev);
     }
   }
@@ -689,7 +712,7 @@ FLT_DEV void emitEdge(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& 
       const float d = lmWordScore(c, cur, i, label) - lexMax;
       const double s = score + c.lmWeight * (double)d + c.wordScore;
       if (s < tau) continue;
-      const int slot = allocCand(cta, c, w);
+      const int slot = allocCand(cta, c, w, s);
       if (slot >= 0) putCand(c, w, cur, slot, s, i, n, label, 0, CF_NEW, d, ev);
     }
   }
@@ -697,7 +720,7 @@ FLT_DEV void emitEdge(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& 
     const float d = lmWordScore(c, cur, i, c.unk) - lexMax;
     const double s = score + c.lmWeight * (double)d + c.unkScore;
     if (!(s < tau)) {
-      const int slot = allocCand(cta, c, w);
+      const int slot = allocCand(cta, c, w, s);
       if (slot >= 0) putCand(c, w, cur, slot, s, i, n, c.unk, 0, CF_NEW, d, ev);
     }
   }
@@ -1134,21 +1157,8 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
     }
     if (c.silScore < 0) tau += c.silScore; // keeps the bound valid if a counted cell is the sil one
   }
-  // wide cells
-  if (c.wideRanked) {
-    const short* itemRow = w.itemRow();
-    const int* wideOff = w.wideOff();
-    for (int x = cta.tid; x < wideItems; x += cta.nthr) {
-      const int r = itemRow[x]; // row rank (0-based)
-      emitWide(cta, c, w, cur, f, w.rows().leaderOfRank(r), x - wideOff[r], tau);
-    }
-  }
-  // stay / repeat / blank
-  for (int i = cta.tid; i < nH; i += cta.nthr) {
-    emitSpecials(cta, c, w, cur, f, i, tau);
-    if (c.wideRanked) emitSilCell(cta, c, w, cur, f, i, tau);
-  }
-  // trie edges
+  // trie edge items: prefix sums of the hypotheses' degrees
+  int edgeItems = 0;
   if (c.lexicon) {
     const TrieDev& t = c.trie;
     int* deg = w.rows().deg();
@@ -1158,27 +1168,105 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
     }
     cta.sync();
     ctaExclusiveScan(cta, deg, w.rows().degTmp(), nH);
-    const int items = deg[nH];
-    for (int x = cta.tid; x < items; x += cta.nthr) {
-      const int i = searchOffsets(deg, nH + 1, x);
-      const int k = x - deg[i];
-      const int lex = cur.lex(i);
-      if (c.wideRanked && lex == 0) {
-        const int n = t.rootLabTok[k];
-        emitEdge(cta, c, w, cur, f, i, n, t.rootChild[n], true, tau);
-      } else {
-        const int e = t.childOff[lex] + k;
-        emitEdge(cta, c, w, cur, f, i, t.childTok[e], t.childNode[e], false, tau);
+    edgeItems = deg[nH];
+  }
+  auto emitAll = [&]() {
+    // wide cells
+    if (c.wideRanked) {
+      const short* itemRow = w.itemRow();
+      const int* wideOff = w.wideOff();
+      for (int x = cta.tid; x < wideItems; x += cta.nthr) {
+        const int r = itemRow[x]; // row rank (0-based)
+        emitWide(cta, c, w, cur, f, w.rows().leaderOfRank(r), x - wideOff[r], tau);
       }
     }
+    // stay / repeat / blank
+    for (int i = cta.tid; i < nH; i += cta.nthr) {
+      emitSpecials(cta, c, w, cur, f, i, tau);
+      if (c.wideRanked) emitSilCell(cta, c, w, cur, f, i, tau);
+    }
+    // trie edges
+    if (c.lexicon) {
+      const TrieDev& t = c.trie;
+      const int* deg = w.rows().deg();
+      for (int x = cta.tid; x < edgeItems; x += cta.nthr) {
+        const int i = searchOffsets(deg, nH + 1, x);
+        const int k = x - deg[i];
+        const int lex = cur.lex(i);
+        if (c.wideRanked && lex == 0) {
+          const int n = t.rootLabTok[k];
+          emitEdge(cta, c, w, cur, f, i, n, t.rootChild[n], true, tau);
+        } else {
+          const int e = t.childOff[lex] + k;
+          emitEdge(cta, c, w, cur, f, i, t.childTok[e], t.childNode[e], false, tau);
+        }
+      }
+    }
+    cta.sync();
+  };
+  // Two-pass pruning for the lexicon decoder (no corner bound there): histogram the scores of
+  // everything the frame would propose, keep the bins that hold the best ~3K candidates.
+  const bool prune = c.prune2 != 0;
+  if (prune) {
+    if (cta.tid == 0) {
+      // candidate scores lie below best hypothesis + bonuses for log-probability emissions; the
+      // span follows the beam's own spread. Neither affects exactness (bins clamp, result verified).
+      double hi = cur.score(0);
+      if (c.silScore > 0) hi += c.silScore;
+      if (c.wordScore > 0) hi += c.wordScore;
+      double span = 2.0 * (cur.score(0) - cur.score(nH - 1)) + 12.0;
+      span = span > 96.0 ? 96.0 : span;
+      if (c.beamThreshold + 4.0 < span) span = c.beamThreshold + 4.0;
+      const double lo = hi - span;
+      const u64 lb = f64Bits(lo);
+      sc[SC_PLO_LO] = (int)(unsigned)lb;
+      sc[SC_PLO_HI] = (int)(unsigned)(lb >> 32);
+      sc[SC_PSCALE] = (int)f32Bits((float)kPruneBins / (float)span);
+      sc[SC_PMODE] = 1;
+      sc[SC_BIN] = 0; // fewer candidates than wanted: keep every bin
+    }
+    cta.sync();
+    emitAll(); // pass 1: histogram only
+    // cut = lowest bin with fewer than `want` candidates in higher bins (one warp; bins re-zeroed)
+    findCutBin(cta, w, 3 * c.K + 64);
+    cta.sync();
+    if (cta.tid == 0) {
+      sc[SC_PMODE] = 2;
+      sc[SC_PCUT] = sc[SC_BIN];
+    }
+    cta.sync();
   }
-  cta.sync();
+  emitAll();
   int nCand = sc[SC_NCAND];
   if (sc[SC_OVF]) {
     if (cta.tid == 0) *status |= 1;
     nCand = nCand < c.capC ? nCand : c.capC;
   }
   phaseMerge(cta, c, w, nCand);
+  if (prune && sc[SC_PCUT] > 0 && sc[SC_NREP] < c.K) {
+    // the kept bins hold fewer than K merge groups: take everything (rare)
+    cta.sync();
+    for (int x = cta.tid; x < nCand; x += cta.nthr)
+      if (w.cand().parflag(x) & CF_ALIVE) w.mh()[w.cslot()[x]] = -1;
+    if (cta.tid == 0) {
+      sc[SC_NREP] = 0;
+      sc[SC_OR_LO] = 0;
+      sc[SC_OR_HI] = 0;
+      sc[SC_AND_LO] = -1;
+      sc[SC_AND_HI] = -1;
+      sc[SC_NCAND] = 0;
+      sc[SC_PCUT] = 0;
+    }
+    cta.sync();
+    emitAll();
+    nCand = sc[SC_NCAND];
+    if (sc[SC_OVF]) {
+      if (cta.tid == 0) *status |= 1;
+      nCand = nCand < c.capC ? nCand : c.capC;
+    }
+    phaseMerge(cta, c, w, nCand);
+  }
+  if (prune && cta.tid == 0) sc[SC_PMODE] = 0; // decodeEnd's candidates are not pruned
   const int nRep = sc[SC_NREP];
   const int nSel = phaseSelect(cta, c, w, nRep);
 #if FLT_DEVICE_BUILD

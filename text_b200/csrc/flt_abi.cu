@@ -534,8 +534,12 @@ void planFor(flt_decoder& d, int N) {
     const int rows = c.lfFast ? (r - 1) / 2 + 1 : r;
     d.wideOffHost[r] = d.wideOffHost[r - 1] + std::min(c.Mwide, K / rows + 3 + (d.lexicon ? 2 : 0));
   }
-  const long long narrowBudget = d.lexicon ? std::max<long long>(4096, 24LL * K) : 0;
-  long long capC = (long long)(c.wideRanked ? d.wideOffHost[K] : 0) + 3LL * K + narrowBudget * d.capBoost;
+  // lexicon decoder, max-merge: two-pass histogram pruning keeps ~3K+64 candidates per frame (plus
+  // the rest of the cut bin), so the workspace fits shared memory
+  c.prune2 = d.lexicon && !o.logAdd && !getenv("FLT_NO_PRUNE2");
+  const long long narrowBudget = d.lexicon ? (c.prune2 ? 512 : std::max<long long>(4096, 24LL * K)) : 0;
+  long long capC = c.prune2 ? 3LL * K + 64 + narrowBudget * d.capBoost
+                            : (long long)(c.wideRanked ? d.wideOffHost[K] : 0) + 3LL * K + narrowBudget * d.capBoost;
   capC = (capC + 63) / 64 * 64;
   if (capC > (1LL << 26)) throw FltError(FLT_ERR_RUNTIME, "candidate capacity exceeded");
   c.capC = (int)capC;
