@@ -75,11 +75,11 @@ struct FltError : std::runtime_error {
 };
 
 constexpr int kThreads = 256; // token-select kernel
-int decThreads() {            // beam-step kernel (tunable for experiments)
+int decThreadsEnv() { // FLT_DEC_THREADS overrides the plan (experiments)
   static int t = [] {
     const char* e = getenv("FLT_DEC_THREADS");
-    int v = e ? atoi(e) : 256;
-    return (v == 64 || v == 128 || v == 256 || v == 512) ? v : 256;
+    const int v = e ? atoi(e) : 0;
+    return (v == 64 || v == 128 || v == 256 || v == 512) ? v : 0;
   }();
   return t;
 }
@@ -99,11 +99,11 @@ void launchTopM(const TopMCfg& c, const TopMArgs& a, int grid, size_t smem, rt::
   (void)s;
 #endif
 }
-void launchDecode(const DecCfg& c, const BatchArgs& a, int grid, size_t smem, rt::Stream s) {
+void launchDecode(const DecCfg& c, const BatchArgs& a, int grid, size_t smem, rt::Stream s, int threads) {
 #if FLT_DEVICE_BUILD
-  if (smem && decThreads() == 512) flt_k_decode512<<<grid, 512, smem, s>>>(c, a);
-  else if (smem) flt_k_decode<<<grid, decThreads(), smem, s>>>(c, a);
-  else flt_k_decode_gmem<<<grid, decThreads(), 0, s>>>(c, a);
+  if (smem && threads == 512) flt_k_decode512<<<grid, 512, smem, s>>>(c, a);
+  else if (smem) flt_k_decode<<<grid, threads, smem, s>>>(c, a);
+  else flt_k_decode_gmem<<<grid, threads > 256 ? 256 : threads, 0, s>>>(c, a);
   FLT_RT_TRY(cudaGetLastError());
 #else
   std::vector<char> sm(c.lay.total + 16);
@@ -113,6 +113,7 @@ void launchDecode(const DecCfg& c, const BatchArgs& a, int grid, size_t smem, rt
   }
   (void)s;
   (void)smem;
+  (void)threads;
 #endif
 }
 void launchFused(const DecCfg& c, const TopMCfg& tc, const FuseLay& fl, const BatchArgs& a, int grid,
@@ -416,6 +417,7 @@ struct flt_decoder {
   DecCfg cfg{};
   TopMCfg tcfg{};
   bool needTopM = false;
+  int threads = 256;  // threads per utterance of the beam-step kernel
   bool fused = false; // select + step in one kernel (fused_core.h)
   TopMCfg ftcfg{};
   FuseLay flay{};
@@ -497,6 +499,8 @@ void planFor(flt_decoder& d, int N) {
       throw FltError(FLT_ERR_RUNTIME, "[KenLM] Invalid user token index: " + std::to_string(maxIdx));
   }
 
+  // the lexicon step has ~4x the work items per frame of the lexicon-free one
+  d.threads = decThreadsEnv() ? decThreadsEnv() : (d.lexicon ? 512 : 256);
   const int K = c.K;
   const int bstEff = std::min(o.beamSizeToken, N);
   c.wideRanked = d.lexicon ? (c.ctc && !c.hasUnk) : 1;
@@ -561,7 +565,7 @@ void planFor(flt_decoder& d, int N) {
       }
     }
   }
-  c.listInSmem = d.needTopM && c.M <= 2 * decThreads();
+  c.listInSmem = d.needTopM && c.M <= 2 * d.threads;
 
   rt::Stream s = d.stream;
   c.wideOff = upload(d.dWideOff, d.wideOffHost, s);
@@ -597,7 +601,7 @@ void planFor(flt_decoder& d, int N) {
   // CTA's shared memory; two CTAs per SM need <= 113 KB each
   d.fused = false;
   if (c.lfFast && !getenv("FLT_NO_FUSED") && N % 4 == 0 && want <= 32 * (kFusedProducers / 32) &&
-      decThreads() == 256) {
+      d.threads == 256) {
     TopMCfg ft = t;
     ft.P = std::max(kFusedProducers, nextPow2(want));
     ft.capS = kProdCap;
@@ -644,12 +648,12 @@ void planFor(flt_decoder& d, int N) {
                                     (int)std::max<size_t>(d.wsBytes, 48 * 1024)));
     FLT_RT_TRY(cudaFuncSetAttribute(flt_k_decode512, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)std::max<size_t>(d.wsBytes, 48 * 1024)));
-    if (decThreads() == 512)
+    if (d.threads == 512)
       FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode512, 512, d.wsBytes));
     else
-      FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode, decThreads(), d.wsBytes));
+      FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode, d.threads, d.wsBytes));
   } else {
-    FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode_gmem, decThreads(), 0));
+    FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode_gmem, d.threads > 256 ? 256 : d.threads, 0));
     occ2 = std::min(occ2, 4);
   }
   d.gridMax = std::max(1, occ2) * d.numSMs;
@@ -764,7 +768,7 @@ void runChunk(flt_decoder& d, const float* dEmis, int Bc, int T, int N, const in
       a.wsStride = (long long)d.wsBytes;
     }
     KernelTimer kt(d, 1);
-    launchDecode(c, a, grid, d.useSmemFlag ? d.wsBytes : 0, s);
+    launchDecode(c, a, grid, d.useSmemFlag ? d.wsBytes : 0, s, d.threads);
     d.launches++;
   }
   BacktraceArgs b{};

@@ -95,6 +95,20 @@ FLT_DEV void bulkLoad(void* dst, const void* src, uint32_t bytes, u64* b) {
                "l"(src), "r"(bytes), "r"(smemU32(b))
                : "memory");
 }
+// same with an L2 evict-first policy: emission rows are read once, the back-pointer history the
+// step writes (and the backtrace re-reads) should be what stays in the 126 MB L2
+FLT_DEV u64 l2EvictFirstPolicy() {
+  u64 pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+FLT_DEV void bulkLoadHint(void* dst, const void* src, uint32_t bytes, u64* b, u64 pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smemU32(dst)),
+      "l"(src), "r"(bytes), "r"(smemU32(b)), "l"(pol)
+      : "memory");
+}
 FLT_DEV void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
 
@@ -372,6 +386,7 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
     if (p.tid < 4) ps.cnt[p.tid] = 0;
     p.sync();
     ProdGuess pg{bitsF32(0x7F800000u), 0.25f};
+    const u64 pol = l2EvictFirstPolicy();
     // rows of this CTA in order: (b, t) for b = bid, bid + nblk, ...; `r` counts them
     uint32_t r = 0;
     int nb = whole.bid, nt = 0; // the next row to stage
@@ -386,7 +401,7 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
     advance(nb, nt);
     if (nb < a.B && p.tid == 0) { // prime the stage
       mbarArriveExpectTx(v.mbar(MB_ROW_FULL), rowBytes);
-      bulkLoad(v.row(), a.emis + ((long long)nb * a.T + nt) * c.N, rowBytes, v.mbar(MB_ROW_FULL));
+      bulkLoadHint(v.row(), a.emis + ((long long)nb * a.T + nt) * c.N, rowBytes, v.mbar(MB_ROW_FULL), pol);
     }
     while (nb < a.B) {
       const int b = nb, t = nt;
@@ -403,7 +418,7 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
             if (hasNext && p.tid == 0) { // the stage is free: stream the next row in behind the select
               fenceProxyAsync();
               mbarArriveExpectTx(v.mbar(MB_ROW_FULL), rowBytes);
-              bulkLoad(v.row(), gnext, rowBytes, v.mbar(MB_ROW_FULL));
+              bulkLoadHint(v.row(), gnext, rowBytes, v.mbar(MB_ROW_FULL), pol);
             }
           },
           [&]() { mbarWaitRelaxed(v.mbar(MB_LIST_FREE0 + slot), ((r >> 1) + 1) & 1); });
