@@ -64,3 +64,9 @@ def test_ragged_lengths_and_many_utterances(A, G):
     lengths[:4] = [0, 1, T, T - 1]
     spec = spec_lexfree(N, 16, N, 1e9)
     run_case(A, G, spec, em, lengths)
+
+
+def test_long_ragged_checkpoints(A, G):
+    from test_model_parity import run_long_ragged
+
+    run_long_ragged(A, G, 1e-4)

@@ -45,3 +45,37 @@ def test_lexfree(A, M, name, spec, em):
 @pytest.mark.parametrize("name,spec,em", parity_cases.lexicon_cases(), ids=lambda v: v if isinstance(v, str) else "")
 def test_lexicon(A, M, name, spec, em):
     run_case(A, M, spec, em)
+
+
+def long_ragged_case():
+    """Utterances spanning several backtrace checkpoints (every 32 history rows), lengths on and
+    around the checkpoint boundaries."""
+    from cases import spec_lexfree, spec_lexicon
+    from text_b200 import synth
+
+    N, T = 24, 200
+    lens = np.array([200, 33, 64, 97, 31, 32, 0, 1], np.int32)
+    em = synth.emissions(len(lens), T, N, seed=10, sigma=2.0)
+    specs = [spec_lexfree(N, 8, N, 1e9),
+             spec_lexicon(N, 12, N, synth.lexicon(60, N, 2, 4, seed=2, exclude=(0, N - 1)), 1e9, word_score=0.3)]
+    return specs, em, lens
+
+
+def run_long_ragged(A, G, tol):
+    specs, em, lens = long_ragged_case()
+    checked = 0
+    for spec in specs:
+        ba, bg = Built(A, spec), Built(G, spec)
+        got = bg.O.decode_batch(bg.dec, em, spec["opt"].beamSize, lens)
+        for b in range(len(lens)):
+            ra = ba.decode(em[b][: lens[b]])
+            if has_ties(ra) or A.tie_events(ba.dec):
+                continue
+            assert_same_nbest(ra, got[b], tol, what=f"utt {b} len {lens[b]}")
+            checked += 1
+        ba.close(), bg.close()
+    assert checked >= 8
+
+
+def test_long_ragged_checkpoints(A, M):
+    run_long_ragged(A, M, 1e-9)

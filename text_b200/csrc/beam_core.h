@@ -56,7 +56,7 @@ struct Lay {
   int cslot;     // int [capC]: merge-table slot of each candidate
   int gath;      // int [64]: members of the cut bin (one-warp finish of the radix select)
   // lexicon-free fast step (beam_lf.h)
-  int lfSlotB, lfSlotOf, lfCbin, lfAbove;
+  int lfSlotB, lfSlotOf, lfCbin, lfAbove, lfDesc;
   int total;
 };
 
@@ -101,6 +101,9 @@ struct BatchArgs {
   int* hParent;         // history [B, T+2, K]
   int* hTok;
   int* hWord;           // null for the lexicon-free decoder
+  int* hSkip;           // [B, nCp, K] skip pointers: row 32j -> index of the ancestor in row 32(j-1)
+  int* hSkipFin;        // [B, K]      finish row -> index of the ancestor in its checkpoint row
+  int nCp;              // checkpoint rows per utterance: (T + 1) / 32 + 1
   double* finScore;     // [B, K, 3]
   int* finCount;        // [B]
   int* status;          // [B] bit0 = candidate overflow
@@ -113,7 +116,7 @@ struct BatchArgs {
 struct Beam {
   double* d;  // [3][K] score, emittingModelScore, lmScore
   u64* fp;    // [2][K] LM-state fingerprint (+ [2][K] fingerprint of the parent state, beam_lf.h)
-  int* iv;    // [4][K] lex, tok, prevBlank, nctx; then ctx [K][kMaxCtx]
+  int* iv;    // [5][K] lex, tok, prevBlank, nctx, anc; then ctx [K][kMaxCtx]
   int K;
   FLT_DEV double& score(int i) const { return d[i]; }
   FLT_DEV double& am(int i) const { return d[K + i]; }
@@ -126,7 +129,8 @@ struct Beam {
   FLT_DEV int& tok(int i) const { return iv[K + i]; }
   FLT_DEV int& pb(int i) const { return iv[2 * K + i]; }
   FLT_DEV int& nctx(int i) const { return iv[3 * K + i]; }
-  FLT_DEV int* ctx(int i) const { return iv + 4 * K + i * kMaxCtx; }
+  FLT_DEV int& anc(int i) const { return iv[4 * K + i]; } // ancestor at the last checkpoint row (backtrace)
+  FLT_DEV int* ctx(int i) const { return iv + 5 * K + i * kMaxCtx; }
 };
 
 constexpr int CF_PB = 1, CF_NEW = 2, CF_ALIVE = 4, CF_FINISH = 8;
@@ -222,7 +226,7 @@ FLT_HD void makeLayout(DecCfg& c) {
   for (int b = 0; b < 2; ++b) {
     L.beamD[b] = take(sizeof(double) * 3 * K);
     L.beamFp[b] = take(sizeof(u64) * (lf ? 4 : 2) * K);
-    L.beamI[b] = take(sizeof(int) * (4 * K + (c.lm.kind ? K * kMaxCtx : 0)));
+    L.beamI[b] = take(sizeof(int) * (5 * K + (c.lm.kind ? K * kMaxCtx : 0)));
   }
   L.rowHash = take(sizeof(int) * c.capRH);
   L.rowI = take(lf ? 0 : sizeof(int) * (kRowsInts * K + 8));
@@ -247,6 +251,7 @@ FLT_HD void makeLayout(DecCfg& c) {
   L.lfSlotOf = take(lf ? sizeof(int) * K : 0);
   L.lfCbin = take(lf ? sizeof(unsigned short) * 2 * c.capC : 0); // bin, arrival order in the bin
   L.lfAbove = take(lf ? sizeof(unsigned short) * 16 * c.lfBins : 0); // one copy per warp (<= 16)
+  L.lfDesc = take(lf ? sizeof(int) * c.capC : 0);                      // static work-item descriptors
   L.total = (int)off;
 }
 
@@ -424,6 +429,18 @@ FLT_DEV bool candBetter(const Cand& cd, int a, int b) {
   return (cd.flags(a) & CF_PB) < (cd.flags(b) & CF_PB);
 }
 
+/* ------------------------------------------------------------------ backtrace skip pointers --- */
+// A final hypothesis is traced back through T+2 history rows (Utils.h:229-250): a chain of T+2
+// dependent loads. Every hypothesis therefore carries the index of its ancestor in the last
+// checkpoint row (rows 0, 32, 64, ...); checkpoint rows and the finish row store it, and the
+// backtrace first hops checkpoint to checkpoint (T/32 loads), then walks all 32-row segments in
+// parallel.
+constexpr int kCpShift = 5, kCpRows = 1 << kCpShift;
+// ancestor index carried by the hypothesis written to history row hRow with parent p
+FLT_DEV int skipCarry(const Beam& cur, int hRow, int p) {
+  return ((hRow - 1) & (kCpRows - 1)) == 0 ? p : cur.anc(p);
+}
+
 /* ------------------------------------------------------------------ the frame step ---------- */
 struct FrameIn {
   const float* e;      // emission row [N] (global)
@@ -435,6 +452,8 @@ struct FrameIn {
   int listIsSet;       // the list holds the whole token set (lexicon-free, beamSizeToken < N)
   int specReady;       // spec[] already holds this frame's gathered emissions
   const float* eNext;  // next frame's emission row or null (beam_lf.h prefetches its gathers)
+  int hRow;            // index of the history row being written (frame t+1; len+1 for the finish)
+  int* hSkip;          // where its skip pointers go: a checkpoint row (hRow % 32 == 0), the finish row, else null
   int* hParent;        // history row to write (frame t+1), [K]
   int* hTok;
   int* hWord;
@@ -1086,6 +1105,9 @@ FLT_DEV void phaseFinalize(const Cta& cta, const DecCfg& c, const Ws& w, const B
       f.hParent[q] = p;
       f.hTok[q] = n;
       if (f.hWord) f.hWord[q] = cd.word(x);
+      const int an = skipCarry(cur, f.hRow, p);
+      nxt.anc(q) = an;
+      if (f.hSkip) f.hSkip[q] = an;
     }
   }
   if (cta.tid == 0) { // scalars for the next frame's merge / select
@@ -1324,6 +1346,7 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
                          const Beam& nxt, const FrameIn& f, unsigned long long* stats, LfCarry& carry);
 FLT_DEV void lfFinish(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, const Beam& nxt,
                       const FrameIn& f);
+FLT_DEV void lfBuildItemDesc(const Cta& cta, const DecCfg& c, const Ws& w);
 
 // One CTA decodes utterances bid, bid+nblk, ... start to finish. `base` is the CTA's workspace:
 // shared memory or a global slab.
@@ -1336,6 +1359,7 @@ FLT_DEV void ctaInitWorkspace(const Cta& cta, const DecCfg& c, const Ws& w, char
     int* slotB = (int*)(base + c.lay.lfSlotB);
     for (int i = cta.tid; i < c.capRH; i += cta.nthr) slotB[i] = -1;
     for (int i = cta.tid; i < c.lfBins; i += cta.nthr) w.hist()[i] = 0;
+    lfBuildItemDesc(cta, c, w);
   } else {
     for (int i = cta.tid; i < c.capH; i += cta.nthr) w.mh()[i] = -1;
     for (int i = cta.tid; i < 256; i += cta.nthr) w.hist()[i] = 0;
@@ -1406,6 +1430,8 @@ FLT_DEV FrameIn finishFrameIn(const DecCfg& c, const BatchArgs& a, int b, int le
   f.listIsSet = 0;
   f.specReady = 0;
   f.eNext = nullptr;
+  f.hRow = len + 1;
+  f.hSkip = a.hSkipFin + (long long)b * c.K;
   const long long h = ((long long)b * (a.T + 2) + (len + 1)) * c.K;
   f.hParent = a.hParent + h;
   f.hTok = a.hTok + h;
@@ -1467,6 +1493,8 @@ FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char
       f.hParent = a.hParent + h;
       f.hTok = a.hTok + h;
       f.hWord = a.hWord ? a.hWord + h : nullptr;
+      f.hRow = t + 1;
+      f.hSkip = ((t + 1) & (kCpRows - 1)) == 0 ? a.hSkip + ((long long)b * a.nCp + ((t + 1) >> kCpShift)) * K : nullptr;
       if (c.lfFast) lfFrameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.stats, carry);
       else frameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.status + b, a.stats);
       if (pf) {
@@ -1510,37 +1538,66 @@ struct BacktraceArgs {
   const int* hParent;
   const int* hTok;
   const int* hWord; // may be null
+  const int* hSkip;    // [B, nCp, K]
+  const int* hSkipFin; // [B, K]
   const int* finCount;
   const int* lengths;
-  int B, T, K, nbest;
+  int B, T, K, nbest, nCp;
   int* outTok;  // [B, nbest, T+2]
   int* outWord; // [B, nbest, T+2]
 };
+constexpr int kBtMaxCp = 288; // checkpoint indices one item keeps in shared memory (T <= ~9200)
 
-// item = (utterance b, rank r): walk the parent indices from the finish record to the seed
-// (Utils.h:229-250); positions past len+1 are -1.
-FLT_DEV void backtraceItem(const BacktraceArgs& a, long long item) {
+// rows (lo, hi] of item (b, r), starting from hypothesis k of row hi
+FLT_DEV void backtraceSegment(const BacktraceArgs& a, int b, int* ot, int* ow, int hi, int lo, int k) {
+  for (int row = hi; row > lo; --row) {
+    const long long h = ((long long)b * (a.T + 2) + row) * a.K + k;
+    ot[row] = a.hTok[h];
+    ow[row] = a.hWord ? a.hWord[h] : -1;
+    k = a.hParent[h];
+  }
+}
+
+// item = (utterance b, rank r), handled by `nlane` cooperating lanes (a warp; 1 in the host model):
+// getHypothesis (Utils.h:229-250); positions past len+1 are -1. cpIdx: >= kBtMaxCp ints of scratch.
+FLT_DEV void backtraceItem(const BacktraceArgs& a, long long item, int lane, int nlane, int* cpIdx) {
   const int b = (int)(item / a.nbest), r = (int)(item % a.nbest);
   const int len = a.lengths ? a.lengths[b] : a.T;
   int* ot = a.outTok + item * (a.T + 2);
   int* ow = a.outWord + item * (a.T + 2);
-  for (int i = len + 2; i < a.T + 2; ++i) {
+  for (int i = len + 2 + lane; i < a.T + 2; i += nlane) {
     ot[i] = -1;
     ow[i] = -1;
   }
   if (r >= a.finCount[b]) {
-    for (int i = 0; i < len + 2 && i < a.T + 2; ++i) {
+    for (int i = lane; i < len + 2 && i < a.T + 2; i += nlane) {
       ot[i] = -1;
       ow[i] = -1;
     }
     return;
   }
-  int k = r;
-  for (int fidx = len + 1; fidx >= 0; --fidx) {
-    const long long h = ((long long)b * (a.T + 2) + fidx) * a.K + k;
-    ot[fidx] = a.hTok[h];
-    ow[fidx] = a.hWord ? a.hWord[h] : -1;
-    k = a.hParent[h];
+  const int F = len + 1;               // finish row
+  const int J = (F - 1) >> kCpShift;   // its checkpoint row is kCpRows * J
+  if (J + 1 > kBtMaxCp) {              // very long utterance: plain walk
+    if (lane == 0) backtraceSegment(a, b, ot, ow, F, -1, r);
+    return;
+  }
+  if (lane == 0) { // hop checkpoint to checkpoint: cpIdx[j] = index of the ancestor in row kCpRows * j
+    int k = a.hSkipFin[(long long)b * a.K + r];
+    cpIdx[J] = k;
+    for (int j = J; j >= 1; --j) {
+      k = a.hSkip[((long long)b * a.nCp + j) * a.K + k];
+      cpIdx[j - 1] = k;
+    }
+  }
+#if FLT_DEVICE_BUILD
+  __syncwarp();
+#endif
+  // segments: s = J + 1 is (kCpRows * J, F] from r; s = 1..J is (kCpRows (s-1), kCpRows s]; s = 0 is row 0
+  for (int s = lane; s <= J + 1; s += nlane) {
+    if (s == J + 1) backtraceSegment(a, b, ot, ow, F, J << kCpShift, r);
+    else if (s == 0) backtraceSegment(a, b, ot, ow, 0, -1, cpIdx[0]);
+    else backtraceSegment(a, b, ot, ow, s << kCpShift, (s - 1) << kCpShift, cpIdx[s]);
   }
 }
 

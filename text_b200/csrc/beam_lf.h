@@ -85,12 +85,12 @@ FLT_DEV double lfScore(const DecCfg& c, const Beam& cur, int p, int n, float ev,
 FLT_DEV bool lfCell(const DecCfg& c, const Beam& cur, const LfTab& t, int i, int n, float ev,
                     double tau, double& score) {
   if (!lfEligible(c, cur, i, n)) return false;
+  score = lfScore(c, cur, i, n, ev, true);
+  if (score < tau) return false; // about half of the cells end here: test the bound first
   const int s = t.slotOf[i];
   const int a = t.a[s], b = t.b[s];
   const int partner = a == i ? b : a;
   if (partner >= 0 && partner < i && lfEligible(c, cur, partner, n)) return false; // the better member emits
-  score = lfScore(c, cur, i, n, ev, true);
-  if (score < tau) return false;
   // a hypothesis already in the child state whose repeat has the same key (child(S,n), n, 0)
   u64 ca, cb;
   fpChild(cur.fpA(i), cur.fpB(i), n, ca, cb);
@@ -180,8 +180,19 @@ struct LfPhaseClock {
   }
 };
 
-// Work items of a frame: [0, wideItems) = cells (hypothesis, ranked column); then nH repeat items,
-// nH blank items and (silScore > 0 only) nH sil cells. Item x owns candidate slot x.
+FLT_DEV int* lfItemDesc(const Ws& w) { return (int*)(w.base + w.c->lay.lfDesc); }
+// Work items of a frame: [0, wideTotal) = cells (hypothesis, ranked column) of all K hypotheses;
+// then K repeat items, K blank items and (silScore > 0 only) K sil cells. Item x owns candidate
+// slot x; items of hypotheses >= nH are dead. desc = hypothesis | column << 12 | kind << 24.
+FLT_DEV void lfBuildItemDesc(const Cta& cta, const DecCfg& c, const Ws& w) {
+  int* desc = lfItemDesc(w);
+  const int K = c.K;
+  for (int p = cta.tid; p < K; p += cta.nthr) {
+    for (int x = c.wideOff[p]; x < c.wideOff[p + 1]; ++x) desc[x] = p | ((x - c.wideOff[p]) << 12);
+    for (int kind = 1; kind <= 3; ++kind) desc[c.wideTotal + (kind - 1) * K + p] = p | (kind << 24);
+  }
+}
+
 FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur,
                          const Beam& nxt, const FrameIn& f, unsigned long long* stats, LfCarry& carry) {
   int* sc = w.sc();
@@ -266,21 +277,25 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
   pc.mark(0);
 
   // (2) candidates, each in the slot of its work item, and the histogram of their scores
-  const short* itemRow = w.itemRow();
-  const int* wideOff = w.wideOff();
-  const int wideItems = wideOff[nH];
-  const int nKinds = c.silScore > 0 ? 3 : 2;
-  const int items = wideItems + nKinds * nH;
+  // item x -> (hypothesis, column | kind) is fixed for the CTA's lifetime (lfItemDesc, built once):
+  // cells of hypothesis p first (all K hypotheses), then K repeat, K blank and K sil-cell items
+  const int* desc = lfItemDesc(w);
+  const int items = c.wideTotal + (c.silScore > 0 ? 3 : 2) * K;
   unsigned short* cbin = lfCbin(w);
   unsigned short* cslot = cbin + c.capC;
   for (int x = cta.tid; x < items; x += cta.nthr) {
     bool alive = false;
     double score = 0.0;
-    int par = 0, tok = 0, flags = 0;
+    int tok = 0, flags = 0;
     float ev = 0.0f;
-    if (x < wideItems) {
-      par = itemRow[x];
-      const int j = x - wideOff[par];
+    const int dsc = desc[x];
+    const int par = dsc & 0xFFF, kind = dsc >> 24;
+    if (par >= nH) {
+      cd.parflag(x) = 0;
+      continue;
+    }
+    if (kind == 0) {
+      const int j = (dsc >> 12) & 0xFFF;
       if (j < f.listLen) {
         tok = f.topTok[j];
         ev = f.topVal[j];
@@ -289,14 +304,11 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
         if (tok >= 0 && !(tok == c.sil && c.silScore > 0)) alive = lfCell(c, cur, t, par, tok, ev, tau, score);
       }
     } else {
-      const int y = x - wideItems;
-      const int kind = (y >= nH ? 1 : 0) + (y >= 2 * nH ? 1 : 0);
-      par = y - kind * nH;
-      if (kind == 0) {
+      if (kind == 1) {
         tok = cur.tok(par);
         ev = spec[par];
         alive = lfRepeat(c, cur, t, f, par, ev, tau, score);
-      } else if (kind == 1) {
+      } else if (kind == 2) {
         tok = c.blank;
         ev = spec[K];
         flags = CF_PB;
@@ -493,6 +505,9 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
       }
       f.hParent[q] = p;
       f.hTok[q] = n;
+      const int an = skipCarry(cur, f.hRow, p);
+      nxt.anc(q) = an;
+      if (f.hSkip) f.hSkip[q] = an;
       // the emission this hypothesis needs in the next frame: issue the (L2 / HBM) load now, it
       // lands while the barrier and the next frame's first phase run
       if (q == cta.tid && f.eNext && n >= 0 && n < c.N) carry.eOwn = f.eNext[n];
@@ -553,6 +568,7 @@ FLT_DEV void lfFinish(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& 
       nxt.lm(q) = cur.lm(i) + (double)0.0f;
       f.hParent[q] = i;
       f.hTok[q] = c.sil;
+      f.hSkip[q] = skipCarry(cur, f.hRow, i);
     }
     if (i == nH - 1) sc[SC_NH] = q + keep[i];
   }

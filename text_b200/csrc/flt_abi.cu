@@ -56,9 +56,12 @@ __global__ void __launch_bounds__(kFusedConsumers + kFusedProducers, 2)
   Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
   fusedCta(cta, c, tc, fl, a, smem);
 }
-__global__ void flt_k_backtrace(BacktraceArgs a) {
-  const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (item < (long long)a.B * a.nbest) backtraceItem(a, item);
+// one warp per (utterance, rank): checkpoint hops by lane 0, then the 32-row segments in parallel
+__global__ void __launch_bounds__(128) flt_k_backtrace(BacktraceArgs a) {
+  __shared__ int cp[4][kBtMaxCp];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long item = (long long)blockIdx.x * 4 + warp;
+  if (item < (long long)a.B * a.nbest) backtraceItem(a, item, lane, 32, cp[warp]);
 }
 #endif
 
@@ -134,10 +137,11 @@ void launchBacktrace(const BacktraceArgs& a, rt::Stream s) {
   const long long items = (long long)a.B * a.nbest;
   if (items == 0) return;
 #if FLT_DEVICE_BUILD
-  flt_k_backtrace<<<(unsigned)((items + 127) / 128), 128, 0, s>>>(a);
+  flt_k_backtrace<<<(unsigned)((items + 3) / 4), 128, 0, s>>>(a);
   FLT_RT_TRY(cudaGetLastError());
 #else
-  for (long long i = 0; i < items; ++i) backtraceItem(a, i);
+  std::vector<int> cp(kBtMaxCp);
+  for (long long i = 0; i < items; ++i) backtraceItem(a, i, 0, 1, cp.data());
   (void)s;
 #endif
 }
@@ -427,6 +431,7 @@ struct flt_decoder {
   std::vector<int> wideOffHost;
   rt::DevBuf dWideOff, dBias, dTrans;
   // batch buffers
+  rt::DevBuf hSkip, hSkipFin;
   rt::DevBuf topTok, topVal, thr, hPar, hTok, hWord, finScore, finCount, status, ws, outTok,
       outWord, dLengths, staging[2], dStats;
   int lastB = 0, lastT = 0, launches = 0;
@@ -438,7 +443,7 @@ struct flt_decoder {
   ~flt_decoder() {
     for (rt::DevBuf* b : {&dWideOff, &dBias, &dTrans, &topTok, &topVal, &thr, &hPar, &hTok, &hWord,
                           &finScore, &finCount, &status, &ws, &outTok, &outWord, &dLengths,
-                          &staging[0], &staging[1], &dStats})
+                          &staging[0], &staging[1], &dStats, &hSkip, &hSkipFin})
       b->release();
 #if FLT_DEVICE_BUILD
     for (int i = 0; i < 2; ++i) {
@@ -749,6 +754,11 @@ void runChunk(flt_decoder& d, const float* dEmis, int Bc, int T, int N, const in
   d.hPar.reserve(sizeof(int) * hist);
   d.hTok.reserve(sizeof(int) * hist);
   if (d.lexicon) d.hWord.reserve(sizeof(int) * hist);
+  a.nCp = (T + 1) / kCpRows + 1;
+  d.hSkip.reserve(sizeof(int) * (size_t)Bc * a.nCp * K);
+  d.hSkipFin.reserve(sizeof(int) * (size_t)Bc * K);
+  a.hSkip = d.hSkip.as<int>();
+  a.hSkipFin = d.hSkipFin.as<int>();
   a.hParent = d.hPar.as<int>();
   a.hTok = d.hTok.as<int>();
   a.hWord = d.lexicon ? d.hWord.as<int>() : nullptr;
@@ -775,6 +785,9 @@ void runChunk(flt_decoder& d, const float* dEmis, int Bc, int T, int N, const in
   b.hParent = a.hParent;
   b.hTok = a.hTok;
   b.hWord = a.hWord;
+  b.hSkip = a.hSkip;
+  b.hSkipFin = a.hSkipFin;
+  b.nCp = a.nCp;
   b.finCount = a.finCount;
   b.lengths = dLen;
   b.B = Bc;
