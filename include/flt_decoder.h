@@ -123,6 +123,22 @@ void* flt_decoder_stream(flt_decoder* dec);
 int flt_nbest_copy(flt_decoder* dec, int32_t nbest, int32_t* tokens, int32_t* words,
                    double* scores, int32_t* counts);
 
+/* ---- Online decoding of ONE utterance: decodeBegin / decodeStep(chunk) / decodeEnd / prune /
+ * nDecodedFramesInBuffer / getBestHypothesis / getAllFinalHypothesis (decoder/Decoder.h:18-35,
+ * decoder/LexiconDecoder.cpp:285-325, decoder/LexiconFreeDecoder.cpp:188-227, decoder/Utils.h:268-342).
+ * The beam stays on the device between chunks; chunk emissions [T,N] may be host or device memory.
+ * tokens / words rows hold maxLen entries; *len / lens[r] = frames in the buffer + 1 (0 = none). */
+int flt_stream_begin(flt_decoder* dec, int32_t N);
+int flt_stream_step(flt_decoder* dec, const float* emissions, int32_t T, int32_t N);
+int flt_stream_end(flt_decoder* dec);
+int flt_stream_prune(flt_decoder* dec, int32_t lookBack);
+int flt_stream_frames_in_buffer(flt_decoder* dec, int32_t* out);
+int flt_stream_n_hypothesis(flt_decoder* dec, int32_t* out);
+int flt_stream_best(flt_decoder* dec, int32_t lookBack, int32_t maxLen, int32_t* tokens, int32_t* words,
+                    double* scores3, int32_t* len);
+int flt_stream_all_final(flt_decoder* dec, int32_t maxHyp, int32_t maxLen, int32_t* tokens,
+                         int32_t* words, double* scores3, int32_t* lens, int32_t* count);
+
 /* Device addresses of the last batch's n-best buffers (valid until the next flt_decode_batch* call
  * on this decoder; synchronise the decoder's stream before reading them from another stream):
  * tokens / words [B, nbestSetting, T+2] int32, scores [B, beamSize, 3] fp64, counts [B] int32.

@@ -57,3 +57,33 @@ class FltBackend:
             out.append(dict(n=n, scores=r["scores"][b, :n], tokens=r["tokens"][b, :n, :L],
                             words=r["words"][b, :n, :L], total=int(r["counts"][b])))
         return out
+
+    # ---- online decoding, same surface as pyoracle.Oracle
+    def decode_begin(self, dec):
+        self._stream_N = None
+        self._stream_dec = dec
+
+    def decode_step(self, dec, emissions):
+        e = np.ascontiguousarray(emissions, np.float32)
+        if self._stream_N is None:
+            self._stream_N = e.shape[1]
+            self.api.stream_begin(dec, e.shape[1])
+        self.api.stream_step(dec, e)
+
+    def decode_end(self, dec):
+        self.api.stream_end(dec)
+
+    def prune(self, dec, look_back=0):
+        self.api.stream_prune(dec, look_back)
+
+    def n_hypothesis(self, dec):
+        return self.api.stream_n_hypothesis(dec)
+
+    def n_frames_in_buffer(self, dec):
+        return self.api.stream_frames_in_buffer(dec)
+
+    def best(self, dec, look_back, max_len):
+        return self.api.stream_best(dec, look_back, max_len)
+
+    def all_final(self, dec, max_hyp, max_len):
+        return self.api.stream_all_final(dec, max_hyp, max_len)

@@ -71,6 +71,17 @@ SYMBOLS = {
     "flt_decoder_stream": (C.c_void_p, [C.c_void_p]),
     "flt_nbest_copy": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                  C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+    "flt_stream_begin": (C.c_int, [C.c_void_p, C.c_int32]),
+    "flt_stream_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "flt_stream_end": (C.c_int, [C.c_void_p]),
+    "flt_stream_prune": (C.c_int, [C.c_void_p, C.c_int32]),
+    "flt_stream_frames_in_buffer": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "flt_stream_n_hypothesis": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "flt_stream_best": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                  C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+    "flt_stream_all_final": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_int32)]),
     "flt_nbest_device_ptrs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                         C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "flt_decoder_last_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
@@ -228,6 +239,52 @@ class Api:
         self._ck(self.lib.flt_nbest_copy(dec, nbest, _i32p(tokens), _i32p(words),
                                          scores.ctypes.data_as(C.POINTER(C.c_double)), _i32p(counts)))
         return dict(tokens=tokens, words=words, scores=scores, counts=counts)
+
+    # ---- online decoding (one utterance)
+    def stream_begin(self, dec, N):
+        self._ck(self.lib.flt_stream_begin(dec, N))
+
+    def stream_step(self, dec, emissions):
+        e = np.ascontiguousarray(emissions, np.float32)
+        T, N = e.shape
+        self._ck(self.lib.flt_stream_step(dec, e.ctypes.data, T, N))
+
+    def stream_end(self, dec):
+        self._ck(self.lib.flt_stream_end(dec))
+
+    def stream_prune(self, dec, look_back=0):
+        self._ck(self.lib.flt_stream_prune(dec, look_back))
+
+    def stream_frames_in_buffer(self, dec):
+        n = C.c_int32()
+        self._ck(self.lib.flt_stream_frames_in_buffer(dec, C.byref(n)))
+        return n.value
+
+    def stream_n_hypothesis(self, dec):
+        n = C.c_int32()
+        self._ck(self.lib.flt_stream_n_hypothesis(dec, C.byref(n)))
+        return n.value
+
+    def stream_best(self, dec, look_back, max_len):
+        scores = np.zeros(3, np.float64)
+        tokens = np.full(max_len, -1, np.int32)
+        words = np.full(max_len, -1, np.int32)
+        n = C.c_int32()
+        self._ck(self.lib.flt_stream_best(dec, look_back, max_len, _i32p(tokens), _i32p(words),
+                                          scores.ctypes.data_as(C.POINTER(C.c_double)), C.byref(n)))
+        return dict(scores=scores, tokens=tokens[:n.value], words=words[:n.value])
+
+    def stream_all_final(self, dec, max_hyp, max_len):
+        scores = np.zeros((max_hyp, 3), np.float64)
+        tokens = np.full((max_hyp, max_len), -1, np.int32)
+        words = np.full((max_hyp, max_len), -1, np.int32)
+        lens = np.zeros(max_hyp, np.int32)
+        n = C.c_int32()
+        self._ck(self.lib.flt_stream_all_final(dec, max_hyp, max_len, _i32p(tokens), _i32p(words),
+                                               scores.ctypes.data_as(C.POINTER(C.c_double)), _i32p(lens),
+                                               C.byref(n)))
+        k = min(n.value, max_hyp)
+        return dict(n=k, scores=scores[:k], tokens=tokens[:k], words=words[:k], lens=lens[:k])
 
     def nbest_device(self, dec, B, T, nbest, K):
         """The last batch's n-best buffers as torch CUDA tensors that alias the decoder's memory

@@ -110,6 +110,14 @@ struct BatchArgs {
   char* wsGlobal;       // per-CTA workspace slabs (used when the workspace does not fit smem)
   long long wsStride;
   unsigned long long* stats; // optional [4]: frames, candidates, merge groups, survivors (sums)
+  // online decoding (Decoder.h:18-35): one utterance, the beam carried across launches
+  char* streamBeam;     // saved beam (null = offline)
+  int streamRestore;    // 1 = start from the saved beam instead of the seed (decodeBegin)
+  int streamNoFinish;   // 1 = decodeStep chunk (no decodeEnd)
+  int streamFrame0;     // frames decoded before this chunk (ASG transitions skip global frame 0)
+  double streamShift;   // subtracted from the restored scores (prune()'s normalisation, Utils.h:333-341)
+  double* hScore;       // [T+2, K, 3] score / emittingModelScore / lmScore per history record, or null
+  int* hCount;          // [T+2] hypotheses per history row, or null
 };
 
 /* ------------------------------------------------------------------ workspace views ---------- */
@@ -454,6 +462,8 @@ struct FrameIn {
   const float* eNext;  // next frame's emission row or null (beam_lf.h prefetches its gathers)
   int hRow;            // index of the history row being written (frame t+1; len+1 for the finish)
   int* hSkip;          // where its skip pointers go: a checkpoint row (hRow % 32 == 0), the finish row, else null
+  double* hScore;      // this row's [K,3] scores (online decoding) or null
+  int* hCount;         // this row's hypothesis count (online decoding) or null
   int* hParent;        // history row to write (frame t+1), [K]
   int* hTok;
   int* hWord;
@@ -1108,6 +1118,11 @@ FLT_DEV void phaseFinalize(const Cta& cta, const DecCfg& c, const Ws& w, const B
       const int an = skipCarry(cur, f.hRow, p);
       nxt.anc(q) = an;
       if (f.hSkip) f.hSkip[q] = an;
+      if (f.hScore) {
+        f.hScore[3 * q] = score;
+        f.hScore[3 * q + 1] = nxt.am(q);
+        f.hScore[3 * q + 2] = nxt.lm(q);
+      }
     }
   }
   if (cta.tid == 0) { // scalars for the next frame's merge / select
@@ -1120,6 +1135,7 @@ FLT_DEV void phaseFinalize(const Cta& cta, const DecCfg& c, const Ws& w, const B
     sc[SC_AND_HI] = -1;
   }
   cta.sync();
+  if (f.hCount && cta.tid == 0) *f.hCount = sc[SC_NH];
 }
 
 // One frame: cur -> nxt. All threads of the CTA call this with identical arguments.
@@ -1432,11 +1448,44 @@ FLT_DEV FrameIn finishFrameIn(const DecCfg& c, const BatchArgs& a, int b, int le
   f.eNext = nullptr;
   f.hRow = len + 1;
   f.hSkip = a.hSkipFin + (long long)b * c.K;
+  f.hScore = a.hScore ? a.hScore + (long long)(len + 1) * c.K * 3 : nullptr;
+  f.hCount = a.hCount ? a.hCount + (len + 1) : nullptr;
   const long long h = ((long long)b * (a.T + 2) + (len + 1)) * c.K;
   f.hParent = a.hParent + h;
   f.hTok = a.hTok + h;
   f.hWord = a.hWord ? a.hWord + h : nullptr;
   return f;
+}
+
+// Online decoding: the live beam (its three workspace arrays and the hypothesis count) is kept in a
+// global slot between decodeStep launches. Layout: [int nH, pad to 16][beamD][beamFp][beamI].
+FLT_HD size_t streamBeamBytes(const DecCfg& c) {
+  const Lay& L = c.lay;
+  return 16 + (size_t)(L.beamFp[0] - L.beamD[0]) + (size_t)(L.beamI[0] - L.beamFp[0]) +
+         (size_t)(L.beamD[1] - L.beamI[0]);
+}
+FLT_DEV void streamSaveBeam(const Cta& cta, const DecCfg& c, const Ws& w, const BatchArgs& a, int curIdx) {
+  const Lay& L = c.lay;
+  const int n = (int)(streamBeamBytes(c) - 16) / 4; // the three arrays are contiguous per beam
+  const int* src = (const int*)(w.base + L.beamD[curIdx]);
+  int* dst = (int*)(a.streamBeam + 16);
+  for (int i = cta.tid; i < n; i += cta.nthr) dst[i] = src[i];
+  if (cta.tid == 0) *(int*)a.streamBeam = w.sc()[SC_NH];
+}
+FLT_DEV void streamRestoreBeam(const Cta& cta, const DecCfg& c, const Ws& w, const BatchArgs& a) {
+  const Lay& L = c.lay;
+  const int n = (int)(streamBeamBytes(c) - 16) / 4;
+  const int* src = (const int*)(a.streamBeam + 16);
+  int* dst = (int*)(w.base + L.beamD[0]);
+  for (int i = cta.tid; i < n; i += cta.nthr) dst[i] = src[i];
+  const int nH = *(const int*)a.streamBeam;
+  cta.sync();
+  const Beam B0 = w.beam(0);
+  for (int i = cta.tid; i < nH; i += cta.nthr) B0.score(i) -= a.streamShift; // Utils.h:339-341
+  if (cta.tid == 0) {
+    w.sc()[SC_NH] = nH;
+    a.status[0] = 0;
+  }
 }
 
 FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char* base) {
@@ -1447,7 +1496,8 @@ FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char
     const int len = a.lengths ? a.lengths[b] : a.T;
     int curIdx = 0;
     cta.sync(); // previous utterance fully retired
-    if (cta.tid == 0) seedUtterance(c, w, a, b);
+    if (a.streamBeam && a.streamRestore) streamRestoreBeam(cta, c, w, a);
+    else if (cta.tid == 0) seedUtterance(c, w, a, b);
     LfCarry carry{0.0f, 0.0f, 0.0f, 0};
     // token list of frame 0 into the workspace
     const long long row0 = (long long)b * a.T;
@@ -1485,9 +1535,11 @@ FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char
       }
       f.listLen = c.M;
       f.thrVal = a.thrVal ? a.thrVal[row] : 0.0f;
-      f.first = t == 0;
+      f.first = a.streamFrame0 + t == 0;
       f.listIsSet = !c.lexicon;
       f.specReady = 0;
+      f.hScore = a.hScore ? a.hScore + (long long)(t + 1) * K * 3 : nullptr;
+      f.hCount = a.hCount ? a.hCount + (t + 1) : nullptr;
       f.eNext = t + 1 < len ? f.e + c.N : nullptr;
       const long long h = ((long long)b * (a.T + 2) + (t + 1)) * K;
       f.hParent = a.hParent + h;
@@ -1519,6 +1571,11 @@ FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char
       if (w.sc()[SC_NH] == 0) break;
       curIdx ^= 1;
       cta.sync();
+    }
+    if (a.streamBeam && a.streamNoFinish) { // decodeStep chunk: keep the beam for the next launch
+      cta.sync();
+      streamSaveBeam(cta, c, w, a, curIdx);
+      continue;
     }
     int nFin = 0;
     if (w.sc()[SC_NH] != 0) {

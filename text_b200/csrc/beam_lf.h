@@ -508,6 +508,11 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
       const int an = skipCarry(cur, f.hRow, p);
       nxt.anc(q) = an;
       if (f.hSkip) f.hSkip[q] = an;
+      if (f.hScore) {
+        f.hScore[3 * q] = score;
+        f.hScore[3 * q + 1] = nxt.am(q);
+        f.hScore[3 * q + 2] = nxt.lm(q);
+      }
       // the emission this hypothesis needs in the next frame: issue the (L2 / HBM) load now, it
       // lands while the barrier and the next frame's first phase run
       if (q == cta.tid && f.eNext && n >= 0 && n < c.N) carry.eOwn = f.eNext[n];
@@ -520,6 +525,7 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
   }
   cta.sync(); // ---- B5
   pc.mark(4);
+  if (f.hCount && cta.tid == 0) *f.hCount = sc[SC_NH];
 }
 
 // decodeEnd (LexiconFreeDecoder.cpp:127-158) with ZeroLM: finish() returns the same state and 0,
@@ -569,10 +575,16 @@ FLT_DEV void lfFinish(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& 
       f.hParent[q] = i;
       f.hTok[q] = c.sil;
       f.hSkip[q] = skipCarry(cur, f.hRow, i);
+      if (f.hScore) {
+        f.hScore[3 * q] = nxt.score(q);
+        f.hScore[3 * q + 1] = nxt.am(q);
+        f.hScore[3 * q + 2] = nxt.lm(q);
+      }
     }
     if (i == nH - 1) sc[SC_NH] = q + keep[i];
   }
   cta.sync();
+  if (f.hCount && cta.tid == 0) *f.hCount = sc[SC_NH];
 }
 
 } // namespace flt

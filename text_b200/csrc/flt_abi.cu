@@ -421,6 +421,20 @@ struct flt_decoder {
   DecCfg cfg{};
   TopMCfg tcfg{};
   bool needTopM = false;
+  // online decoding of one utterance (Decoder.h:18-35): the beam lives on the device between
+  // decodeStep launches, the per-frame records are mirrored on the host for prune / best
+  struct SHyp {
+    double score, am, lm;
+    int parent, token, word;
+  };
+  struct Online {
+    bool begun = false;
+    int N = 0, nDecoded = 0, nPruned = 0;
+    bool haveBeam = false;
+    double shift = 0.0;
+    std::vector<std::vector<SHyp>> hyp; // rows in the buffer (row 0 = oldest kept frame)
+  } on;
+  rt::DevBuf sBeam, sScore, sCount, sEmis;
   int threads = 256;  // threads per utterance of the beam-step kernel
   bool fused = false; // select + step in one kernel (fused_core.h)
   TopMCfg ftcfg{};
@@ -443,7 +457,7 @@ struct flt_decoder {
   ~flt_decoder() {
     for (rt::DevBuf* b : {&dWideOff, &dBias, &dTrans, &topTok, &topVal, &thr, &hPar, &hTok, &hWord,
                           &finScore, &finCount, &status, &ws, &outTok, &outWord, &dLengths,
-                          &staging[0], &staging[1], &dStats, &hSkip, &hSkipFin})
+                          &staging[0], &staging[1], &dStats, &hSkip, &hSkipFin, &sBeam, &sScore, &sCount, &sEmis})
       b->release();
 #if FLT_DEVICE_BUILD
     for (int i = 0; i < 2; ++i) {
@@ -907,6 +921,173 @@ void checkStatus(flt_decoder& d) {
 
 } // namespace
 
+namespace {
+
+// One launch of online decoding: T frames of one utterance (T = 0 with finish = decodeEnd only).
+// Appends the new history rows to the host mirror.
+void runStream(flt_decoder& d, const float* emis, int T, int N, bool finish) {
+  planFor(d, N);
+  const DecCfg& c = d.cfg;
+  const int K = c.K;
+  rt::Stream s = d.stream;
+  const float* dEmis = emis;
+  if (T > 0 && !rt::isDevicePtr(emis)) {
+    d.sEmis.reserve(sizeof(float) * (size_t)T * N);
+    rt::h2d(d.sEmis.p, emis, sizeof(float) * (size_t)T * N, s);
+    dEmis = d.sEmis.as<float>();
+  }
+  BatchArgs a{};
+  a.emis = dEmis;
+  a.B = 1;
+  a.T = T;
+  a.lengths = nullptr;
+  if (d.needTopM && T > 0) {
+    d.topTok.reserve(sizeof(int) * (size_t)T * c.M);
+    d.topVal.reserve(sizeof(float) * (size_t)T * c.M);
+    if (!c.setAll) d.thr.reserve(sizeof(float) * (size_t)T);
+    TopMArgs ta{};
+    ta.emis = dEmis;
+    ta.rows = T;
+    ta.outTok = d.topTok.as<int>();
+    ta.outVal = d.topVal.as<float>();
+    ta.outThr = c.setAll ? nullptr : d.thr.as<float>();
+    TopMCfg tc = d.tcfg;
+    if ((reinterpret_cast<uintptr_t>(dEmis) & 15) != 0) tc.fast = 0;
+    launchTopM(tc, ta, std::min(T, d.topmGridMax), d.topmSmem, s);
+    a.topTok = ta.outTok;
+    a.topVal = ta.outVal;
+    a.thrVal = ta.outThr;
+  }
+  const size_t rows = (size_t)T + 2;
+  d.hPar.reserve(sizeof(int) * rows * K);
+  d.hTok.reserve(sizeof(int) * rows * K);
+  d.hWord.reserve(sizeof(int) * rows * K);
+  d.sScore.reserve(sizeof(double) * rows * K * 3);
+  d.sCount.reserve(sizeof(int) * rows);
+  d.sBeam.reserve(streamBeamBytes(c));
+  d.finScore.reserve(sizeof(double) * (size_t)K * 3);
+  d.finCount.reserve(sizeof(int));
+  d.status.reserve(sizeof(int));
+  a.nCp = (T + 1) / kCpRows + 1;
+  d.hSkip.reserve(sizeof(int) * (size_t)a.nCp * K);
+  d.hSkipFin.reserve(sizeof(int) * (size_t)K);
+  rt::devZero(d.sCount.p, sizeof(int) * rows, s);
+  a.hSkip = d.hSkip.as<int>();
+  a.hSkipFin = d.hSkipFin.as<int>();
+  a.hParent = d.hPar.as<int>();
+  a.hTok = d.hTok.as<int>();
+  a.hWord = d.lexicon ? d.hWord.as<int>() : nullptr;
+  a.finScore = d.finScore.as<double>();
+  a.finCount = d.finCount.as<int>();
+  a.status = d.status.as<int>();
+  a.stats = nullptr;
+  a.streamBeam = d.sBeam.as<char>();
+  a.streamRestore = d.on.haveBeam ? 1 : 0;
+  a.streamNoFinish = finish ? 0 : 1;
+  a.streamFrame0 = d.on.nDecoded;
+  a.streamShift = d.on.shift;
+  a.hScore = d.sScore.as<double>();
+  a.hCount = d.sCount.as<int>();
+  if (!d.useSmemFlag) {
+    d.ws.reserve(d.wsBytes);
+    a.wsGlobal = d.ws.as<char>();
+    a.wsStride = (long long)d.wsBytes;
+  }
+  launchDecode(c, a, 1, d.useSmemFlag ? d.wsBytes : 0, s, d.threads);
+  // mirror the new rows: frames 1..T (+ the finish row T+1)
+  const int nNew = T + (finish ? 1 : 0);
+  std::vector<int> par(rows * K), tok(rows * K), wrd(rows * K, -1), cnt(rows), st(1);
+  std::vector<double> sc(rows * K * 3);
+  rt::d2h(par.data(), d.hPar.p, sizeof(int) * rows * K, s);
+  rt::d2h(tok.data(), d.hTok.p, sizeof(int) * rows * K, s);
+  if (d.lexicon) rt::d2h(wrd.data(), d.hWord.p, sizeof(int) * rows * K, s);
+  rt::d2h(sc.data(), d.sScore.p, sizeof(double) * rows * K * 3, s);
+  rt::d2h(cnt.data(), d.sCount.p, sizeof(int) * rows, s);
+  rt::d2h(st.data(), d.status.p, sizeof(int), s);
+  rt::sync(s);
+  if (st[0] & 1) throw FltError(FLT_ERR_RUNTIME, "candidate capacity exceeded");
+  for (int r = 1; r <= nNew; ++r) {
+    std::vector<flt_decoder::SHyp> row(cnt[r]);
+    for (int q = 0; q < cnt[r]; ++q) {
+      const size_t o = (size_t)r * K + q;
+      row[q] = flt_decoder::SHyp{sc[o * 3], sc[o * 3 + 1], sc[o * 3 + 2], par[o], tok[o], wrd[o]};
+    }
+    d.on.hyp.push_back(std::move(row));
+  }
+  d.on.haveBeam = true;
+  d.on.shift = 0.0;
+  d.on.nDecoded += nNew;
+}
+
+using SHyp = flt_decoder::SHyp;
+constexpr int kLookBackLimit = 100; // Utils.h:28
+
+bool onlineComplete(const flt_decoder& d, int frame, int k) { // LexiconDecoder.h:97-99
+  if (!d.lexicon) return true;
+  const SHyp& h = d.on.hyp[frame][k];
+  return h.parent < 0 || d.on.hyp[frame - 1][h.parent].word >= 0;
+}
+// Utils.h:268-310: (frame, index) of the ancestor or index -1; lookBack is updated
+std::pair<int, int> onlineBestAncestor(const flt_decoder& d, int finalFrame, int& lookBack) {
+  const auto& fin = d.on.hyp[finalFrame];
+  if (fin.empty()) return {-1, -1};
+  int bk = 0;
+  for (int r = 1; r < (int)fin.size(); ++r)
+    if (fin[r].score > fin[bk].score) bk = r;
+  int f = finalFrame, k = bk, n = 0;
+  auto up = [&]() {
+    k = d.on.hyp[f][k].parent;
+    --f;
+    if (k < 0) f = -1;
+  };
+  while (k >= 0 && n < lookBack) {
+    ++n;
+    up();
+  }
+  const int maxLB = lookBack + kLookBackLimit;
+  while (k >= 0) {
+    if (onlineComplete(d, f, k)) break;
+    ++n;
+    up();
+    if (n == maxLB) break;
+  }
+  lookBack = n;
+  return {k >= 0 ? f : -1, k};
+}
+// Utils.h:229-250
+int onlineFill(const flt_decoder& d, int frame, int k, int finalFrame, int stride, double* scores3,
+               int32_t* tokens, int32_t* words) {
+  const SHyp& h0 = d.on.hyp[frame][k];
+  if (scores3) {
+    scores3[0] = h0.score;
+    scores3[1] = h0.am;
+    scores3[2] = h0.lm;
+  }
+  for (int j = 0; j <= finalFrame && j < stride; ++j) {
+    if (tokens) tokens[j] = -1;
+    if (words) words[j] = -1;
+  }
+  int i = 0, f = frame;
+  while (k >= 0 && f >= 0) {
+    const SHyp& h = d.on.hyp[f][k];
+    const int pos = finalFrame - i;
+    if (pos >= 0 && pos < stride) {
+      if (tokens) tokens[pos] = h.token;
+      if (words) words[pos] = d.lexicon ? h.word : -1;
+    }
+    k = h.parent;
+    --f;
+    ++i;
+  }
+  return finalFrame + 1;
+}
+void requireOnline(const flt_decoder* d) {
+  if (!d) throw FltError(FLT_ERR_INVALID, "null decoder");
+  if (!d->on.begun) throw FltError(FLT_ERR_INVALID, "flt_stream_begin has not been called");
+}
+
+} // namespace
+
 /* ================================================================================ C ABI ===== */
 extern "C" {
 
@@ -1181,6 +1362,107 @@ int flt_nbest_device_ptrs(flt_decoder* dec, int32_t** tokens, int32_t** words, d
     if (words) *words = dec->outWord.as<int32_t>();
     if (scores) *scores = dec->finScore.as<double>();
     if (counts) *counts = dec->finCount.as<int32_t>();
+  });
+}
+
+int flt_stream_begin(flt_decoder* dec, int32_t N) {
+  return guarded([&] {
+    if (!dec) throw FltError(FLT_ERR_INVALID, "null decoder");
+    requireDevice(dec->device);
+    planFor(*dec, N);
+    auto& on = dec->on;
+    on = flt_decoder::Online{};
+    on.begun = true;
+    on.N = N;
+    on.hyp.push_back({SHyp{0.0, 0.0, 0.0, -1, dec->sil, -1}}); // LexiconDecoder.cpp:26-27
+  });
+}
+int flt_stream_step(flt_decoder* dec, const float* emissions, int32_t T, int32_t N) {
+  return guarded([&] {
+    requireOnline(dec);
+    if (N != dec->on.N) throw FltError(FLT_ERR_INVALID, "N differs from flt_stream_begin");
+    if (T < 0 || (!emissions && T > 0)) throw FltError(FLT_ERR_INVALID, "bad chunk");
+    requireDevice(dec->device);
+    if (T > 0) runStream(*dec, emissions, T, N, false);
+  });
+}
+int flt_stream_end(flt_decoder* dec) {
+  return guarded([&] {
+    requireOnline(dec);
+    requireDevice(dec->device);
+    runStream(*dec, nullptr, 0, dec->on.N, true);
+  });
+}
+int flt_stream_prune(flt_decoder* dec, int32_t lookBack) {
+  return guarded([&] {
+    requireOnline(dec);
+    auto& on = dec->on;
+    if (on.nDecoded - on.nPruned - lookBack < 1) return; // LexiconDecoder.cpp:304-309
+    const int finalFrame = on.nDecoded - on.nPruned;
+    int lb = lookBack;
+    if (onlineBestAncestor(*dec, finalFrame, lb).second < 0) return;
+    lookBack = lb;
+    const int startFrame = on.nDecoded - on.nPruned - lookBack;
+    if (startFrame < 1) return;
+    // Utils.h:312-342: keep rows [startFrame, startFrame + lookBack], orphan row 0, normalise the
+    // newest row (= the device beam: applied when the next launch restores it)
+    std::vector<std::vector<SHyp>> kept(on.hyp.begin() + startFrame, on.hyp.begin() + startFrame + lookBack + 1);
+    on.hyp.swap(kept);
+    for (SHyp& h : on.hyp[0]) h.parent = -1;
+    if (!on.hyp[lookBack].empty()) {
+      double largest = on.hyp[lookBack].front().score;
+      for (const SHyp& h : on.hyp[lookBack]) largest = std::max(largest, h.score);
+      for (SHyp& h : on.hyp[lookBack]) h.score -= largest;
+      if (lookBack == (int)on.hyp.size() - 1) on.shift += largest;
+    }
+    on.nPruned = on.nDecoded - lookBack;
+  });
+}
+int flt_stream_frames_in_buffer(flt_decoder* dec, int32_t* out) {
+  return guarded([&] {
+    requireOnline(dec);
+    if (!out) throw FltError(FLT_ERR_INVALID, "null out");
+    *out = dec->on.nDecoded - dec->on.nPruned + 1; // LexiconDecoder.cpp:300-302
+  });
+}
+int flt_stream_n_hypothesis(flt_decoder* dec, int32_t* out) {
+  return guarded([&] {
+    requireOnline(dec);
+    if (!out) throw FltError(FLT_ERR_INVALID, "null out");
+    const int finalFrame = dec->on.nDecoded - dec->on.nPruned;
+    *out = (int)dec->on.hyp[finalFrame].size();
+  });
+}
+int flt_stream_best(flt_decoder* dec, int32_t lookBack, int32_t maxLen, int32_t* tokens, int32_t* words,
+                    double* scores3, int32_t* len) {
+  return guarded([&] {
+    requireOnline(dec);
+    if (!len) throw FltError(FLT_ERR_INVALID, "null len");
+    *len = 0;
+    const int finalFrame = dec->on.nDecoded - dec->on.nPruned;
+    if (dec->lexicon && finalFrame - lookBack < 1) return; // LexiconDecoder.cpp:285-288
+    int lb = lookBack;
+    const auto anc = onlineBestAncestor(*dec, finalFrame, lb);
+    if (anc.second < 0) return;
+    *len = onlineFill(*dec, anc.first, anc.second, finalFrame - lb, maxLen, scores3, tokens, words);
+  });
+}
+int flt_stream_all_final(flt_decoder* dec, int32_t maxHyp, int32_t maxLen, int32_t* tokens, int32_t* words,
+                         double* scores3, int32_t* lens, int32_t* count) {
+  return guarded([&] {
+    requireOnline(dec);
+    if (!count) throw FltError(FLT_ERR_INVALID, "null count");
+    const int finalFrame = dec->on.nDecoded - dec->on.nPruned;
+    *count = 0;
+    if (finalFrame < 1) return; // LexiconDecoder.cpp:276-283
+    const auto& fin = dec->on.hyp[finalFrame];
+    for (int r = 0; r < (int)fin.size() && r < maxHyp; ++r) {
+      const int L = onlineFill(*dec, finalFrame, r, finalFrame, maxLen, scores3 ? scores3 + 3 * r : nullptr,
+                               tokens ? tokens + (size_t)r * maxLen : nullptr,
+                               words ? words + (size_t)r * maxLen : nullptr);
+      if (lens) lens[r] = L;
+    }
+    *count = (int)fin.size();
   });
 }
 

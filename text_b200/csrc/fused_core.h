@@ -360,6 +360,8 @@ FLT_DEV FrameIn fusedFrameIn(const DecCfg& c, const BatchArgs& a, const FusedVie
   f.hParent = a.hParent + h;
   f.hTok = a.hTok + h;
   f.hWord = nullptr;
+  f.hScore = nullptr;
+  f.hCount = nullptr;
   f.hRow = t + 1;
   f.hSkip = ((t + 1) & (kCpRows - 1)) == 0 ? a.hSkip + ((long long)b * a.nCp + ((t + 1) >> kCpShift)) * c.K : nullptr;
   return f;

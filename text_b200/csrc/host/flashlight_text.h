@@ -17,8 +17,6 @@
 // ::setNbest. Differences, all loud:
 //   * LM objects other than ZeroLM / KenLM (ARPA file) cannot be used by the decoders
 //     (std::invalid_argument): a user-defined LM::score cannot run on the device.
-//   * Online use: decodeBegin / decodeStep(chunk) / decodeEnd buffer the chunks and decode at
-//     decodeEnd; getBestHypothesis / prune before decodeEnd throw std::runtime_error.
 //   * TrieNode objects returned by insert / search are value snapshots (children not populated).
 #pragma once
 #include <cmath>
@@ -291,45 +289,93 @@ class Decoder {
   Decoder(const Decoder&) = delete;
   Decoder& operator=(const Decoder&) = delete;
 
+  // Online decoding (Decoder.h:18-35): the beam stays on the device between chunks.
   virtual void decodeBegin() {
-    buffer_.clear();
-    bufT_ = 0;
-    bufN_ = 0;
+    online_ = true;
+    begun_ = false; // flt_stream_begin needs N: issued by the first decodeStep
     final_.clear();
-    ended_ = false;
   }
-  // chunks are buffered; the device decodes at decodeEnd (see the header comment)
   virtual void decodeStep(const float* emissions, int T, int N) {
-    if (bufT_ > 0 && N != bufN_) throw std::invalid_argument("decodeStep: N changed between chunks");
-    bufN_ = N;
-    buffer_.insert(buffer_.end(), emissions, emissions + (size_t)T * N);
-    bufT_ += T;
-    ended_ = false;
+    if (!online_) decodeBegin();
+    if (!begun_) {
+      detail::check(flt_stream_begin(h_, N));
+      begun_ = true;
+      onlineN_ = N;
+    }
+    detail::check(flt_stream_step(h_, emissions, T, N));
   }
   virtual void decodeEnd() {
-    auto all = decodeBatch(buffer_.data(), 1, bufT_, bufN_ > 0 ? bufN_ : 1);
-    final_ = std::move(all[0]);
-    ended_ = true;
+    if (!online_) decodeBegin();
+    if (!begun_) {
+      detail::check(flt_stream_begin(h_, onlineN_ > 0 ? onlineN_ : 1));
+      begun_ = true;
+    }
+    detail::check(flt_stream_end(h_));
   }
   // Decoder.h:51-57
   virtual std::vector<DecodeResult> decode(const float* emissions, int T, int N) {
     auto all = decodeBatch(emissions, 1, T, N);
+    online_ = false;
     final_ = all[0];
-    bufT_ = T;
-    ended_ = true;
+    offlineFrames_ = T + 1;
     return std::move(all[0]);
   }
-  virtual void prune(int /*lookBack*/ = 0) {
-    if (!ended_) throw std::runtime_error("prune() before decodeEnd() is not supported on the device path yet");
+  virtual void prune(int lookBack = 0) {
+    if (online_ && begun_) detail::check(flt_stream_prune(h_, lookBack));
   }
-  virtual int nDecodedFramesInBuffer() const { return bufT_ + (ended_ ? 1 : 0); }
+  virtual int nDecodedFramesInBuffer() const {
+    if (!(online_ && begun_)) return online_ ? 1 : offlineFrames_ + 1;
+    int n = 0;
+    detail::check(flt_stream_frames_in_buffer(h_, &n));
+    return n;
+  }
   virtual DecodeResult getBestHypothesis(int lookBack = 0) const {
-    if (!ended_ || lookBack != 0)
-      throw std::runtime_error("getBestHypothesis() with lookBack or before decodeEnd() is not supported on the device path yet");
-    return final_.empty() ? DecodeResult() : final_[0];
+    if (!(online_ && begun_)) {
+      if (online_ || lookBack != 0) return DecodeResult();
+      return final_.empty() ? DecodeResult() : final_[0];
+    }
+    int frames = 0;
+    detail::check(flt_stream_frames_in_buffer(h_, &frames));
+    DecodeResult d(frames);
+    double sc[3] = {0, 0, 0};
+    int len = 0;
+    detail::check(flt_stream_best(h_, lookBack, frames, d.tokens.data(), d.words.data(), sc, &len));
+    if (len == 0) return DecodeResult();
+    d.tokens.resize(len);
+    d.words.resize(len);
+    d.score = sc[0];
+    d.emittingModelScore = sc[1];
+    d.lmScore = sc[2];
+    return d;
   }
-  virtual std::vector<DecodeResult> getAllFinalHypothesis() const { return final_; }
-  int nHypothesis() const { return (int)final_.size(); }
+  virtual std::vector<DecodeResult> getAllFinalHypothesis() const {
+    if (!(online_ && begun_)) return final_;
+    int frames = 0, count = 0;
+    detail::check(flt_stream_frames_in_buffer(h_, &frames));
+    const int K = beamSize();
+    std::vector<int32_t> tok((size_t)K * frames), wrd((size_t)K * frames), lens(K);
+    std::vector<double> sc((size_t)K * 3);
+    detail::check(flt_stream_all_final(h_, K, frames, tok.data(), wrd.data(), sc.data(), lens.data(), &count));
+    std::vector<DecodeResult> out;
+    for (int r = 0; r < count && r < K; ++r) {
+      DecodeResult d(lens[r]);
+      d.score = sc[3 * r];
+      d.emittingModelScore = sc[3 * r + 1];
+      d.lmScore = sc[3 * r + 2];
+      for (int i = 0; i < lens[r]; ++i) {
+        d.tokens[i] = tok[(size_t)r * frames + i];
+        d.words[i] = wrd[(size_t)r * frames + i];
+      }
+      out.push_back(std::move(d));
+    }
+    return out;
+  }
+  int nHypothesis() const {
+    if (!(online_ && begun_)) return (int)final_.size();
+    int n = 0;
+    detail::check(flt_stream_n_hypothesis(h_, &n));
+    return n;
+  }
 
   // B utterances at once. emissions: row-major [B,T,N] fp32, host or device memory; lengths
   // (host, optional): valid frames per utterance; nbest <= beamSize hypotheses are materialised
@@ -369,10 +415,9 @@ class Decoder {
  protected:
   virtual int beamSize() const = 0;
   flt_decoder* h_ = nullptr;
-  std::vector<float> buffer_;
-  int bufT_ = 0, bufN_ = 0;
-  std::vector<DecodeResult> final_;
-  bool ended_ = false;
+  std::vector<DecodeResult> final_; // result of the last offline decode()
+  bool online_ = false, begun_ = false;
+  int onlineN_ = 0, offlineFrames_ = 0;
 };
 
 namespace detail {
