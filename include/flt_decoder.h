@@ -152,14 +152,15 @@ int flt_decoder_last_launches(const flt_decoder* dec, int32_t* out);
 /* Per-kernel device time of the last flt_decode_batch* call, from CUDA events recorded on the
  * decoder's stream around each launch (only while timing is on): ms4 / launches4 index
  * 0 = token-beam select, 1 = beam step, 2 = n-best backtrace, 3 = fused select + step.
- * Synchronises the stream. */
+ * Synchronises the stream. on = 1: events only; on = 2: also the in-kernel work / phase counters
+ * read by flt_decoder_last_stats (they cost a few hundred cycles per frame). */
 int flt_decoder_set_timing(flt_decoder* dec, int32_t on);
 int flt_decoder_last_kernel_ms(flt_decoder* dec, float* ms4, int32_t* launches4);
 /* Beam-step work counters of the last call (collected while timing is on), summed over frames:
  * out16[0..3] = {frames stepped, work items, live candidates (merge groups), survivors};
  * out16[4..10] = SM cycles thread 0 of the lexicon-free step spent in each phase (hash insert,
  * emit, scan, rank, new beam, wait for the producers, hand-over + emission gather); rest 0. */
-int flt_decoder_last_stats(flt_decoder* dec, uint64_t* out16);
+int flt_decoder_last_stats(flt_decoder* dec, uint64_t* out16); /* 32 entries; [16..27] per-warp emit time */
 int flt_decoder_workspace_bytes(const flt_decoder* dec, int64_t* out);
 
 /* Stand-alone entry to the token-beam select kernel (decoder/LexiconFreeDecoder.cpp:39-51:

@@ -308,7 +308,8 @@ class Api:
         self._ck(self.lib.flt_decoder_last_launches(dec, C.byref(n)))
         return n.value
 
-    def set_timing(self, dec, on=True):
+    def set_timing(self, dec, on=1):
+        """0 off, 1 CUDA events per launch, 2 also in-kernel work / phase counters."""
         self._ck(self.lib.flt_decoder_set_timing(dec, int(on)))
 
     def last_kernel_ms(self, dec):
@@ -319,7 +320,7 @@ class Api:
         return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(names)}
 
     def last_stats(self, dec):
-        v = (C.c_uint64 * 16)()
+        v = (C.c_uint64 * 32)()
         self._ck(self.lib.flt_decoder_last_stats(dec, v))
         frames = max(int(v[0]), 1)
         out = dict(frames=int(v[0]), candidates_per_frame=v[1] / frames, groups_per_frame=v[2] / frames,
@@ -328,6 +329,7 @@ class Api:
             names = ("insert", "emit", "scan", "rank", "new_beam", "wait_list", "handover_gather")
             out["phase_cycles_per_frame"] = {n: round(v[4 + i] / frames, 1) for i, n in enumerate(names)}
             out["select_guess_misses"] = int(v[11])
+            out["emit_cycles_per_warp"] = [round(v[16 + i] / frames, 1) for i in range(12) if v[16 + i]]
         return out
 
     def workspace_bytes(self, dec):

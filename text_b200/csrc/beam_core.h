@@ -85,6 +85,7 @@ struct DecCfg {
   int tauA[16];
   int tauCol[16];
   const int* wideOff; // [K+1]: wideOff[r] = sum_{q=1..r} J_q, J_q = min(Mwide, K/q + 3 (+slack))
+  const int* lfDesc;  // [wideTotal + 3K] work items of the lexicon-free step (beam_lf.h), column-major
   Lay lay;
   TrieDev trie;
   LmDev lm;

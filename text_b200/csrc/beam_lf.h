@@ -72,28 +72,57 @@ FLT_DEV bool lfBetter(const Cand& cd, int a, int b) {
   return (cd.flags(a) & CF_PB) < (cd.flags(b) & CF_PB);
 }
 
-// candidate score of hypothesis p taking token n with emission ev (LexiconFreeDecoder.cpp:64-67,
-// :75 with ZeroLM's 0.0f; transitions only enter emittingModelScore, :59-63)
-FLT_DEV double lfScore(const DecCfg& c, const Beam& cur, int p, int n, float ev, bool isNew) {
-  double score = cur.score(p) + (double)ev;
+// candidate score of a hypothesis with score ps taking token n with emission ev
+// (LexiconFreeDecoder.cpp:64-67, :75 with ZeroLM's 0.0f; transitions only enter
+// emittingModelScore, :59-63)
+FLT_DEV double lfScoreOf(const DecCfg& c, double ps, int n, float ev, bool isNew) {
+  double score = ps + (double)ev;
   if (n == c.sil) score += c.silScore;
   if (isNew) score = score + c.lmWeight * (double)0.0f;
   return score;
 }
+FLT_DEV double lfScore(const DecCfg& c, const Beam& cur, int p, int n, float ev, bool isNew) {
+  return lfScoreOf(c, cur.score(p), n, ev, isNew);
+}
 
-// new-token candidate of hypothesis i with token n: true if it is to be materialised
-FLT_DEV bool lfCell(const DecCfg& c, const Beam& cur, const LfTab& t, int i, int n, float ev,
-                    double tau, double& score) {
-  if (!lfEligible(c, cur, i, n)) return false;
-  score = lfScore(c, cur, i, n, ev, true);
-  if (score < tau) return false; // about half of the cells end here: test the bound first
+// everything an item needs about its hypothesis, loaded up front so that the shared-memory
+// latencies overlap instead of chaining behind the item's branches
+struct LfHyp {
+  int i, tok, pb;
+  int sa, sb;   // the (at most two) members of its row
+  double score;
+  u64 fa, fb;   // fingerprint of its LM state (cells) or of the parent state (repeat items)
+};
+FLT_DEV LfHyp lfLoadHyp(const Beam& cur, const LfTab& t, int i, bool parentFp) {
+  LfHyp h;
+  h.i = i;
+  h.tok = cur.tok(i);
+  h.pb = cur.pb(i);
+  h.score = cur.score(i);
+  h.fa = parentFp ? cur.pfpA(i) : cur.fpA(i);
+  h.fb = parentFp ? cur.pfpB(i) : cur.fpB(i);
   const int s = t.slotOf[i];
-  const int a = t.a[s], b = t.b[s];
-  const int partner = a == i ? b : a;
+  h.sa = t.a[s];
+  h.sb = t.b[s];
+  return h;
+}
+FLT_DEV bool lfEligibleH(const DecCfg& c, const LfHyp& h, int n) {
+  if (c.ctc) return n != c.blank && (n != h.tok || h.pb);
+  return n != h.tok;
+}
+
+// new-token candidate of hypothesis h with token n: true if it is to be materialised
+FLT_DEV bool lfCell(const DecCfg& c, const Beam& cur, const LfTab& t, const LfHyp& h, int n, float ev,
+                    double tau, double& score) {
+  if (!lfEligibleH(c, h, n)) return false;
+  score = lfScoreOf(c, h.score, n, ev, true);
+  if (score < tau) return false; // about half of the cells end here: test the bound first
+  const int i = h.i;
+  const int partner = h.sa == i ? h.sb : h.sa;
   if (partner >= 0 && partner < i && lfEligible(c, cur, partner, n)) return false; // the better member emits
   // a hypothesis already in the child state whose repeat has the same key (child(S,n), n, 0)
   u64 ca, cb;
-  fpChild(cur.fpA(i), cur.fpB(i), n, ca, cb);
+  fpChild(h.fa, h.fb, n, ca, cb);
   int ma = -1, mb = -1;
   if (lfProbe(t, cur, ca, cb, ma, mb)) {
     int m = -1;
@@ -107,17 +136,17 @@ FLT_DEV bool lfCell(const DecCfg& c, const Beam& cur, const LfTab& t, int i, int
   return true;
 }
 
-// repeat candidate of hypothesis i (LexiconFreeDecoder.cpp:98-110)
-FLT_DEV bool lfRepeat(const DecCfg& c, const Beam& cur, const LfTab& t, const FrameIn& f, int i,
+// repeat candidate of hypothesis h (LexiconFreeDecoder.cpp:98-110); h carries the PARENT state's fingerprint
+FLT_DEV bool lfRepeat(const DecCfg& c, const Beam& cur, const LfTab& t, const FrameIn& f, const LfHyp& h,
                       float eOwn, double tau, double& score) {
-  const int n = cur.tok(i);
-  const bool isRepeat = c.ctc ? (!cur.pb(i) && n != c.blank) : true;
+  const int n = h.tok, i = h.i;
+  const bool isRepeat = c.ctc ? (!h.pb && n != c.blank) : true;
   if (!(isRepeat && n >= 0 && n < c.N && inTokenSetV(c, f, n, eOwn))) return false;
-  score = lfScore(c, cur, i, n, eOwn, false);
+  score = lfScoreOf(c, h.score, n, eOwn, false);
   if (score < tau) return false;
   // new token n from the parent state merges into the same key
   int ma = -1, mb = -1;
-  if (lfProbe(t, cur, cur.pfpA(i), cur.pfpB(i), ma, mb)) {
+  if (lfProbe(t, cur, h.fa, h.fb, ma, mb)) {
     int p = -1;
     if (lfEligible(c, cur, ma, n)) p = ma;
     if (mb >= 0 && lfEligible(c, cur, mb, n) && (p < 0 || mb < p)) p = mb;
@@ -129,16 +158,14 @@ FLT_DEV bool lfRepeat(const DecCfg& c, const Beam& cur, const LfTab& t, const Fr
   return true;
 }
 
-// blank candidate of hypothesis i (LexiconFreeDecoder.cpp:86-97): the better member of a row emits
-FLT_DEV bool lfBlank(const DecCfg& c, const Beam& cur, const LfTab& t, const FrameIn& f, int i,
-                     float eBlank, double tau, double& score) {
+// blank candidate of hypothesis h (LexiconFreeDecoder.cpp:86-97): the better member of a row emits
+FLT_DEV bool lfBlank(const DecCfg& c, const FrameIn& f, const LfHyp& h, float eBlank, double tau,
+                     double& score) {
   if (!c.ctc) return false;
-  const int s = t.slotOf[i];
-  const int a = t.a[s], b = t.b[s];
-  const int partner = a == i ? b : a;
-  if (partner >= 0 && partner < i) return false;
+  const int partner = h.sa == h.i ? h.sb : h.sa;
+  if (partner >= 0 && partner < h.i) return false;
   if (!inTokenSetV(c, f, c.blank, eBlank)) return false;
-  score = lfScore(c, cur, i, c.blank, eBlank, false);
+  score = lfScoreOf(c, h.score, c.blank, eBlank, false);
   return !(score < tau);
 }
 
@@ -181,16 +208,15 @@ struct LfPhaseClock {
 };
 
 FLT_DEV int* lfItemDesc(const Ws& w) { return (int*)(w.base + w.c->lay.lfDesc); }
-// Work items of a frame: [0, wideTotal) = cells (hypothesis, ranked column) of all K hypotheses;
-// then K repeat items, K blank items and (silScore > 0 only) K sil cells. Item x owns candidate
+// Work items of a frame: [0, wideTotal) = cells (hypothesis, ranked column) of all K hypotheses,
+// column-major; then K repeat items, K blank items and (silScore > 0 only) K sil cells. Item x owns candidate
 // slot x; items of hypotheses >= nH are dead. desc = hypothesis | column << 12 | kind << 24.
 FLT_DEV void lfBuildItemDesc(const Cta& cta, const DecCfg& c, const Ws& w) {
+  // the host orders the cells column-major (column 0 of every hypothesis, then column 1, ...): the
+  // cells most likely to survive the bound sit together in the first warps' first sweep, and the
+  // late sweeps are mostly cells that end at the bound test
   int* desc = lfItemDesc(w);
-  const int K = c.K;
-  for (int p = cta.tid; p < K; p += cta.nthr) {
-    for (int x = c.wideOff[p]; x < c.wideOff[p + 1]; ++x) desc[x] = p | ((x - c.wideOff[p]) << 12);
-    for (int kind = 1; kind <= 3; ++kind) desc[c.wideTotal + (kind - 1) * K + p] = p | (kind << 24);
-  }
+  for (int x = cta.tid; x < c.capC; x += cta.nthr) desc[x] = c.lfDesc[x];
 }
 
 FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur,
@@ -294,6 +320,7 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
       cd.parflag(x) = 0;
       continue;
     }
+    const LfHyp h = lfLoadHyp(cur, t, par, kind == 1);
     if (kind == 0) {
       const int j = (dsc >> 12) & 0xFFF;
       if (j < f.listLen) {
@@ -301,23 +328,23 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
         ev = f.topVal[j];
         flags = CF_NEW;
         // a boosted sil is not rank-dominated: every hypothesis proposes it as a special item
-        if (tok >= 0 && !(tok == c.sil && c.silScore > 0)) alive = lfCell(c, cur, t, par, tok, ev, tau, score);
+        if (tok >= 0 && !(tok == c.sil && c.silScore > 0)) alive = lfCell(c, cur, t, h, tok, ev, tau, score);
       }
     } else {
       if (kind == 1) {
-        tok = cur.tok(par);
+        tok = h.tok;
         ev = spec[par];
-        alive = lfRepeat(c, cur, t, f, par, ev, tau, score);
+        alive = lfRepeat(c, cur, t, f, h, ev, tau, score);
       } else if (kind == 2) {
         tok = c.blank;
         ev = spec[K];
         flags = CF_PB;
-        alive = lfBlank(c, cur, t, f, par, ev, tau, score);
+        alive = lfBlank(c, f, h, ev, tau, score);
       } else {
         tok = c.sil;
         ev = spec[K + 1];
         flags = CF_NEW;
-        if (inTokenSetV(c, f, tok, ev)) alive = lfCell(c, cur, t, par, tok, ev, tau, score);
+        if (inTokenSetV(c, f, tok, ev)) alive = lfCell(c, cur, t, h, tok, ev, tau, score);
       }
     }
     if (alive) {
@@ -422,7 +449,7 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
   cta.sync(); // ---- B3
   pc.mark(2);
   // (4) exact ranks among the nRel relevant candidates by counting: `parts` adjacent lanes share
-  // one candidate and split the list between them (equal scores: the lower work item first)
+  // one candidate and split the list between them (equal scores: lower parent, then lower token)
   int* ranked = w.surv() + c.capP;
   {
     int lg = 0;
@@ -446,7 +473,7 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
         }
         if (tie) // another candidate with exactly this score: settle by work item (rare)
           for (int qb = part; qb < nRel; qb += parts)
-            if (lkey[qb] == ka && list[qb] < xa) ++cnt;
+            if (lkey[qb] == ka && qb != qa && lfBetter(cd, list[qb], xa)) ++cnt;
       }
 #if FLT_DEVICE_BUILD
       for (int o = 1; o < parts; o <<= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);

@@ -414,7 +414,8 @@ struct flt_decoder {
   std::vector<cudaEvent_t> evPool; // kernel timing: (start, stop) pairs, kind = index % 3
   size_t evUsed = 0;
 #endif
-  bool timing = false;
+  bool timing = false;   // CUDA events around each launch
+  bool counters = false; // in-kernel work / phase counters (costs a few hundred cycles per frame)
   std::vector<int> evKinds;
   // plan
   int planN = -1;
@@ -443,7 +444,7 @@ struct flt_decoder {
   size_t wsBytes = 0, topmSmem = 0;
   int gridMax = 1, topmGridMax = 1;
   std::vector<int> wideOffHost;
-  rt::DevBuf dWideOff, dBias, dTrans;
+  rt::DevBuf dWideOff, dBias, dTrans, dLfDesc;
   // batch buffers
   rt::DevBuf hSkip, hSkipFin;
   rt::DevBuf topTok, topVal, thr, hPar, hTok, hWord, finScore, finCount, status, ws, outTok,
@@ -455,7 +456,7 @@ struct flt_decoder {
   bool haveLengths = false;
 
   ~flt_decoder() {
-    for (rt::DevBuf* b : {&dWideOff, &dBias, &dTrans, &topTok, &topVal, &thr, &hPar, &hTok, &hWord,
+    for (rt::DevBuf* b : {&dWideOff, &dBias, &dTrans, &dLfDesc, &topTok, &topVal, &thr, &hPar, &hTok, &hWord,
                           &finScore, &finCount, &status, &ws, &outTok, &outWord, &dLengths,
                           &staging[0], &staging[1], &dStats, &hSkip, &hSkipFin, &sBeam, &sScore, &sCount, &sEmis})
       b->release();
@@ -588,6 +589,17 @@ void planFor(flt_decoder& d, int N) {
 
   rt::Stream s = d.stream;
   c.wideOff = upload(d.dWideOff, d.wideOffHost, s);
+  c.lfDesc = nullptr;
+  if (c.lfFast) {
+    std::vector<int> desc;
+    for (int j = 0; j < c.Mwide; ++j)
+      for (int p = 0; p < K; ++p)
+        if (j < d.wideOffHost[p + 1] - d.wideOffHost[p]) desc.push_back(p | (j << 12));
+    for (int kind = 1; kind <= 3; ++kind)
+      for (int p = 0; p < K; ++p) desc.push_back(p | (kind << 24));
+    desc.resize(c.capC, 0xFFF); // padding: hypothesis 4095 >= nH, dead
+    c.lfDesc = upload(d.dLfDesc, desc, s);
+  }
   c.trans = nullptr;
   if (!c.ctc && !d.trans.empty()) c.trans = upload(d.dTrans, d.trans, s);
   if (d.lexicon) {
@@ -780,7 +792,7 @@ void runChunk(flt_decoder& d, const float* dEmis, int Bc, int T, int N, const in
   a.finCount = d.finCount.as<int>() + outBase;
   a.status = d.status.as<int>() + outBase;
   const int grid = std::max(1, std::min(Bc, fused ? d.fusedGridMax : d.gridMax));
-  a.stats = d.timing ? d.dStats.as<unsigned long long>() : nullptr;
+  a.stats = d.counters ? d.dStats.as<unsigned long long>() : nullptr;
   if (fused) {
     KernelTimer kt(d, 3);
     launchFused(c, d.ftcfg, d.flay, a, grid, s);
@@ -829,9 +841,9 @@ void prepareBatch(flt_decoder& d, int B, int T, int N) {
   d.lastB = B;
   d.lastT = T;
   d.launches = 0;
-  if (d.timing) {
-    d.dStats.reserve(sizeof(unsigned long long) * 16);
-    rt::devZero(d.dStats.p, sizeof(unsigned long long) * 16, d.stream);
+  if (d.counters) {
+    d.dStats.reserve(sizeof(unsigned long long) * 32);
+    rt::devZero(d.dStats.p, sizeof(unsigned long long) * 32, d.stream);
   }
 #if FLT_DEVICE_BUILD
   d.evUsed = 0;
@@ -1476,6 +1488,7 @@ int flt_decoder_set_timing(flt_decoder* dec, int32_t on) {
   return guarded([&] {
     if (!dec) throw FltError(FLT_ERR_INVALID, "null decoder");
     dec->timing = on != 0;
+    dec->counters = on >= 2;
   });
 }
 int flt_decoder_last_kernel_ms(flt_decoder* dec, float* ms3, int32_t* launches3) {
@@ -1499,9 +1512,9 @@ int flt_decoder_last_kernel_ms(flt_decoder* dec, float* ms3, int32_t* launches3)
 int flt_decoder_last_stats(flt_decoder* dec, uint64_t* out4) {
   return guarded([&] {
     if (!dec || !out4) throw FltError(FLT_ERR_INVALID, "null argument");
-    for (int k = 0; k < 16; ++k) out4[k] = 0;
+    for (int k = 0; k < 32; ++k) out4[k] = 0;
     if (!dec->dStats.p) return;
-    rt::d2h(out4, dec->dStats.p, sizeof(uint64_t) * 16, dec->stream);
+    rt::d2h(out4, dec->dStats.p, sizeof(uint64_t) * 32, dec->stream);
     rt::sync(dec->stream);
   });
 }
