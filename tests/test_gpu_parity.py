@@ -70,3 +70,9 @@ def test_long_ragged_checkpoints(A, G):
     from test_model_parity import run_long_ragged
 
     run_long_ragged(A, G, 1e-4)
+
+
+def test_masked_emissions(A, G):
+    from test_model_parity import run_masked
+
+    run_masked(A, G, 1e-4)

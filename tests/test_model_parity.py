@@ -79,3 +79,48 @@ def run_long_ragged(A, G, tol):
 
 def test_long_ragged_checkpoints(A, M):
     run_long_ragged(A, M, 1e-9)
+
+
+def masked_cases():
+    """Emission rows with -inf entries (masked tokens): fewer finite values than list entries wanted
+    (short token lists), rows with a handful of finite values, and heavy masking with a lexicon."""
+    from cases import spec_lexfree, spec_lexicon
+    from text_b200 import synth
+
+    out = []
+    rng = np.random.default_rng(4)
+    for N, K, frac in ((64, 50, 0.4), (64, 10, 0.9), (200, 50, 0.5), (40, 16, 0.2)):
+        em = synth.emissions(2, 30, N, seed=N + K, sigma=2.0)
+        mask = rng.random((2, 30, N)) < frac
+        mask[:, :, 0] = False      # sil stays finite
+        mask[:, :, N - 1] = False  # blank stays finite
+        em = em.copy()
+        em[mask] = -np.inf
+        out.append((spec_lexfree(N, K, N, 1e9), em))
+    N = 40
+    em = synth.emissions(2, 30, N, seed=77, sigma=2.0).copy()
+    mask = rng.random((2, 30, N)) < 0.3
+    mask[:, :, 0] = False
+    mask[:, :, N - 1] = False
+    em[mask] = -np.inf
+    out.append((spec_lexicon(N, 20, N, synth.lexicon(150, N, 2, 4, seed=3, exclude=(0, N - 1)), 1e9, word_score=0.2), em))
+    return out
+
+
+def run_masked(A, G, tol):
+    checked = 0
+    for spec, em in masked_cases():
+        ba, bg = Built(A, spec), Built(G, spec)
+        got = bg.O.decode_batch(bg.dec, em, spec["opt"].beamSize)
+        for b, e in enumerate(em):
+            ra = ba.decode(e)
+            if has_ties(ra) or A.tie_events(ba.dec):
+                continue
+            assert_same_nbest(ra, got[b], tol, what=f"masked utt {b}")
+            checked += 1
+        ba.close(), bg.close()
+    assert checked >= 4
+
+
+def test_masked_emissions(A, M):
+    run_masked(A, M, 1e-9)

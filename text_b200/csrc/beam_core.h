@@ -57,6 +57,7 @@ struct Lay {
   int gath;      // int [64]: members of the cut bin (one-warp finish of the radix select)
   // lexicon-free fast step (beam_lf.h)
   int lfSlotB, lfSlotOf, lfCbin, lfAbove, lfDesc;
+  int pruneCache; // u8 per work item: 1 + best histogram bin its candidates reached in pass 1 (two-pass pruning)
   int total;
 };
 
@@ -142,6 +143,7 @@ struct Beam {
   FLT_DEV int* ctx(int i) const { return iv + 5 * K + i * kMaxCtx; }
 };
 
+constexpr int kPruneEdgeCap = 4096; // trie-edge work items whose pass-1 result is cached
 constexpr int CF_PB = 1, CF_NEW = 2, CF_ALIVE = 4, CF_FINISH = 8;
 constexpr int kIntMax = 0x7FFFFFFF;
 
@@ -191,6 +193,7 @@ enum { // ws.sc[] scalars
 struct Ws {
   char* base;
   const DecCfg* c;
+  int* itemBin = nullptr; // pass 1 of the two-pass pruning: best bin reached by the current work item
   FLT_DEV Beam beam(int b) const {
     const Lay& L = c->lay;
     return Beam{(double*)(base + L.beamD[b]), (u64*)(base + L.beamFp[b]), (int*)(base + L.beamI[b]), c->K};
@@ -261,6 +264,7 @@ FLT_HD void makeLayout(DecCfg& c) {
   L.lfCbin = take(lf ? sizeof(unsigned short) * 2 * c.capC : 0); // bin, arrival order in the bin
   L.lfAbove = take(lf ? sizeof(unsigned short) * 16 * c.lfBins : 0); // one copy per warp (<= 16)
   L.lfDesc = take(lf ? sizeof(int) * c.capC : 0);                      // static work-item descriptors
+  L.pruneCache = take(c.prune2 ? (size_t)c.wideTotal + c.K + kPruneEdgeCap : 0);
   L.total = (int)off;
 }
 
@@ -583,7 +587,8 @@ constexpr int kPruneBins = 256;
 FLT_DEV int pruneBin(const int* sc, double score) {
   const double lo = bitsF64(((u64)(unsigned)sc[SC_PLO_HI] << 32) | (unsigned)sc[SC_PLO_LO]);
   const float pos = (float)(score - lo) * bitsF32((uint32_t)sc[SC_PSCALE]);
-  return pos >= (float)(kPruneBins - 1) ? kPruneBins - 1 : (pos > 0.0f ? (int)pos : 0);
+  // bins 0..254: 1 + bin fits the one-byte per-item cache of the two-pass pruning
+  return pos >= (float)(kPruneBins - 2) ? kPruneBins - 2 : (pos > 0.0f ? (int)pos : 0);
 }
 
 // slot for a candidate that survived the pruning bound (compact: only live candidates are stored)
@@ -593,6 +598,7 @@ FLT_DEV int allocCand(const Cta& cta, const DecCfg& c, const Ws& w, double score
     const int bin = pruneBin(w.sc(), score);
     if (mode == 1) {
       atomAdd(&w.hist()[bin], 1);
+      if (w.itemBin && bin > *w.itemBin) *w.itemBin = bin;
       return -1;
     }
     if (bin < w.sc()[SC_PCUT]) return -1;
@@ -1209,36 +1215,56 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
     ctaExclusiveScan(cta, deg, w.rows().degTmp(), nH);
     edgeItems = deg[nH];
   }
-  auto emitAll = [&]() {
+  // pass 1 records, per work item, the best bin any of its candidates reached; pass 2 skips the
+  // items that cannot reach the cut without recomputing them (their gathers are the expensive part)
+  int localBin = -1;
+  Ws wp = w;
+  unsigned char* pcache = c.prune2 ? (unsigned char*)(w.base + c.lay.pruneCache) : nullptr;
+  auto emitAll = [&](int pass) { // 0 = no pruning, 1 = histogram pass, 2 = materialise
+    const int cut = pass == 2 ? sc[SC_PCUT] : 0;
+    wp.itemBin = pass == 1 ? &localBin : nullptr;
+    auto skip = [&](int slot) { return pass == 2 && pcache && (int)pcache[slot] <= cut; };
+    auto note = [&](int slot) {
+      if (pass == 1) pcache[slot] = (unsigned char)(localBin + 1);
+      localBin = -1;
+    };
     // wide cells
     if (c.wideRanked) {
       const short* itemRow = w.itemRow();
       const int* wideOff = w.wideOff();
       for (int x = cta.tid; x < wideItems; x += cta.nthr) {
+        if (skip(x)) continue;
         const int r = itemRow[x]; // row rank (0-based)
-        emitWide(cta, c, w, cur, f, w.rows().leaderOfRank(r), x - wideOff[r], tau);
+        emitWide(cta, c, wp, cur, f, w.rows().leaderOfRank(r), x - wideOff[r], tau);
+        note(x);
       }
     }
     // stay / repeat / blank
     for (int i = cta.tid; i < nH; i += cta.nthr) {
-      emitSpecials(cta, c, w, cur, f, i, tau);
-      if (c.wideRanked) emitSilCell(cta, c, w, cur, f, i, tau);
+      if (skip(c.wideTotal + i)) continue;
+      emitSpecials(cta, c, wp, cur, f, i, tau);
+      if (c.wideRanked) emitSilCell(cta, c, wp, cur, f, i, tau);
+      note(c.wideTotal + i);
     }
     // trie edges
     if (c.lexicon) {
       const TrieDev& t = c.trie;
       const int* deg = w.rows().deg();
       for (int x = cta.tid; x < edgeItems; x += cta.nthr) {
+        const bool cached = x < kPruneEdgeCap;
+        if (cached && skip(c.wideTotal + c.K + x)) continue;
         const int i = searchOffsets(deg, nH + 1, x);
         const int k = x - deg[i];
         const int lex = cur.lex(i);
         if (c.wideRanked && lex == 0) {
           const int n = t.rootLabTok[k];
-          emitEdge(cta, c, w, cur, f, i, n, t.rootChild[n], true, tau);
+          emitEdge(cta, c, wp, cur, f, i, n, t.rootChild[n], true, tau);
         } else {
           const int e = t.childOff[lex] + k;
-          emitEdge(cta, c, w, cur, f, i, t.childTok[e], t.childNode[e], false, tau);
+          emitEdge(cta, c, wp, cur, f, i, t.childTok[e], t.childNode[e], false, tau);
         }
+        if (cached) note(c.wideTotal + c.K + x);
+        else localBin = -1;
       }
     }
     cta.sync();
@@ -1265,7 +1291,7 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
       sc[SC_BIN] = 0; // fewer candidates than wanted: keep every bin
     }
     cta.sync();
-    emitAll(); // pass 1: histogram only
+    emitAll(1); // pass 1: histogram only
     // cut = lowest bin with fewer than `want` candidates in higher bins (one warp; bins re-zeroed)
     findCutBin(cta, w, 3 * c.K + 64);
     cta.sync();
@@ -1275,7 +1301,7 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
     }
     cta.sync();
   }
-  emitAll();
+  emitAll(prune ? 2 : 0);
   int nCand = sc[SC_NCAND];
   if (sc[SC_OVF]) {
     if (cta.tid == 0) *status |= 1;
@@ -1297,7 +1323,7 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
       sc[SC_PCUT] = 0;
     }
     cta.sync();
-    emitAll();
+    emitAll(2);
     nCand = sc[SC_NCAND];
     if (sc[SC_OVF]) {
       if (cta.tid == 0) *status |= 1;
