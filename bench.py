@@ -64,37 +64,66 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).
+    NVML (pynvml) polls every few ms; nvidia-smi is the fallback when NVML is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.sm, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _nvml_sample(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in (("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown),
+                          ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                          ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown),
+                          ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _smi_sample(self):
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                             timeout=5).stdout.strip()
+        if not out:
+            return
+        r = [x.strip() for x in out.split(",")]
+        if r[0].replace(".", "").isdigit():
+            self.sm.append(float(r[0]))
+        if r[1].replace(".", "").isdigit():
+            self.max_mhz = float(r[1])
+        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if r[3 + i].lower().startswith("active"):
+                self.reasons.add(name)
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                self._nvml_sample() if self.nvml else self._smi_sample()
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.002 if self.nvml else 0.2)
 
     def summary(self):
         self.stop_flag = True
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(sm),
+                "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def build_spec(a, beam, bst):
