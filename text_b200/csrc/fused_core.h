@@ -310,6 +310,7 @@ FLT_DEV void topmRowStaged(const Cta& p, const TopMCfg& c, TopMSmem& s, ProdGues
       return;
     }
     // adversarial row (ties en masse, -inf padding): generic path below
+    p.sync(); // everyone has read cnt[0]
     for (int bn = p.tid; bn < kProdBins; bn += p.nthr) hist[bn] = 0;
     if (p.tid == 0) s.cnt[0] = 0;
     pg.g = bitsF32(0x7F800000u);
