@@ -33,7 +33,10 @@ def parse():
     p.add_argument("--steps", type=int, default=5)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--workload", default="lexfree", choices=["lexfree", "lexicon"])
+    p.add_argument("--workload", default="lexfree", choices=["lexfree", "lexicon", "lexicon_lm"],
+                   help="lexfree = BASELINE configs[1]; lexicon = configs[2]; lexicon_lm = configs[3] with a synthetic 4-gram")
+    p.add_argument("--lm-weight", type=float, default=2.0)
+    p.add_argument("--ngrams", default="500000,500000,250000", help="2-,3-,4-gram counts of the synthetic ARPA")
     p.add_argument("--batch", type=int, default=256, help="utterances per GPU")
     p.add_argument("--frames", type=int, default=1000)
     p.add_argument("--tokens", type=int, default=10000)
@@ -51,6 +54,9 @@ def parse():
 
 def workload_name(a, beam, bst):
     kind = "LexiconFreeDecoder" if a.workload == "lexfree" else f"LexiconDecoder {a.words}-word Trie"
+    if a.workload == "lexicon_lm":
+        return (f"{kind}, synthetic 4-gram ARPA ({a.ngrams} 2/3/4-grams), lmWeight={a.lm_weight}, CTC, N={a.tokens}, "
+                f"T={a.frames}, beam={beam}, beamSizeToken={bst}, beamThreshold={a.threshold}, batch={a.batch}/GPU")
     return (f"{kind}, ZeroLM, CTC, N={a.tokens}, T={a.frames}, beam={beam}, beamSizeToken={bst}, "
             f"batch={a.batch}/GPU")
 
@@ -134,6 +140,13 @@ def build_spec(a, beam, bst):
     if a.workload == "lexfree":
         return spec_lexfree(N, beam, bst, a.threshold, sil=0, blank=N - 1)
     sp = synth.lexicon(a.words, N, 2, 5, seed=7, exclude=(0, N - 1))
+    if a.workload == "lexicon_lm":
+        counts = [0] + [int(x) for x in a.ngrams.split(",")]
+        path = os.path.join(synth.cache_dir(), f"bench4_{a.words}_{'_'.join(map(str, counts))}.arpa")
+        if not os.path.exists(path):
+            synth.write_arpa(path, a.words, order=4, counts=counts, seed=11)
+        return spec_lexicon(N, beam, bst, sp, a.threshold, sil=0, blank=N - 1, unk=a.words, lm_weight=a.lm_weight,
+                            lm=("arpa", path, synth.word_names(a.words) + ["<unk>"]))
     return spec_lexicon(N, beam, bst, sp, a.threshold, sil=0, blank=N - 1, unk=a.words)
 
 
@@ -182,7 +195,7 @@ def run_reference(a):
         return
     from text_b200 import synth
 
-    beam = a.beam or (50 if a.workload == "lexfree" else 100)
+    beam = a.beam or {"lexfree": 50, "lexicon": 100, "lexicon_lm": 200}[a.workload]
     bst = a.bst or a.tokens
     spec = build_spec(a, beam, bst)
     Ts = sample_frames(a, bst)
@@ -230,7 +243,7 @@ def run_ours(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    beam = a.beam or (50 if a.workload == "lexfree" else 100)
+    beam = a.beam or {"lexfree": 50, "lexicon": 100, "lexicon_lm": 200}[a.workload]
     bst = a.bst or a.tokens
     B, T, N = a.batch, a.frames, a.tokens
     nbest = a.nbest or beam

@@ -57,6 +57,13 @@ under a profiler are never bench values: the bench lines come from separate runs
 | `{rnd}_{tag}_bench_lexicon.json` | cfg 3: Lexicon 200k words, ZeroLM, beam=100, bst=N, B=256 | {lx['value']:.0f} | {lx['ms_per_step']:.2f} | {kms(lx)} | beam step (latency-bound) | — | {lx['cpu_baseline']['value']:.3f} (12-frame prefix, extrapolated) |
 | `{rnd}_{tag}_bench_reference.json` | `bench.py --impl reference`, cfg 2 | {rf['value']:.3f} | — | — | — | — | = value |
 
+Other configurations: `r01_cfg4_bench_lexicon_lm.json` — BASELINE configs[3] shape (Lexicon 200k words +
+synthetic 4-gram ARPA with 500k/500k/250k 2/3/4-grams, lmWeight 2, beam 200, beamThreshold 25, T=1500,
+B=512, bst=N): 941 utt/s (select 58 + step 483 + backtrace 2 ms; workspace in global memory at this beam),
+n-best exact on the sample, reference CPU 0.50 utt/s on 16 threads. `r01_mg4_*.json`: 4 GPUs, 129.4 k utt/s =
+4.00x of one GPU (weak scaling); the e2e leg does not scale on this box — the host link delivers about
+55-60 GB/s in total however many GPUs pull from it (2 GPUs: 29 GB/s each, 4 GPUs: 7 GB/s each).
+
 Earlier lines of this round: `r01_bench_v0_*.json` (first correct path, 6.4 k utt/s), `r01_s1_*.json` (two
 kernels, generic step: 17.6 k utt/s), `r01_s2_*.json` (first fused kernel: 29.5 k utt/s),
 `r01_mg2_*.json` (2 GPUs: 59.0 k utt/s = 2.00x of the same build's 1-GPU line).
