@@ -9,7 +9,7 @@
 //   flashlight/lib/text/decoder/LexiconFreeDecoder.h:20-28,100-139 LexiconFreeDecoderOptions, LexiconFreeDecoder
 //   flashlight/lib/text/decoder/Trie.h:21-92               SmearingMode, TrieNode, Trie
 //   flashlight/lib/text/decoder/lm/LM.h:21-85, lm/ZeroLM.h, lm/KenLM.h:52-67
-//   flashlight/lib/text/dictionary/Dictionary.h:23-66      Dictionary (only what KenLM's ctor needs)
+//   flashlight/lib/text/dictionary/*                       Dictionary, loadWords, ... (flashlight_dictionary.h)
 // compiles unchanged for the decode path. All decoding runs on the GPU; there is no CPU decoder
 // behind these classes (constructing a decoder without a CUDA device throws std::runtime_error).
 //
@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "../../../include/flt_decoder.h"
+#include "flashlight_dictionary.h"
 
 namespace fl {
 namespace lib {
@@ -62,47 +63,6 @@ struct DecodeResult {
   std::vector<int> tokens;
   explicit DecodeResult(int length = 0)
       : score(0), emittingModelScore(0), lmScore(0), words(length, -1), tokens(length, -1) {}
-};
-
-/* ------------------------------------------------------------------ Dictionary (subset) ------ */
-class Dictionary {
- public:
-  Dictionary() = default;
-  explicit Dictionary(const std::vector<std::string>& tkns) {
-    for (const auto& t : tkns) addEntry(t);
-  }
-  size_t entrySize() const { return entry2idx_.size(); }
-  size_t indexSize() const { return idx2entry_.size(); }
-  void addEntry(const std::string& entry, int idx) {
-    if (entry2idx_.count(entry)) throw std::invalid_argument("Duplicate entry name in dictionary '" + entry + "'");
-    entry2idx_[entry] = idx;
-    if (!idx2entry_.count(idx)) idx2entry_[idx] = entry;
-  }
-  void addEntry(const std::string& entry) {
-    int idx = (int)idx2entry_.size();
-    while (idx2entry_.count(idx)) ++idx;
-    addEntry(entry, idx);
-  }
-  std::string getEntry(int idx) const {
-    auto it = idx2entry_.find(idx);
-    if (it == idx2entry_.end()) throw std::invalid_argument("Unknown index in dictionary '" + std::to_string(idx) + "'");
-    return it->second;
-  }
-  int getIndex(const std::string& entry) const {
-    auto it = entry2idx_.find(entry);
-    if (it == entry2idx_.end()) {
-      if (defaultIndex_ < 0) throw std::invalid_argument("Unknown entry in dictionary: '" + entry + "'");
-      return defaultIndex_;
-    }
-    return it->second;
-  }
-  bool contains(const std::string& entry) const { return entry2idx_.count(entry) > 0; }
-  void setDefaultIndex(int idx) { defaultIndex_ = idx; }
-
- private:
-  std::unordered_map<std::string, int> entry2idx_;
-  std::unordered_map<int, std::string> idx2entry_;
-  int defaultIndex_ = -1;
 };
 
 /* ------------------------------------------------------------------ Trie.h ------------------ */
@@ -483,6 +443,22 @@ class LexiconFreeDecoder : public Decoder {
   int sil_, blank_;
   std::vector<float> transitions_;
 };
+
+// One-shot setup (test/decoder/DecoderTest.cpp:126-146): every spelling of every lexicon word goes into
+// a Trie with the word's LM score (lm->score from the start state), then the Trie is smeared.
+inline TriePtr buildTrie(const LexiconMap& lexicon, const Dictionary& tokenDict, const Dictionary& wordDict,
+                         const LMPtr& lm, int silIdx, int maxReps = 0, SmearingMode smear = SmearingMode::MAX) {
+  auto trie = std::make_shared<Trie>((int)tokenDict.indexSize(), silIdx);
+  auto start = lm->start(false);
+  for (const auto& kv : lexicon) {
+    const int usrIdx = wordDict.getIndex(kv.first);
+    float score = 0.0f;
+    if (!kv.second.empty()) score = lm->score(start, usrIdx).second;
+    for (const auto& spelling : kv.second) trie->insert(tkn2Idx(spelling, tokenDict, maxReps), usrIdx, score);
+  }
+  trie->smear(smear);
+  return trie;
+}
 
 } // namespace text
 } // namespace lib

@@ -105,17 +105,30 @@ PYBIND11_MODULE(flashlight_lib_text_decoder, m) {
 
   py::class_<ZeroLM, ZeroLMPtr, LM>(m, "ZeroLM").def(py::init<>());
 
+  // dictionary / lexicon setup path (bindings/python/flashlight/lib/text/_dictionary.cpp:33-60)
   py::class_<Dictionary>(m, "Dictionary")
       .def(py::init<>())
+      .def(py::init<const std::string&>(), "filename"_a)
       .def(py::init<const std::vector<std::string>&>(), "tkns"_a)
       .def("entry_size", &Dictionary::entrySize)
       .def("index_size", &Dictionary::indexSize)
       .def("add_entry", py::overload_cast<const std::string&, int>(&Dictionary::addEntry), "entry"_a, "idx"_a)
       .def("add_entry", py::overload_cast<const std::string&>(&Dictionary::addEntry), "entry"_a)
       .def("get_entry", &Dictionary::getEntry, "idx"_a)
+      .def("set_default_index", &Dictionary::setDefaultIndex, "idx"_a)
       .def("get_index", &Dictionary::getIndex, "entry"_a)
       .def("contains", &Dictionary::contains, "entry"_a)
-      .def("set_default_index", &Dictionary::setDefaultIndex, "idx"_a);
+      .def("is_contiguous", &Dictionary::isContiguous)
+      .def("map_entries_to_indices", &Dictionary::mapEntriesToIndices, "entries"_a)
+      .def("map_indices_to_entries", &Dictionary::mapIndicesToEntries, "indices"_a);
+  m.def("create_word_dict", &createWordDict, "lexicon"_a);
+  m.def("load_words", &loadWords, "filename"_a, "max_words"_a = -1);
+  m.def("pack_replabels", &packReplabels, "tokens"_a, "dict"_a, "max_reps"_a);
+  m.def("unpack_replabels", &unpackReplabels, "tokens"_a, "dict"_a, "max_reps"_a);
+  m.def("tkn_to_idx", &tkn2Idx, "spelling"_a, "token_dict"_a, "max_reps"_a);
+  m.def("split_wrd", &splitWrd, "word"_a);
+  m.def("build_trie", &buildTrie, "lexicon"_a, "token_dict"_a, "word_dict"_a, "lm"_a, "sil_idx"_a,
+        "max_reps"_a = 0, "smear_mode"_a = SmearingMode::MAX);
 
   py::class_<KenLM, KenLMPtr, LM>(m, "KenLM")
       .def(py::init<const std::string&, const Dictionary&>(), "path"_a, "usr_token_dict"_a);
