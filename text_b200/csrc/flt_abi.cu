@@ -652,8 +652,8 @@ void planFor(flt_decoder& d, int N) {
     TopMSmem ts2;
     fl.prod = take(carveTopM(nullptr, ft, ts2), 16);
     fl.row = take((size_t)N * 4, 128);
-    for (int k = 0; k < 2; ++k) fl.list[k] = take(8 * (size_t)c.M, 16);
-    for (int k = 0; k < 2; ++k) fl.thr[k] = take(4, 4);
+    for (int k = 0; k < kFusedRing; ++k) fl.list[k] = take(8 * (size_t)c.M, 16);
+    for (int k = 0; k < kFusedRing; ++k) fl.thr[k] = take(4, 4);
     fl.mbar = take(8 * MB_COUNT, 8);
     fl.total = (int)((off + 127) / 128 * 128);
     d.ftcfg = ft;
@@ -672,7 +672,9 @@ void planFor(flt_decoder& d, int N) {
   int occ = 1;
   FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, flt_k_topm, kThreads, d.topmSmem));
   d.topmGridMax = std::max(1, occ) * d.numSMs;
-  const bool smemOk = d.wsBytes <= std::min<size_t>(smemMax, 110 * 1024);
+  // <= 110 KB keeps two CTAs per SM; FLT_SMEM_KB raises the limit (one CTA per SM) for experiments
+  const size_t smemLimit = getenv("FLT_SMEM_KB") ? (size_t)atoi(getenv("FLT_SMEM_KB")) * 1024 : 110 * 1024;
+  const bool smemOk = d.wsBytes <= std::min<size_t>(smemMax, smemLimit);
   int occ2 = 1;
   if (smemOk) {
     FLT_RT_TRY(cudaFuncSetAttribute(flt_k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -14,7 +14,7 @@
 //
 // so that every emission row is read from HBM exactly once (4N bytes per frame, the §8d figure), no
 // token list ever goes through HBM, and the bandwidth-bound select is hidden behind the
-// latency-bound step: the producers run up to two rows ahead of the consumers.
+// latency-bound step: the producers run up to four rows ahead of the consumers.
 //
 // Replaces decoder/LexiconFreeDecoder.cpp:39-51 (partial_sort per frame) and :53-125 (decodeStep)
 // together; same results as the two-kernel path (flt_k_topm + flt_k_decode), which remains for
@@ -31,18 +31,20 @@ namespace flt {
 #endif
 constexpr int kFusedConsumers = FLT_FUSED_CONSUMERS; // threads (the first warps of the CTA)
 constexpr int kFusedProducers = 128; // threads (the last 4 warps)
+constexpr int kFusedRing = 4;        // token lists the producers may run ahead of the consumers (pow2)
+constexpr int kFusedRingLog = 2;
 
 struct FuseLay {       // byte offsets from the CTA's shared-memory base
   int ws;              // consumer workspace (DecCfg::lay)
   int prod;            // producer scratch (TopMSmem)
   int row;             // staged emission row [N] fp32, 16-byte aligned
-  int list[2];         // token list ring: int tok[M], float val[M]
-  int thr[2];          // cut value of the token set per ring slot
-  int mbar;            // 5 mbarriers: rowFull, listReady[2], listFree[2]
+  int list[kFusedRing]; // token list ring: int tok[M], float val[M]
+  int thr[kFusedRing];  // cut value of the token set per ring slot
+  int mbar;            // mbarriers: rowFull, listReady[ring], listFree[ring]
   int total;
 };
 
-enum { MB_ROW_FULL = 0, MB_LIST_READY0, MB_LIST_READY1, MB_LIST_FREE0, MB_LIST_FREE1, MB_COUNT };
+enum { MB_ROW_FULL = 0, MB_LIST_READY0 = 1, MB_LIST_FREE0 = 1 + kFusedRing, MB_COUNT = 1 + 2 * kFusedRing };
 
 /* ------------------------------------------------------------------ mbarrier / bulk copy ------ */
 #if FLT_DEVICE_BUILD
@@ -122,8 +124,11 @@ constexpr int kProdCap = 512;  // survivor capacity (TopMCfg::capS of the fused 
 // guess follows the previous row's exact want-th value minus a margin that adapts to how many
 // elements passed. A miss (too few / too many survivors) costs one exact two-pass select from L2.
 struct ProdGuess {
-  float g;      // bound to try on the next row; +inf = none yet
-  float margin; // fraction of (row maximum - want-th value) the guess sits below the want-th value
+  float g;        // bound to try on the next row; +inf = none yet
+  float margin;   // fraction of (row maximum - want-th value) the guess sits below the want-th value
+  float missRate; // running rate of guess misses
+  int exactRows;  // rows left in exact mode (two passes over the stage, no guess)
+  int exactSpell; // length of the next exact-mode spell
 };
 
 #if FLT_DEVICE_BUILD
@@ -192,22 +197,16 @@ FLT_DEV void topmRowStaged(const Cta& p, const TopMCfg& c, TopMSmem& s, ProdGues
     unsigned long long* sv = s.sortBuf + c.capS;
     const int minExpected = want < N ? want : N;
     const float ninf = bitsF32(0xFF800000u);
-    // ---- one pass over the stage against the running guess
-    float bound = pg.g;
-    float top = prodFilter(p, c, s, (const float4*)row, bound, sv);
-    p.sync(); // every thread is done reading the stage
-    stageFree();
-    int ns = s.cnt[0];
-    if (!(ns >= minExpected && ns <= c.capS && ns <= 2 * p.nthr)) {
-      // ---- miss: exact bound from the per-thread maxima (pass 1), then filter again (pass 2), L2
-      if (stats && p.tid == 0) atomicAdd(stats + 11, 1ull);
-      p.sync(); // everyone has read cnt[0]
-      const float4* g4 = (const float4*)grow;
+    auto okCount = [&](int n) { return n >= minExpected && n <= c.capS && n <= 2 * p.nthr; };
+    float bound = pg.g, top;
+    int ns;
+    // exact bound from the per-thread maxima of the row at r4 (pass 1), then the filter (pass 2)
+    auto exactSelect = [&](const float4* r4, bool global) {
       const int nvec = N >> 2;
       float m = ninf;
 #pragma unroll 4
       for (int v = p.tid; v < nvec; v += p.nthr) {
-        const float4 x = __ldg(g4 + v);
+        const float4 x = global ? __ldg(r4 + v) : r4[v];
         m = fmaxf(m, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
       }
       const float sorted = warpSortDesc(m, lane);
@@ -216,15 +215,44 @@ FLT_DEV void topmRowStaged(const Cta& p, const TopMCfg& c, TopMSmem& s, ProdGues
       if (lane == 0) bnd[warp] = tw;
       if (p.tid == 0) s.cnt[0] = 0;
       p.sync();
-      bound = bnd[0];
-      for (int i = 1; i < nw; ++i) bound = fminf(bound, bnd[i]);
-      bound = fmaxf(bound, bitsF32(0xFF7FFFFFu)); // -inf never passes
+      float bd = bnd[0];
+      for (int i = 1; i < nw; ++i) bd = fminf(bd, bnd[i]);
+      bd = fmaxf(bd, bitsF32(0xFF7FFFFFu)); // -inf never passes
       p.sync(); // bnd[] is reused below
-      top = prodFilter(p, c, s, g4, bound, sv);
+      const float tp = prodFilter(p, c, s, r4, bd, sv);
       p.sync();
+      bound = bd;
+      return tp;
+    };
+    if (pg.exactRows > 0) {
+      // ---- exact mode (the guesses kept missing: peaky rows whose level moves from frame to frame):
+      // both passes read the stage, which is released after the second
+      --pg.exactRows;
+      top = exactSelect((const float4*)row, false);
+      stageFree();
       ns = s.cnt[0];
+    } else {
+      // ---- guess mode: one pass over the stage against the running guess, stage released at once
+      top = prodFilter(p, c, s, (const float4*)row, bound, sv);
+      p.sync(); // every thread is done reading the stage
+      stageFree();
+      ns = s.cnt[0];
+      const bool miss = !okCount(ns);
+      pg.missRate = 0.9f * pg.missRate + (miss ? 0.1f : 0.0f);
+      if (miss) {
+        // exact two-pass select of this row from L2
+        if (stats && p.tid == 0) atomicAdd(stats + 11, 1ull);
+        p.sync(); // everyone has read cnt[0]
+        top = exactSelect((const float4*)grow, true);
+        ns = s.cnt[0];
+        if (pg.missRate > 0.2f) { // stop guessing for a while; the spell doubles each time (<= 4096 rows)
+          pg.exactRows = pg.exactSpell;
+          pg.exactSpell = pg.exactSpell < 4096 ? pg.exactSpell * 2 : 4096;
+          pg.missRate = 0.0f;
+        }
+      }
     }
-    if (ns >= minExpected && ns <= c.capS && ns <= 2 * p.nthr) {
+    if (okCount(ns)) {
       // ---- rank the survivors: linear histogram over [bound, row maximum], exact order inside bins
       {
         const unsigned tk = __reduce_max_sync(0xffffffffu, orderedKey32(top));
@@ -302,8 +330,8 @@ FLT_DEV void topmRowStaged(const Cta& p, const TopMCfg& c, TopMSmem& s, ProdGues
       if (p.tid == 0) s.cnt[0] = 0;
       // next row's guess: below this row's want-th value by a margin that tracks the survivor count
       const float wth = bitsF32((uint32_t)s.cnt[1]);
-      if (ns > want + (3 * want) / 4) pg.margin *= 0.85f;
-      else if (ns < want + want / 4) pg.margin *= 1.25f;
+      if (ns > 2 * want + want / 2) pg.margin *= 0.85f;
+      else if (ns < want + want / 2) pg.margin *= 1.25f;
       pg.margin = fminf(fmaxf(pg.margin, 0.02f), 4.0f);
       pg.g = wth - pg.margin * (top - wth);
       p.sync();
@@ -390,7 +418,7 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
     for (int i = p.tid; i < 2 * kProdBins + tc.capS; i += p.nthr) ps.rankCnt[i] = 0;
     if (p.tid < 4) ps.cnt[p.tid] = 0;
     p.sync();
-    ProdGuess pg{bitsF32(0x7F800000u), 0.25f};
+    ProdGuess pg{bitsF32(0x7F800000u), 0.25f, 0.0f, 0, 64};
     const u64 pol = l2EvictFirstPolicy();
     // rows of this CTA in order: (b, t) for b = bid, bid + nblk, ...; `r` counts them
     uint32_t r = 0;
@@ -414,7 +442,7 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
       advance(nb, nt); // (nb, nt) = the row after (b, t)
       const float* grow = a.emis + ((long long)b * a.T + t) * c.N;
       mbarWait(v.mbar(MB_ROW_FULL), r & 1);
-      const int slot = (int)(r & 1);
+      const int slot = (int)(r & (kFusedRing - 1));
       const bool hasNext = nb < a.B;
       const float* gnext = hasNext ? a.emis + ((long long)nb * a.T + nt) * c.N : nullptr;
       topmRowStaged(
@@ -426,7 +454,7 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
               bulkLoadHint(v.row(), gnext, rowBytes, v.mbar(MB_ROW_FULL), pol);
             }
           },
-          [&]() { mbarWaitRelaxed(v.mbar(MB_LIST_FREE0 + slot), ((r >> 1) + 1) & 1); });
+          [&]() { mbarWaitRelaxed(v.mbar(MB_LIST_FREE0 + slot), ((r >> kFusedRingLog) + 1) & 1); });
       if (p.tid == 0) mbarArrive(v.mbar(MB_LIST_READY0 + slot));
       ++r;
     }
@@ -448,15 +476,15 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
     LfCarry carry{0.0f, 0.0f, 0.0f, 0};
     cta.sync();
     for (int t = 0; t < len; ++t, ++g) {
-      const int slot = (int)(g & 1); // ring slot = running row count & 1, on both sides
+      const int slot = (int)(g & (kFusedRing - 1)); // ring slot = running row count mod ring, on both sides
       LfPhaseClock oc; // time spent waiting for the producers
       oc.start(cta, a.stats);
 #if FLT_DEVICE_BUILD
-      mbarWait(v.mbar(MB_LIST_READY0 + slot), (g >> 1) & 1);
+      mbarWait(v.mbar(MB_LIST_READY0 + slot), (g >> kFusedRingLog) & 1);
 #else
       { // host model: the producer's work for row (b, t), inline
         const float* grow = a.emis + ((long long)b * a.T + t) * c.N;
-        ProdGuess pg{0.0f, 0.0f};
+        ProdGuess pg{0.0f, 0.0f, 0.0f, 0, 64};
         topmRowStaged(cta, tc, ps, pg, nullptr, grow, grow, v.listTok(slot), v.listVal(slot, c.M), v.thr(slot), [] {}, [] {});
       }
 #endif
