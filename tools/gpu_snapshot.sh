@@ -8,6 +8,7 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1
 ( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 ) > $OUT/pytest_gpu.txt
 ( timeout 600 python bench.py --steps 5 --warmup 3 ) > $OUT/bench_lexfree.json 2> $OUT/bench_lexfree.err
+( timeout 600 python bench.py --steps 5 --warmup 3 --sigma 4 --no-e2e --no-cpu-baseline ) > $OUT/bench_lexfree_sigma4.json 2> $OUT/bench_lexfree_sigma4.err
 ( timeout 600 python bench.py --steps 5 --warmup 3 --bst 50 ) > $OUT/bench_lexfree_bst50.json 2> $OUT/bench_lexfree_bst50.err
 ( timeout 600 python bench.py --steps 3 --warmup 3 --workload lexicon --no-e2e ) > $OUT/bench_lexicon.json 2> $OUT/bench_lexicon.err
 ( FLT_NO_FUSED=1 timeout 600 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline ) > $OUT/bench_lexfree_twokernel.json 2> $OUT/bench_lexfree_twokernel.err

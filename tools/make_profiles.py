@@ -6,10 +6,15 @@ tag, rnd = sys.argv[1], sys.argv[2]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src, dst = os.path.join(ROOT, "gpurun_out", tag), os.path.join(ROOT, "profiles")
 names = ["bench_lexfree", "bench_lexfree_bst50", "bench_lexicon", "bench_lexfree_twokernel", "bench_reference"]
+extra = ["bench_lexfree_sigma4"]
 J = {}
 for n in names:
     shutil.copy(os.path.join(src, n + ".json"), os.path.join(dst, f"{rnd}_{tag}_{n}.json"))
     J[n] = json.load(open(os.path.join(src, n + ".json")))
+for n in extra:
+    if os.path.exists(os.path.join(src, n + ".json")):
+        shutil.copy(os.path.join(src, n + ".json"), os.path.join(dst, f"{rnd}_{tag}_{n}.json"))
+        J[n] = json.load(open(os.path.join(src, n + ".json")))
 shutil.copy(os.path.join(src, "launches.csv"), os.path.join(dst, f"{rnd}_{tag}_launches_lexfree.csv"))
 rows = list(csv.DictReader(l for l in open(os.path.join(src, "launches.csv")) if not l.startswith("==")))
 agg = collections.OrderedDict()
@@ -53,6 +58,7 @@ under a profiler are never bench values: the bench lines come from separate runs
 |---|---|---|---|---|---|---|---|
 | `{rnd}_{tag}_bench_lexfree.json` | cfg 2: LexFree, N=10000, T=1000, beam=50, bst=N, B=256 | {b['value']:.0f} | {b['ms_per_step']:.2f} | {kms(b)} | {b['roofline']['achieved']:.0f} / {b['roofline']['peak']:.0f} GB/s = {b['roofline']['frac'] * 100:.1f} % | {b['e2e']['value']:.0f} | {b['cpu_baseline']['value']:.3f} (12-frame prefix, extrapolated: the reference allocates ~66 MB of LMState per frame at bst=N) |
 | `{rnd}_{tag}_bench_lexfree_bst50.json` | same, bst=50 | {b50['value']:.0f} | {b50['ms_per_step']:.2f} | {kms(b50)} | {b50['roofline']['frac'] * 100:.1f} % | {b50['e2e']['value']:.0f} | {b50['cpu_baseline']['value']:.1f} (full length) |
+| `{rnd}_{tag}_bench_lexfree_sigma4.json` | cfg 2 with peaky emissions (sigma = 4; the fused producers run in exact mode) | {J.get('bench_lexfree_sigma4', {}).get('value', 0):.0f} | {J.get('bench_lexfree_sigma4', {}).get('ms_per_step', 0):.2f} | {kms(J['bench_lexfree_sigma4']) if 'bench_lexfree_sigma4' in J else ''} | — | — | — |
 | `{rnd}_{tag}_bench_lexfree_twokernel.json` | cfg 2 through the two-kernel path (`FLT_NO_FUSED=1`) | {tk['value']:.0f} | {tk['ms_per_step']:.2f} | {kms(tk)} | — | — | — |
 | `{rnd}_{tag}_bench_lexicon.json` | cfg 3: Lexicon 200k words, ZeroLM, beam=100, bst=N, B=256 | {lx['value']:.0f} | {lx['ms_per_step']:.2f} | {kms(lx)} | beam step (latency-bound) | — | {lx['cpu_baseline']['value']:.3f} (12-frame prefix, extrapolated) |
 | `{rnd}_{tag}_bench_reference.json` | `bench.py --impl reference`, cfg 2 | {rf['value']:.3f} | — | — | — | — | = value |
