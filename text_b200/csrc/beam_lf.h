@@ -484,12 +484,11 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
   cta.sync(); // ---- B4
   pc.mark(3);
   for (int bn = cta.tid; bn < NB; bn += cta.nthr) hist[bn] = 0;
-  const int nL = total;
 #if FLT_DEVICE_BUILD
   if (stats && cta.tid == 0) {
     atomicAdd(stats + 0, 1ull);
     atomicAdd(stats + 1, (unsigned long long)items);
-    atomicAdd(stats + 2, (unsigned long long)nL); // live candidates
+    atomicAdd(stats + 2, (unsigned long long)total); // live candidates
     atomicAdd(stats + 3, (unsigned long long)nSel);
   }
 #else

@@ -28,19 +28,19 @@ using namespace flt;
 /* =============================================================================== kernels ==== */
 #if FLT_DEVICE_BUILD
 __global__ void __launch_bounds__(256, 3) flt_k_topm(TopMCfg c, TopMArgs a) {
-  extern __shared__ __align__(16) char smem[];
+  extern __shared__ __align__(128) char smem[];
   Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
   topmCta(cta, c, a, smem);
 }
 // workspace in shared memory (the fast path: every access is an LDS/STS with constant-bank offsets)
 __global__ void __launch_bounds__(256) flt_k_decode(DecCfg c, BatchArgs a) {
-  extern __shared__ __align__(16) char smem[];
+  extern __shared__ __align__(128) char smem[];
   Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
   decodeCta(cta, c, a, smem);
 }
 // same, 512 threads per utterance (two CTAs per SM): small batches leave SMs under-occupied
 __global__ void __launch_bounds__(512, 2) flt_k_decode512(DecCfg c, BatchArgs a) {
-  extern __shared__ __align__(16) char smem[];
+  extern __shared__ __align__(128) char smem[];
   Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
   decodeCta(cta, c, a, smem);
 }
