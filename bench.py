@@ -312,43 +312,57 @@ def run_ours(a):
     h2d = B * T * N * 4
     d2h = B * nbest * (T + 2) * 4 * 2 + B * nbest * 3 * 8 + B * 4
     if not a.no_e2e:
-        host = torch.empty((B, T, N), dtype=torch.float32, pin_memory=True)
-        host.copy_(em)
-        torch.cuda.synchronize()
-        res = None
-        for _ in range(min(a.warmup, 2)):
-            api.decode_batch_ptr(dec, host.data_ptr(), B, T, N)
-            res = api.nbest(dec, B, T, nbest)
-        from text_b200 import shard
-
-        def collect():
-            # N > 1: the n-best blocks of every rank go to rank 0 over NCCL (device buffers, no host
-            # round trip), rank 0 then reads the job's result; N = 1: plain device->host copy
-            if world == 1:
-                return api.nbest(dec, B, T, nbest)
-            api.synchronize(dec)
-            nb = api.nbest_device(dec, B, T, nbest, beam)
-            local = dict(tokens=nb["tokens"], words=nb["words"], scores=nb["scores"][:, :nbest].contiguous(),
-                         counts=nb["counts"])
-            return shard.gather_nbest(local, world * B, T, nbest, dev)
-
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(a.steps):
-            api.decode_batch_ptr(dec, host.data_ptr(), B, T, N)
-            res = collect()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        # every rank pins its own 10 GB batch: agree first that all of them could (a rank that failed
+        # alone would leave the others waiting in the collectives below)
+        host, err = None, ""
+        try:
+            host = torch.empty((B, T, N), dtype=torch.float32, pin_memory=True)
+            host.copy_(em)
+        except Exception as ex:
+            host, err = None, f"{type(ex).__name__}: {ex}"[:300]
+        flag = torch.tensor([1.0 if host is not None else 0.0], device=dev)
         if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        e2e = {"value": world * B * a.steps / dt, "unit": "utt/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": dt / a.steps * 1e3,
-               "note": "pinned host emissions -> flt_decode_batch (PCIe copy pipelined with the "
-                       "kernels) -> " + ("flt_nbest_copy" if world == 1 else "NCCL gather of the n-best blocks to rank 0 -> host")
-                       + "; bound by the host link: " f"{h2d / (dt / a.steps) / 1e9:.1f} GB/s H2D achieved per GPU"}
-        del host
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() < 0.5:
+            e2e = {"value": None, "unit": "utt/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "error": err or "another rank could not pin its host batch"}
+            host = None
+        else:
+            torch.cuda.synchronize()
+            res = None
+            for _ in range(min(a.warmup, 2)):
+                api.decode_batch_ptr(dec, host.data_ptr(), B, T, N)
+                res = api.nbest(dec, B, T, nbest)
+            from text_b200 import shard
+
+            def collect():
+                # N > 1: the n-best blocks of every rank go to rank 0 over NCCL (device buffers, no host
+                # round trip), rank 0 then reads the job's result; N = 1: plain device->host copy
+                if world == 1:
+                    return api.nbest(dec, B, T, nbest)
+                api.synchronize(dec)
+                nb = api.nbest_device(dec, B, T, nbest, beam)
+                local = dict(tokens=nb["tokens"], words=nb["words"], scores=nb["scores"][:, :nbest].contiguous(),
+                             counts=nb["counts"])
+                return shard.gather_nbest(local, world * B, T, nbest, dev)
+
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(a.steps):
+                api.decode_batch_ptr(dec, host.data_ptr(), B, T, N)
+                res = collect()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+            e2e = {"value": world * B * a.steps / dt, "unit": "utt/s", "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h, "ms_per_step": dt / a.steps * 1e3,
+                   "note": "pinned host emissions -> flt_decode_batch (PCIe copy pipelined with the "
+                           "kernels) -> " + ("flt_nbest_copy" if world == 1 else "NCCL gather of the n-best blocks to rank 0 -> host")
+                           + "; bound by the host link: " f"{h2d / (dt / a.steps) / 1e9:.1f} GB/s H2D achieved per GPU"}
+            del host
 
     if rank != 0:
         if world > 1:

@@ -188,12 +188,11 @@ FLT_DEV void topmRowStaged(const Cta& p, const TopMCfg& c, TopMSmem& s, ProdGues
   if (c.fast) {
     const int lane = p.tid & 31, warp = p.tid >> 5, nw = p.nthr >> 5;
     // scratch: sortBuf [0,capS) survivors grouped by bin | [capS,2capS) survivors as collected;
-    // red: per-warp bounds / maxima; rankCnt: histogram [kProdBins], above [kProdBins] per warp is
-    // kept in registers, survivor (bin, slot) [2][capS] u16
+    // red: per-warp bounds / maxima; rankCnt: histogram [kProdBins], above [kProdBins]; a survivor's
+    // (bin, slot) stays in its thread's registers
     float* bnd = (float*)s.red;          // [nw] per-warp bound, [32 + nw] per-warp maximum
     int* hist = s.rankCnt;               // [kProdBins] zero on entry, re-zeroed below
     int* above = s.rankCnt + kProdBins;  // [kProdBins]
-    unsigned short* sbin = (unsigned short*)(s.rankCnt + 2 * kProdBins); // [2][capS]
     unsigned long long* sv = s.sortBuf + c.capS;
     const int minExpected = want < N ? want : N;
     const float ninf = bitsF32(0xFF800000u);
