@@ -270,14 +270,23 @@ struct ODecoder {
       int c = cmpKey(cands[a], cands[b]);
       return c == 0 ? cands[a].score > cands[b].score : c > 0;
     });
+    // logAdd: another implementation's exp/log1p may differ from this libm in the last bit, so
+    // scores closer than `near` count as ties too (which member leads a group, who makes the cut)
+    auto nearTie = [&](double a, double b) {
+      return opt.logAdd && std::fabs(a - b) <= 1e-9 * std::max(1.0, std::fabs(a));
+    };
     int n = 1;
+    bool headFresh = true; // head.score is still the group's best member's own score
     for (int i = 1; i < (int)order.size(); ++i) {
       Hyp& head = cands[order[n - 1]];
       const Hyp& cur = cands[order[i]];
       if (cmpKey(cur, head) != 0) {
         order[n++] = order[i];
+        headFresh = true;
       } else {
         if (cur.score == head.score && !opt.logAdd) ++tieEvents;
+        if (headFresh && nearTie(cur.score, head.score)) ++tieEvents;
+        headFresh = false;
         double mx = std::max(head.score, cur.score);
         if (opt.logAdd) {
           double mn = std::min(head.score, cur.score);
@@ -295,7 +304,9 @@ struct ODecoder {
       return a < b;
     });
     int fin = std::min(n, (int)opt.beamSize);
-    if (fin < n && cands[order[fin - 1]].score == cands[order[fin]].score) ++tieEvents;
+    if (fin < n && (cands[order[fin - 1]].score == cands[order[fin]].score ||
+                    nearTie(cands[order[fin - 1]].score, cands[order[fin]].score)))
+      ++tieEvents;
     for (int i = 0; i < fin; ++i) out.push_back(cands[order[i]]);
   }
 

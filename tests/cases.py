@@ -72,3 +72,17 @@ def assert_same_nbest(a, b, score_tol=1e-4, what=""):
     np.testing.assert_array_equal(a["words"], b["words"], err_msg=f"{what}: words")
     np.testing.assert_allclose(a["scores"], b["scores"], rtol=0, atol=score_tol,
                                err_msg=f"{what}: scores")
+
+
+def assert_close_nbest(a, b, score_tol=1e-4, near=1e-9, what=""):
+    """n-best comparison for logAdd decoding, whose exp/log1p may round differently on the two
+    sides: scores within `score_tol`; token / word strings equal position by position, except that
+    neighbours whose oracle scores lie within `near` of each other may be swapped."""
+    assert a["n"] == b["n"], f"{what}: n-best size {a['n']} vs {b['n']}"
+    sa = a["scores"][:, 0]
+    for i in range(a["n"]):
+        cand = [j for j in range(a["n"]) if abs(sa[j] - sa[i]) <= near * max(1.0, abs(sa[i]))]
+        ok = any(np.array_equal(a["tokens"][j], b["tokens"][i]) and
+                 np.array_equal(a["words"][j], b["words"][i]) and
+                 np.allclose(a["scores"][j], b["scores"][i], rtol=0, atol=score_tol) for j in cand)
+        assert ok, f"{what}: rank {i} differs (tokens / words / scores)"

@@ -86,3 +86,54 @@ def lexicon_cases():
         em = synth.emissions(B, T, N, seed=2000 + len(out), sigma=2.0)
         out.append((name, spec, em))
     return out
+
+
+def widened_cases():
+    """Modes without rank dominance (full expansion on the device): logAdd merging, the token-level
+    n-gram LM of the lexicon-free decoder, isLmToken in the lexicon decoder. `exact` = scores are
+    expected bit-equal on the GPU too (no exp/log1p involved)."""
+    path, words = _arpa("p_small4.arpa", 300, 4, [0, 3000, 3000, 2000], 3)
+    out = []
+
+    def lexfree(name, N, T, beam, bst, thr, crit, log_add, sil_score, lm, lmw, sigma):
+        tr = np.random.default_rng(5).random(N * N, dtype=np.float32) if crit == po.ASG else None
+        lmspec = ("zero",) if lm == "zero" else ("arpa", path, words[:N])
+        spec = spec_lexfree(N, beam, bst, thr, sil=0, blank=(N - 1 if crit == po.CTC else -1),
+                            criterion=crit, log_add=log_add, sil_score=sil_score, lm_weight=lmw,
+                            lm=lmspec, transitions=tr)
+        em = synth.emissions(3, T, N, seed=3000 + len(out), sigma=sigma)
+        out.append((name, spec, em, not log_add))
+
+    lexfree("lf_logadd_ctc", 29, 80, 10, 29, 1e9, po.CTC, True, 0.0, "zero", 0.0, 1.0)
+    lexfree("lf_logadd_bst_thr", 40, 60, 12, 9, 12.0, po.CTC, True, -0.3, "zero", 0.0, 2.0)
+    lexfree("lf_logadd_asg", 40, 60, 12, 40, 1e9, po.ASG, True, 0.0, "zero", 0.0, 1.0)
+    lexfree("lf_logadd_wide", 500, 30, 50, 500, 25.0, po.CTC, True, 0.0, "zero", 0.0, 3.0)
+    lexfree("lf_tokenlm_ctc", 40, 60, 15, 40, 1e9, po.CTC, False, 0.0, "arpa", 0.8, 1.0)
+    lexfree("lf_tokenlm_bst_thr", 40, 60, 15, 10, 20.0, po.CTC, False, 0.2, "arpa", 1.3, 2.0)
+    lexfree("lf_tokenlm_asg", 40, 60, 15, 40, 1e9, po.ASG, False, 0.0, "arpa", 0.8, 1.0)
+    lexfree("lf_tokenlm_logadd", 40, 60, 15, 40, 30.0, po.CTC, True, 0.0, "arpa", 0.8, 2.0)
+
+    def lexicon(name, N, T, W, lens, beam, bst, thr, crit, log_add, sil_score, word_score, unk_score,
+                lm, lmw, token_lm):
+        sp = synth.lexicon(W, N, lens[0], lens[1], seed=7, exclude=(0, N - 1))
+        tr = np.random.default_rng(5).random(N * N, dtype=np.float32) if crit == po.ASG else None
+        if lm == "zero":
+            lmspec = ("zero",)
+        else:
+            lmspec = ("arpa", path, words[:N] if token_lm else words)
+        spec = spec_lexicon(N, beam, bst, sp, thr, sil=0, blank=(N - 1 if crit == po.CTC else -1),
+                            criterion=crit, log_add=log_add, sil_score=sil_score, lm_weight=lmw,
+                            word_score=word_score, unk_score=unk_score, lm=lmspec, transitions=tr,
+                            unk=W, is_lm_token=token_lm)
+        em = synth.emissions(3, T, N, seed=4000 + len(out), sigma=2.0)
+        out.append((name, spec, em, not log_add))
+
+    lexicon("lex_logadd_zero", 30, 60, 200, (2, 4), 20, 30, 1e9, po.CTC, True, 0.0, 0.3, NEG_INF, "zero", 0.0, False)
+    lexicon("lex_logadd_bst_thr", 30, 60, 200, (1, 4), 20, 8, 15.0, po.CTC, True, -0.2, 1.0, NEG_INF, "zero", 0.0, False)
+    lexicon("lex_logadd_arpa", 40, 60, 300, (1, 3), 40, 40, 30.0, po.CTC, True, 0.0, 0.5, NEG_INF, "arpa", 1.5, False)
+    lexicon("lex_logadd_asg_unk", 40, 50, 300, (2, 3), 30, 40, 30.0, po.ASG, True, 0.0, 0.5, -3.0, "arpa", 1.5, False)
+    lexicon("lex_tokenlm_arpa", 30, 60, 200, (2, 4), 20, 30, 1e9, po.CTC, False, 0.0, 0.4, NEG_INF, "arpa", 0.7, True)
+    lexicon("lex_tokenlm_bst_unk", 30, 40, 100, (2, 4), 20, 10, 25.0, po.CTC, False, -0.1, 0.43, -3.7, "arpa", 0.7, True)
+    lexicon("lex_tokenlm_zero", 30, 60, 200, (2, 4), 20, 30, 1e9, po.CTC, False, 0.0, 0.4, NEG_INF, "zero", 0.0, True)
+    lexicon("lex_tokenlm_logadd", 30, 40, 60, (2, 4), 20, 30, 40.0, po.ASG, True, 0.0, 0.4, NEG_INF, "arpa", 0.7, True)
+    return out

@@ -76,3 +76,19 @@ def test_masked_emissions(A, G):
     from test_model_parity import run_masked
 
     run_masked(A, G, 1e-4)
+
+
+@pytest.mark.parametrize("name,spec,em,exact", parity_cases.widened_cases(), ids=lambda v: v if isinstance(v, str) else "")
+def test_widened_modes(A, G, name, spec, em, exact):
+    """logAdd merging, token-level n-gram LM (lexicon-free), isLmToken (lexicon): full expansion on the
+    device. Without logAdd the scores are bit-equal; with it exp/log1p differ from libm in the last
+    bit, so scores carry the north star's 1e-4 and near-equal neighbours may swap."""
+    from test_model_parity import run_widened
+
+    run_widened(A, G, spec, em, exact, 1e-4)
+    if exact:
+        ba, bg = Built(A, spec), Built(G, spec)
+        ra, rg = ba.decode(em[0]), bg.decode(em[0], spec["opt"].beamSize)
+        if not (A.tie_events(ba.dec) or has_ties(ra)):
+            assert np.array_equal(ra["scores"], rg["scores"]), "scores not bit-equal"
+        ba.close(), bg.close()

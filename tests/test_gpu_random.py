@@ -2,7 +2,7 @@
 import pytest
 
 from oracle import pyoracle as po
-from test_model_random import draw_lexfree, draw_lexicon, run_random
+from test_model_random import draw_lexfree, draw_lexicon, draw_widened, run_random
 
 pytestmark = pytest.mark.gpu
 
@@ -29,4 +29,9 @@ def test_lexfree_random(A, G, seed):
 
 @pytest.mark.parametrize("seed", [10, 11, 12, 13])
 def test_lexicon_random(A, G, seed):
-    run_random(A, G, draw_lexicon, seed, 30, 1e-4)
+    run_random(A, G, draw_lexicon, draw_widened, seed, 30, 1e-4)
+
+
+@pytest.mark.parametrize("seed", [20, 21, 22, 23])
+def test_widened_random(A, G, seed):
+    run_random(A, G, draw_widened, seed, 40, 1e-4)

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import parity_cases
-from cases import Built, assert_same_nbest, has_ties
+from cases import Built, assert_close_nbest, assert_same_nbest, has_ties
 from flt_backend import FltBackend
 from oracle import pyoracle as po
 
@@ -124,3 +124,28 @@ def run_masked(A, G, tol):
 
 def test_masked_emissions(A, M):
     run_masked(A, M, 1e-9)
+
+
+def run_widened(A, G, spec, em, exact, tol):
+    """logAdd / token-LM modes (parity_cases.widened_cases). `exact`: strings and scores as strict as
+    everywhere else; otherwise (logAdd) near-equal neighbours may swap and scores carry `tol`."""
+    ba, bg = Built(A, spec), Built(G, spec)
+    got = bg.O.decode_batch(bg.dec, em, spec["opt"].beamSize)
+    checked = 0
+    for b, e in enumerate(em):
+        ra = ba.decode(e)
+        if A.tie_events(ba.dec) or has_ties(ra):
+            continue
+        if exact:
+            assert_same_nbest(ra, got[b], tol, what=f"utt {b}")
+        else:
+            assert_close_nbest(ra, got[b], max(tol, 1e-9), what=f"utt {b}")
+        checked += 1
+    ba.close(), bg.close()
+    assert checked, "all utterances had tie events: vacuous"
+
+
+@pytest.mark.parametrize("name,spec,em,exact", parity_cases.widened_cases(), ids=lambda v: v if isinstance(v, str) else "")
+def test_widened_modes(A, M, name, spec, em, exact):
+    # same libm on both sides here: logAdd scores are bit-equal too
+    run_widened(A, M, spec, em, True, 1e-9)

@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from cases import Built, assert_same_nbest, has_ties, spec_lexfree, spec_lexicon
+from cases import Built, assert_close_nbest, assert_same_nbest, has_ties, spec_lexfree, spec_lexicon
 from oracle import pyoracle as po
 from text_b200 import synth
 
@@ -67,6 +67,46 @@ def draw_lexicon(rng):
     return spec, em, None
 
 
+def draw_widened(rng):
+    """logAdd merging and token-level LMs (full expansion on the device), both decoders."""
+    log_add = bool(rng.random() < 0.6)
+    path, words = arpa()
+    crit = int(rng.choice([po.CTC, po.CTC, po.ASG]))
+    T = int(rng.integers(1, 30))
+    thr = float(rng.choice([1e9, 25.0, 8.0]))
+    if rng.random() < 0.5:
+        N = int(rng.integers(3, 120))
+        K = int(rng.choice([1, 3, 10, 30, 64, 100]))
+        token_lm = bool(rng.random() < 0.5) or not log_add
+        bst = int(rng.choice([N, max(1, N // 2), min(N, K), min(N, 5)]))
+        tr = rng.random(N * N, dtype=np.float32) if crit == po.ASG else None
+        spec = spec_lexfree(N, K, bst, thr, sil=0, blank=(N - 1 if crit == po.CTC else -1), criterion=crit,
+                            log_add=log_add, sil_score=float(rng.choice([0.0, -0.5, 0.7])),
+                            lm_weight=float(rng.choice([0.5, 1.5])) if token_lm else 0.0,
+                            lm=("arpa", path, words[:N]) if token_lm else ("zero",), transitions=tr)
+    else:
+        N = int(rng.integers(8, 80))
+        K = int(rng.choice([1, 3, 10, 30, 100]))
+        mn, mx = int(rng.choice([1, 2])), int(rng.choice([3, 5]))
+        W = int(rng.choice([20, 60, 200]))
+        W = min(W, max(1, sum((N - 2) ** l for l in range(mn, mx + 1)) // 2))
+        bst = int(rng.choice([N, max(1, N // 2), min(N, 6)]))
+        mode = rng.choice(["zero", "word", "token", "token_zero"]) if log_add else rng.choice(["token", "token_zero"])
+        token_lm = mode in ("token", "token_zero")
+        lm = ("zero",) if mode in ("zero", "token_zero") else ("arpa", path, words[:N] if token_lm else words)
+        sp = synth.lexicon(W, N, mn, mx, seed=int(rng.integers(1000)), exclude=(0, N - 1))
+        tr = rng.random(N * N, dtype=np.float32) if crit == po.ASG else None
+        spec = spec_lexicon(N, K, bst, sp, thr, sil=0, blank=(N - 1 if crit == po.CTC else -1),
+                            criterion=crit, log_add=log_add, sil_score=float(rng.choice([0.0, -0.5, 0.4])),
+                            lm_weight=float(rng.choice([0.5, 2.0])) if lm[0] == "arpa" else 0.0,
+                            word_score=float(rng.choice([0.0, 0.53, -1.1])),
+                            unk_score=float(rng.choice([float("-inf"), -2.3])), lm=lm, transitions=tr,
+                            unk=300 if mode == "word" else W, is_lm_token=token_lm)
+    em = synth.emissions(3, T, N, seed=int(rng.integers(1 << 30)), sigma=float(rng.choice([1.0, 2.0, 4.0])))
+    lengths = rng.integers(0, T + 1, size=3).astype(np.int32) if rng.random() < 0.3 else None
+    return spec, em, lengths
+
+
 def run_random(A, G, draw, seed, rounds, tol):
     rng = np.random.default_rng(seed)
     checked = 0
@@ -78,7 +118,11 @@ def run_random(A, G, draw, seed, rounds, tol):
             ra = ba.decode(e if lengths is None else e[: lengths[b]])
             if has_ties(ra) or A.tie_events(ba.dec):
                 continue
-            assert_same_nbest(ra, got[b], tol, what=f"seed {seed} spec {spec['opt'].beamSize}/{spec['N']}")
+            what = f"seed {seed} spec {spec['opt'].beamSize}/{spec['N']}"
+            if spec["opt"].logAdd and tol > 1e-9:  # device exp/log1p vs libm: last-bit differences
+                assert_close_nbest(ra, got[b], tol, what=what)
+            else:
+                assert_same_nbest(ra, got[b], tol, what=what)
             checked += 1
         ba.close(), bg.close()
     assert checked > rounds // 2
@@ -104,3 +148,8 @@ def test_lexfree_random(A, M, seed):
 @pytest.mark.parametrize("seed", [10, 11])
 def test_lexicon_random(A, M, seed):
     run_random(A, M, draw_lexicon, seed, 30, 1e-9)
+
+
+@pytest.mark.parametrize("seed", [20, 21])
+def test_widened_random(A, M, seed):
+    run_random(A, M, draw_widened, seed, 40, 1e-9)

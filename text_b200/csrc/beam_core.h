@@ -57,6 +57,7 @@ struct Lay {
   int gath;      // int [64]: members of the cut bin (one-warp finish of the radix select)
   // lexicon-free fast step (beam_lf.h)
   int lfSlotB, lfSlotOf, lfCbin, lfAbove, lfDesc;
+  int lnk, lhead; // int [capC] each (logAdd): members of a merge group chained behind its best member
   int pruneCache; // u8 per work item: 1 + best histogram bin its candidates reached in pass 1 (two-pass pruning)
   int total;
 };
@@ -81,6 +82,9 @@ struct DecCfg {
   int wideTotal;  // wideOff[K]
   int prune2;     // 1 = two-pass histogram pruning of the candidates (lexicon decoder)
   int lfFast;     // 1 = lexicon-free fast step (beam_lf.h): cells indexed by hypothesis, no merge table
+  int full;       // 1 = lexicon-free decoder expands every hypothesis x every token of the set (logAdd
+                  //     merging or an n-gram token LM: no row / rank dominance to prune with)
+  int lmToken;    // 1 = LexiconDecoder with a token-level LM (isLmToken, LexiconDecoder.cpp:82-86)
   int lfBins;     // histogram bins of its select (pow2, multiple of 32)
   int nTau;       // pruning rectangles: rows 1..tauA[k] x columns 0..tauCol[k] hold >= K regular cells
   int tauA[16];
@@ -220,6 +224,8 @@ struct Ws {
   FLT_DEV short* itemRow() const { return (short*)(base + c->lay.itemRow); }
   FLT_DEV int* cslot() const { return (int*)(base + c->lay.cslot); }
   FLT_DEV int* gath() const { return (int*)(base + c->lay.gath); }
+  FLT_DEV int* lnk() const { return (int*)(base + c->lay.lnk); }
+  FLT_DEV int* lhead() const { return (int*)(base + c->lay.lhead); }
   FLT_DEV u64* rkey() const { return (u64*)(base + c->lay.candKey); } // reps' score keys (reuses keyA)
 };
 
@@ -264,6 +270,8 @@ FLT_HD void makeLayout(DecCfg& c) {
   L.lfCbin = take(lf ? sizeof(unsigned short) * 2 * c.capC : 0); // bin, arrival order in the bin
   L.lfAbove = take(lf ? sizeof(unsigned short) * 16 * c.lfBins : 0); // one copy per warp (<= 16)
   L.lfDesc = take(lf ? sizeof(int) * c.capC : 0);                      // static work-item descriptors
+  L.lnk = take(c.logAdd ? sizeof(int) * c.capC : 0);
+  L.lhead = take(c.logAdd ? sizeof(int) * c.capC : 0);
   L.pruneCache = take(c.prune2 ? (size_t)c.wideTotal + c.K + kPruneEdgeCap : 0);
   L.total = (int)off;
 }
@@ -409,7 +417,7 @@ FLT_DEV int searchOffsets(const int* off, int n, int x) {
 // label that names the candidate's new LM state: token (lexicon-free), word (lexicon), -1 (finish)
 FLT_DEV int candLabel(const DecCfg& c, const Cand& cd, int x) {
   if (cd.flags(x) & CF_FINISH) return -1;
-  return c.lexicon ? cd.word(x) : cd.tok(x);
+  return (c.lexicon && !c.lmToken) ? cd.word(x) : cd.tok(x);
 }
 
 FLT_DEV void putCand(const DecCfg& c, const Ws& w, const Beam& cur, int slot, double score, int par,
@@ -424,7 +432,7 @@ FLT_DEV void putCand(const DecCfg& c, const Ws& w, const Beam& cur, int slot, do
   cd.ce(slot) = ev;
   u64 sa = cur.fpA(par), sb = cur.fpB(par);
   if (flags & CF_NEW) {
-    const int label = (flags & CF_FINISH) ? -1 : (c.lexicon ? word : tok);
+    const int label = (flags & CF_FINISH) ? -1 : ((c.lexicon && !c.lmToken) ? word : tok);
     fpChild(sa, sb, label, sa, sb);
   }
   candKeyOf(sa, sb, lex, tok, flags & CF_PB, cd.keyA(slot), cd.keyB(slot));
@@ -733,6 +741,33 @@ FLT_DEV void emitEdge(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& 
   double score = cur.score(i) + am;
   if (n == c.sil) score += c.silScore;
   const bool hasKids = t.childOff[child + 1] > t.childOff[child];
+  const int l0 = t.labelOff[child], l1 = t.labelOff[child + 1];
+  if (c.lmToken) {
+    // token-level LM (LexiconDecoder.cpp:82-86): one LM step per trie edge, shared by the inner-node
+    // candidate, the word ends and unk; the new LM state is child(state, n) for all of them
+    const float ls = lmWordScore(c, cur, i, n);
+    const double base = score + c.lmWeight * (double)ls;
+    if (hasKids && newTokenEligible(c, cur, i, n) && !(base < tau)) {
+      const int slot = allocCand(cta, c, w, base);
+      if (slot >= 0) putCand(c, w, cur, slot, base, i, n, -1, child, CF_NEW, ls, ev);
+    }
+    if (!(lex == 0 && cur.tok(i) == n)) {
+      for (int l = l0; l < l1; ++l) {
+        const double s = base + c.wordScore;
+        if (s < tau) continue;
+        const int slot = allocCand(cta, c, w, s);
+        if (slot >= 0) putCand(c, w, cur, slot, s, i, n, t.labels[l], 0, CF_NEW, ls, ev);
+      }
+    }
+    if (l0 == l1 && c.hasUnk) {
+      const double s = base + c.unkScore;
+      if (!(s < tau)) {
+        const int slot = allocCand(cta, c, w, s);
+        if (slot >= 0) putCand(c, w, cur, slot, s, i, n, c.unk, 0, CF_NEW, ls, ev);
+      }
+    }
+    return;
+  }
   if (!labelsOnly && hasKids && newTokenEligible(c, cur, i, n)) {
     const float d = t.maxScore[child] - lexMax;
     const double s = score + c.lmWeight * (double)d;
@@ -741,7 +776,6 @@ FLT_DEV void emitEdge(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& 
       if (slot >= 0) putCand(c, w, cur, slot, s, i, n, -1, child, 0, d, ev);
     }
   }
-  const int l0 = t.labelOff[child], l1 = t.labelOff[child + 1];
   if (!(lex == 0 && cur.tok(i) == n)) { // LexiconDecoder.cpp:114-122
     for (int l = l0; l < l1; ++l) {
       const int label = t.labels[l];
@@ -759,6 +793,28 @@ FLT_DEV void emitEdge(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& 
       const int slot = allocCand(cta, c, w, s);
       if (slot >= 0) putCand(c, w, cur, slot, s, i, n, c.unk, 0, CF_NEW, d, ev);
     }
+  }
+}
+
+// Full expansion of the lexicon-free decoder (LexiconFreeDecoder.cpp:53-112): hypothesis i with
+// token n of the token set (value ev). Used when nothing can be pruned by rank: logAdd merging (every
+// member of a group counts) or an n-gram token LM (the LM score differs per hypothesis and token).
+FLT_DEV void emitFullLf(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, int i, int n,
+                        float ev, double tau) {
+  const int prevTok = cur.tok(i);
+  double score = cur.score(i) + (double)ev; // transitions reach only emittingModelScore (:59-64)
+  if (n == c.sil) score += c.silScore;
+  const bool isNew = c.ctc ? (n != c.blank && (n != prevTok || cur.pb(i))) : n != prevTok;
+  if (isNew) {
+    const float ls = lmWordScore(c, cur, i, n);
+    score = score + c.lmWeight * (double)ls;
+    if (score < tau) return;
+    const int slot = allocCand(cta, c, w, score);
+    if (slot >= 0) putCand(c, w, cur, slot, score, i, n, -1, 0, CF_NEW, ls, ev);
+  } else {
+    if (score < tau) return;
+    const int slot = allocCand(cta, c, w, score);
+    if (slot >= 0) putCand(c, w, cur, slot, score, i, n, -1, 0, (c.ctc && n == c.blank) ? CF_PB : 0, 0.0f, ev);
   }
 }
 
@@ -794,14 +850,76 @@ FLT_DEV void phaseMerge(const Cta& cta, const DecCfg& c, const Ws& w, int nCand)
       s = (s + 1) & mask;
     }
     cslot[x] = (int)s;
+    if (c.logAdd) w.lhead()[x] = -1;
   }
   cta.sync();
+  // logAdd (Utils.h:161-165,185-195): candidates below best - beamThreshold are dropped BEFORE the
+  // merge; the others of a group are chained behind its best member, which then adds them up in
+  // descending score order exactly as the reference's sorted run does
+  double thrPre = negInf();
+  if (c.logAdd) {
+    u64 mx = 0;
+    for (int x = cta.tid; x < nCand; x += cta.nthr)
+      if (cd.parflag(x) & CF_ALIVE) {
+        const u64 k = orderedKey64(cd.score(x));
+        mx = k > mx ? k : mx;
+      }
+#if FLT_DEVICE_BUILD
+    mx = ctaMax64(cta, mx, w.red());
+#endif
+    thrPre = keyToDouble(mx) - c.beamThreshold;
+    int* lnk = w.lnk();
+    int* lhead = w.lhead();
+    for (int x = cta.tid; x < nCand; x += cta.nthr) {
+      if (!(cd.parflag(x) & CF_ALIVE)) continue;
+      const int r = mh[cslot[x]];
+      if (r == x || !(cd.score(x) >= thrPre)) continue;
+#if FLT_DEVICE_BUILD
+      lnk[x] = atomicExch(&lhead[r], x);
+#else
+      lnk[x] = lhead[r];
+      lhead[r] = x;
+#endif
+    }
+    cta.sync();
+  }
   u64* rkey = w.rkey();
   int* rep = w.rep();
   u64 orK = 0, andK = ~0ull;
   for (int x = cta.tid; x < nCand; x += cta.nthr) {
     if (!(cd.parflag(x) & CF_ALIVE)) continue;
     if (mh[cslot[x]] != x) continue;
+    if (c.logAdd) {
+      if (!(cd.score(x) >= thrPre)) { // the group's best is below the threshold: so are all
+        mh[cslot[x]] = -1;            // (the select clears the slots of the groups it is given)
+        continue;
+      }
+      const int* lnk = w.lnk();
+      const int head = w.lhead()[x];
+      if (head >= 0) {
+        double acc = cd.score(x);
+        double lastS = 0.0;
+        int lastI = -1; // members are visited by (score desc, index asc); -1 = none visited yet
+        for (;;) {
+          int best = -1;
+          double bs = 0.0;
+          for (int m = head; m >= 0; m = lnk[m]) {
+            const double sm = cd.score(m);
+            if (lastI >= 0 && !(sm < lastS || (sm == lastS && m > lastI))) continue;
+            if (best < 0 || sm > bs || (sm == bs && m < best)) {
+              best = m;
+              bs = sm;
+            }
+          }
+          if (best < 0) break;
+          const double hi = acc > bs ? acc : bs, lo = acc > bs ? bs : acc;
+          acc = hi + flt_log1p(flt_exp(lo - hi));
+          lastS = bs;
+          lastI = best;
+        }
+        cd.score(x) = acc;
+      }
+    }
     const int r = aggInc(&sc[SC_NREP], cta.tid);
     const u64 k = orderedKey64(cd.score(x));
     rep[r] = x;
@@ -1084,7 +1202,8 @@ FLT_DEV void phaseFinalize(const Cta& cta, const DecCfg& c, const Ws& w, const B
     if (cta.tid == 0) sc[SC_NH] = 0;
   } else {
     // candidatesBestScore_ - beamThreshold (LexiconDecoder.cpp:217-224)
-    const double thrScore = cd.score(ranked[0]) - c.beamThreshold;
+    // (logAdd: the threshold was applied to the candidates before they were merged, phaseMerge)
+    const double thrScore = c.logAdd ? negInf() : cd.score(ranked[0]) - c.beamThreshold;
     for (int q = cta.tid; q < nSel; q += cta.nthr) {
       const int x = ranked[q];
       const double score = cd.score(x);
@@ -1202,6 +1321,17 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
     }
     if (c.silScore < 0) tau += c.silScore; // keeps the bound valid if a counted cell is the sil one
   }
+  if (c.full && c.ctc) {
+    // the best hypothesis' blank candidate exists whenever blank is in the token set, so the frame's
+    // best candidate scores at least as much: anything below that minus beamThreshold is dropped by
+    // the reference's own filter (Utils.h:131-144,161-165)
+    const float eB = spec[c.K];
+    if (inTokenSetV(c, f, c.blank, eB)) {
+      double sb = cur.score(0) + (double)eB;
+      if (c.blank == c.sil) sb += c.silScore;
+      tau = sb - c.beamThreshold;
+    }
+  }
   // trie edge items: prefix sums of the hypotheses' degrees
   int edgeItems = 0;
   if (c.lexicon) {
@@ -1239,8 +1369,27 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
         note(x);
       }
     }
+    // lexicon-free full expansion: every hypothesis x every token of the set (blank and repeat are
+    // two of its cells)
+    if (c.full) {
+      const int S = c.setAll ? c.N : f.listLen;
+      const long long items = (long long)nH * S;
+      for (long long x = cta.tid; x < items; x += cta.nthr) {
+        const int i = (int)(x / S), j = (int)(x - (long long)i * S);
+        int n = j;
+        float ev;
+        if (c.setAll) {
+          ev = f.e[j];
+        } else {
+          n = f.topTok[j];
+          if (n < 0) continue;
+          ev = f.topVal[j];
+        }
+        emitFullLf(cta, c, wp, cur, i, n, ev, tau);
+      }
+    }
     // stay / repeat / blank
-    for (int i = cta.tid; i < nH; i += cta.nthr) {
+    for (int i = cta.tid; i < (c.full ? 0 : nH); i += cta.nthr) {
       if (skip(c.wideTotal + i)) continue;
       emitSpecials(cta, c, wp, cur, f, i, tau);
       if (c.wideRanked) emitSilCell(cta, c, wp, cur, f, i, tau);

@@ -498,24 +498,30 @@ void planFor(flt_decoder& d, int N) {
   if (!(o.beamThreshold >= 0)) throw FltError(FLT_ERR_INVALID, "beamThreshold must be >= 0");
   if (o.criterionType != FLT_CRITERION_CTC && o.criterionType != FLT_CRITERION_ASG)
     throw FltError(FLT_ERR_UNSUPPORTED, "criterion type must be ASG or CTC for these decoders");
-  if (o.logAdd)
-    throw FltError(FLT_ERR_UNSUPPORTED, "logAdd=true is not implemented on the device path yet");
-  if (d.isLmToken)
-    throw FltError(FLT_ERR_UNSUPPORTED, "token-level LM (isLmToken) is not implemented on the device path yet");
-  if (!d.lexicon && d.lm->kind != 0)
-    throw FltError(FLT_ERR_UNSUPPORTED, "LexiconFreeDecoder with an n-gram LM is not implemented on the device path yet");
   if (d.sil < 0 || d.sil >= N) throw FltError(FLT_ERR_INVALID, "sil index out of range for N");
   if (c.ctc && (d.blank < 0 || d.blank >= N))
     throw FltError(FLT_ERR_INVALID, "blank index out of range for N (CTC)");
   if (!c.ctc && !d.trans.empty() && (long long)d.trans.size() < (long long)N * N)
     throw FltError(FLT_ERR_INVALID, "transitions must hold N*N entries (ASG)");
   if (d.lexicon && d.trie->maxChildren < 1) throw FltError(FLT_ERR_INVALID, "empty trie");
+  c.lmToken = d.lexicon && d.isLmToken;
+  // lexicon-free decoder without rank dominance (logAdd merging, n-gram token LM): full expansion
+  c.full = !d.lexicon && (o.logAdd || d.lm->kind != 0);
   if (d.lm->kind == 1) {
+    // indices the LM will be asked about (KenLM::score throws on the first one out of range,
+    // lm/KenLM.cpp:64-68; here the whole range is checked up front)
     int maxIdx = -1;
-    for (auto& nd : d.trie->nodes)
-      for (int l : nd.labels) maxIdx = std::max(maxIdx, l);
-    if (c.hasUnk) maxIdx = std::max(maxIdx, d.unk);
-    if (maxIdx >= (int)d.lm->usr2lm.size() || (c.hasUnk && d.unk < 0))
+    if (!d.lexicon) {
+      maxIdx = N - 1;
+    } else if (c.lmToken) {
+      for (auto& nd : d.trie->nodes)
+        for (auto& kv : nd.kids) maxIdx = std::max(maxIdx, kv.first);
+    } else {
+      for (auto& nd : d.trie->nodes)
+        for (int l : nd.labels) maxIdx = std::max(maxIdx, l);
+      if (c.hasUnk) maxIdx = std::max(maxIdx, d.unk);
+    }
+    if (maxIdx >= (int)d.lm->usr2lm.size() || (d.lexicon && !c.lmToken && c.hasUnk && d.unk < 0))
       throw FltError(FLT_ERR_RUNTIME, "[KenLM] Invalid user token index: " + std::to_string(maxIdx));
   }
 
@@ -523,8 +529,8 @@ void planFor(flt_decoder& d, int N) {
   d.threads = decThreadsEnv() ? decThreadsEnv() : (d.lexicon ? 512 : 256);
   const int K = c.K;
   const int bstEff = std::min(o.beamSizeToken, N);
-  c.wideRanked = d.lexicon ? (c.ctc && !c.hasUnk) : 1;
-  if (!c.ctc && !d.lexicon) c.wideRanked = 1; // ASG transitions never touch the lexicon-free score
+  // ranked wide rows need max-merge and scores that follow the per-frame token order
+  c.wideRanked = d.lexicon ? (c.ctc && !c.hasUnk && !o.logAdd && !c.lmToken) : !c.full;
   d.needTopM = c.wideRanked || !c.setAll;
   TopMCfg t{};
   t.N = N;
@@ -536,7 +542,7 @@ void planFor(flt_decoder& d, int N) {
     c.M = (d.lexicon || c.setAll) ? c.Mwide : bstEff; // lexicon-free restricted: list = whole set
   } else {
     c.Mwide = 0;
-    c.M = 1;
+    c.M = (c.full && !c.setAll) ? bstEff : 1; // full expansion: the list is the whole token set
   }
   const int want = c.setAll ? c.M : bstEff;
   if (want > 2048)
@@ -549,7 +555,7 @@ void planFor(flt_decoder& d, int N) {
   t.fast = (N % 4 == 0) && N <= 4 * kFastVec * kThreads && want <= 256 && c.M <= 256;
   t.stage = !t.fast && (size_t)N * 4 <= 100 * 1024;
   // lexicon-free fast step (beam_lf.h): ZeroLM max-merge, candidate indices fit 16 bits
-  c.lfFast = !d.lexicon && d.lm->kind == 0 && !o.logAdd && K <= 256 && !getenv("FLT_NO_LF");
+  c.lfFast = !d.lexicon && !c.full && K <= 256 && !getenv("FLT_NO_LF");
   c.lfBins = std::min(1024, std::max(256, nextPow2(4 * K)));
   // wide offsets
   d.wideOffHost.assign(K + 1, 0);
@@ -561,9 +567,14 @@ void planFor(flt_decoder& d, int N) {
   // lexicon decoder, max-merge: two-pass histogram pruning keeps ~3K+64 candidates per frame (plus
   // the rest of the cut bin), so the workspace fits shared memory
   c.prune2 = d.lexicon && !o.logAdd && !getenv("FLT_NO_PRUNE2");
-  const long long narrowBudget = d.lexicon ? (c.prune2 ? 512 : std::max<long long>(4096, 24LL * K)) : 0;
+  // full expansion proposes up to K * |token set| candidates; a finite beamThreshold usually leaves
+  // far fewer, so start from a budget and let the overflow retry (capBoost) grow it
+  const long long fullCells = c.full ? (long long)K * (c.setAll ? N : bstEff) : 0;
+  const long long narrowBudget = d.lexicon ? (c.prune2 ? 512 : std::max<long long>(4096, 24LL * K))
+                                           : (c.full ? std::max<long long>(8192, 64LL * K) : 0);
   long long capC = c.prune2 ? 3LL * K + 64 + narrowBudget * d.capBoost
                             : (long long)(c.wideRanked ? d.wideOffHost[K] : 0) + 3LL * K + narrowBudget * d.capBoost;
+  if (c.full) capC = 3LL * K + std::min(fullCells, narrowBudget * d.capBoost);
   capC = (capC + 63) / 64 * 64;
   if (capC > (1LL << 26)) throw FltError(FLT_ERR_RUNTIME, "candidate capacity exceeded");
   c.capC = (int)capC;
