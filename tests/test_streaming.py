@@ -10,14 +10,22 @@ from oracle import pyoracle as po
 from text_b200 import synth
 
 
-def run_streaming(A, G, lexicon, chunk, look_back, prune_every, tol):
+def run_streaming(A, G, lexicon, chunk, look_back, prune_every, tol, mode="max"):
     N, T = 30, 90
     em = synth.emissions(1, T, N, seed=91, sigma=2.0)[0]
+    log_add = mode in ("logadd", "tokenlm_logadd")
+    lm, lmw = ("zero",), 0.0
+    if mode.startswith("tokenlm"):  # token-level 4-gram (full expansion on the device)
+        import parity_cases
+
+        path, words = parity_cases._arpa("p_small4.arpa", 300, 4, [0, 3000, 3000, 2000], 3)
+        lm, lmw = ("arpa", path, words[:N]), 0.8
     if lexicon:
-        sp = synth.lexicon(200, N, 2, 4, seed=7, exclude=(0, N - 1))
-        spec = spec_lexicon(N, 20, N, sp, 1e9, word_score=0.3)
+        sp = synth.lexicon(60 if mode != "max" else 200, N, 2, 4, seed=7, exclude=(0, N - 1))
+        spec = spec_lexicon(N, 20, N, sp, 1e9 if mode == "max" else 30.0, word_score=0.3, log_add=log_add,
+                            lm=lm, lm_weight=lmw, is_lm_token=mode.startswith("tokenlm"))
     else:
-        spec = spec_lexfree(N, 12, N, 1e9)
+        spec = spec_lexfree(N, 12, N, 1e9 if mode == "max" else 30.0, log_add=log_add, lm=lm, lm_weight=lmw)
     ba, bg = Built(A, spec), Built(G, spec)
     for O, b in ((A, ba), (G, bg)):
         O.decode_begin(b.dec)
@@ -59,6 +67,14 @@ def test_streaming_logic_harness(lexicon, chunk, look_back, prune_every):
     run_streaming(po.Oracle("ora"), FltBackend("model"), lexicon, chunk, look_back, prune_every, 1e-9)
 
 
+@pytest.mark.parametrize("lexicon", [False, True])
+@pytest.mark.parametrize("mode", ["logadd", "tokenlm", "tokenlm_logadd"])
+def test_streaming_full_expansion_modes(lexicon, mode):
+    from flt_backend import FltBackend
+
+    run_streaming(po.Oracle("ora"), FltBackend("model"), lexicon, 15, 4, 2, 1e-9, mode)
+
+
 def test_unpruned_chunks_equal_offline_decode():
     """Without prune(), chunked decodeStep + decodeEnd gives exactly decode()'s n-best."""
     from flt_backend import FltBackend
@@ -89,3 +105,12 @@ def test_streaming_cuda(lexicon, chunk, look_back, prune_every):
     from flt_backend import FltBackend
 
     run_streaming(po.Oracle("ora"), FltBackend("cuda"), lexicon, chunk, look_back, prune_every, 1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lexicon", [False, True])
+@pytest.mark.parametrize("mode", ["logadd", "tokenlm"])
+def test_streaming_full_expansion_modes_cuda(lexicon, mode):
+    from flt_backend import FltBackend
+
+    run_streaming(po.Oracle("ora"), FltBackend("cuda"), lexicon, 15, 4, 2, 1e-4, mode)

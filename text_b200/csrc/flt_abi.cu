@@ -566,15 +566,15 @@ void planFor(flt_decoder& d, int N) {
   }
   // lexicon decoder, max-merge: two-pass histogram pruning keeps ~3K+64 candidates per frame (plus
   // the rest of the cut bin), so the workspace fits shared memory
-  c.prune2 = d.lexicon && !o.logAdd && !getenv("FLT_NO_PRUNE2");
+  c.prune2 = (d.lexicon || (c.full && !getenv("FLT_NO_PRUNE2_FULL"))) && !o.logAdd && !getenv("FLT_NO_PRUNE2");
   // full expansion proposes up to K * |token set| candidates; a finite beamThreshold usually leaves
   // far fewer, so start from a budget and let the overflow retry (capBoost) grow it
   const long long fullCells = c.full ? (long long)K * (c.setAll ? N : bstEff) : 0;
   const long long narrowBudget = d.lexicon ? (c.prune2 ? 512 : std::max<long long>(4096, 24LL * K))
-                                           : (c.full ? std::max<long long>(8192, 64LL * K) : 0);
+                                           : (c.full ? (c.prune2 ? 512 : std::max<long long>(8192, 64LL * K)) : 0);
   long long capC = c.prune2 ? 3LL * K + 64 + narrowBudget * d.capBoost
                             : (long long)(c.wideRanked ? d.wideOffHost[K] : 0) + 3LL * K + narrowBudget * d.capBoost;
-  if (c.full) capC = 3LL * K + std::min(fullCells, narrowBudget * d.capBoost);
+  if (c.full && !c.prune2) capC = 3LL * K + std::min(fullCells, narrowBudget * d.capBoost);
   capC = (capC + 63) / 64 * 64;
   if (capC > (1LL << 26)) throw FltError(FLT_ERR_RUNTIME, "candidate capacity exceeded");
   c.capC = (int)capC;
