@@ -289,6 +289,9 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # one synchronous decode first: data-dependent candidate capacities (lexicon enumeration, full
+    # expansion) are grown by flt_decode_batch's overflow retry and then stay for the async steps
+    api.decode_batch_ptr(dec, em.data_ptr(), B, T, N)
     for _ in range(a.warmup):
         step()
     api.synchronize(dec)

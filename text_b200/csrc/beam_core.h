@@ -84,6 +84,8 @@ struct DecCfg {
   int lfFast;     // 1 = lexicon-free fast step (beam_lf.h): cells indexed by hypothesis, no merge table
   int full;       // 1 = lexicon-free decoder expands every hypothesis x every token of the set (logAdd
                   //     merging or an n-gram token LM: no row / rank dominance to prune with)
+  int rootList;   // 1 = lexicon decoder, beamSizeToken < N, no ranked rows: root hypotheses walk the
+                  //     frame's token list (bst entries) instead of the root's ~N trie edges
   int lmToken;    // 1 = LexiconDecoder with a token-level LM (isLmToken, LexiconDecoder.cpp:82-86)
   int lfBins;     // histogram bins of its select (pow2, multiple of 32)
   int nTau;       // pruning rectangles: rows 1..tauA[k] x columns 0..tauCol[k] hold >= K regular cells
@@ -1339,7 +1341,9 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
     int* deg = w.rows().deg();
     for (int i = cta.tid; i < nH; i += cta.nthr) {
       const int lex = cur.lex(i);
-      deg[i] = (c.wideRanked && lex == 0) ? t.nRootLab : t.childOff[lex + 1] - t.childOff[lex];
+      if (lex == 0 && c.wideRanked) deg[i] = t.nRootLab;
+      else if (lex == 0 && c.rootList) deg[i] = f.listLen;
+      else deg[i] = t.childOff[lex + 1] - t.childOff[lex];
     }
     cta.sync();
     ctaExclusiveScan(cta, deg, w.rows().degTmp(), nH);
@@ -1408,6 +1412,10 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
         if (c.wideRanked && lex == 0) {
           const int n = t.rootLabTok[k];
           emitEdge(cta, c, wp, cur, f, i, n, t.rootChild[n], true, tau);
+        } else if (c.rootList && lex == 0) {
+          const int n = f.topTok[k];
+          const int child = n >= 0 ? t.rootChild[n] : -1;
+          if (child >= 0) emitEdge(cta, c, wp, cur, f, i, n, child, false, tau);
         } else {
           const int e = t.childOff[lex] + k;
           emitEdge(cta, c, wp, cur, f, i, t.childTok[e], t.childNode[e], false, tau);
@@ -1565,6 +1573,9 @@ FLT_DEV void ctaInitWorkspace(const Cta& cta, const DecCfg& c, const Ws& w, char
     sc[SC_OR_HI] = 0;
     sc[SC_AND_LO] = -1;
     sc[SC_AND_HI] = -1;
+    sc[SC_PMODE] = 0; // allocCand reads these in every mode; only the two-pass pruning sets them
+    sc[SC_PCUT] = 0;
+    sc[SC_BIN] = 0;
   }
   for (int r = cta.tid; r < K; r += cta.nthr) // row rank of every wide work item
     for (int x = c.wideOff[r]; x < c.wideOff[r + 1]; ++x) w.itemRow()[x] = (short)r;
@@ -1712,7 +1723,7 @@ FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char
       f.listLen = c.M;
       f.thrVal = a.thrVal ? a.thrVal[row] : 0.0f;
       f.first = a.streamFrame0 + t == 0;
-      f.listIsSet = !c.lexicon;
+      f.listIsSet = !c.lexicon || c.rootList;
       f.specReady = 0;
       f.hScore = a.hScore ? a.hScore + (long long)(t + 1) * K * 3 : nullptr;
       f.hCount = a.hCount ? a.hCount + (t + 1) : nullptr;

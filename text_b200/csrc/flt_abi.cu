@@ -94,7 +94,7 @@ void launchTopM(const TopMCfg& c, const TopMArgs& a, int grid, size_t smem, rt::
   flt_k_topm<<<grid, kThreads, smem, s>>>(c, a);
   FLT_RT_TRY(cudaGetLastError());
 #else
-  std::vector<char> sm(smem + 16);
+  std::vector<char> sm(smem + 16, (char)0x5A); // shared memory is never zero for free
   for (int b = 0; b < grid; ++b) {
     Cta cta{0, 1, b, grid};
     topmCta(cta, c, a, sm.data());
@@ -109,7 +109,7 @@ void launchDecode(const DecCfg& c, const BatchArgs& a, int grid, size_t smem, rt
   else flt_k_decode_gmem<<<grid, threads > 256 ? 256 : threads, 0, s>>>(c, a);
   FLT_RT_TRY(cudaGetLastError());
 #else
-  std::vector<char> sm(c.lay.total + 16);
+  std::vector<char> sm(c.lay.total + 16, (char)0x5A); // shared memory is never zero for free
   for (int b = 0; b < grid; ++b) {
     Cta cta{0, 1, b, grid};
     decodeCta(cta, c, a, sm.data());
@@ -125,7 +125,7 @@ void launchFused(const DecCfg& c, const TopMCfg& tc, const FuseLay& fl, const Ba
   flt_k_fused<<<grid, kFusedConsumers + kFusedProducers, fl.total, s>>>(c, tc, fl, a);
   FLT_RT_TRY(cudaGetLastError());
 #else
-  std::vector<char> sm(fl.total + 128);
+  std::vector<char> sm(fl.total + 128, (char)0x5A);
   for (int b = 0; b < grid; ++b) {
     Cta cta{0, 1, b, grid};
     fusedCta(cta, c, tc, fl, a, sm.data());
@@ -170,7 +170,7 @@ struct flt_trie {
   mutable bool uploaded = false;
   mutable TrieDev dev{};
   mutable rt::DevBuf dChildOff, dChildTok, dChildNode, dMaxScore, dLabelOff, dLabels, dRootChild,
-      dRootLabTok;
+      dRootLabTok, dEdge, dRootRec;
   mutable std::vector<int> rootChildHost;
 
   static double logAdd(double a, double b) { // Trie.cpp:66-77
@@ -212,6 +212,24 @@ struct flt_trie {
       if (kv.first >= 0 && kv.first < maxChildren) rootChildHost[kv.first] = kv.second;
       if (!nodes[kv.second].labels.empty()) rootLabTok.push_back(kv.first);
     }
+    // packed edge records (tables.h): labels per node are capped at 6 (Trie.cpp:40-46)
+    auto recOf = [&](int tok, int node) {
+      EdgeRec r;
+      r.tok = tok;
+      r.node = node;
+      r.maxScore = maxScore[node];
+      const int nl = labelOff[node + 1] - labelOff[node];
+      if (nl > 7 || labelOff[node] >= (1 << 28)) throw FltError(FLT_ERR_RUNTIME, "trie too large for the edge records");
+      r.meta = (childOff[node + 1] > childOff[node] ? 1 : 0) | (nl << 1) | (int)((unsigned)labelOff[node] << 4);
+      return r;
+    };
+    std::vector<EdgeRec> edge(childTok.size());
+    for (size_t e = 0; e < childTok.size(); ++e) edge[e] = recOf(childTok[e], childNode[e]);
+    std::vector<EdgeRec> rootRec(rootChildHost.size(), EdgeRec{-1, -1, 0.0f, 0});
+    for (size_t n = 0; n < rootChildHost.size(); ++n)
+      if (rootChildHost[n] >= 0) rootRec[n] = recOf((int)n, rootChildHost[n]);
+    dev.edge = upload(dEdge, edge, s);
+    dev.rootRec = upload(dRootRec, rootRec, s);
     dev.nNodes = nn;
     dev.childOff = upload(dChildOff, childOff, s);
     dev.childTok = upload(dChildTok, childTok, s);
@@ -228,6 +246,7 @@ struct flt_trie {
   ~flt_trie() {
     dChildOff.release(), dChildTok.release(), dChildNode.release(), dMaxScore.release();
     dLabelOff.release(), dLabels.release(), dRootChild.release(), dRootLabTok.release();
+    dEdge.release(), dRootRec.release();
   }
 };
 
@@ -542,7 +561,9 @@ void planFor(flt_decoder& d, int N) {
     c.M = (d.lexicon || c.setAll) ? c.Mwide : bstEff; // lexicon-free restricted: list = whole set
   } else {
     c.Mwide = 0;
-    c.M = (c.full && !c.setAll) ? bstEff : 1; // full expansion: the list is the whole token set
+    // full expansion / unranked lexicon rows with a token beam: the list is the whole token set
+    c.rootList = d.lexicon && !c.setAll;
+    c.M = ((c.full || c.rootList) && !c.setAll) ? bstEff : 1;
   }
   const int want = c.setAll ? c.M : bstEff;
   if (want > 2048)

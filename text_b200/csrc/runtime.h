@@ -65,7 +65,13 @@ inline bool isPinnedPtr(const void* p) {
 }
 #else
 using Stream = void*;
-inline void* devAlloc(size_t bytes) { return malloc(bytes ? bytes : 16); }
+// filled with a garbage pattern: "device" memory is never zero for free, and a kernel that relies on
+// it must fail in the logic harness too
+inline void* devAlloc(size_t bytes) {
+  void* p = malloc(bytes ? bytes : 16);
+  if (p) memset(p, 0x5A, bytes ? bytes : 16);
+  return p;
+}
 inline void devFree(void* p) { free(p); }
 inline void h2d(void* d, const void* h, size_t bytes, Stream) { memcpy(d, h, bytes); }
 inline void d2h(void* h, const void* d, size_t bytes, Stream) { memcpy(h, d, bytes); }

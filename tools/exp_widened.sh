@@ -12,5 +12,3 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 ( timeout 300 python bench.py --steps 3 --warmup 3 --workload lexicon --log-add --bst 100 --threshold 25 --no-e2e --batch 128 ) > $OUT/bench_lexicon_logadd_bst100.json 2> $OUT/bench_lexicon_logadd_bst100.err
 ( timeout 300 python bench.py --steps 3 --warmup 3 --log-add --threshold 25 --no-e2e --frames 200 --sigma 4 ) > $OUT/bench_lexfree_logadd_bstN_sigma4.json 2> $OUT/bench_lexfree_logadd_bstN_sigma4.err
 ls -la $OUT
-( FLT_NO_PRUNE2_FULL=1 timeout 300 python bench.py --steps 3 --warmup 3 --workload lexfree_tokenlm --bst 50 --threshold 25 --no-e2e --no-cpu-baseline ) > $OUT/bench_lexfree_tokenlm_bst50_noprune.json 2> $OUT/bench_lexfree_tokenlm_bst50_noprune.err
-ls -la $OUT
