@@ -29,7 +29,7 @@ def test_lexfree_random(A, G, seed):
 
 @pytest.mark.parametrize("seed", [10, 11, 12, 13])
 def test_lexicon_random(A, G, seed):
-    run_random(A, G, draw_lexicon, draw_widened, seed, 30, 1e-4)
+    run_random(A, G, draw_lexicon, seed, 30, 1e-4)
 
 
 @pytest.mark.parametrize("seed", [20, 21, 22, 23])
