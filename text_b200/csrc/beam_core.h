@@ -1745,6 +1745,16 @@ FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char
       f.hWord = a.hWord ? a.hWord + h : nullptr;
       f.hRow = t + 1;
       f.hSkip = ((t + 1) & (kCpRows - 1)) == 0 ? a.hSkip + ((long long)b * a.nCp + ((t + 1) >> kCpShift)) * K : nullptr;
+#if FLT_DEVICE_BUILD
+      // The step gathers a few hundred scattered emissions per frame (trie edges, stay / blank); the
+      // select kernel streamed this row long ago, so they would each pay a DRAM round trip. Pull the
+      // NEXT frame's row into L2 now, one 128-byte line per thread, while this frame is processed.
+      if (f.eNext && !c.lfFast) {
+        const char* nx = (const char*)f.eNext;
+        for (int off = cta.tid * 128; off < c.N * 4; off += cta.nthr * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + off));
+      }
+#endif
       if (c.lfFast) lfFrameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.stats, carry);
       else frameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.status + b, a.stats);
       if (pf) {
