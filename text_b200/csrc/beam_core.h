@@ -57,7 +57,6 @@ struct Lay {
   int gath;      // int [64]: members of the cut bin (one-warp finish of the radix select)
   // lexicon-free fast step (beam_lf.h)
   int lfSlotB, lfSlotOf, lfCbin, lfAbove, lfDesc;
-  int eoff, lexMax; // int / float [K] (lexicon): childOff[lex] and maxScore[lex] of every hypothesis
   int lnk, lhead; // int [capC] each (logAdd): members of a merge group chained behind its best member
   int pruneCache; // u8 per work item: 1 + best histogram bin its candidates reached in pass 1 (two-pass pruning)
   int total;
@@ -227,8 +226,6 @@ struct Ws {
   FLT_DEV short* itemRow() const { return (short*)(base + c->lay.itemRow); }
   FLT_DEV int* cslot() const { return (int*)(base + c->lay.cslot); }
   FLT_DEV int* gath() const { return (int*)(base + c->lay.gath); }
-  FLT_DEV int* eoff() const { return (int*)(base + c->lay.eoff); }
-  FLT_DEV float* lexMax() const { return (float*)(base + c->lay.lexMax); }
   FLT_DEV int* lnk() const { return (int*)(base + c->lay.lnk); }
   FLT_DEV int* lhead() const { return (int*)(base + c->lay.lhead); }
   FLT_DEV u64* rkey() const { return (u64*)(base + c->lay.candKey); } // reps' score keys (reuses keyA)
@@ -275,8 +272,6 @@ FLT_HD void makeLayout(DecCfg& c) {
   L.lfCbin = take(lf ? sizeof(unsigned short) * 2 * c.capC : 0); // bin, arrival order in the bin
   L.lfAbove = take(lf ? sizeof(unsigned short) * 16 * c.lfBins : 0); // one copy per warp (<= 16)
   L.lfDesc = take(lf ? sizeof(int) * c.capC : 0);                      // static work-item descriptors
-  L.eoff = take(c.lexicon ? sizeof(int) * K : 0);
-  L.lexMax = take(c.lexicon ? sizeof(float) * K : 0);
   L.lnk = take(c.logAdd ? sizeof(int) * c.capC : 0);
   L.lhead = take(c.logAdd ? sizeof(int) * c.capC : 0);
   L.pruneCache = take(c.prune2 ? (size_t)c.wideTotal + c.K + kPruneEdgeCap : 0);
@@ -644,12 +639,11 @@ FLT_DEV void emitRowToken(const Cta& cta, const DecCfg& c, const Ws& w, const Be
     if (slot >= 0) putCand(c, w, cur, slot, score, p, n, -1, 0, CF_NEW, 0.0f, ev);
   } else {
     // LexiconDecoder.cpp:62-110, prevLex == root, CTC (ranked mode excludes ASG)
-    const EdgeRec rec = c.trie.rootRec[n];
-    const int child = rec.node;
-    if (child < 0 || !edgeHasKids(rec)) return;
+    const int child = c.trie.rootChild[n];
+    if (child < 0 || c.trie.childOff[child + 1] == c.trie.childOff[child]) return;
     double score = cur.score(p) + (double)ev;
     if (n == c.sil) score += c.silScore;
-    const float d = rec.maxScore - 0.0f;
+    const float d = c.trie.maxScore[child] - 0.0f;
     score = score + c.lmWeight * (double)d;
     if (score < tau) return;
     const int slot = allocCand(cta, c, w, score);
@@ -738,20 +732,18 @@ FLT_DEV float lmWordScore(const DecCfg& c, const Beam& cur, int p, int usrIdx) {
 }
 
 // one trie edge of hypothesis i: child node `child` reached by token n (LexiconDecoder.cpp:62-164)
-// (everything about the child comes with its packed record: no further gathers but the labels)
 FLT_DEV void emitEdge(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, const FrameIn& f,
-                      int i, const EdgeRec rec, bool labelsOnly, double tau) {
-  const int n = rec.tok, child = rec.node;
+                      int i, int n, int child, bool labelsOnly, double tau) {
   const float ev = f.e[n];
   if (!inTokenSetV(c, f, n, ev)) return;
   const TrieDev& t = c.trie;
   const int lex = cur.lex(i);
-  const float lexMax = w.lexMax()[i];
+  const float lexMax = lex == 0 ? 0.0f : t.maxScore[lex];
   const double am = amOf(c, f, ev, n, cur.tok(i));
   double score = cur.score(i) + am;
   if (n == c.sil) score += c.silScore;
-  const bool hasKids = edgeHasKids(rec);
-  const int l0 = edgeLabelOff(rec), l1 = l0 + edgeLabels(rec);
+  const bool hasKids = t.childOff[child + 1] > t.childOff[child];
+  const int l0 = t.labelOff[child], l1 = t.labelOff[child + 1];
   if (c.lmToken) {
     // token-level LM (LexiconDecoder.cpp:82-86): one LM step per trie edge, shared by the inner-node
     // candidate, the word ends and unk; the new LM state is child(state, n) for all of them
@@ -779,7 +771,7 @@ FLT_DEV void emitEdge(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& 
     return;
   }
   if (!labelsOnly && hasKids && newTokenEligible(c, cur, i, n)) {
-    const float d = rec.maxScore - lexMax;
+    const float d = t.maxScore[child] - lexMax;
     const double s = score + c.lmWeight * (double)d;
     if (!(s < tau)) {
       const int slot = allocCand(cta, c, w, s);
@@ -1349,12 +1341,9 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
     int* deg = w.rows().deg();
     for (int i = cta.tid; i < nH; i += cta.nthr) {
       const int lex = cur.lex(i);
-      const int e0 = t.childOff[lex];
       if (lex == 0 && c.wideRanked) deg[i] = t.nRootLab;
       else if (lex == 0 && c.rootList) deg[i] = f.listLen;
-      else deg[i] = t.childOff[lex + 1] - e0;
-      w.eoff()[i] = e0;
-      w.lexMax()[i] = lex == 0 ? 0.0f : t.maxScore[lex]; // LexiconDecoder.cpp:58-59
+      else deg[i] = t.childOff[lex + 1] - t.childOff[lex];
     }
     cta.sync();
     ctaExclusiveScan(cta, deg, w.rows().degTmp(), nH);
@@ -1421,15 +1410,15 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
         const int k = x - deg[i];
         const int lex = cur.lex(i);
         if (c.wideRanked && lex == 0) {
-          emitEdge(cta, c, wp, cur, f, i, t.rootRec[t.rootLabTok[k]], true, tau);
+          const int n = t.rootLabTok[k];
+          emitEdge(cta, c, wp, cur, f, i, n, t.rootChild[n], true, tau);
         } else if (c.rootList && lex == 0) {
           const int n = f.topTok[k];
-          if (n >= 0) {
-            const EdgeRec rec = t.rootRec[n];
-            if (rec.node >= 0) emitEdge(cta, c, wp, cur, f, i, rec, false, tau);
-          }
+          const int child = n >= 0 ? t.rootChild[n] : -1;
+          if (child >= 0) emitEdge(cta, c, wp, cur, f, i, n, child, false, tau);
         } else {
-          emitEdge(cta, c, wp, cur, f, i, t.edge[w.eoff()[i] + k], false, tau);
+          const int e = t.childOff[lex] + k;
+          emitEdge(cta, c, wp, cur, f, i, t.childTok[e], t.childNode[e], false, tau);
         }
         if (cached) note(c.wideTotal + c.K + x);
         else localBin = -1;

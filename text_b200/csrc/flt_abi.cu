@@ -170,7 +170,7 @@ struct flt_trie {
   mutable bool uploaded = false;
   mutable TrieDev dev{};
   mutable rt::DevBuf dChildOff, dChildTok, dChildNode, dMaxScore, dLabelOff, dLabels, dRootChild,
-      dRootLabTok, dEdge, dRootRec;
+      dRootLabTok;
   mutable std::vector<int> rootChildHost;
 
   static double logAdd(double a, double b) { // Trie.cpp:66-77
@@ -212,24 +212,6 @@ struct flt_trie {
       if (kv.first >= 0 && kv.first < maxChildren) rootChildHost[kv.first] = kv.second;
       if (!nodes[kv.second].labels.empty()) rootLabTok.push_back(kv.first);
     }
-    // packed edge records (tables.h): labels per node are capped at 6 (Trie.cpp:40-46)
-    auto recOf = [&](int tok, int node) {
-      EdgeRec r;
-      r.tok = tok;
-      r.node = node;
-      r.maxScore = maxScore[node];
-      const int nl = labelOff[node + 1] - labelOff[node];
-      if (nl > 7 || labelOff[node] >= (1 << 28)) throw FltError(FLT_ERR_RUNTIME, "trie too large for the edge records");
-      r.meta = (childOff[node + 1] > childOff[node] ? 1 : 0) | (nl << 1) | (int)((unsigned)labelOff[node] << 4);
-      return r;
-    };
-    std::vector<EdgeRec> edge(childTok.size());
-    for (size_t e = 0; e < childTok.size(); ++e) edge[e] = recOf(childTok[e], childNode[e]);
-    std::vector<EdgeRec> rootRec(rootChildHost.size(), EdgeRec{-1, -1, 0.0f, 0});
-    for (size_t n = 0; n < rootChildHost.size(); ++n)
-      if (rootChildHost[n] >= 0) rootRec[n] = recOf((int)n, rootChildHost[n]);
-    dev.edge = upload(dEdge, edge, s);
-    dev.rootRec = upload(dRootRec, rootRec, s);
     dev.nNodes = nn;
     dev.childOff = upload(dChildOff, childOff, s);
     dev.childTok = upload(dChildTok, childTok, s);
@@ -246,7 +228,6 @@ struct flt_trie {
   ~flt_trie() {
     dChildOff.release(), dChildTok.release(), dChildNode.release(), dMaxScore.release();
     dLabelOff.release(), dLabels.release(), dRootChild.release(), dRootLabTok.release();
-    dEdge.release(), dRootRec.release();
   }
 };
 

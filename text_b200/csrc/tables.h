@@ -11,18 +11,6 @@ namespace flt {
 constexpr int kMaxOrder = 6;          // FL_TEXT_KENLM_MAX_ORDER, decoder/lm/CMakeLists.txt:3
 constexpr int kMaxCtx = kMaxOrder - 1;
 
-// Everything the frame step needs to know about the node an edge leads to, in one 16-byte record
-// (one 128-bit gather instead of tok / node / childOff x2 / maxScore / labelOff x2):
-// meta = hasChildren | nLabels << 1 | labelOff[node] << 4.
-struct alignas(16) EdgeRec {
-  int tok, node;
-  float maxScore;
-  int meta;
-};
-FLT_HD bool edgeHasKids(const EdgeRec& r) { return (r.meta & 1) != 0; }
-FLT_HD int edgeLabels(const EdgeRec& r) { return (r.meta >> 1) & 7; }
-FLT_HD int edgeLabelOff(const EdgeRec& r) { return (int)((unsigned)r.meta >> 4); }
-
 struct TrieDev {
   int nNodes;
   const int* childOff;    // [nNodes+1] CSR row offsets
@@ -34,8 +22,6 @@ struct TrieDev {
   const int* rootChild;   // [N]        node reached from the root by token n, or -1
   int nRootLab;           // root children that carry labels (single-token words)
   const int* rootLabTok;  // [nRootLab] their tokens
-  const EdgeRec* edge;    // [nEdges]   packed record per CSR edge
-  const EdgeRec* rootRec; // [N]        packed record of the root's child by token (node = -1: none)
 };
 
 struct F2 {
