@@ -81,11 +81,14 @@ struct DecCfg {
   int capP;       // pow2 >= K
   int wideTotal;  // wideOff[K]
   int prune2;     // 1 = two-pass histogram pruning of the candidates (lexicon decoder)
+  int pruneWant;  // candidates the kept bins must hold (>= K; the result is verified to hold K groups)
   int lfFast;     // 1 = lexicon-free fast step (beam_lf.h): cells indexed by hypothesis, no merge table
   int full;       // 1 = lexicon-free decoder expands every hypothesis x every token of the set (logAdd
                   //     merging or an n-gram token LM: no row / rank dominance to prune with)
   int rootList;   // 1 = lexicon decoder, beamSizeToken < N, no ranked rows: root hypotheses walk the
                   //     frame's token list (bst entries) instead of the root's ~N trie edges
+  int wide;       // 1 = any of full / logAdd / lmToken / rootList: the kernels instantiated with W = true
+                  //     (the max-merge kernels are compiled without those paths)
   int lmToken;    // 1 = LexiconDecoder with a token-level LM (isLmToken, LexiconDecoder.cpp:82-86)
   int lfBins;     // histogram bins of its select (pow2, multiple of 32)
   int nTau;       // pruning rectangles: rows 1..tauA[k] x columns 0..tauCol[k] hold >= K regular cells
@@ -732,6 +735,7 @@ FLT_DEV float lmWordScore(const DecCfg& c, const Beam& cur, int p, int usrIdx) {
 }
 
 // one trie edge of hypothesis i: child node `child` reached by token n (LexiconDecoder.cpp:62-164)
+template <bool W>
 FLT_DEV void emitEdge(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, const FrameIn& f,
                       int i, int n, int child, bool labelsOnly, double tau) {
   const float ev = f.e[n];
@@ -744,7 +748,7 @@ FLT_DEV void emitEdge(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& 
   if (n == c.sil) score += c.silScore;
   const bool hasKids = t.childOff[child + 1] > t.childOff[child];
   const int l0 = t.labelOff[child], l1 = t.labelOff[child + 1];
-  if (c.lmToken) {
+  if (W && c.lmToken) {
     // token-level LM (LexiconDecoder.cpp:82-86): one LM step per trie edge, shared by the inner-node
     // candidate, the word ends and unk; the new LM state is child(state, n) for all of them
     const float ls = lmWordScore(c, cur, i, n);
@@ -824,7 +828,9 @@ FLT_DEV void emitFullLf(const Cta& cta, const DecCfg& c, const Ws& w, const Beam
 // (Utils.h:168-198, max-merge). The merge table is empty on entry; representatives (the group
 // maxima) are collected into rep[] with their order-preserving score keys in rkey[], and the
 // AND / OR of all keys is accumulated for the radix select. Two barriers.
+template <bool W>
 FLT_DEV void phaseMerge(const Cta& cta, const DecCfg& c, const Ws& w, int nCand) {
+  const bool logAdd = W && c.logAdd;
   const Cand cd = w.cand();
   int* mh = w.mh();
   int* cslot = w.cslot();
@@ -852,14 +858,14 @@ FLT_DEV void phaseMerge(const Cta& cta, const DecCfg& c, const Ws& w, int nCand)
       s = (s + 1) & mask;
     }
     cslot[x] = (int)s;
-    if (c.logAdd) w.lhead()[x] = -1;
+    if (logAdd) w.lhead()[x] = -1;
   }
   cta.sync();
   // logAdd (Utils.h:161-165,185-195): candidates below best - beamThreshold are dropped BEFORE the
   // merge; the others of a group are chained behind its best member, which then adds them up in
   // descending score order exactly as the reference's sorted run does
   double thrPre = negInf();
-  if (c.logAdd) {
+  if (logAdd) {
     u64 mx = 0;
     for (int x = cta.tid; x < nCand; x += cta.nthr)
       if (cd.parflag(x) & CF_ALIVE) {
@@ -891,7 +897,7 @@ FLT_DEV void phaseMerge(const Cta& cta, const DecCfg& c, const Ws& w, int nCand)
   for (int x = cta.tid; x < nCand; x += cta.nthr) {
     if (!(cd.parflag(x) & CF_ALIVE)) continue;
     if (mh[cslot[x]] != x) continue;
-    if (c.logAdd) {
+    if (logAdd) {
       if (!(cd.score(x) >= thrPre)) { // the group's best is below the threshold: so are all
         mh[cslot[x]] = -1;            // (the select clears the slots of the groups it is given)
         continue;
@@ -1267,8 +1273,10 @@ FLT_DEV void phaseFinalize(const Cta& cta, const DecCfg& c, const Ws& w, const B
 }
 
 // One frame: cur -> nxt. All threads of the CTA call this with identical arguments.
+template <bool W>
 FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur,
                        const Beam& nxt, const FrameIn& f, int* status, unsigned long long* stats) {
+  const bool full = W && c.full, rootList = W && c.rootList;
   int* sc = w.sc();
   const int nH = sc[SC_NH];
   if (nH == 0) return; // the beam died (Utils.h:155-158): every later frame is empty
@@ -1323,7 +1331,7 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
     }
     if (c.silScore < 0) tau += c.silScore; // keeps the bound valid if a counted cell is the sil one
   }
-  if (c.full && c.ctc) {
+  if (full && c.ctc) {
     // the best hypothesis' blank candidate exists whenever blank is in the token set, so the frame's
     // best candidate scores at least as much: anything below that minus beamThreshold is dropped by
     // the reference's own filter (Utils.h:131-144,161-165)
@@ -1342,7 +1350,7 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
     for (int i = cta.tid; i < nH; i += cta.nthr) {
       const int lex = cur.lex(i);
       if (lex == 0 && c.wideRanked) deg[i] = t.nRootLab;
-      else if (lex == 0 && c.rootList) deg[i] = f.listLen;
+      else if (lex == 0 && rootList) deg[i] = f.listLen;
       else deg[i] = t.childOff[lex + 1] - t.childOff[lex];
     }
     cta.sync();
@@ -1375,7 +1383,7 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
     }
     // lexicon-free full expansion: every hypothesis x every token of the set (blank and repeat are
     // two of its cells)
-    if (c.full) {
+    if (full) {
       const int S = c.setAll ? c.N : f.listLen;
       const long long items = (long long)nH * S;
       for (long long x = cta.tid; x < items; x += cta.nthr) {
@@ -1393,7 +1401,7 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
       }
     }
     // stay / repeat / blank
-    for (int i = cta.tid; i < (c.full ? 0 : nH); i += cta.nthr) {
+    for (int i = cta.tid; i < (full ? 0 : nH); i += cta.nthr) {
       if (skip(c.wideTotal + i)) continue;
       emitSpecials(cta, c, wp, cur, f, i, tau);
       if (c.wideRanked) emitSilCell(cta, c, wp, cur, f, i, tau);
@@ -1411,14 +1419,14 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
         const int lex = cur.lex(i);
         if (c.wideRanked && lex == 0) {
           const int n = t.rootLabTok[k];
-          emitEdge(cta, c, wp, cur, f, i, n, t.rootChild[n], true, tau);
-        } else if (c.rootList && lex == 0) {
+          emitEdge<W>(cta, c, wp, cur, f, i, n, t.rootChild[n], true, tau);
+        } else if (rootList && lex == 0) {
           const int n = f.topTok[k];
           const int child = n >= 0 ? t.rootChild[n] : -1;
-          if (child >= 0) emitEdge(cta, c, wp, cur, f, i, n, child, false, tau);
+          if (child >= 0) emitEdge<W>(cta, c, wp, cur, f, i, n, child, false, tau);
         } else {
           const int e = t.childOff[lex] + k;
-          emitEdge(cta, c, wp, cur, f, i, t.childTok[e], t.childNode[e], false, tau);
+          emitEdge<W>(cta, c, wp, cur, f, i, t.childTok[e], t.childNode[e], false, tau);
         }
         if (cached) note(c.wideTotal + c.K + x);
         else localBin = -1;
@@ -1450,7 +1458,7 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
     cta.sync();
     emitAll(1); // pass 1: histogram only
     // cut = lowest bin with fewer than `want` candidates in higher bins (one warp; bins re-zeroed)
-    findCutBin(cta, w, 3 * c.K + 64);
+    findCutBin(cta, w, c.pruneWant);
     cta.sync();
     if (cta.tid == 0) {
       sc[SC_PMODE] = 2;
@@ -1464,7 +1472,7 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
     if (cta.tid == 0) *status |= 1;
     nCand = nCand < c.capC ? nCand : c.capC;
   }
-  phaseMerge(cta, c, w, nCand);
+  phaseMerge<W>(cta, c, w, nCand);
   if (prune && sc[SC_PCUT] > 0 && sc[SC_NREP] < c.K) {
     // the kept bins hold fewer than K merge groups: take everything (rare)
     cta.sync();
@@ -1486,7 +1494,7 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
       if (cta.tid == 0) *status |= 1;
       nCand = nCand < c.capC ? nCand : c.capC;
     }
-    phaseMerge(cta, c, w, nCand);
+    phaseMerge<W>(cta, c, w, nCand);
   }
   if (prune && cta.tid == 0) sc[SC_PMODE] = 0; // decodeEnd's candidates are not pruned
   const int nRep = sc[SC_NREP];
@@ -1505,6 +1513,7 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
 }
 
 // decodeEnd (LexiconFreeDecoder.cpp:127-158, LexiconDecoder.cpp:231-274) as one more "frame".
+template <bool W>
 FLT_DEV void finishStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur,
                         const Beam& nxt, const FrameIn& f) {
   int* sc = w.sc();
@@ -1531,7 +1540,7 @@ FLT_DEV void finishStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam
     putCand(c, w, cur, i, score, i, c.sil, -1, cur.lex(i), flags, ls, 0.0f);
   }
   cta.sync();
-  phaseMerge(cta, c, w, nH);
+  phaseMerge<W>(cta, c, w, nH);
   const int nSel = phaseSelect(cta, c, w, sc[SC_NREP]);
   phaseFinalize(cta, c, w, cur, nxt, f, nSel);
 }
@@ -1675,6 +1684,7 @@ FLT_DEV void streamRestoreBeam(const Cta& cta, const DecCfg& c, const Ws& w, con
   }
 }
 
+template <bool W>
 FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char* base) {
   const Ws w{base, &c};
   const int K = c.K;
@@ -1745,7 +1755,7 @@ FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char
       }
 #endif
       if (c.lfFast) lfFrameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.stats, carry);
-      else frameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.status + b, a.stats);
+      else frameStep<W>(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.status + b, a.stats);
       if (pf) {
 #if FLT_DEVICE_BUILD
 #pragma unroll
@@ -1778,7 +1788,7 @@ FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char
     if (w.sc()[SC_NH] != 0) {
       const FrameIn f = finishFrameIn(c, a, b, len);
       if (c.lfFast) lfFinish(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f);
-      else finishStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f);
+      else finishStep<W>(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f);
       curIdx ^= 1;
       nFin = w.sc()[SC_NH];
     }

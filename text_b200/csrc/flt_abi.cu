@@ -36,18 +36,34 @@ __global__ void __launch_bounds__(256, 3) flt_k_topm(TopMCfg c, TopMArgs a) {
 __global__ void __launch_bounds__(256) flt_k_decode(DecCfg c, BatchArgs a) {
   extern __shared__ __align__(128) char smem[];
   Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
-  decodeCta(cta, c, a, smem);
+  decodeCta<false>(cta, c, a, smem);
 }
 // same, 512 threads per utterance (two CTAs per SM): small batches leave SMs under-occupied
 __global__ void __launch_bounds__(512, 2) flt_k_decode512(DecCfg c, BatchArgs a) {
   extern __shared__ __align__(128) char smem[];
   Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
-  decodeCta(cta, c, a, smem);
+  decodeCta<false>(cta, c, a, smem);
 }
 // workspace in a global slab per CTA (beams / candidate sets too large for shared memory)
 __global__ void __launch_bounds__(256) flt_k_decode_gmem(DecCfg c, BatchArgs a) {
   Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
-  decodeCta(cta, c, a, a.wsGlobal + (long long)blockIdx.x * a.wsStride);
+  decodeCta<false>(cta, c, a, a.wsGlobal + (long long)blockIdx.x * a.wsStride);
+}
+// the same three with the full-expansion paths compiled in (DecCfg::wide: logAdd merging, token-level
+// LMs, unranked rows walking the token list); kept out of the kernels above, which they slowed by 6 %
+__global__ void __launch_bounds__(256) flt_k_decode_wide(DecCfg c, BatchArgs a) {
+  extern __shared__ __align__(128) char smem[];
+  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
+  decodeCta<true>(cta, c, a, smem);
+}
+__global__ void __launch_bounds__(512, 2) flt_k_decode512_wide(DecCfg c, BatchArgs a) {
+  extern __shared__ __align__(128) char smem[];
+  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
+  decodeCta<true>(cta, c, a, smem);
+}
+__global__ void __launch_bounds__(256) flt_k_decode_gmem_wide(DecCfg c, BatchArgs a) {
+  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
+  decodeCta<true>(cta, c, a, a.wsGlobal + (long long)blockIdx.x * a.wsStride);
 }
 // token-beam select + beam step fused: 8 consumer + 4 producer warps per utterance (fused_core.h)
 __global__ void __launch_bounds__(kFusedConsumers + kFusedProducers, 2)
@@ -104,15 +120,16 @@ void launchTopM(const TopMCfg& c, const TopMArgs& a, int grid, size_t smem, rt::
 }
 void launchDecode(const DecCfg& c, const BatchArgs& a, int grid, size_t smem, rt::Stream s, int threads) {
 #if FLT_DEVICE_BUILD
-  if (smem && threads == 512) flt_k_decode512<<<grid, 512, smem, s>>>(c, a);
-  else if (smem) flt_k_decode<<<grid, threads, smem, s>>>(c, a);
-  else flt_k_decode_gmem<<<grid, threads > 256 ? 256 : threads, 0, s>>>(c, a);
+  if (smem && threads == 512) (c.wide ? flt_k_decode512_wide : flt_k_decode512)<<<grid, 512, smem, s>>>(c, a);
+  else if (smem) (c.wide ? flt_k_decode_wide : flt_k_decode)<<<grid, threads, smem, s>>>(c, a);
+  else (c.wide ? flt_k_decode_gmem_wide : flt_k_decode_gmem)<<<grid, threads > 256 ? 256 : threads, 0, s>>>(c, a);
   FLT_RT_TRY(cudaGetLastError());
 #else
   std::vector<char> sm(c.lay.total + 16, (char)0x5A); // shared memory is never zero for free
   for (int b = 0; b < grid; ++b) {
     Cta cta{0, 1, b, grid};
-    decodeCta(cta, c, a, sm.data());
+    if (c.wide) decodeCta<true>(cta, c, a, sm.data());
+    else decodeCta<false>(cta, c, a, sm.data());
   }
   (void)s;
   (void)smem;
@@ -546,6 +563,7 @@ void planFor(flt_decoder& d, int N) {
     c.rootList = d.lexicon && !c.setAll;
     c.M = ((c.full || c.rootList) && !c.setAll) ? bstEff : 1;
   }
+  c.wide = c.full || o.logAdd || c.lmToken || c.rootList;
   const int want = c.setAll ? c.M : bstEff;
   if (want > 2048)
     throw FltError(FLT_ERR_UNSUPPORTED,
@@ -574,6 +592,10 @@ void planFor(flt_decoder& d, int N) {
   const long long fullCells = c.full ? (long long)K * (c.setAll ? N : bstEff) : 0;
   const long long narrowBudget = d.lexicon ? (c.prune2 ? 512 : std::max<long long>(4096, 24LL * K))
                                            : (c.full ? (c.prune2 ? 512 : std::max<long long>(8192, 64LL * K)) : 0);
+  // kept candidates: 3K+64 by default; FLT_PRUNE_WANT=<percent of K> (+32) for experiments. Exactness
+  // does not depend on it: a frame whose kept bins hold fewer than K merge groups is redone without the cut
+  c.pruneWant = 3 * K + 64;
+  if (const char* e = getenv("FLT_PRUNE_WANT")) c.pruneWant = std::max(K + 1, (int)((long long)K * atoi(e) / 100) + 32);
   long long capC = c.prune2 ? 3LL * K + 64 + narrowBudget * d.capBoost
                             : (long long)(c.wideRanked ? d.wideOffHost[K] : 0) + 3LL * K + narrowBudget * d.capBoost;
   if (c.full && !c.prune2) capC = 3LL * K + std::min(fullCells, narrowBudget * d.capBoost);
@@ -689,17 +711,20 @@ void planFor(flt_decoder& d, int N) {
   const size_t smemLimit = getenv("FLT_SMEM_KB") ? (size_t)atoi(getenv("FLT_SMEM_KB")) * 1024 : 110 * 1024;
   const bool smemOk = d.wsBytes <= std::min<size_t>(smemMax, smemLimit);
   int occ2 = 1;
+  auto* k256 = c.wide ? flt_k_decode_wide : flt_k_decode;
+  auto* k512 = c.wide ? flt_k_decode512_wide : flt_k_decode512;
+  auto* kGmem = c.wide ? flt_k_decode_gmem_wide : flt_k_decode_gmem;
   if (smemOk) {
-    FLT_RT_TRY(cudaFuncSetAttribute(flt_k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FLT_RT_TRY(cudaFuncSetAttribute(k256, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)std::max<size_t>(d.wsBytes, 48 * 1024)));
-    FLT_RT_TRY(cudaFuncSetAttribute(flt_k_decode512, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FLT_RT_TRY(cudaFuncSetAttribute(k512, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)std::max<size_t>(d.wsBytes, 48 * 1024)));
     if (d.threads == 512)
-      FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode512, 512, d.wsBytes));
+      FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k512, 512, d.wsBytes));
     else
-      FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode, d.threads, d.wsBytes));
+      FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k256, d.threads, d.wsBytes));
   } else {
-    FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, flt_k_decode_gmem, d.threads > 256 ? 256 : d.threads, 0));
+    FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, kGmem, d.threads > 256 ? 256 : d.threads, 0));
     occ2 = std::min(occ2, 4);
   }
   d.gridMax = std::max(1, occ2) * d.numSMs;
