@@ -325,7 +325,11 @@ class Api:
         frames = max(int(v[0]), 1)
         out = dict(frames=int(v[0]), candidates_per_frame=v[1] / frames, groups_per_frame=v[2] / frames,
                    survivors_per_frame=v[3] / frames)
-        if any(v[4:11]):
+        if v[31]:  # generic step (beam_core.h frameStep): SM cycles of thread 0 per phase
+            names = ("rows", "degrees_scan", "pass1_histogram", "cut_bin", "pass2_emit", "merge", "select",
+                     "new_beam")
+            out["phase_cycles_per_frame"] = {n: round(v[4 + i] / frames, 1) for i, n in enumerate(names)}
+        elif any(v[4:11]):
             names = ("insert", "emit", "scan", "rank", "new_beam", "wait_list", "handover_gather")
             out["phase_cycles_per_frame"] = {n: round(v[4 + i] / frames, 1) for i, n in enumerate(names)}
             out["select_guess_misses"] = int(v[11])

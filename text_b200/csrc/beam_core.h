@@ -193,6 +193,8 @@ enum { // ws.sc[] scalars
   SC_NH = 0, SC_NCAND, SC_NREP, SC_NSEL, SC_NROWS, SC_OVF, SC_BIN, SC_NEED, SC_BINCOUNT, SC_NICE,
   SC_NGATH, SC_OR_LO, SC_OR_HI, SC_AND_LO, SC_AND_HI,
   SC_PMODE, SC_PCUT, SC_PLO_LO, SC_PLO_HI, SC_PSCALE, // two-pass candidate pruning (frameStep)
+  SC_TLO, SC_THI, // previous phase stamp of thread 0 (counters on)
+  SC_WANT, SC_WHOLD, // two-pass pruning: candidates to keep this frame; frames left at the wide setting
   SC_WCNT /* 32 warp counters follow */,
   SC_COUNT = SC_WCNT + 32
 };
@@ -1307,6 +1309,22 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
       sc[SC_NCAND] = 0;
     }
   };
+  // per-phase SM cycles of thread 0 (only when the host asked for counters: stats != null), summed
+  // over frames into stats[4 + phase]; stats[31] marks the generic step's phase names for the host
+#if FLT_DEVICE_BUILD
+  auto mark = [&](int k) __attribute__((always_inline)) { // k < 0: start stamp only
+    if (stats && cta.tid == 0) {
+      const long long t = clock64();
+      const long long t0 = (long long)(((u64)(unsigned)sc[SC_THI] << 32) | (unsigned)sc[SC_TLO]);
+      if (k >= 0) atomicAdd(stats + 4 + k, (unsigned long long)(t - t0));
+      sc[SC_TLO] = (int)(unsigned)t;
+      sc[SC_THI] = (int)(unsigned)((u64)t >> 32);
+    }
+  };
+  mark(-1);
+#else
+  auto mark = [&](int) {};
+#endif
   int wideItems = 0;
   if (c.wideRanked) {
     phaseRows(cta, c, w, cur, nH, publish);
@@ -1315,6 +1333,7 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
     publish();
     cta.sync();
   }
+  mark(0); // rows
   // Pruning bound (exact): any rectangle rows 1..a x columns 0..col of the (row rank x ranked
   // token) grid holds >= a*(col-2) >= K regular cells, i.e. K distinct merge groups, each scoring
   // at least fl(s + e_col) where s bounds the a-th row's best member from below. A candidate below
@@ -1454,11 +1473,18 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
       sc[SC_PSCALE] = (int)f32Bits((float)kPruneBins / (float)span);
       sc[SC_PMODE] = 1;
       sc[SC_BIN] = 0; // fewer candidates than wanted: keep every bin
+      // keep ~1.5 K candidates; after a frame whose kept bins held fewer than K merge groups (it was
+      // redone without the cut) fall back to 3K+64 for a while
+      const int hold = sc[SC_WHOLD];
+      sc[SC_WANT] = hold > 0 ? 3 * c.K + 64 : c.pruneWant;
+      if (hold > 0) sc[SC_WHOLD] = hold - 1;
     }
     cta.sync();
+    mark(1); // degrees + scan
     emitAll(1); // pass 1: histogram only
+    mark(2); // pass 1
     // cut = lowest bin with fewer than `want` candidates in higher bins (one warp; bins re-zeroed)
-    findCutBin(cta, w, c.pruneWant);
+    findCutBin(cta, w, sc[SC_WANT]);
     cta.sync();
     if (cta.tid == 0) {
       sc[SC_PMODE] = 2;
@@ -1466,7 +1492,9 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
     }
     cta.sync();
   }
+  mark(3); // cut bin
   emitAll(prune ? 2 : 0);
+  mark(4); // pass 2 (or the only pass)
   int nCand = sc[SC_NCAND];
   if (sc[SC_OVF]) {
     if (cta.tid == 0) *status |= 1;
@@ -1486,6 +1514,7 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
       sc[SC_AND_HI] = -1;
       sc[SC_NCAND] = 0;
       sc[SC_PCUT] = 0;
+      sc[SC_WHOLD] = 64;
     }
     cta.sync();
     emitAll(2);
@@ -1498,9 +1527,12 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
   }
   if (prune && cta.tid == 0) sc[SC_PMODE] = 0; // decodeEnd's candidates are not pruned
   const int nRep = sc[SC_NREP];
+  mark(5); // merge
   const int nSel = phaseSelect(cta, c, w, nRep);
+  mark(6); // select
 #if FLT_DEVICE_BUILD
   if (stats && cta.tid == 0) {
+    stats[31] = 1ull;
     atomicAdd(stats + 0, 1ull);
     atomicAdd(stats + 1, (unsigned long long)nCand);
     atomicAdd(stats + 2, (unsigned long long)nRep);
@@ -1510,6 +1542,7 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
   (void)stats;
 #endif
   phaseFinalize(cta, c, w, cur, nxt, f, nSel);
+  mark(7); // new beam + history
 }
 
 // decodeEnd (LexiconFreeDecoder.cpp:127-158, LexiconDecoder.cpp:231-274) as one more "frame".
@@ -1582,6 +1615,7 @@ FLT_DEV void ctaInitWorkspace(const Cta& cta, const DecCfg& c, const Ws& w, char
     sc[SC_OR_HI] = 0;
     sc[SC_AND_LO] = -1;
     sc[SC_AND_HI] = -1;
+    sc[SC_WHOLD] = 0;
     sc[SC_PMODE] = 0; // allocCand reads these in every mode; only the two-pass pruning sets them
     sc[SC_PCUT] = 0;
     sc[SC_BIN] = 0;

@@ -592,10 +592,11 @@ void planFor(flt_decoder& d, int N) {
   const long long fullCells = c.full ? (long long)K * (c.setAll ? N : bstEff) : 0;
   const long long narrowBudget = d.lexicon ? (c.prune2 ? 512 : std::max<long long>(4096, 24LL * K))
                                            : (c.full ? (c.prune2 ? 512 : std::max<long long>(8192, 64LL * K)) : 0);
-  // kept candidates: 3K+64 by default; FLT_PRUNE_WANT=<percent of K> (+32) for experiments. Exactness
-  // does not depend on it: a frame whose kept bins hold fewer than K merge groups is redone without the cut
-  c.pruneWant = 3 * K + 64;
-  if (const char* e = getenv("FLT_PRUNE_WANT")) c.pruneWant = std::max(K + 1, (int)((long long)K * atoi(e) / 100) + 32);
+  // candidates the two-pass pruning keeps per frame: 1.5K+32 (FLT_PRUNE_WANT=<percent of K> to change);
+  // 3K+64 for 64 frames after a frame had to be redone (beam_core.h). Exactness does not depend on it: a
+  // frame whose kept bins hold fewer than K merge groups is redone without the cut. Measured on cfg 3:
+  // 300 % 31.3 ms, 200 % 30.0 ms, 150 % 29.3 ms, 125 % 49.5 ms (redo storms)
+  c.pruneWant = std::max(K + 1, (int)((long long)K * (getenv("FLT_PRUNE_WANT") ? atoi(getenv("FLT_PRUNE_WANT")) : 150) / 100) + 32);
   long long capC = c.prune2 ? 3LL * K + 64 + narrowBudget * d.capBoost
                             : (long long)(c.wideRanked ? d.wideOffHost[K] : 0) + 3LL * K + narrowBudget * d.capBoost;
   if (c.full && !c.prune2) capC = 3LL * K + std::min(fullCells, narrowBudget * d.capBoost);
