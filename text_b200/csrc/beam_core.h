@@ -57,6 +57,8 @@ struct Lay {
   int gath;      // int [64]: members of the cut bin (one-warp finish of the radix select)
   // lexicon-free fast step (beam_lf.h)
   int lfSlotB, lfSlotOf, lfCbin, lfAbove, lfDesc;
+  int listNode, listMax; // int / float [Mwide] (lexicon, ranked rows): root child reached by each list
+                         // token (-1: none or childless) and its smeared score, gathered once per frame
   int lnk, lhead; // int [capC] each (logAdd): members of a merge group chained behind its best member
   int pruneCache; // u8 per work item: 1 + best histogram bin its candidates reached in pass 1 (two-pass pruning)
   int total;
@@ -231,6 +233,8 @@ struct Ws {
   FLT_DEV short* itemRow() const { return (short*)(base + c->lay.itemRow); }
   FLT_DEV int* cslot() const { return (int*)(base + c->lay.cslot); }
   FLT_DEV int* gath() const { return (int*)(base + c->lay.gath); }
+  FLT_DEV int* listNode() const { return (int*)(base + c->lay.listNode); }
+  FLT_DEV float* listMax() const { return (float*)(base + c->lay.listMax); }
   FLT_DEV int* lnk() const { return (int*)(base + c->lay.lnk); }
   FLT_DEV int* lhead() const { return (int*)(base + c->lay.lhead); }
   FLT_DEV u64* rkey() const { return (u64*)(base + c->lay.candKey); } // reps' score keys (reuses keyA)
@@ -277,6 +281,8 @@ FLT_HD void makeLayout(DecCfg& c) {
   L.lfCbin = take(lf ? sizeof(unsigned short) * 2 * c.capC : 0); // bin, arrival order in the bin
   L.lfAbove = take(lf ? sizeof(unsigned short) * 16 * c.lfBins : 0); // one copy per warp (<= 16)
   L.lfDesc = take(lf ? sizeof(int) * c.capC : 0);                      // static work-item descriptors
+  L.listNode = take(c.lexicon && c.wideRanked ? sizeof(int) * c.Mwide : 0);
+  L.listMax = take(c.lexicon && c.wideRanked ? sizeof(float) * c.Mwide : 0);
   L.lnk = take(c.logAdd ? sizeof(int) * c.capC : 0);
   L.lhead = take(c.logAdd ? sizeof(int) * c.capC : 0);
   L.pruneCache = take(c.prune2 ? (size_t)c.wideTotal + c.K + kPruneEdgeCap : 0);
@@ -627,8 +633,10 @@ FLT_DEV int allocCand(const Cta& cta, const DecCfg& c, const Ws& w, double score
 }
 
 // new-token expansion of the row led by hypothesis i with token n (value ev)
+// (j = column of n in the frame's ranked list, whose root child is cached in the workspace; -1 = n is
+// not taken from the list)
 FLT_DEV void emitRowToken(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, int i, int n,
-                          float ev, double tau) {
+                          float ev, double tau, int j = -1) {
   int p = i;
   if (!newTokenEligible(c, cur, p, n)) {
     p = w.rows().m2(i);
@@ -644,11 +652,20 @@ FLT_DEV void emitRowToken(const Cta& cta, const DecCfg& c, const Ws& w, const Be
     if (slot >= 0) putCand(c, w, cur, slot, score, p, n, -1, 0, CF_NEW, 0.0f, ev);
   } else {
     // LexiconDecoder.cpp:62-110, prevLex == root, CTC (ranked mode excludes ASG)
-    const int child = c.trie.rootChild[n];
-    if (child < 0 || c.trie.childOff[child + 1] == c.trie.childOff[child]) return;
+    int child;
+    float ms;
+    if (j >= 0) { // gathered once per frame for the whole list (frameStep)
+      child = w.listNode()[j];
+      if (child < 0) return;
+      ms = w.listMax()[j];
+    } else {
+      child = c.trie.rootChild[n];
+      if (child < 0 || c.trie.childOff[child + 1] == c.trie.childOff[child]) return;
+      ms = c.trie.maxScore[child];
+    }
     double score = cur.score(p) + (double)ev;
     if (n == c.sil) score += c.silScore;
-    const float d = c.trie.maxScore[child] - 0.0f;
+    const float d = ms - 0.0f;
     score = score + c.lmWeight * (double)d;
     if (score < tau) return;
     const int slot = allocCand(cta, c, w, score);
@@ -664,7 +681,7 @@ FLT_DEV void emitWide(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& 
   if (n < 0) return;                 // short list (fewer eligible tokens than columns)
   if (c.ctc && n == c.blank) return; // blank is never a new token
   if (n == c.sil && c.silScore > 0) return; // boosted sil is not rank-dominated: emitSilCell
-  emitRowToken(cta, c, w, cur, i, n, f.topVal[j], tau);
+  emitRowToken(cta, c, w, cur, i, n, f.topVal[j], tau, c.lexicon ? j : -1);
 }
 
 // With silScore > 0 the sil expansion of a wide row is not dominated by the cells left of it in
@@ -1041,6 +1058,40 @@ FLT_DEV int phaseSelect(const Cta& cta, const DecCfg& c, const Ws& w, int nRep) 
     }
     nSel = nRep;
     cta.sync();
+  } else if ((long long)nRep * nRep <= 1024LL * cta.nthr) { // <= 724 groups at 512 threads
+    // A few hundred groups (the two-pass pruning keeps ~1.5 K candidates): rank every group by
+    // counting the groups that beat it — `parts` adjacent lanes share one group and add their slices
+    // up with shuffles — and keep ranks < K. One barrier instead of the radix passes below; same
+    // comparator, hence the same total order.
+    int lg = 0;
+    while (lg < 5 && (nRep << (lg + 1)) <= cta.nthr) ++lg;
+    const int parts = 1 << lg;
+    const int slice = (nRep + parts - 1) >> lg;
+    for (int base = 0; base < (nRep << lg); base += cta.nthr) {
+      const int t = base + cta.tid;
+      const int a = t >> lg, part = t & (parts - 1);
+      const bool valid = a < nRep;
+      int cnt = 0;
+      int xa = -1;
+      if (valid) {
+        const u64 ka = rkey[a];
+        xa = rep[a];
+        const int lo = part * slice, hi = lo + slice < nRep ? lo + slice : nRep;
+        for (int b = lo; b < hi; ++b) {
+          const u64 kb = rkey[b];
+          cnt += (kb > ka || (kb == ka && b != a && candBetter(cd, rep[b], xa))) ? 1 : 0;
+        }
+      }
+#if FLT_DEVICE_BUILD
+      for (int o = 1; o < parts; o <<= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+#endif
+      if (valid && part == 0) {
+        mh[cslot[xa]] = -1; // leave the merge table empty
+        if (cnt < K) ranked[cnt] = xa;
+      }
+    }
+    cta.sync();
+    return K;
   } else {
     const u64 orK = ((u64)(unsigned)sc[SC_OR_HI] << 32) | (unsigned)sc[SC_OR_LO];
     const u64 andK = ((u64)(unsigned)sc[SC_AND_HI] << 32) | (unsigned)sc[SC_AND_LO];
@@ -1293,8 +1344,39 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
     if (c.ctc) eBlank = f.e[c.blank];
     eSil = f.e[c.sil];
   }
+  // lexicon, ranked rows: what the ~K ln K wide cells need to know about the root child of each list
+  // token (node, has children, smeared score) is gathered ONCE per list entry, by the threads at the
+  // far end of the CTA, instead of once per cell
+  const bool listCache = c.lexicon && c.wideRanked;
+  const int lj = cta.nthr - 2 - cta.tid; // list entry cached by this thread
+  int ljNode = -1;
+  float ljMax = 0.0f;
+  auto listInfo = [&](int j, int& node, float& ms) __attribute__((always_inline)) {
+    node = -1;
+    ms = 0.0f;
+    const int n = f.topTok[j];
+    if (n < 0) return;
+    const int child = c.trie.rootChild[n];
+    if (child < 0 || c.trie.childOff[child + 1] == c.trie.childOff[child]) return;
+    node = child;
+    ms = c.trie.maxScore[child];
+  };
+  if (listCache && lj >= 0 && lj < f.listLen) listInfo(lj, ljNode, ljMax);
   float* spec = w.spec();
   auto publish = [&]() {
+    if (listCache) {
+      if (lj >= 0 && lj < f.listLen) {
+        w.listNode()[lj] = ljNode;
+        w.listMax()[lj] = ljMax;
+      }
+      for (int j = cta.nthr - 1 + cta.tid; j < f.listLen; j += cta.nthr) { // lists longer than the CTA
+        int node;
+        float ms;
+        listInfo(j, node, ms);
+        w.listNode()[j] = node;
+        w.listMax()[j] = ms;
+      }
+    }
     if (cta.tid < nH) spec[cta.tid] = eOwn;
     for (int i = cta.tid + cta.nthr; i < nH; i += cta.nthr) { // beams wider than the CTA
       const int n = ownToken(c, cur, i);
