@@ -83,6 +83,7 @@ struct DecCfg {
   int capP;       // pow2 >= K
   int wideTotal;  // wideOff[K]
   int prune2;     // 1 = two-pass histogram pruning of the candidates (lexicon decoder)
+  int dbg;        // experiment switches (FLT_DBG): 1 = no direct-rank select, 2 = no aggregated histogram adds
   int pruneWant;  // candidates the kept bins must hold (>= K; the result is verified to hold K groups)
   int lfFast;     // 1 = lexicon-free fast step (beam_lf.h): cells indexed by hypothesis, no merge table
   int full;       // 1 = lexicon-free decoder expands every hypothesis x every token of the set (logAdd
@@ -618,7 +619,15 @@ FLT_DEV int allocCand(const Cta& cta, const DecCfg& c, const Ws& w, double score
   if (mode) {
     const int bin = pruneBin(w.sc(), score);
     if (mode == 1) {
-      atomAdd(&w.hist()[bin], 1);
+#if FLT_DEVICE_BUILD
+      // candidates of one frame crowd into a few bins: lanes that arrive together with the same bin
+      // add once (shared-memory atomics on one address serialise)
+      if (!(c.dbg & 2)) {
+        const unsigned peers = __match_any_sync(__activemask(), bin);
+        if ((__ffs(peers) - 1) == (cta.tid & 31)) atomicAdd(&w.hist()[bin], __popc(peers));
+      } else
+#endif
+        atomAdd(&w.hist()[bin], 1);
       if (w.itemBin && bin > *w.itemBin) *w.itemBin = bin;
       return -1;
     }
@@ -1058,11 +1067,12 @@ FLT_DEV int phaseSelect(const Cta& cta, const DecCfg& c, const Ws& w, int nRep) 
     }
     nSel = nRep;
     cta.sync();
-  } else if ((long long)nRep * nRep <= 1024LL * cta.nthr) { // <= 724 groups at 512 threads
+  } else if (!(c.dbg & 1) && (long long)nRep * nRep <= 256LL * cta.nthr) { // <= 362 groups at 512 threads
     // A few hundred groups (the two-pass pruning keeps ~1.5 K candidates): rank every group by
-    // counting the groups that beat it — `parts` adjacent lanes share one group and add their slices
-    // up with shuffles — and keep ranks < K. One barrier instead of the radix passes below; same
-    // comparator, hence the same total order.
+    // counting the groups whose score key is larger — `parts` adjacent lanes share one group and add
+    // their slices up with shuffles — and keep ranks < K. One barrier instead of the radix passes
+    // below. Equal keys are rare; a group that has any is ranked again with the full deterministic
+    // comparator, so the total order is the same as on the radix path.
     int lg = 0;
     while (lg < 5 && (nRep << (lg + 1)) <= cta.nthr) ++lg;
     const int parts = 1 << lg;
@@ -1071,21 +1081,30 @@ FLT_DEV int phaseSelect(const Cta& cta, const DecCfg& c, const Ws& w, int nRep) 
       const int t = base + cta.tid;
       const int a = t >> lg, part = t & (parts - 1);
       const bool valid = a < nRep;
-      int cnt = 0;
-      int xa = -1;
+      int cnt = 0, eq = 0;
+      u64 ka = 0;
       if (valid) {
-        const u64 ka = rkey[a];
-        xa = rep[a];
+        ka = rkey[a];
         const int lo = part * slice, hi = lo + slice < nRep ? lo + slice : nRep;
+#pragma unroll 4
         for (int b = lo; b < hi; ++b) {
           const u64 kb = rkey[b];
-          cnt += (kb > ka || (kb == ka && b != a && candBetter(cd, rep[b], xa))) ? 1 : 0;
+          cnt += kb > ka ? 1 : 0;
+          eq += kb == ka ? 1 : 0;
         }
       }
 #if FLT_DEVICE_BUILD
-      for (int o = 1; o < parts; o <<= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      for (int o = 1; o < parts; o <<= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        eq += __shfl_xor_sync(0xffffffffu, eq, o);
+      }
 #endif
       if (valid && part == 0) {
+        const int xa = rep[a];
+        if (eq > 1) { // ties (eq counts the group itself): exact order among the equal keys
+          for (int b = 0; b < nRep; ++b)
+            if (b != a && rkey[b] == ka && candBetter(cd, rep[b], xa)) ++cnt;
+        }
         mh[cslot[xa]] = -1; // leave the merge table empty
         if (cnt < K) ranked[cnt] = xa;
       }

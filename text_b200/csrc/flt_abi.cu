@@ -564,6 +564,7 @@ void planFor(flt_decoder& d, int N) {
     c.M = ((c.full || c.rootList) && !c.setAll) ? bstEff : 1;
   }
   c.wide = c.full || o.logAdd || c.lmToken || c.rootList;
+  c.dbg = getenv("FLT_DBG") ? atoi(getenv("FLT_DBG")) : 0;
   const int want = c.setAll ? c.M : bstEff;
   if (want > 2048)
     throw FltError(FLT_ERR_UNSUPPORTED,

@@ -70,6 +70,25 @@ n-best exact on the sample, reference CPU 0.50 utt/s on 16 threads. `r01_mg4_*.j
 4.00x of one GPU (weak scaling); the e2e leg does not scale on this box — the host link delivers about
 55-60 GB/s in total however many GPUs pull from it (2 GPUs: 29 GB/s each, 4 GPUs: 7 GB/s each).
 
+Full-expansion modes (DESIGN.md §3.1; `tools/exp_widened.sh`, `tools/exp_w3.sh`; N=10000, T=1000, B=256, CTC,
+beamThreshold 25; n-best of the 2-utterance sample equal to the compiled reference over all 1000 frames):
+
+| file | workload | utt/s | kernels | reference CPU utt/s (16 threads, full length) |
+|---|---|---|---|---|
+| `r01_w2_bench_lexfree_logadd_bst50.json` | LexFree, logAdd, beam 50, bst 50 | 2337 | select 3.7 + step 105.9 ms | 20.8 |
+| `r01_w3_bench_lexfree_tokenlm_bst50.json` | LexFree + synthetic 4-gram token LM (500k/500k/250k), lmWeight 2, beam 50, bst 50 | 3057 | select 3.8 + step 79.7 ms | 18.1 |
+| `r01_w3_bench_lexicon_logadd_bst100.json` | Lexicon 200k words, logAdd, beam 100, bst 100 | 4454 | select 5.4 + step 51.6 ms | 87.5 (B=128 run of `w2`) |
+| `r01_w2_bench_lexfree_logadd_bstN_sigma4.json` | LexFree, logAdd, beam 50, bst = N (500 k candidates per frame), sigma 4, T=200 | 34.5 | step 7418 ms | 0.54 (12-frame prefix, extrapolated) |
+
+`r01_w3_pytest_gpu.txt`: the GPU suite of that build (203 passed).
+
+Lexicon step (cfg 3) phase breakdown, SM cycles per frame of thread 0 (`beam_step_work.phase_cycles_per_frame`
+of `{rnd}_{tag}_bench_lexicon.json`): {", ".join(f"{k} {v:.0f}" for k, v in lx["beam_step_work"].get("phase_cycles_per_frame", {}).items())}.
+History of that step this round: 64.9 ms (generic step, workspace in global memory) -> 39.6 (two-pass pruning,
+shared memory) -> 31.6 (512 threads, per-item pruning cache) -> 29.5 (keep 1.5K+32 instead of 3K+64; `gpurun_out/ab2`:
+3K 31.3, 2K 30.0, 1.5K 29.3, 1.25K 49.5 ms) -> {lx['kernels']['beam_step']['ms']:.1f} ms (list-side cache of the root children, direct
+rank-by-counting select). Packed 16-byte edge records were tried and reverted (`gpurun_out/ab1`: 34.1 vs 33.5 ms).
+
 Earlier lines of this round: `r01_bench_v0_*.json` (first correct path, 6.4 k utt/s), `r01_s1_*.json` (two
 kernels, generic step: 17.6 k utt/s), `r01_s2_*.json` (first fused kernel: 29.5 k utt/s),
 `r01_mg2_*.json` (2 GPUs: 59.0 k utt/s = 2.00x of the same build's 1-GPU line).
