@@ -83,7 +83,7 @@ struct DecCfg {
   int capP;       // pow2 >= K
   int wideTotal;  // wideOff[K]
   int prune2;     // 1 = two-pass histogram pruning of the candidates (lexicon decoder)
-  int dbg;        // experiment switches (FLT_DBG): 1 = no direct-rank select, 2 = no aggregated histogram adds
+  int dbg;        // experiment switches (FLT_DBG): 1 = no direct-rank select (radix passes only)
   int pruneWant;  // candidates the kept bins must hold (>= K; the result is verified to hold K groups)
   int lfFast;     // 1 = lexicon-free fast step (beam_lf.h): cells indexed by hypothesis, no merge table
   int full;       // 1 = lexicon-free decoder expands every hypothesis x every token of the set (logAdd
@@ -619,15 +619,7 @@ FLT_DEV int allocCand(const Cta& cta, const DecCfg& c, const Ws& w, double score
   if (mode) {
     const int bin = pruneBin(w.sc(), score);
     if (mode == 1) {
-#if FLT_DEVICE_BUILD
-      // candidates of one frame crowd into a few bins: lanes that arrive together with the same bin
-      // add once (shared-memory atomics on one address serialise)
-      if (!(c.dbg & 2)) {
-        const unsigned peers = __match_any_sync(__activemask(), bin);
-        if ((__ffs(peers) - 1) == (cta.tid & 31)) atomicAdd(&w.hist()[bin], __popc(peers));
-      } else
-#endif
-        atomAdd(&w.hist()[bin], 1);
+      atomAdd(&w.hist()[bin], 1); // (warp-aggregating these with match.any was measured slower)
       if (w.itemBin && bin > *w.itemBin) *w.itemBin = bin;
       return -1;
     }
