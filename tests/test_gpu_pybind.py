@@ -100,6 +100,61 @@ def test_lexfree_zero_lm_device_pointer():
     ba.close()
 
 
+def test_log_add_and_token_lm_through_python_names(tmp_path):
+    """log_add=True (lexicon-free) and is_token_lm=True (lexicon + KenLM over tokens) with the
+    reference's constructor signatures; both run as a full expansion on the device."""
+    from cases import assert_close_nbest
+    from flashlight.lib.text.decoder import (CriterionType, LexiconDecoder, LexiconDecoderOptions,
+                                             LexiconFreeDecoder, LexiconFreeDecoderOptions, SmearingMode, Trie,
+                                             ZeroLM)
+    from flashlight.lib.text.decoder.kenlm import KenLM
+    from flashlight.lib.text.dictionary import Dictionary
+
+    A = po.Oracle("ora")
+    N, T = 40, 50
+    em = synth.emissions(3, T, N, seed=17, sigma=2.0)
+    # lexicon-free, logAdd
+    opts = LexiconFreeDecoderOptions(beam_size=12, beam_size_token=10, beam_threshold=20.0, lm_weight=0.0,
+                                     sil_score=-0.2, log_add=True, criterion_type=CriterionType.CTC)
+    dec = LexiconFreeDecoder(opts, ZeroLM(), 0, N - 1, [])
+    ba = Built(A, spec_lexfree(N, 12, 10, 20.0, sil_score=-0.2, log_add=True))
+    checked = 0
+    for b in range(len(em)):
+        e = np.ascontiguousarray(em[b])
+        ra = ba.decode(e)
+        if has_ties(ra) or A.tie_events(ba.dec):
+            continue
+        assert_close_nbest(ra, _as_res(dec.decode(e.ctypes.data, T, N), T), 1e-4, what=f"logAdd utt {b}")
+        checked += 1
+    ba.close()
+    # lexicon decoder with a token-level n-gram LM
+    W = 60
+    path = str(tmp_path / "tok.arpa")
+    synth.write_arpa(path, N, order=3, counts=[0, 600, 400], seed=5)
+    toks = synth.word_names(N)
+    spell = synth.lexicon(W, N, 2, 4, seed=7, exclude=(0, N - 1))
+    lm = KenLM(path, Dictionary(toks))
+    trie = Trie(N, 0)
+    for w, sp in enumerate(spell):
+        trie.insert([int(x) for x in sp], w, 0.0)
+    trie.smear(SmearingMode.MAX)
+    lopts = LexiconDecoderOptions(beam_size=20, beam_size_token=N, beam_threshold=1e9, lm_weight=0.7,
+                                  word_score=0.4, unk_score=-math.inf, sil_score=0.0, log_add=False,
+                                  criterion_type=CriterionType.CTC)
+    ldec = LexiconDecoder(lopts, trie, lm, 0, N - 1, W, [], True)
+    bl = Built(A, spec_lexicon(N, 20, N, spell, 1e9, lm_weight=0.7, word_score=0.4, lm=("arpa", path, toks),
+                               unk=W, is_lm_token=True))
+    for b in range(len(em)):
+        e = np.ascontiguousarray(em[b])
+        ra = bl.decode(e)
+        if has_ties(ra) or A.tie_events(bl.dec):
+            continue
+        assert_same_nbest(ra, _as_res(ldec.decode(e.ctypes.data, T, N), T), 1e-4, what=f"token LM utt {b}")
+        checked += 1
+    bl.close()
+    assert checked >= 2
+
+
 def test_cpp_mirror_program(tmp_path):
     """tests/cpp/mirror_test.cpp is written against fl::lib::text like the reference's DecoderTest."""
     exe = str(tmp_path / "mirror_test")

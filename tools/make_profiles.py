@@ -6,7 +6,7 @@ tag, rnd = sys.argv[1], sys.argv[2]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src, dst = os.path.join(ROOT, "gpurun_out", tag), os.path.join(ROOT, "profiles")
 names = ["bench_lexfree", "bench_lexfree_bst50", "bench_lexicon", "bench_lexfree_twokernel", "bench_reference"]
-extra = ["bench_lexfree_sigma4"]
+extra = ["bench_lexfree_sigma4", "bench_lexfree_logadd_bst50", "bench_lexfree_tokenlm_bst50", "bench_lexicon_logadd_bst100"]
 J = {}
 for n in names:
     shutil.copy(os.path.join(src, n + ".json"), os.path.join(dst, f"{rnd}_{tag}_{n}.json"))
@@ -16,6 +16,9 @@ for n in extra:
         shutil.copy(os.path.join(src, n + ".json"), os.path.join(dst, f"{rnd}_{tag}_{n}.json"))
         J[n] = json.load(open(os.path.join(src, n + ".json")))
 shutil.copy(os.path.join(src, "launches.csv"), os.path.join(dst, f"{rnd}_{tag}_launches_lexfree.csv"))
+for n in ("pytest_gpu.txt", "smoke.txt"):
+    if os.path.exists(os.path.join(src, n)):
+        shutil.copy(os.path.join(src, n), os.path.join(dst, f"{rnd}_{tag}_{n}"))
 rows = list(csv.DictReader(l for l in open(os.path.join(src, "launches.csv")) if not l.startswith("==")))
 agg = collections.OrderedDict()
 for r in rows:
@@ -32,6 +35,8 @@ caps = [("prof", "fused select+step + backtrace, cfg 2 full size (B=256, T=1000,
         ("prof_twokernel", "two-kernel path (FLT_NO_FUSED=1), T=250"), ("prof_lexicon", "lexicon workload (cfg 3 shape), T=100")]
 ncu_md, traffic = [], {}
 for f, title in caps:
+    if not os.path.exists(os.path.join(src, f + ".ncu-rep")):
+        continue
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), os.path.join(src, f + ".ncu-rep"), title],
                          capture_output=True, text=True).stdout
     body, _, tr = out.partition("TRAFFIC ")
@@ -46,6 +51,15 @@ if "flt_k_fused" in traffic:
               open(os.path.join(dst, "traffic.json"), "w"), indent=1)
 ph = b["beam_step_work"].get("phase_cycles_per_frame", {})
 kms = lambda d: ", ".join(f"{k} {v['ms']:.2f} ms" for k, v in d["kernels"].items())
+
+
+def wide_row(name, what, ref):
+    d = J.get(name)
+    if not d:
+        return f"| — | {what} | not run in this snapshot | | {ref} |"
+    return (f"| `{rnd}_{tag}_{name}.json` | {what} | {d['value']:.0f} | {kms(d)} | {ref} (runs `w2`/`w3` of the same "
+            f"workload, `r01_w2_*`, `r01_w3_*`) |")
+
 md = f"""# profiles/ — measured evidence, round 1
 
 Everything here was produced on a B200 through `gpurun` by `tools/gpu_snapshot.sh` (snapshot `{tag}`) and
@@ -75,12 +89,12 @@ beamThreshold 25; n-best of the 2-utterance sample equal to the compiled referen
 
 | file | workload | utt/s | kernels | reference CPU utt/s (16 threads, full length) |
 |---|---|---|---|---|
-| `r01_w2_bench_lexfree_logadd_bst50.json` | LexFree, logAdd, beam 50, bst 50 | 2337 | select 3.7 + step 105.9 ms | 20.8 |
-| `r01_w3_bench_lexfree_tokenlm_bst50.json` | LexFree + synthetic 4-gram token LM (500k/500k/250k), lmWeight 2, beam 50, bst 50 | 3057 | select 3.8 + step 79.7 ms | 18.1 |
-| `r01_w3_bench_lexicon_logadd_bst100.json` | Lexicon 200k words, logAdd, beam 100, bst 100 | 4454 | select 5.4 + step 51.6 ms | 87.5 (B=128 run of `w2`) |
+{wide_row('bench_lexfree_logadd_bst50', 'LexFree, logAdd, beam 50, bst 50', '20.8')}
+{wide_row('bench_lexfree_tokenlm_bst50', 'LexFree + synthetic 4-gram token LM (500k/500k/250k), lmWeight 2, beam 50, bst 50', '18.1')}
+{wide_row('bench_lexicon_logadd_bst100', 'Lexicon 200k words, logAdd, beam 100, bst 100', '87.5')}
 | `r01_w2_bench_lexfree_logadd_bstN_sigma4.json` | LexFree, logAdd, beam 50, bst = N (500 k candidates per frame), sigma 4, T=200 | 34.5 | step 7418 ms | 0.54 (12-frame prefix, extrapolated) |
 
-`r01_w3_pytest_gpu.txt`: the GPU suite of that build (203 passed).
+`{rnd}_{tag}_pytest_gpu.txt`, `{rnd}_{tag}_smoke.txt`: the GPU suite and `__graft_entry__.smoke()` of this snapshot's build.
 
 Lexicon step (cfg 3) phase breakdown, SM cycles per frame of thread 0 (`beam_step_work.phase_cycles_per_frame`
 of `{rnd}_{tag}_bench_lexicon.json`): {", ".join(f"{k} {v:.0f}" for k, v in lx["beam_step_work"].get("phase_cycles_per_frame", {}).items())}.
