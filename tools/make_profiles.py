@@ -103,6 +103,9 @@ shared memory) -> 31.6 (512 threads, per-item pruning cache) -> 29.5 (keep 1.5K+
 3K 31.3, 2K 30.0, 1.5K 29.3, 1.25K 49.5 ms) -> {lx['kernels']['beam_step']['ms']:.1f} ms (list-side cache of the root children, direct
 rank-by-counting select). Packed 16-byte edge records were tried and reverted (`gpurun_out/ab1`: 34.1 vs 33.5 ms).
 
+`r01_mg2c_*.json`: 2 GPUs on the final build (`tools/exp_mgpu.sh`): 62.3 k utt/s (weak scaling, max over ranks),
+e2e 1.39 k utt/s, reference arm under torchrun.
+
 Earlier lines of this round: `r01_bench_v0_*.json` (first correct path, 6.4 k utt/s), `r01_s1_*.json` (two
 kernels, generic step: 17.6 k utt/s), `r01_s2_*.json` (first fused kernel: 29.5 k utt/s),
 `r01_mg2_*.json` (2 GPUs: 59.0 k utt/s = 2.00x of the same build's 1-GPU line).
