@@ -96,6 +96,11 @@ beamThreshold 25; n-best of the 2-utterance sample equal to the compiled referen
 
 `{rnd}_{tag}_pytest_gpu.txt`, `{rnd}_{tag}_smoke.txt`: the GPU suite and `__graft_entry__.smoke()` of this snapshot's build.
 
+`r01_san2_sanitizer.txt`, `r01_san2_pytest_gpu.txt` (`tools/gpu_sanitize_wide.sh`, final build): compute-sanitizer
+memcheck 0 errors and racecheck 0 hazards over the full-expansion parity cases and the lexicon step; whole GPU suite
+206 passed. `r01_fs2_pytest_fullsize.txt`: the full-size property tests (`tests/test_gpu_fullsize.py`, cfg 2 and cfg 3
+at B=256, T=1000, N=10000) on their own.
+
 Lexicon step (cfg 3) phase breakdown, SM cycles per frame of thread 0 (`beam_step_work.phase_cycles_per_frame`
 of `{rnd}_{tag}_bench_lexicon.json`): {", ".join(f"{k} {v:.0f}" for k, v in lx["beam_step_work"].get("phase_cycles_per_frame", {}).items())}.
 History of that step this round: 64.9 ms (generic step, workspace in global memory) -> 39.6 (two-pass pruning,
