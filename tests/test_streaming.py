@@ -75,6 +75,34 @@ def test_streaming_full_expansion_modes(lexicon, mode):
     run_streaming(po.Oracle("ora"), FltBackend("model"), lexicon, 15, 4, 2, 1e-9, mode)
 
 
+@pytest.mark.parametrize("lexicon,mode", [(False, "logadd"), (True, "logadd"), (True, "max")])
+def test_streaming_overflow_retry(monkeypatch, lexicon, mode):
+    """A chunk whose frames overflow the candidate capacity is repeated with a larger one from the beam
+    saved before it (FLT_TEST_CAP starts the capacity tiny); results equal the oracle's."""
+    from flt_backend import FltBackend
+
+    monkeypatch.setenv("FLT_TEST_CAP", "4")
+    run_streaming(po.Oracle("ora"), FltBackend("model"), lexicon, 15, 4, 2, 1e-9, mode)
+
+
+def test_batch_overflow_retry(monkeypatch):
+    from flt_backend import FltBackend
+    import parity_cases
+    from cases import assert_same_nbest, has_ties
+
+    monkeypatch.setenv("FLT_TEST_CAP", "4")
+    A, M = po.Oracle("ora"), FltBackend("model")
+    for name, spec, em, exact in parity_cases.widened_cases()[:2] + parity_cases.widened_cases()[8:10]:
+        ba, bm = Built(A, spec), Built(M, spec)
+        got = bm.O.decode_batch(bm.dec, em, spec["opt"].beamSize)
+        for b, e in enumerate(em):
+            ra = ba.decode(e)
+            if has_ties(ra) or A.tie_events(ba.dec):
+                continue
+            assert_same_nbest(ra, got[b], 1e-9, what=f"{name} utt {b}")
+        ba.close(), bm.close()
+
+
 def test_unpruned_chunks_equal_offline_decode():
     """Without prune(), chunked decodeStep + decodeEnd gives exactly decode()'s n-best."""
     from flt_backend import FltBackend
@@ -113,4 +141,13 @@ def test_streaming_cuda(lexicon, chunk, look_back, prune_every):
 def test_streaming_full_expansion_modes_cuda(lexicon, mode):
     from flt_backend import FltBackend
 
+    run_streaming(po.Oracle("ora"), FltBackend("cuda"), lexicon, 15, 4, 2, 1e-4, mode)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lexicon,mode", [(False, "logadd"), (True, "max")])
+def test_streaming_overflow_retry_cuda(monkeypatch, lexicon, mode):
+    from flt_backend import FltBackend
+
+    monkeypatch.setenv("FLT_TEST_CAP", "4")
     run_streaming(po.Oracle("ora"), FltBackend("cuda"), lexicon, 15, 4, 2, 1e-4, mode)

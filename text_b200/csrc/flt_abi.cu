@@ -452,7 +452,7 @@ struct flt_decoder {
     double shift = 0.0;
     std::vector<std::vector<SHyp>> hyp; // rows in the buffer (row 0 = oldest kept frame)
   } on;
-  rt::DevBuf sBeam, sScore, sCount, sEmis;
+  rt::DevBuf sBeam, sBeamBackup, sScore, sCount, sEmis;
   int threads = 256;  // threads per utterance of the beam-step kernel
   bool fused = false; // select + step in one kernel (fused_core.h)
   TopMCfg ftcfg{};
@@ -475,7 +475,7 @@ struct flt_decoder {
   ~flt_decoder() {
     for (rt::DevBuf* b : {&dWideOff, &dBias, &dTrans, &dLfDesc, &topTok, &topVal, &thr, &hPar, &hTok, &hWord,
                           &finScore, &finCount, &status, &ws, &outTok, &outWord, &dLengths,
-                          &staging[0], &staging[1], &dStats, &hSkip, &hSkipFin, &sBeam, &sScore, &sCount, &sEmis})
+                          &staging[0], &staging[1], &dStats, &hSkip, &hSkipFin, &sBeam, &sBeamBackup, &sScore, &sCount, &sEmis})
       b->release();
 #if FLT_DEVICE_BUILD
     for (int i = 0; i < 2; ++i) {
@@ -598,9 +598,11 @@ void planFor(flt_decoder& d, int N) {
   // frame whose kept bins hold fewer than K merge groups is redone without the cut. Measured on cfg 3:
   // 300 % 31.3 ms, 200 % 30.0 ms, 150 % 29.3 ms, 125 % 49.5 ms (redo storms)
   c.pruneWant = std::max(K + 1, (int)((long long)K * (getenv("FLT_PRUNE_WANT") ? atoi(getenv("FLT_PRUNE_WANT")) : 150) / 100) + 32);
-  long long capC = c.prune2 ? 3LL * K + 64 + narrowBudget * d.capBoost
-                            : (long long)(c.wideRanked ? d.wideOffHost[K] : 0) + 3LL * K + narrowBudget * d.capBoost;
-  if (c.full && !c.prune2) capC = 3LL * K + std::min(fullCells, narrowBudget * d.capBoost);
+  // FLT_TEST_CAP=<n>: start from a tiny budget so that tests reach the overflow retry
+  const long long budget0 = getenv("FLT_TEST_CAP") ? std::max(1, atoi(getenv("FLT_TEST_CAP"))) : narrowBudget;
+  long long capC = c.prune2 ? 3LL * K + 64 + budget0 * d.capBoost
+                            : (long long)(c.wideRanked ? d.wideOffHost[K] : 0) + 3LL * K + budget0 * d.capBoost;
+  if (c.full && !c.prune2) capC = 3LL * K + std::min(fullCells, budget0 * d.capBoost);
   capC = (capC + 63) / 64 * 64;
   if (capC > (1LL << 26)) throw FltError(FLT_ERR_RUNTIME, "candidate capacity exceeded");
   c.capC = (int)capC;
@@ -979,7 +981,9 @@ namespace {
 
 // One launch of online decoding: T frames of one utterance (T = 0 with finish = decodeEnd only).
 // Appends the new history rows to the host mirror.
-void runStream(flt_decoder& d, const float* emis, int T, int N, bool finish) {
+// Returns false (nothing mirrored, the saved beam untouched) if a frame overflowed the candidate
+// capacity; runStream then grows the capacity and repeats the chunk.
+bool runStreamOnce(flt_decoder& d, const float* emis, int T, int N, bool finish) {
   planFor(d, N);
   const DecCfg& c = d.cfg;
   const int K = c.K;
@@ -1035,6 +1039,11 @@ void runStream(flt_decoder& d, const float* emis, int T, int N, bool finish) {
   a.finCount = d.finCount.as<int>();
   a.status = d.status.as<int>();
   a.stats = nullptr;
+  // the launch overwrites the saved beam: keep a copy so that an overflowed chunk can be repeated
+  if (d.on.haveBeam) {
+    d.sBeamBackup.reserve(streamBeamBytes(c));
+    rt::d2d(d.sBeamBackup.p, d.sBeam.p, streamBeamBytes(c), s);
+  }
   a.streamBeam = d.sBeam.as<char>();
   a.streamRestore = d.on.haveBeam ? 1 : 0;
   a.streamNoFinish = finish ? 0 : 1;
@@ -1059,7 +1068,11 @@ void runStream(flt_decoder& d, const float* emis, int T, int N, bool finish) {
   rt::d2h(cnt.data(), d.sCount.p, sizeof(int) * rows, s);
   rt::d2h(st.data(), d.status.p, sizeof(int), s);
   rt::sync(s);
-  if (st[0] & 1) throw FltError(FLT_ERR_RUNTIME, "candidate capacity exceeded");
+  if (st[0] & 1) {
+    if (d.on.haveBeam) rt::d2d(d.sBeam.p, d.sBeamBackup.p, streamBeamBytes(c), s);
+    rt::sync(s);
+    return false;
+  }
   for (int r = 1; r <= nNew; ++r) {
     std::vector<flt_decoder::SHyp> row(cnt[r]);
     for (int q = 0; q < cnt[r]; ++q) {
@@ -1071,6 +1084,17 @@ void runStream(flt_decoder& d, const float* emis, int T, int N, bool finish) {
   d.on.haveBeam = true;
   d.on.shift = 0.0;
   d.on.nDecoded += nNew;
+  return true;
+}
+
+void runStream(flt_decoder& d, const float* emis, int T, int N, bool finish) {
+  for (int attempt = 0;; ++attempt) {
+    if (runStreamOnce(d, emis, T, N, finish)) return;
+    // data-dependent candidate counts (lexicon enumeration, full expansion): grow and redo the chunk
+    if (attempt >= 6) throw FltError(FLT_ERR_RUNTIME, "candidate capacity exceeded");
+    d.capBoost *= 4;
+    d.planN = -1;
+  }
 }
 
 using SHyp = flt_decoder::SHyp;

@@ -44,6 +44,9 @@ inline void d2h(void* h, const void* d, size_t bytes, Stream s) {
 inline void devZero(void* d, size_t bytes, Stream s) {
   if (bytes) FLT_RT_TRY(cudaMemsetAsync(d, 0, bytes, s));
 }
+inline void d2d(void* dst, const void* src, size_t bytes, Stream s) {
+  if (bytes) FLT_RT_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
+}
 inline void sync(Stream s) { FLT_RT_TRY(cudaStreamSynchronize(s)); }
 inline bool isDevicePtr(const void* p) {
   cudaPointerAttributes a;
@@ -74,6 +77,7 @@ inline void* devAlloc(size_t bytes) {
 }
 inline void devFree(void* p) { free(p); }
 inline void h2d(void* d, const void* h, size_t bytes, Stream) { memcpy(d, h, bytes); }
+inline void d2d(void* dst, const void* src, size_t bytes, Stream) { memcpy(dst, src, bytes); }
 inline void d2h(void* h, const void* d, size_t bytes, Stream) { memcpy(h, d, bytes); }
 inline void devZero(void* d, size_t bytes, Stream) { memset(d, 0, bytes); }
 inline void sync(Stream) {}
