@@ -101,6 +101,9 @@ memcheck 0 errors and racecheck 0 hazards over the full-expansion parity cases a
 206 passed. `r01_fs2_pytest_fullsize.txt`: the full-size property tests (`tests/test_gpu_fullsize.py`, cfg 2 and cfg 3
 at B=256, T=1000, N=10000) on their own.
 
+`r01_fin1_pytest_gpu.txt`, `r01_fin1_bench_lexfree.json`: GPU suite (208 passed) and default bench line (32.35 k utt/s,
+e2e 1.20 k utt/s) of the last commit of the round (streaming overflow retry added after snapshot `s5`).
+
 Lexicon step (cfg 3) phase breakdown, SM cycles per frame of thread 0 (`beam_step_work.phase_cycles_per_frame`
 of `{rnd}_{tag}_bench_lexicon.json`): {", ".join(f"{k} {v:.0f}" for k, v in lx["beam_step_work"].get("phase_cycles_per_frame", {}).items())}.
 History of that step this round: 64.9 ms (generic step, workspace in global memory) -> 39.6 (two-pass pruning,
