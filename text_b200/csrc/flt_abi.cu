@@ -543,7 +543,9 @@ void planFor(flt_decoder& d, int N) {
   }
 
   // the lexicon step has ~4x the work items per frame of the lexicon-free one
-  d.threads = decThreadsEnv() ? decThreadsEnv() : (d.lexicon ? 512 : 256);
+  // ... and the full expansion with an n-gram token LM is bound by its table probes: twice the threads
+  // keep twice the gathers in flight (measured: 87.8 -> 49.5 ms per step at beam 50, bst 50)
+  d.threads = decThreadsEnv() ? decThreadsEnv() : ((d.lexicon || (c.full && d.lm->kind != 0)) ? 512 : 256);
   const int K = c.K;
   const int bstEff = std::min(o.beamSizeToken, N);
   // ranked wide rows need max-merge and scores that follow the per-frame token order
