@@ -104,6 +104,11 @@ at B=256, T=1000, N=10000) on their own.
 `r01_fin1_pytest_gpu.txt`, `r01_fin1_bench_lexfree.json`: GPU suite (208 passed) and default bench line (32.35 k utt/s,
 e2e 1.20 k utt/s) of the last commit of the round (streaming overflow retry added after snapshot `s5`).
 
+`r01_fin2_bench_lexfree_tokenlm_bst50.json`, `r01_fin2_pytest_gpu.txt`: the token-LM full expansion with 512 threads per
+utterance (last change of the round; `r01_wprof_ncu_lines_tokenlm_step.txt` showed 55 % of its stall samples on the
+n-gram table probes at 22 % occupancy): 4.8 k utt/s (step 49.5 ms, was 87.6), n-best equal to the compiled reference over
+1000 frames; GPU suite 208 passed.
+
 Lexicon step (cfg 3) phase breakdown, SM cycles per frame of thread 0 (`beam_step_work.phase_cycles_per_frame`
 of `{rnd}_{tag}_bench_lexicon.json`): {", ".join(f"{k} {v:.0f}" for k, v in lx["beam_step_work"].get("phase_cycles_per_frame", {}).items())}.
 History of that step this round: 64.9 ms (generic step, workspace in global memory) -> 39.6 (two-pass pruning,
