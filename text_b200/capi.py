@@ -325,7 +325,13 @@ class Api:
         frames = max(int(v[0]), 1)
         out = dict(frames=int(v[0]), candidates_per_frame=v[1] / frames, groups_per_frame=v[2] / frames,
                    survivors_per_frame=v[3] / frames)
-        if v[31]:  # generic step (beam_core.h frameStep): SM cycles of thread 0 per phase
+        if v[30]:  # single-pass step with a guessed cut (beam_gx.h)
+            names = ("expand_merge", "compact", "rank_new_beam")
+            out["phase_cycles_per_frame"] = {n: round(v[4 + i] / frames, 1) for i, n in enumerate(names)}
+            out["phase_cycles_per_frame"]["wait_list"] = round(v[9] / frames, 1)
+            out["guess_redo_frames"] = int(v[12])
+            out["select_guess_misses"] = int(v[11])
+        elif v[31]:  # generic step (beam_core.h frameStep): SM cycles of thread 0 per phase
             names = ("rows", "degrees_scan", "pass1_histogram", "cut_bin", "pass2_emit", "merge", "select",
                      "new_beam")
             out["phase_cycles_per_frame"] = {n: round(v[4 + i] / frames, 1) for i, n in enumerate(names)}

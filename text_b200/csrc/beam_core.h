@@ -61,6 +61,13 @@ struct Lay {
                          // token (-1: none or childless) and its smeared score, gathered once per frame
   int lnk, lhead; // int [capC] each (logAdd): members of a merge group chained behind its best member
   int pruneCache; // u8 per work item: 1 + best histogram bin its candidates reached in pass 1 (two-pass pruning)
+  // single-pass step with a guessed cut (beam_gx.h)
+  int beamX[2];   // int [3][K] per beam: Trie cache of each hypothesis (first edge, #edges | #labels, smeared score)
+  int gxCandX;    // int [3][capC]: the same for each candidate's lex node
+  int gxChunk;    // int2 [2][capChunks]: item chunk descriptors of each beam
+  int gxBits;     // u32 [2][(K+31)/32]: hypotheses at the Trie root (walkers) of each beam
+  int gxList;     // int4 [2][Mwide]: root child of each list entry (lexicon), double-buffered
+  int gxBest;     // u64: best representative score key of the frame
   int total;
 };
 
@@ -94,6 +101,9 @@ struct DecCfg {
                   //     (the max-merge kernels are compiled without those paths)
   int lmToken;    // 1 = LexiconDecoder with a token-level LM (isLmToken, LexiconDecoder.cpp:82-86)
   int lfBins;     // histogram bins of its select (pow2, multiple of 32)
+  int gx;         // 1 = single-pass step with a guessed cut (beam_gx.h)
+  int capChunks;  // its item chunk descriptors per beam
+  float lmUpper;  // n-gram LM: no word scores above this (log10): bound used to skip hopeless probes
   int nTau;       // pruning rectangles: rows 1..tauA[k] x columns 0..tauCol[k] hold >= K regular cells
   int tauA[16];
   int tauCol[16];
@@ -140,6 +150,7 @@ struct Beam {
   u64* fp;    // [2][K] LM-state fingerprint (+ [2][K] fingerprint of the parent state, beam_lf.h)
   int* iv;    // [5][K] lex, tok, prevBlank, nctx, anc; then ctx [K][kMaxCtx]
   int K;
+  int* xv = nullptr; // [3][K] Trie cache (beam_gx.h)
   FLT_DEV double& score(int i) const { return d[i]; }
   FLT_DEV double& am(int i) const { return d[K + i]; }
   FLT_DEV double& lm(int i) const { return d[2 * K + i]; }
@@ -198,7 +209,9 @@ enum { // ws.sc[] scalars
   SC_PMODE, SC_PCUT, SC_PLO_LO, SC_PLO_HI, SC_PSCALE, // two-pass candidate pruning (frameStep)
   SC_TLO, SC_THI, // previous phase stamp of thread 0 (counters on)
   SC_WANT, SC_WHOLD, // two-pass pruning: candidates to keep this frame; frames left at the wide setting
-  SC_WCNT /* 32 warp counters follow */,
+  SC_GXCUTBIN, SC_GXKEPT, // beam_gx.h: cut bin of the exact redo and the proposals it keeps
+  SC_GX,                  // beam_gx.h: two sets of per-frame scalars (12 ints)
+  SC_WCNT = SC_GX + 12 /* 32 warp counters follow */,
   SC_COUNT = SC_WCNT + 32
 };
 
@@ -210,7 +223,8 @@ struct Ws {
   int* itemBin = nullptr; // pass 1 of the two-pass pruning: best bin reached by the current work item
   FLT_DEV Beam beam(int b) const {
     const Lay& L = c->lay;
-    return Beam{(double*)(base + L.beamD[b]), (u64*)(base + L.beamFp[b]), (int*)(base + L.beamI[b]), c->K};
+    return Beam{(double*)(base + L.beamD[b]), (u64*)(base + L.beamFp[b]), (int*)(base + L.beamI[b]), c->K,
+                (int*)(base + L.beamX[b])};
   }
   FLT_DEV Rows rows() const {
     return Rows{(int*)(base + c->lay.rowHash), (int*)(base + c->lay.rowI), c->K};
@@ -253,37 +267,45 @@ FLT_HD void makeLayout(DecCfg& c) {
   const int K = c.K;
   Lay& L = c.lay;
   const bool lf = c.lfFast != 0;
+  const bool gx = c.gx != 0;
+  const bool gxl = gx && c.lexicon;
   for (int b = 0; b < 2; ++b) {
     L.beamD[b] = take(sizeof(double) * 3 * K);
     L.beamFp[b] = take(sizeof(u64) * (lf ? 4 : 2) * K);
     L.beamI[b] = take(sizeof(int) * (5 * K + (c.lm.kind ? K * kMaxCtx : 0)));
+    L.beamX[b] = take(gxl ? sizeof(int) * 3 * K : 0); // inside the beam block: saved / restored with it
   }
-  L.rowHash = take(sizeof(int) * c.capRH);
-  L.rowI = take(lf ? 0 : sizeof(int) * (kRowsInts * K + 8));
+  L.rowHash = take(gx ? 0 : sizeof(int) * c.capRH);
+  L.rowI = take(lf || gx ? 0 : sizeof(int) * (kRowsInts * K + 8));
   L.candScore = take(sizeof(double) * c.capC);
   L.candKey = take(sizeof(u64) * (lf ? 1 : 2) * c.capC);
   L.candI = take(sizeof(int) * (lf ? 3 : 6) * c.capC);
   L.mh = take(lf ? 0 : sizeof(int) * c.capH);
   L.rep = take(sizeof(int) * c.capC);
-  L.surv = take(sizeof(int) * 2 * c.capP);
-  L.skey = take(lf ? 0 : sizeof(u64) * c.capP);
-  L.pos = take(lf ? 0 : sizeof(int) * c.capP);
+  L.surv = take(gx ? 0 : sizeof(int) * 2 * c.capP);
+  L.skey = take(lf || gx ? 0 : sizeof(u64) * c.capP);
+  L.pos = take(lf || gx ? 0 : sizeof(int) * c.capP);
   L.hist = take(sizeof(int) * (lf && c.lfBins > 256 ? c.lfBins : 256));
   L.sc = take(sizeof(int) * SC_COUNT);
   L.red = take(sizeof(u64) * 64);
   for (int b = 0; b < 2; ++b) L.list[b] = take(c.listInSmem ? 8 * (size_t)c.M : 0);
-  L.spec = take(sizeof(float) * (K + 2));
-  L.wideOff = take(sizeof(int) * (K + 1));
-  L.itemRow = take(sizeof(short) * (c.wideTotal + 2));
+  L.spec = take(gx ? 0 : sizeof(float) * (K + 2));
+  L.wideOff = take(gx ? 0 : sizeof(int) * (K + 1));
+  L.itemRow = take(gx ? 0 : sizeof(short) * (c.wideTotal + 2));
   L.cslot = take(lf ? 0 : sizeof(int) * c.capC);
-  L.gath = take(sizeof(int) * 64);
+  L.gath = take(gx ? 0 : sizeof(int) * 64);
+  L.gxCandX = take(gxl ? sizeof(int) * 3 * c.capC : 0);
+  L.gxChunk = take(gxl ? sizeof(int) * 2 * 2 * (size_t)c.capChunks : 0);
+  L.gxBits = take(gx ? sizeof(int) * 2 * ((K + 31) / 32) : 0);
+  L.gxList = take(gxl ? sizeof(int) * 4 * 2 * (size_t)c.Mwide : 0);
+  L.gxBest = take(gx ? 16 : 0);
   L.lfSlotB = take(lf ? sizeof(int) * c.capRH : 0);
   L.lfSlotOf = take(lf ? sizeof(int) * K : 0);
   L.lfCbin = take(lf ? sizeof(unsigned short) * 2 * c.capC : 0); // bin, arrival order in the bin
   L.lfAbove = take(lf ? sizeof(unsigned short) * 16 * c.lfBins : 0); // one copy per warp (<= 16)
   L.lfDesc = take(lf ? sizeof(int) * c.capC : 0);                      // static work-item descriptors
-  L.listNode = take(c.lexicon && c.wideRanked ? sizeof(int) * c.Mwide : 0);
-  L.listMax = take(c.lexicon && c.wideRanked ? sizeof(float) * c.Mwide : 0);
+  L.listNode = take(c.lexicon && c.wideRanked && !gx ? sizeof(int) * c.Mwide : 0);
+  L.listMax = take(c.lexicon && c.wideRanked && !gx ? sizeof(float) * c.Mwide : 0);
   L.lnk = take(c.logAdd ? sizeof(int) * c.capC : 0);
   L.lhead = take(c.logAdd ? sizeof(int) * c.capC : 0);
   L.pruneCache = take(c.prune2 ? (size_t)c.wideTotal + c.K + kPruneEdgeCap : 0);
@@ -485,7 +507,9 @@ struct FrameIn {
   float thrVal;        // cut value of the token set (unused when setAll)
   int first;           // global frame 0 (ASG transitions are skipped, LexiconDecoder.cpp:70-73)
   int listIsSet;       // the list holds the whole token set (lexicon-free, beamSizeToken < N)
-  int specReady;       // spec[] already holds this frame's gathered emissions
+  int specReady;       // spec[] (beam_lf.h) / eBlank, eSil (beam_gx.h) already hold this frame's emissions
+  float eBlank, eSil;  // e[blank], e[sil] of this frame when specReady (beam_gx.h, fused kernel)
+  const int* listInfo; // int4 per list entry: root child of the token (beam_gx.h, lexicon)
   const float* eNext;  // next frame's emission row or null (beam_lf.h prefetches its gathers)
   int hRow;            // index of the history row being written (frame t+1; len+1 for the finish)
   int* hSkip;          // where its skip pointers go: a checkpoint row (hRow % 32 == 0), the finish row, else null

@@ -12,6 +12,7 @@
 #include <limits>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -20,6 +21,7 @@
 #include "runtime.h"
 #include "beam_core.h"
 #include "beam_lf.h"
+#include "beam_gx.h"
 #include "topm_core.h"
 #include "fused_core.h"
 
@@ -64,6 +66,24 @@ __global__ void __launch_bounds__(512, 2) flt_k_decode512_wide(DecCfg c, BatchAr
 __global__ void __launch_bounds__(256) flt_k_decode_gmem_wide(DecCfg c, BatchArgs a) {
   Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
   decodeCta<true>(cta, c, a, a.wsGlobal + (long long)blockIdx.x * a.wsStride);
+}
+// the single-pass step with a guessed cut (beam_gx.h), two-kernel path: token lists from flt_k_topm
+template <bool LEX>
+__global__ void __launch_bounds__(256) flt_k_gx(DecCfg c, BatchArgs a) {
+  extern __shared__ __align__(128) char smem[];
+  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
+  gxDecodeCta<LEX>(cta, c, a, smem);
+}
+template <bool LEX>
+__global__ void __launch_bounds__(512, 2) flt_k_gx512(DecCfg c, BatchArgs a) {
+  extern __shared__ __align__(128) char smem[];
+  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
+  gxDecodeCta<LEX>(cta, c, a, smem);
+}
+template <bool LEX>
+__global__ void __launch_bounds__(256) flt_k_gx_gmem(DecCfg c, BatchArgs a) {
+  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
+  gxDecodeCta<LEX>(cta, c, a, a.wsGlobal + (long long)blockIdx.x * a.wsStride);
 }
 // token-beam select + beam step fused: 8 consumer + 4 producer warps per utterance (fused_core.h)
 __global__ void __launch_bounds__(kFusedConsumers + kFusedProducers, 2)
@@ -120,7 +140,11 @@ void launchTopM(const TopMCfg& c, const TopMArgs& a, int grid, size_t smem, rt::
 }
 void launchDecode(const DecCfg& c, const BatchArgs& a, int grid, size_t smem, rt::Stream s, int threads) {
 #if FLT_DEVICE_BUILD
-  if (smem && threads == 512) (c.wide ? flt_k_decode512_wide : flt_k_decode512)<<<grid, 512, smem, s>>>(c, a);
+  if (c.gx) {
+    if (smem && threads == 512) (c.lexicon ? flt_k_gx512<true> : flt_k_gx512<false>)<<<grid, 512, smem, s>>>(c, a);
+    else if (smem) (c.lexicon ? flt_k_gx<true> : flt_k_gx<false>)<<<grid, threads, smem, s>>>(c, a);
+    else (c.lexicon ? flt_k_gx_gmem<true> : flt_k_gx_gmem<false>)<<<grid, threads > 256 ? 256 : threads, 0, s>>>(c, a);
+  } else if (smem && threads == 512) (c.wide ? flt_k_decode512_wide : flt_k_decode512)<<<grid, 512, smem, s>>>(c, a);
   else if (smem) (c.wide ? flt_k_decode_wide : flt_k_decode)<<<grid, threads, smem, s>>>(c, a);
   else (c.wide ? flt_k_decode_gmem_wide : flt_k_decode_gmem)<<<grid, threads > 256 ? 256 : threads, 0, s>>>(c, a);
   FLT_RT_TRY(cudaGetLastError());
@@ -128,7 +152,9 @@ void launchDecode(const DecCfg& c, const BatchArgs& a, int grid, size_t smem, rt
   std::vector<char> sm(c.lay.total + 16, (char)0x5A); // shared memory is never zero for free
   for (int b = 0; b < grid; ++b) {
     Cta cta{0, 1, b, grid};
-    if (c.wide) decodeCta<true>(cta, c, a, sm.data());
+    if (c.gx && c.lexicon) gxDecodeCta<true>(cta, c, a, sm.data());
+    else if (c.gx) gxDecodeCta<false>(cta, c, a, sm.data());
+    else if (c.wide) decodeCta<true>(cta, c, a, sm.data());
     else decodeCta<false>(cta, c, a, sm.data());
   }
   (void)s;
@@ -183,12 +209,21 @@ struct HNode {
 struct flt_trie {
   int maxChildren, rootIdx;
   std::vector<HNode> nodes;
-  // device image (built on first use)
-  mutable bool uploaded = false;
-  mutable TrieDev dev{};
-  mutable rt::DevBuf dChildOff, dChildTok, dChildNode, dMaxScore, dLabelOff, dLabels, dRootChild,
-      dRootLabTok;
-  mutable std::vector<int> rootChildHost;
+  // device images, one per CUDA device that a decoder uses the Trie on (built on first use there);
+  // the Trie is frozen once the first exists
+  struct Image {
+    TrieDev dev{};
+    rt::DevBuf childOff, childTok, childNode, maxScore, labelOff, labels, rootChild, rootLabTok, edge, node,
+        rootLabEdge;
+    ~Image() {
+      for (rt::DevBuf* b : {&childOff, &childTok, &childNode, &maxScore, &labelOff, &labels, &rootChild,
+                            &rootLabTok, &edge, &node, &rootLabEdge})
+        b->release();
+    }
+  };
+  mutable std::mutex mu;
+  mutable std::map<int, std::unique_ptr<Image>> images;
+  mutable bool frozen = false;
 
   static double logAdd(double a, double b) { // Trie.cpp:66-77
     if (a < b) std::swap(a, b);
@@ -206,8 +241,12 @@ struct flt_trie {
       else if (mode == FLT_SMEAR_MAX && cm > nodes[n].maxScore) nodes[n].maxScore = cm;
     }
   }
-  void ensureUploaded(rt::Stream s) const {
-    if (uploaded) return;
+  // the flattened Trie on `device` (the caller has made it current); thread-safe
+  const TrieDev& deviceImage(int device, rt::Stream s) const {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = images.find(device);
+    if (it != images.end()) return it->second->dev;
+    std::unique_ptr<Image> im(new Image);
     const int nn = (int)nodes.size();
     std::vector<int> childOff(nn + 1, 0), childTok, childNode, labelOff(nn + 1, 0), labels;
     std::vector<float> maxScore(nn);
@@ -223,28 +262,48 @@ struct flt_trie {
     }
     childOff[nn] = (int)childTok.size();
     labelOff[nn] = (int)labels.size();
-    rootChildHost.assign(std::max(maxChildren, 1), -1);
+    std::vector<int> rootChildHost(std::max(maxChildren, 1), -1);
     std::vector<int> rootLabTok;
     for (auto& kv : nodes[0].kids) {
       if (kv.first >= 0 && kv.first < maxChildren) rootChildHost[kv.first] = kv.second;
       if (!nodes[kv.second].labels.empty()) rootLabTok.push_back(kv.first);
     }
+    // packed records (tables.h)
+    std::vector<int> edge(2 * std::max<size_t>(childTok.size(), 1)), node(4 * (size_t)nn),
+        rootLabEdge(2 * std::max<size_t>(rootLabTok.size(), 1));
+    for (size_t e = 0; e < childTok.size(); ++e) {
+      edge[2 * e] = childTok[e];
+      edge[2 * e + 1] = childNode[e];
+    }
+    for (int i = 0; i < nn; ++i) {
+      const int deg = childOff[i + 1] - childOff[i], nl = labelOff[i + 1] - labelOff[i];
+      if (deg >= (1 << 24)) throw std::runtime_error("trie node with more than 2^24 children");
+      node[4 * (size_t)i] = (int)f32Bits(maxScore[i]);
+      node[4 * (size_t)i + 1] = childOff[i];
+      node[4 * (size_t)i + 2] = deg | (nl << 24);
+      node[4 * (size_t)i + 3] = nl == 1 ? labels[labelOff[i]] : labelOff[i];
+    }
+    for (size_t k = 0; k < rootLabTok.size(); ++k) {
+      rootLabEdge[2 * k] = rootLabTok[k];
+      rootLabEdge[2 * k + 1] = rootChildHost[rootLabTok[k]];
+    }
+    TrieDev& dev = im->dev;
     dev.nNodes = nn;
-    dev.childOff = upload(dChildOff, childOff, s);
-    dev.childTok = upload(dChildTok, childTok, s);
-    dev.childNode = upload(dChildNode, childNode, s);
-    dev.maxScore = upload(dMaxScore, maxScore, s);
-    dev.labelOff = upload(dLabelOff, labelOff, s);
-    dev.labels = upload(dLabels, labels, s);
-    dev.rootChild = upload(dRootChild, rootChildHost, s);
+    dev.childOff = upload(im->childOff, childOff, s);
+    dev.childTok = upload(im->childTok, childTok, s);
+    dev.childNode = upload(im->childNode, childNode, s);
+    dev.maxScore = upload(im->maxScore, maxScore, s);
+    dev.labelOff = upload(im->labelOff, labelOff, s);
+    dev.labels = upload(im->labels, labels, s);
+    dev.rootChild = upload(im->rootChild, rootChildHost, s);
     dev.nRootLab = (int)rootLabTok.size();
-    dev.rootLabTok = upload(dRootLabTok, rootLabTok, s);
+    dev.rootLabTok = upload(im->rootLabTok, rootLabTok, s);
+    dev.edge = (const int2*)upload(im->edge, edge, s);
+    dev.node = (const int4*)upload(im->node, node, s);
+    dev.rootLabEdge = (const int2*)upload(im->rootLabEdge, rootLabEdge, s);
     rt::sync(s);
-    uploaded = true;
-  }
-  ~flt_trie() {
-    dChildOff.release(), dChildTok.release(), dChildNode.release(), dMaxScore.release();
-    dLabelOff.release(), dLabels.release(), dRootChild.release(), dRootLabTok.release();
+    frozen = true;
+    return images.emplace(device, std::move(im)).first->second->dev;
   }
 };
 
@@ -257,9 +316,17 @@ struct flt_lm {
   std::vector<F2> vals[kMaxOrder + 1];
   std::vector<int> usr2lm;
   LmDev host{}; // view over the host vectors (host-side scoring)
-  mutable bool uploaded = false;
-  mutable LmDev dev{};
-  mutable rt::DevBuf dUni, dUsr, dKeys[kMaxOrder + 1], dVals[kMaxOrder + 1];
+  float upper = 0.0f; // no word scores above this: best probability + the positive back-offs
+  struct Image {
+    LmDev dev{};
+    rt::DevBuf uni, usr, keys[kMaxOrder + 1], vals[kMaxOrder + 1];
+    ~Image() {
+      uni.release(), usr.release();
+      for (int n = 0; n <= kMaxOrder; ++n) keys[n].release(), vals[n].release();
+    }
+  };
+  mutable std::mutex mu;
+  mutable std::map<int, std::unique_ptr<Image>> images;
 
   void makeHostView() {
     host = LmDev{};
@@ -271,30 +338,46 @@ struct flt_lm {
     host.nUsr = (int)usr2lm.size();
     host.usr2lm = usr2lm.data();
     host.uni = uni.data();
+    float best = -std::numeric_limits<float>::infinity(), bo = 0.0f;
+    for (const F2& v : uni) best = std::max(best, v.x);
     for (int n = 2; n <= kMaxOrder; ++n) {
       host.keys[n] = keys[n].empty() ? nullptr : keys[n].data();
       host.vals[n] = vals[n].empty() ? nullptr : vals[n].data();
       host.mask[n] = keys[n].empty() ? 0 : (uint32_t)keys[n].size() - 1;
+      for (size_t i = 0; i < keys[n].size(); ++i)
+        if (keys[n][i]) best = std::max(best, vals[n][i].x);
     }
+    // at most one back-off per context order is added to a score (tables.h ngramScore)
+    for (int n = 1; n < std::max(order, 1); ++n) {
+      float m = 0.0f;
+      if (n == 1) {
+        for (const F2& v : uni) m = std::max(m, v.y);
+      } else {
+        for (size_t i = 0; i < keys[n].size(); ++i)
+          if (keys[n][i]) m = std::max(m, vals[n][i].y);
+      }
+      bo += m;
+    }
+    upper = kind == 0 ? 0.0f : best + bo + 1e-3f;
   }
-  void ensureUploaded(rt::Stream s) const {
-    if (uploaded) return;
-    dev = host;
+  // the tables on `device` (the caller has made it current); thread-safe
+  const LmDev& deviceImage(int device, rt::Stream s) const {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = images.find(device);
+    if (it != images.end()) return it->second->dev;
+    std::unique_ptr<Image> im(new Image);
+    im->dev = host;
     if (kind == 1) {
-      dev.usr2lm = upload(dUsr, usr2lm, s);
-      dev.uni = upload(dUni, uni, s);
+      im->dev.usr2lm = upload(im->usr, usr2lm, s);
+      im->dev.uni = upload(im->uni, uni, s);
       for (int n = 2; n <= kMaxOrder; ++n) {
         if (keys[n].empty()) continue;
-        dev.keys[n] = upload(dKeys[n], keys[n], s);
-        dev.vals[n] = upload(dVals[n], vals[n], s);
+        im->dev.keys[n] = upload(im->keys[n], keys[n], s);
+        im->dev.vals[n] = upload(im->vals[n], vals[n], s);
       }
       rt::sync(s);
     }
-    uploaded = true;
-  }
-  ~flt_lm() {
-    dUni.release(), dUsr.release();
-    for (int n = 0; n <= kMaxOrder; ++n) dKeys[n].release(), dVals[n].release();
+    return images.emplace(device, std::move(im)).first->second->dev;
   }
 };
 
@@ -577,8 +660,11 @@ void planFor(flt_decoder& d, int N) {
   // register-resident fast path (alignment of the emission pointer is checked per launch)
   t.fast = (N % 4 == 0) && N <= 4 * kFastVec * kThreads && want <= 256 && c.M <= 256;
   t.stage = !t.fast && (size_t)N * 4 <= 100 * 1024;
+  // single-pass step with a guessed cut (beam_gx.h): max-merge, word-level LM; lexicon: CTC without unk
+  c.gx = !getenv("FLT_NO_GX") && !o.logAdd && K <= 4095 &&
+         (d.lexicon ? c.wideRanked != 0 : !c.full);
   // lexicon-free fast step (beam_lf.h): ZeroLM max-merge, candidate indices fit 16 bits
-  c.lfFast = !d.lexicon && !c.full && K <= 256 && !getenv("FLT_NO_LF");
+  c.lfFast = !c.gx && !d.lexicon && !c.full && K <= 256 && !getenv("FLT_NO_LF");
   c.lfBins = std::min(1024, std::max(256, nextPow2(4 * K)));
   // wide offsets
   d.wideOffHost.assign(K + 1, 0);
@@ -589,7 +675,7 @@ void planFor(flt_decoder& d, int N) {
   }
   // lexicon decoder, max-merge: two-pass histogram pruning keeps ~3K+64 candidates per frame (plus
   // the rest of the cut bin), so the workspace fits shared memory
-  c.prune2 = (d.lexicon || (c.full && !getenv("FLT_NO_PRUNE2_FULL"))) && !o.logAdd && !getenv("FLT_NO_PRUNE2");
+  c.prune2 = !c.gx && (d.lexicon || (c.full && !getenv("FLT_NO_PRUNE2_FULL"))) && !o.logAdd && !getenv("FLT_NO_PRUNE2");
   // full expansion proposes up to K * |token set| candidates; a finite beamThreshold usually leaves
   // far fewer, so start from a budget and let the overflow retry (capBoost) grow it
   const long long fullCells = c.full ? (long long)K * (c.setAll ? N : bstEff) : 0;
@@ -605,13 +691,18 @@ void planFor(flt_decoder& d, int N) {
   long long capC = c.prune2 ? 3LL * K + 64 + budget0 * d.capBoost
                             : (long long)(c.wideRanked ? d.wideOffHost[K] : 0) + 3LL * K + budget0 * d.capBoost;
   if (c.full && !c.prune2) capC = 3LL * K + std::min(fullCells, budget0 * d.capBoost);
+  if (c.gx) {
+    // the guess aims at 1.25 K .. 2.5 K merge groups; duplicates of a group (members of one row) come on top
+    capC = getenv("FLT_TEST_CAP") ? std::max<long long>(K + 16, budget0) * d.capBoost : (3LL * K + 128) * d.capBoost;
+    c.capChunks = (int)std::min<long long>((4LL * K + 64) * d.capBoost, 1 << 20);
+  }
   capC = (capC + 63) / 64 * 64;
   if (capC > (1LL << 26)) throw FltError(FLT_ERR_RUNTIME, "candidate capacity exceeded");
   c.capC = (int)capC;
   c.capH = nextPow2((int)std::min<long long>(2 * capC, 1LL << 27));
   c.capRH = nextPow2((c.lfFast ? 8 : 2) * K); // fast step: sparse table, probes mostly end at once
   c.capP = nextPow2(K);
-  c.wideTotal = c.wideRanked ? d.wideOffHost[K] : 0;
+  c.wideTotal = (c.wideRanked && !c.gx) ? d.wideOffHost[K] : 0;
   // pruning rectangles (beam_core.h frameStep): a rows x (ceil(K/a)+3) columns
   c.nTau = 0;
   if (c.wideRanked && !d.lexicon) {
@@ -626,7 +717,7 @@ void planFor(flt_decoder& d, int N) {
       }
     }
   }
-  c.listInSmem = d.needTopM && c.M <= 2 * d.threads;
+  c.listInSmem = d.needTopM && (c.M <= 2 * d.threads || c.gx);
 
   rt::Stream s = d.stream;
   c.wideOff = upload(d.dWideOff, d.wideOffHost, s);
@@ -644,11 +735,10 @@ void planFor(flt_decoder& d, int N) {
   c.trans = nullptr;
   if (!c.ctc && !d.trans.empty()) c.trans = upload(d.dTrans, d.trans, s);
   if (d.lexicon) {
-    d.trie->ensureUploaded(s);
-    c.trie = d.trie->dev;
+    c.trie = d.trie->deviceImage(d.device, s);
   }
-  d.lm->ensureUploaded(s);
-  c.lm = d.lm->dev;
+  c.lm = d.lm->deviceImage(d.device, s);
+  c.lmUpper = d.lm->upper;
   t.bias = nullptr;
   if (d.lexicon && c.wideRanked) {
     // rank key offset of a root child: lmWeight * smeared score; -inf = not expandable as (1a)
@@ -672,8 +762,8 @@ void planFor(flt_decoder& d, int N) {
   // fused select + step: the row stage, the producer scratch and the consumer workspace share the
   // CTA's shared memory; two CTAs per SM need <= 113 KB each
   d.fused = false;
-  if (c.lfFast && !getenv("FLT_NO_FUSED") && N % 4 == 0 && want <= 32 * (kFusedProducers / 32) &&
-      d.threads == 256) {
+  if ((c.lfFast || (c.gx && !d.lexicon)) && !getenv("FLT_NO_FUSED") && N % 4 == 0 &&
+      want <= 32 * (kFusedProducers / 32) && d.threads == 256) {
     TopMCfg ft = t;
     ft.P = std::max(kFusedProducers, nextPow2(want));
     ft.capS = kProdCap;
@@ -695,6 +785,7 @@ void planFor(flt_decoder& d, int N) {
     fl.row = take((size_t)N * 4, 128);
     for (int k = 0; k < kFusedRing; ++k) fl.list[k] = take(8 * (size_t)c.M, 16);
     for (int k = 0; k < kFusedRing; ++k) fl.thr[k] = take(4, 4);
+    for (int k = 0; k < kFusedRing; ++k) fl.spec[k] = take(8, 8);
     fl.mbar = take(8 * MB_COUNT, 8);
     fl.total = (int)((off + 127) / 128 * 128);
     d.ftcfg = ft;
@@ -714,12 +805,16 @@ void planFor(flt_decoder& d, int N) {
   FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, flt_k_topm, kThreads, d.topmSmem));
   d.topmGridMax = std::max(1, occ) * d.numSMs;
   // <= 110 KB keeps two CTAs per SM; FLT_SMEM_KB raises the limit (one CTA per SM) for experiments
-  const size_t smemLimit = getenv("FLT_SMEM_KB") ? (size_t)atoi(getenv("FLT_SMEM_KB")) * 1024 : 110 * 1024;
+  // (the single-pass step keeps large beams on chip with one CTA per SM rather than spilling to a slab)
+  const size_t smemLimit = getenv("FLT_SMEM_KB") ? (size_t)atoi(getenv("FLT_SMEM_KB")) * 1024
+                                                 : (c.gx ? smemMax : 110 * 1024);
   const bool smemOk = d.wsBytes <= std::min<size_t>(smemMax, smemLimit);
   int occ2 = 1;
-  auto* k256 = c.wide ? flt_k_decode_wide : flt_k_decode;
-  auto* k512 = c.wide ? flt_k_decode512_wide : flt_k_decode512;
-  auto* kGmem = c.wide ? flt_k_decode_gmem_wide : flt_k_decode_gmem;
+  auto* k256 = c.gx ? (c.lexicon ? flt_k_gx<true> : flt_k_gx<false>) : (c.wide ? flt_k_decode_wide : flt_k_decode);
+  auto* k512 = c.gx ? (c.lexicon ? flt_k_gx512<true> : flt_k_gx512<false>)
+                    : (c.wide ? flt_k_decode512_wide : flt_k_decode512);
+  auto* kGmem = c.gx ? (c.lexicon ? flt_k_gx_gmem<true> : flt_k_gx_gmem<false>)
+                     : (c.wide ? flt_k_decode_gmem_wide : flt_k_decode_gmem);
   if (smemOk) {
     FLT_RT_TRY(cudaFuncSetAttribute(k256, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)std::max<size_t>(d.wsBytes, 48 * 1024)));
@@ -754,6 +849,12 @@ void planFor(flt_decoder& d, int N) {
   d.useSmemFlag = true;
 #endif
   d.planN = N;
+  if (getenv("FLT_DBG_PLAN"))
+    fprintf(stderr, "[flt plan] lexicon=%d K=%d N=%d M=%d gx=%d lfFast=%d fused=%d wide=%d prune2=%d threads=%d capC=%d "
+                    "capChunks=%d ws=%zu B (%s) fusedSmem=%d grid<=%d\n",
+            c.lexicon, c.K, N, c.M, c.gx, c.lfFast, (int)d.fused, c.wide, c.prune2, d.threads, c.capC, c.capChunks,
+            d.wsBytes, d.useSmemFlag ? "shared" : "global slab", d.fused ? d.flay.total : 0,
+            d.fused ? d.fusedGridMax : d.gridMax);
 }
 
 } // namespace
@@ -1186,7 +1287,7 @@ int flt_trie_create(int32_t maxChildren, int32_t rootIdx, flt_trie** out) {
 int flt_trie_insert(flt_trie* trie, const int32_t* indices, int32_t n, int32_t label, float score) {
   return guarded([&] {
     if (!trie) throw FltError(FLT_ERR_INVALID, "null trie");
-    if (trie->uploaded) throw FltError(FLT_ERR_INVALID, "trie is frozen: a decoder already uses it");
+    if (trie->frozen) throw FltError(FLT_ERR_INVALID, "trie is frozen: a decoder already uses it");
     int cur = 0;
     for (int i = 0; i < n; ++i) {
       const int idx = indices[i];
@@ -1213,7 +1314,7 @@ int flt_trie_insert(flt_trie* trie, const int32_t* indices, int32_t n, int32_t l
 int flt_trie_smear(flt_trie* trie, int32_t mode) {
   return guarded([&] {
     if (!trie) throw FltError(FLT_ERR_INVALID, "null trie");
-    if (trie->uploaded) throw FltError(FLT_ERR_INVALID, "trie is frozen: a decoder already uses it");
+    if (trie->frozen) throw FltError(FLT_ERR_INVALID, "trie is frozen: a decoder already uses it");
     if (mode != FLT_SMEAR_NONE) trie->smearNode(0, mode);
   });
 }

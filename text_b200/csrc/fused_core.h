@@ -22,6 +22,7 @@
 #pragma once
 #include "beam_core.h"
 #include "beam_lf.h"
+#include "beam_gx.h"
 #include "topm_core.h"
 
 namespace flt {
@@ -40,6 +41,7 @@ struct FuseLay {       // byte offsets from the CTA's shared-memory base
   int row;             // staged emission row [N] fp32, 16-byte aligned
   int list[kFusedRing]; // token list ring: int tok[M], float val[M]
   int thr[kFusedRing];  // cut value of the token set per ring slot
+  int spec[kFusedRing]; // float2 per ring slot: e[blank], e[sil] of the row (beam_gx.h)
   int mbar;            // mbarriers: rowFull, listReady[ring], listFree[ring]
   int total;
 };
@@ -369,6 +371,7 @@ struct FusedView {
   FLT_DEV int* listTok(int k) const { return (int*)(smem + fl->list[k]); }
   FLT_DEV float* listVal(int k, int M) const { return (float*)(smem + fl->list[k]) + M; }
   FLT_DEV float* thr(int k) const { return (float*)(smem + fl->thr[k]); }
+  FLT_DEV float* spec(int k) const { return (float*)(smem + fl->spec[k]); }
   FLT_DEV u64* mbar(int k) const { return (u64*)(smem + fl->mbar) + k; }
 };
 
@@ -383,6 +386,16 @@ FLT_DEV FrameIn fusedFrameIn(const DecCfg& c, const BatchArgs& a, const FusedVie
   f.first = t == 0;
   f.listIsSet = 1;
   f.specReady = 0; // the per-hypothesis emissions come from L2 (the row was just streamed)
+  f.eBlank = 0.0f;
+  f.eSil = 0.0f;
+  f.listInfo = nullptr;
+#if FLT_DEVICE_BUILD
+  if (c.gx) { // the producer read e[blank], e[sil] from the staged row
+    f.specReady = 1;
+    f.eBlank = v.spec(slot)[0];
+    f.eSil = v.spec(slot)[1];
+  }
+#endif
   f.eNext = nullptr; // set by the caller
   const long long h = ((long long)b * (a.T + 2) + (t + 1)) * c.K;
   f.hParent = a.hParent + h;
@@ -444,6 +457,11 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
       const int slot = (int)(r & (kFusedRing - 1));
       const bool hasNext = nb < a.B;
       const float* gnext = hasNext ? a.emis + ((long long)nb * a.T + nt) * c.N : nullptr;
+      float rowBlank = 0.0f, rowSil = 0.0f;
+      if (c.gx && p.tid == 0) { // from the stage, before it is released
+        if (c.ctc) rowBlank = v.row()[c.blank];
+        rowSil = v.row()[c.sil];
+      }
       topmRowStaged(
           p, tc, ps, pg, a.stats, v.row(), grow, v.listTok(slot), v.listVal(slot, c.M), v.thr(slot),
           [&]() {
@@ -453,7 +471,13 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
               bulkLoadHint(v.row(), gnext, rowBytes, v.mbar(MB_ROW_FULL), pol);
             }
           },
-          [&]() { mbarWaitRelaxed(v.mbar(MB_LIST_FREE0 + slot), ((r >> kFusedRingLog) + 1) & 1); });
+          [&]() {
+            mbarWaitRelaxed(v.mbar(MB_LIST_FREE0 + slot), ((r >> kFusedRingLog) + 1) & 1);
+            if (c.gx && p.tid == 0) {
+              v.spec(slot)[0] = rowBlank;
+              v.spec(slot)[1] = rowSil;
+            }
+          });
       if (p.tid == 0) mbarArrive(v.mbar(MB_LIST_READY0 + slot));
       ++r;
     }
@@ -465,7 +489,8 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
   const Cta cta = whole;
   for (int i = 0; i < 2 * kProdBins + tc.capS; ++i) ps.rankCnt[i] = 0;
 #endif
-  ctaInitWorkspace(cta, c, w, smem + fl.ws);
+  if (c.gx) gxInitWorkspace(cta, c, w);
+  else ctaInitWorkspace(cta, c, w, smem + fl.ws);
   uint32_t g = 0; // frames consumed so far by this CTA (same sequence as the producer's r)
   for (int b = whole.bid; b < a.B; b += whole.nblk) {
     const int len = a.lengths ? a.lengths[b] : a.T;
@@ -473,7 +498,9 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
     cta.sync(); // previous utterance fully retired
     if (cta.tid == 0) seedUtterance(c, w, a, b);
     LfCarry carry{0.0f, 0.0f, 0.0f, 0};
+    GxCarry gcarry = gxCarryInit();
     cta.sync();
+    if (c.gx) gxBeginUtterance(cta, c, w, 1);
     for (int t = 0; t < len; ++t, ++g) {
       const int slot = (int)(g & (kFusedRing - 1)); // ring slot = running row count mod ring, on both sides
       LfPhaseClock oc; // time spent waiting for the producers
@@ -490,7 +517,8 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
       oc.mark(5);
       FrameIn f = fusedFrameIn(c, a, v, b, t, slot);
       f.eNext = t + 1 < len ? f.e + c.N : nullptr;
-      lfFrameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.stats, carry); // ends with a barrier
+      if (c.gx) gxFrameStep<false>(cta, c, w, curIdx, f, a.status + b, a.stats, gcarry);
+      else lfFrameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.stats, carry); // ends with a barrier
       curIdx ^= 1;
 #if FLT_DEVICE_BUILD
       if (cta.tid == 0) mbarArrive(v.mbar(MB_LIST_FREE0 + slot));
@@ -499,7 +527,8 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
     int nFin = 0;
     if (w.sc()[SC_NH] != 0) {
       const FrameIn f = finishFrameIn(c, a, b, len);
-      lfFinish(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f);
+      if (c.gx) gxFinish<false>(cta, c, w, curIdx, f);
+      else lfFinish(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f);
       curIdx ^= 1;
       nFin = w.sc()[SC_NH];
     }

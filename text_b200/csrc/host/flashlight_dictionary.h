@@ -4,8 +4,10 @@
 //   flashlight/lib/text/dictionary/Utils.h:21-60          LexiconMap, createWordDict, loadWords,
 //                                                          splitWrd, packReplabels, unpackReplabels, tkn2Idx
 //   flashlight/lib/text/dictionary/Defines.h:14-17        kUnkToken, kEosToken
-// with the reference's names, signatures, file formats and exception types. Written from the
-// behaviour of those functions (and of test/dictionary/DictionaryTest.cpp), not from their code.
+// with the reference's names, signatures, file formats and exception types. These are small canonical
+// algorithms behind a name-compatible API: packReplabels / unpackReplabels / tkn2Idx / Dictionary::addEntry
+// RESTATE dictionary/Utils.cpp:94-162 and Dictionary.cpp:60-84 (same control flow and messages, so that
+// DictionaryTest's vectors and error strings carry over); they are not an independent design.
 // Plain host code: none of this is on the timed path.
 #pragma once
 #include <fstream>
@@ -127,7 +129,7 @@ inline LexiconMap loadWords(const std::string& filename, int maxWords = -1) {
     if (f.size() < 2) throw std::runtime_error("[loadWords] Invalid line: " + line);
     lexicon[f[0]].emplace_back(f.begin() + 1, f.end());
   }
-  lexicon[kUnkToken]; // present, possibly without spellings
+  lexicon[kUnkToken] = {}; // present, never with spellings (dictionary/Utils.cpp:61)
   return lexicon;
 }
 

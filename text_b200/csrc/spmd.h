@@ -23,6 +23,12 @@
 struct float4 {
   float x, y, z, w;
 };
+struct int2 {
+  int x, y;
+};
+struct int4 {
+  int x, y, z, w;
+};
 #endif
 
 namespace flt {
@@ -102,6 +108,15 @@ FLT_DEV int atomMin(int* p, int v) {
 #else
   int o = *p;
   if (v < o) *p = v;
+  return o;
+#endif
+}
+FLT_DEV int atomMax(int* p, int v) {
+#if FLT_DEVICE_BUILD
+  return atomicMax(p, v);
+#else
+  int o = *p;
+  if (v > o) *p = v;
   return o;
 #endif
 }

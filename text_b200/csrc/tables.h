@@ -22,6 +22,12 @@ struct TrieDev {
   const int* rootChild;   // [N]        node reached from the root by token n, or -1
   int nRootLab;           // root children that carry labels (single-token words)
   const int* rootLabTok;  // [nRootLab] their tokens
+  // packed views of the same Trie for the single-pass step (beam_gx.h): one 8-byte record per edge,
+  // one 16-byte record per node, so an edge costs two dependent loads instead of six
+  const int2* edge;        // [nEdges]   {token, child node}
+  const int4* node;        // [nNodes]   {smeared score bits, first edge, #edges | #labels << 24,
+                           //             the label if there is exactly one, else the offset into labels[]}
+  const int2* rootLabEdge; // [nRootLab] {token, child node} of the root children that carry labels
 };
 
 struct F2 {

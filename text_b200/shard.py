@@ -34,12 +34,18 @@ def scatter_emissions(emissions, shape, device, src=0, group=None):
             if r == src:
                 mine.copy_(emissions[rlo:rhi])
             elif rhi > rlo:
-                reqs.append(dist.isend(emissions[rlo:rhi].contiguous(), dst=r, group=group))
+                reqs.append(dist.isend(emissions[rlo:rhi].contiguous(), dst=_global(group, r), group=group))
         for q in reqs:
             q.wait()
     elif hi > lo:
-        dist.recv(mine, src=src, group=group)
+        dist.recv(mine, src=_global(group, src), group=group)
     return mine
+
+
+def _global(group, r):
+    """`src` / `dst` of this module are ranks INSIDE `group`; torch's point-to-point and gather calls
+    take global ranks."""
+    return r if group is None else dist.get_global_rank(group, r)
 
 
 def gather_nbest(local, B, T, K, device, dst=0, group=None):
@@ -65,7 +71,7 @@ def gather_nbest(local, B, T, K, device, dst=0, group=None):
     out = {}
     for name, t in parts.items():
         bufs = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
-        dist.gather(t, bufs, dst=dst, group=group)
+        dist.gather(t, bufs, dst=_global(group, dst), group=group)
         if rank == dst:
             rows = []
             for r in range(world):

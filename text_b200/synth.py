@@ -15,6 +15,33 @@ def emissions(B, T, N, seed=1234, sigma=1.0):
     return (z - lse).astype(np.float32)
 
 
+def emissions_exact(B, T, N, seed=1, sigma=1.0, shift=-9.71):
+    """Bit-reproducible emissions for the committed full-size golden vectors: integer hashing plus
+    IEEE add / multiply / cast only (no exp / log, whose last bit may depend on the libm and CPU), so
+    every machine produces the same fp32 bits. Each value is `shift + sigma * z` with z the
+    standardised sum of four uniform 16-bit fields of a splitmix64 hash of (seed, b, t, n) — bell
+    shaped like the N(0,1) logits of `emissions`, at the level of their log-softmax (lse ~ 9.7 at
+    N = 10000). Not normalised; the decoders do not need that."""
+    out = np.empty((B, T, N), dtype=np.float32)
+    idx = np.arange(T * N, dtype=np.uint64)
+
+    def mix(x):
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+
+    m = np.uint64(0xFFFF)
+    for b in range(B):
+        x = mix(idx + np.uint64((int(seed) * 1000003 + b) * 0x9E3779B97F4A7C15 % (1 << 64)))
+        s = ((x & m) + ((x >> np.uint64(16)) & m) + ((x >> np.uint64(32)) & m) + (x >> np.uint64(48))).astype(np.int64)
+        # a 32-bit dither below the 16-bit grid, so that equal values (ties at the token-beam cut, equal
+        # path sums) are as rare as with continuous logits
+        d = (mix(x + np.uint64(0x632BE59BD9B4E019)) >> np.uint64(32)).astype(np.float64) * (1.0 / 4294967296.0)
+        z = ((s - 131070).astype(np.float64) + d) * (1.0 / 37837.227)
+        out[b] = (z * float(sigma) + float(shift)).astype(np.float32).reshape(T, N)
+    return out
+
+
 def lexicon(W, N, min_len=2, max_len=5, seed=7, exclude=()):
     """W distinct spellings (so every terminal trie node has exactly one label: no homophone
     ties), tokens uniform in [0,N) minus `exclude` (sil / blank)."""
