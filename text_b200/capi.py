@@ -326,10 +326,20 @@ class Api:
         out = dict(frames=int(v[0]), candidates_per_frame=v[1] / frames, groups_per_frame=v[2] / frames,
                    survivors_per_frame=v[3] / frames)
         if v[30]:  # single-pass step with a guessed cut (beam_gx.h)
-            names = ("expand_merge", "compact", "rank_new_beam")
+            names = ("expand", "merge", "compact", "rank_new_beam")
             out["phase_cycles_per_frame"] = {n: round(v[4 + i] / frames, 1) for i, n in enumerate(names)}
             out["phase_cycles_per_frame"]["wait_list"] = round(v[9] / frames, 1)
             out["guess_redo_frames"] = int(v[12])
+            out["redo_events"] = dict(overflow=int(v[13]), miss=int(v[14]), gave_up=int(v[15]))
+            if v[16]:
+                import struct
+
+                out["first_give_up"] = dict(
+                    attempt=int(v[16]) - 1000, want=int(v[17]), n_cand=int(v[18]), n_rep=int(v[19]), flags=int(v[20]),
+                    cut_bin=int(v[21]), kept=int(v[22]), span=struct.unpack("f", struct.pack("I", int(v[23])))[0],
+                    row=int(v[24]), n_hyp=int(v[25]),
+                    beam_spread=struct.unpack("d", struct.pack("Q", int(v[26])))[0],
+                    g_minus_best=struct.unpack("d", struct.pack("Q", int(v[27])))[0])
             out["select_guess_misses"] = int(v[11])
         elif v[31]:  # generic step (beam_core.h frameStep): SM cycles of thread 0 per phase
             names = ("rows", "degrees_scan", "pass1_histogram", "cut_bin", "pass2_emit", "merge", "select",

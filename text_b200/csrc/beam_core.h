@@ -65,7 +65,8 @@ struct Lay {
   int beamX[2];   // int [3][K] per beam: Trie cache of each hypothesis (first edge, #edges | #labels, smeared score)
   int gxCandX;    // int [3][capC]: the same for each candidate's lex node
   int gxChunk;    // int2 [2][capChunks]: item chunk descriptors of each beam
-  int gxBits;     // u32 [2][(K+31)/32]: hypotheses at the Trie root (walkers) of each beam
+  int gxBits;     // int [2][K]: hypotheses at the Trie root (walkers) of each beam
+  int gxStash;    // u8 per work item: 1 + best histogram bin its proposals reached in the first pass
   int gxList;     // int4 [2][Mwide]: root child of each list entry (lexicon), double-buffered
   int gxBest;     // u64: best representative score key of the frame
   int total;
@@ -210,8 +211,8 @@ enum { // ws.sc[] scalars
   SC_TLO, SC_THI, // previous phase stamp of thread 0 (counters on)
   SC_WANT, SC_WHOLD, // two-pass pruning: candidates to keep this frame; frames left at the wide setting
   SC_GXCUTBIN, SC_GXKEPT, // beam_gx.h: cut bin of the exact redo and the proposals it keeps
-  SC_GX,                  // beam_gx.h: two sets of per-frame scalars (12 ints)
-  SC_WCNT = SC_GX + 12 /* 32 warp counters follow */,
+  SC_GX,                  // beam_gx.h: two sets of scalars (2 x 8 ints)
+  SC_WCNT = SC_GX + 16 /* 32 warp counters follow */,
   SC_COUNT = SC_WCNT + 32
 };
 
@@ -281,9 +282,9 @@ FLT_HD void makeLayout(DecCfg& c) {
   L.candKey = take(sizeof(u64) * (lf ? 1 : 2) * c.capC);
   L.candI = take(sizeof(int) * (lf ? 3 : 6) * c.capC);
   L.mh = take(lf ? 0 : sizeof(int) * c.capH);
-  L.rep = take(sizeof(int) * c.capC);
+  L.rep = take(gx ? 0 : sizeof(int) * c.capC);
   L.surv = take(gx ? 0 : sizeof(int) * 2 * c.capP);
-  L.skey = take(lf || gx ? 0 : sizeof(u64) * c.capP);
+  L.skey = take(lf ? 0 : sizeof(u64) * (gx ? c.capC : c.capP));
   L.pos = take(lf || gx ? 0 : sizeof(int) * c.capP);
   L.hist = take(sizeof(int) * (lf && c.lfBins > 256 ? c.lfBins : 256));
   L.sc = take(sizeof(int) * SC_COUNT);
@@ -296,7 +297,8 @@ FLT_HD void makeLayout(DecCfg& c) {
   L.gath = take(gx ? 0 : sizeof(int) * 64);
   L.gxCandX = take(gxl ? sizeof(int) * 3 * c.capC : 0);
   L.gxChunk = take(gxl ? sizeof(int) * 2 * 2 * (size_t)c.capChunks : 0);
-  L.gxBits = take(gx ? sizeof(int) * 2 * ((K + 31) / 32) : 0);
+  L.gxBits = take(gxl ? sizeof(int) * 2 * K : 0);
+  L.gxStash = take(gx ? (gxl ? (size_t)c.capChunks * 8 : 3 * (size_t)c.capP) : 0);
   L.gxList = take(gxl ? sizeof(int) * 4 * 2 * (size_t)c.Mwide : 0);
   L.gxBest = take(gx ? 16 : 0);
   L.lfSlotB = take(lf ? sizeof(int) * c.capRH : 0);

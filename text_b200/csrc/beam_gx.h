@@ -1,35 +1,37 @@
-// beam_gx.h — the single-pass frame step with a guessed cut ("gx"), for both decoders.
+// beam_gx.h — the two-pass frame step ("gx") of both decoders: histogram every proposal, cut, materialise
+// only what can still reach the beam.
 //
 // Replaces, for one frame, LexiconDecoder::decodeStep / LexiconFreeDecoder::decodeStep's expansion
 // (decoder/LexiconDecoder.cpp:54-215, decoder/LexiconFreeDecoder.cpp:53-112) and candidatesStore
 // (decoder/Utils.h:146-225) in the max-merge, word-level-LM, CTC (lexicon) / CTC+ASG (lexicon-free)
 // configurations — the ones BASELINE.json's configs use. Everything else stays on beam_core.h.
 //
-// Idea. The reference materialises every candidate of a frame, then keeps the K best merge groups.
-// A group's score is the maximum of its members (Utils.h:176-198), so for ANY threshold G the K best
-// groups are found exactly from the candidates scoring >= G alone, provided those candidates form
-// at least K groups (a group with a member >= G has its best member >= G; a group without scores
-// < G <= every kept group). The step therefore
-//   E   proposes candidates and materialises only those >= G, where G is GUESSED from the previous
-//       frame (best hypothesis + best proposal of this frame - last frame's exact spread x margin);
-//       each materialised candidate is merged at once into a CTA-private table on its 128-bit
-//       (LM state, lex node, token, prevBlank) key — compare-and-swap on the slot, the loser is
-//       marked dead — so there is no separate merge pass;
-//   C   compacts the surviving group representatives (one per key) and empties the table;
-//   RF  ranks the representatives by counting and the thread that finds rank q < K writes
-//       hypothesis q of the new beam directly (no ranked[] round trip): threshold against the best
-//       (Utils.h:161-165), LM-state fingerprint / n-gram context, back-pointer record, skip pointer.
-// Three CTA barriers per frame. If the guess was too high (< K groups although something was cut) or
-// too low (candidate capacity exceeded), the frame is redone EXACTLY: one histogram pass over all
-// proposals (256 monotone bins) picks G, then E again; the kept set is verified the same way. The
-// result never depends on the guess — only the time does.
+// Exactness. The reference materialises every candidate of a frame, then keeps the K best merge groups.
+// A group's score is the maximum of its members (Utils.h:176-198), so for ANY threshold the K best
+// groups are found exactly from the candidates at or above it alone, provided those candidates form at
+// least K groups (a group with a member above the threshold has its best member there; a group
+// without scores below every kept group). The threshold used here is a bin edge of a monotone map
+// score -> 256 bins, chosen from an exact histogram of the frame's proposals; the kept set is verified
+// to hold >= K groups after the merge (else the cut is lowered and the second pass repeated).
 //
-// Work distribution in E (no row grouping, no prefix sums, no binary searches on the hot path):
+//   E1  every proposal is scored and histogrammed; nothing is stored except one byte per work item
+//       (the best bin its proposals reached)
+//   --  every warp finds the cut bin from the histogram for itself (no single-warp phase, no barrier)
+//   E2  the work items whose byte reaches the cut are evaluated again and their proposals at or above
+//       the cut are materialised (record + 128-bit merge key + ordered score key)
+//   M   one candidate per thread: compare-and-swap into the CTA-private merge table on the
+//       (LM state, lex node, token, prevBlank) key; the loser's score key is zeroed (max-merge)
+//   RF  every live candidate ranks itself by counting larger score keys; the thread that finds rank
+//       q < K writes hypothesis q of the new beam directly: threshold against the best (Utils.h:161-165),
+//       LM-state fingerprint / n-gram context, back-pointer record, skip pointer — and registers the
+//       hypothesis' work items for the next frame.
+// Four CTA barriers per frame, no row grouping, no prefix sums, no binary searches, no compaction.
+//
+// Work distribution:
 //   * "walkers" = hypotheses that expand over the frame's RANKED token list (all hypotheses of the
 //     lexicon-free decoder; hypotheses at the Trie root in the lexicon decoder, ranked by
-//     e[n] + lmWeight * smeared score of root child n). Score is monotone along the list, so a group
-//     of 4..32 lanes walks it in chunks and stops at the first chunk entirely below G. The best
-//     walkers get a whole warp, the tail four lanes each (static schedule over walker ranks).
+//     e[n] + lmWeight * smeared score of root child n). The score is monotone along the list, so eight
+//     lanes per walker go down it in chunks and stop at the first chunk entirely below the bound.
 //   * "items" = everything enumerated directly: the Trie edges of non-root hypotheses, root children
 //     that carry labels (single-token words), stay / blank / repeat. When a hypothesis is created
 //     (RF of the previous frame) its thread reserves the hypothesis' items in a chunk table (8 items
@@ -37,8 +39,8 @@
 //     edges are {token, child} pairs (one coalesced 8-byte load), nodes are 16-byte records
 //     {smeared score, first edge, #edges | #labels, first label}: two dependent L2 round trips per
 //     edge, issued for all items of a sweep before the walkers run, consumed after.
-//   * n-gram word LM: a word end is probed only if its score with the LM's best possible score
-//     still reaches G.
+//   * n-gram word LM: a word end is probed only if its score with the LM's best possible score still
+//     reaches the bound.
 #pragma once
 #include "beam_core.h"
 #include "beam_lf.h"
@@ -47,26 +49,31 @@ namespace flt {
 
 constexpr int kGxChunkLog = 3, kGxChunk = 1 << kGxChunkLog; // items per chunk descriptor
 constexpr int kGxBins = 256;
-constexpr int kGxSweep = 2; // items per thread and sweep (loads of a sweep are in flight together)
+constexpr int kGxSweep = 2;     // items per thread and sweep (loads of a sweep are in flight together)
+constexpr int kGxWalkLanes = 8; // lanes per walker (device)
 
-enum { // per-frame scalars, two sets (index = parity of the beam the frame reads)
-  GX_NCAND = 0, GX_OVF, GX_CUT, GX_NREP, GX_NCHUNK, GX_SET
+enum { // scalars in two sets, index = beam parity p: NCAND / OVF / NDEAD belong to the frame that READS
+       // beam p; NCHUNK / NWALK / NH describe beam p itself (item chunks, walkers, hypotheses)
+  GX_NCAND = 0, GX_OVF, GX_NDEAD, GX_NCHUNK, GX_NWALK, GX_NH, GX_SET = 8
 };
 
-struct GxCarry { // per-utterance state of the guess; uniform over the CTA's threads (registers)
-  double spread; // (reference level - cut) to use on the next frame; +inf = unknown: take everything
-  float mu;      // safety factor applied to the last frame's exact spread
+// Per-utterance state carried from frame to frame; uniform over the CTA's threads (registers).
+struct GxCarry {
+  double cutPrev, D;  // last cut and its offset to (previous cut + emission level): bound of the walkers'
+  int have;           // histogram pass in the lexicon decoder (0 = nothing known, 2 = both)
+  float span;         // score range the histogram covers below its top
   float eBlank, eSil; // e[blank], e[sil] of the NEXT frame, loaded while the current one retires
   int eValid;
 };
-FLT_DEV GxCarry gxCarryInit() { return GxCarry{bitsF64(0x7FF0000000000000ull), 0.30f, 0.0f, 0.0f, 0}; }
+FLT_DEV GxCarry gxCarryInit() { return GxCarry{0.0, 0.0, 0, 32.0f, 0.0f, 0.0f, 0}; }
 
-struct GxFrame { // uniform per attempt
-  double G;      // candidates scoring below are not materialised
+struct GxFrame { // uniform per pass
+  int mode;      // 1 = histogram pass, 0 = materialise
   double floor;  // the reference's own filter: candidates below never survive (Utils.h:161-165)
-  int mode;      // 0 = materialise, 1 = histogram only
-  double hlo;
+  double hlo;    // histogram map: bin = (score - hlo) * hscale, clamped to [0, 255]
   float hscale;
+  int cutBin;    // pass 0: proposals in bins below are left out
+  double stop;   // walkers / LM probes: nothing below this can matter in this pass
 };
 
 /* ------------------------------------------------------------------ workspace views ---------- */
@@ -75,16 +82,17 @@ FLT_DEV int* gxCandX(const Ws& w) { return (int*)(w.base + w.c->lay.gxCandX); } 
 FLT_DEV int* gxChunks(const Ws& w, int set) {                                          // [2][capChunks] x int2
   return (int*)(w.base + w.c->lay.gxChunk) + (size_t)set * 2 * w.c->capChunks;
 }
-FLT_DEV uint32_t* gxBits(const Ws& w, int set) { // walker bitmap [2][(K+31)/32]
-  return (uint32_t*)(w.base + w.c->lay.gxBits) + (size_t)set * ((w.c->K + 31) >> 5);
+FLT_DEV int* gxWalkList(const Ws& w, int set) { // [2][K] hypotheses at the Trie root of each beam
+  return (int*)(w.base + w.c->lay.gxBits) + (size_t)set * w.c->K;
 }
 FLT_DEV int* gxListInfo(const Ws& w, int buf) { // [2][Mwide] x int4 {ms bits, child, eoff, degLab}
   return (int*)(w.base + w.c->lay.gxList) + (size_t)buf * 4 * w.c->Mwide;
 }
+FLT_DEV unsigned char* gxStash(const Ws& w) { return (unsigned char*)(w.base + w.c->lay.gxStash); }
+FLT_DEV u64* gxSkey(const Ws& w) { return (u64*)(w.base + w.c->lay.skey); } // [capC] ordered score keys, 0 = dead
 
-FLT_DEV int gxSpecials(const DecCfg& c) { // directly enumerated specials per hypothesis
-  if (c.lexicon) return (c.silScore > 0 ? 3 : 2);      // stay, blank, boosted-sil cell
-  return (c.silScore > 0 ? 3 : 2);                     // repeat, blank, boosted-sil cell
+FLT_DEV int gxSpecials(const DecCfg& c) { // directly enumerated specials per hypothesis:
+  return c.silScore > 0 ? 3 : 2;          // stay / repeat, blank, boosted-sil cell
 }
 
 // node record of the Trie: {smeared score bits, first edge, #edges | #labels << 24, first label or label offset}
@@ -93,7 +101,7 @@ FLT_DEV int gxNodeLabels(int degLab) { return (unsigned)degLab >> 24; }
 
 /* ------------------------------------------------------------------ hypothesis registration -- */
 // Called by the thread that creates hypothesis q of beam `set`: reserve its items in the chunk table
-// (lexicon) and mark it as a walker if it sits at the Trie root.
+// (lexicon) and list it as a walker if it sits at the Trie root.
 FLT_DEV void gxRegister(const DecCfg& c, const Ws& w, int set, int q, int lex, int degLab) {
   if (!c.lexicon) return;
   int* sc = gxSc(w, set);
@@ -109,19 +117,11 @@ FLT_DEV void gxRegister(const DecCfg& c, const Ws& w, int set, int q, int lex, i
       ch[2 * (base + z) + 1] = cnt - k0 < kGxChunk ? cnt - k0 : kGxChunk;
     }
   }
-  if (lex == 0) {
-#if FLT_DEVICE_BUILD
-    atomicOr(&gxBits(w, set)[q >> 5], 1u << (q & 31));
-#else
-    gxBits(w, set)[q >> 5] |= 1u << (q & 31);
-#endif
-  }
+  if (lex == 0) gxWalkList(w, set)[atomAdd(&sc[GX_NWALK], 1)] = q;
 }
 
 // per-hypothesis Trie cache of a beam entry (lexicon): first edge, #edges | #labels, smeared score
-FLT_DEV void gxSetNode(const DecCfg& c, const Beam& b, int q, int lex, int eoff, int degLab, int msBits) {
-  (void)c;
-  (void)lex;
+FLT_DEV void gxSetNode(const Beam& b, int q, int eoff, int degLab, int msBits) {
   b.xv[q] = eoff;
   b.xv[b.K + q] = degLab;
   b.xv[2 * b.K + q] = msBits;
@@ -130,8 +130,10 @@ FLT_DEV void gxSetNode(const DecCfg& c, const Beam& b, int q, int lex, int eoff,
 // Rebuild the tables of beam `set` from its hypotheses (seed of an utterance, restored online beam).
 FLT_DEV void gxRebuild(const Cta& cta, const DecCfg& c, const Ws& w, int set, int nH) {
   if (!c.lexicon) return;
-  if (cta.tid == 0) gxSc(w, set)[GX_NCHUNK] = 0;
-  for (int i = cta.tid; i < ((c.K + 31) >> 5); i += cta.nthr) gxBits(w, set)[i] = 0;
+  if (cta.tid == 0) {
+    gxSc(w, set)[GX_NCHUNK] = 0;
+    gxSc(w, set)[GX_NWALK] = 0;
+  }
   cta.sync();
   const Beam b = w.beam(set);
   for (int q = cta.tid; q < nH; q += cta.nthr) {
@@ -139,141 +141,152 @@ FLT_DEV void gxRebuild(const Cta& cta, const DecCfg& c, const Ws& w, int set, in
     int4 nd;
     nd.x = 0, nd.y = 0, nd.z = 0, nd.w = 0;
     if (lex != 0) nd = c.trie.node[lex];
-    gxSetNode(c, b, q, lex, nd.y, nd.z, lex == 0 ? 0 : nd.x);
+    gxSetNode(b, q, nd.y, nd.z, lex == 0 ? 0 : nd.x);
     gxRegister(c, w, set, q, lex, nd.z);
   }
   cta.sync();
 }
 
-/* ------------------------------------------------------------------ candidates ---------------- */
-// insert candidate x into the merge table; the better of two candidates with equal keys keeps the
-// slot, the other is marked dead (Utils.h:176-198, max-merge). Callable while other threads insert.
-FLT_DEV void gxInsert(const DecCfg& c, const Ws& w, int x) {
-  const Cand cd = w.cand();
-  int* mh = w.mh();
-  const uint32_t mask = (uint32_t)c.capH - 1;
-#if FLT_DEVICE_BUILD
-  __threadfence_block(); // the record is visible before the slot names it
-#endif
-  const u64 ka = cd.keyA(x), kb = cd.keyB(x);
-  uint32_t s = (uint32_t)ka & mask;
-  for (;;) {
-    int occ = atomCAS(&mh[s], -1, x);
-    if (occ == -1) break;
-    if (cd.keyA(occ) == ka && cd.keyB(occ) == kb) {
-      for (;;) {
-        if (!candBetter(cd, x, occ)) {
-          cd.parflag(x) &= ~CF_ALIVE;
-          break;
-        }
-        const int old = atomCAS(&mh[s], occ, x);
-        if (old == occ) {
-          cd.parflag(occ) &= ~CF_ALIVE;
-          break;
-        }
-        occ = old;
-      }
-      break;
-    }
-    s = (s + 1) & mask;
-  }
-  w.cslot()[x] = (int)s;
-}
-
+/* ------------------------------------------------------------------ proposals ------------------ */
 FLT_DEV int gxBin(const GxFrame& fr, double score) {
   const float pos = (float)(score - fr.hlo) * fr.hscale;
   return pos >= (float)(kGxBins - 1) ? kGxBins - 1 : (pos > 0.0f ? (int)pos : 0);
 }
 
-// one proposal: histogram it (mode 1) or, if it reaches G, materialise and merge it (mode 0).
+// One proposal. Pass 1: histogram it; returns its bin (-1 = below the reference's own filter). Pass 0:
+// materialise it if its bin reaches the cut — record, 128-bit merge key, ordered score key.
 // x0..x2 = Trie cache of the candidate's lex node (first edge, #edges | #labels, smeared score bits).
-FLT_DEV void gxOffer(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, const GxFrame& fr,
-                     int set, double score, int par, int tok, int word, int lex, int flags, float lmd,
-                     float ev, int x0, int x1, int x2, int& cut) {
+FLT_DEV int gxOffer(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, const GxFrame& fr, int set,
+                    double score, int par, int tok, int word, int lex, int flags, float lmd, float ev, int x0,
+                    int x1, int x2) {
+  if (!(score >= fr.floor)) return -1;
+  const int bin = gxBin(fr, score);
   if (fr.mode == 1) {
-    if (score >= fr.floor) atomAdd(&w.hist()[gxBin(fr, score)], 1);
-    return;
+    atomAdd(&w.hist()[bin], 1);
+    return bin;
   }
-  if (!(score >= fr.G)) {
-    if (score >= fr.floor) cut = 1;
-    return;
-  }
+  if (bin < fr.cutBin) return bin;
   int* sc = gxSc(w, set);
   const int slot = aggInc(&sc[GX_NCAND], cta.tid);
   if (slot >= c.capC) {
     sc[GX_OVF] = 1;
-    return;
+    return bin;
   }
-  putCand(c, w, cur, slot, score, par, tok, word, lex, flags, lmd, ev);
+  const Cand cd = w.cand();
+  cd.score(slot) = score;
+  cd.parflag(slot) = (par << 4) | flags | CF_ALIVE;
+  cd.tok(slot) = tok;
+  cd.ce(slot) = ev;
   if (c.lexicon) {
+    cd.word(slot) = word;
+    cd.lex(slot) = lex;
+    cd.lmd(slot) = lmd;
     int* cx = gxCandX(w);
     cx[slot] = x0;
     cx[c.capC + slot] = x1;
     cx[2 * c.capC + slot] = x2;
   }
-  gxInsert(c, w, slot);
+  u64 sa = cur.fpA(par), sb = cur.fpB(par);
+  if (flags & CF_NEW) {
+    const int label = (flags & CF_FINISH) ? -1 : ((c.lexicon && !c.lmToken) ? word : tok);
+    fpChild(sa, sb, label, sa, sb);
+  }
+  candKeyOf(sa, sb, lex, tok, flags & CF_PB, cd.keyA(slot), cd.keyB(slot));
+  gxSkey(w)[slot] = orderedKey64(score);
+  return bin;
+}
+
+// deterministic order of two candidates (candBetter of beam_core.h; the lexicon-free records carry no
+// word / lex fields)
+FLT_DEV bool gxBetter(const DecCfg& c, const Cand& cd, int a, int b) {
+  if (c.lexicon) return candBetter(cd, a, b);
+  const double sa = cd.score(a), sb = cd.score(b);
+  if (sa != sb) return sa > sb;
+  if (cd.par(a) != cd.par(b)) return cd.par(a) < cd.par(b);
+  if (cd.tok(a) != cd.tok(b)) return cd.tok(a) < cd.tok(b);
+  return (cd.flags(a) & CF_PB) < (cd.flags(b) & CF_PB);
+}
+
+// M: the merge, one candidate per thread (every record is visible: a barrier separates it from E2).
+// Candidates with equal (LM state, lex node, token, prevBlank) keys meet in one slot of the CTA-private
+// table; the better one keeps it, the other's score key is zeroed (Utils.h:176-198, max-merge). Also
+// publishes the best score key of the frame and clears the twin set's scalars (the next frame's).
+FLT_DEV void gxPhaseM(const Cta& cta, const DecCfg& c, const Ws& w, int set, int nCand) {
+  const Cand cd = w.cand();
+  int* mh = w.mh();
+  int* cslot = w.cslot();
+  u64* skey = gxSkey(w);
+  int* sc = gxSc(w, set);
+  const uint32_t mask = (uint32_t)c.capH - 1;
+  u64 best = 0;
+  int dead = 0;
+  for (int x = cta.tid; x < nCand; x += cta.nthr) {
+    const u64 ka = cd.keyA(x), kb = cd.keyB(x);
+    const u64 sk = skey[x];
+    best = sk > best ? sk : best;
+    uint32_t s = (uint32_t)ka & mask;
+    for (;;) {
+      int occ = atomCAS(&mh[s], -1, x);
+      if (occ == -1) break;
+      if (cd.keyA(occ) == ka && cd.keyB(occ) == kb) {
+        for (;;) {
+          if (!gxBetter(c, cd, x, occ)) {
+            skey[x] = 0;
+            break;
+          }
+          const int old = atomCAS(&mh[s], occ, x);
+          if (old == occ) {
+            skey[occ] = 0;
+            break;
+          }
+          occ = old;
+        }
+        ++dead;
+        break;
+      }
+      s = (s + 1) & mask;
+    }
+    cslot[x] = (int)s;
+  }
+#if FLT_DEVICE_BUILD
+  {
+    const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)(best >> 32));
+    const unsigned lo = __reduce_max_sync(0xffffffffu, (unsigned)(best >> 32) == hi ? (unsigned)best : 0u);
+    best = ((u64)hi << 32) | lo;
+    if ((cta.tid & 31) == 0 && best) atomicMax((u64*)(w.base + c.lay.gxBest), best);
+    dead = __reduce_add_sync(0xffffffffu, dead);
+    if ((cta.tid & 31) == 0 && dead) atomicAdd(&sc[GX_NDEAD], dead);
+  }
+#else
+  {
+    u64* gb = (u64*)(w.base + c.lay.gxBest);
+    if (best > *gb) *gb = best;
+    sc[GX_NDEAD] += dead;
+  }
+#endif
+  if (cta.tid == 0) {
+    int* gn = gxSc(w, set ^ 1);
+    gn[GX_NCAND] = 0;
+    gn[GX_OVF] = 0;
+    gn[GX_NDEAD] = 0;
+    gn[GX_NH] = 0;
+  }
 }
 
 /* ------------------------------------------------------------------ walkers -------------------- */
-// r-th set bit of the walker bitmap (hypothesis index of walker rank r), -1 if there is none
-FLT_DEV int gxNthWalker(const uint32_t* bits, int words, int r) {
-  for (int k = 0; k < words; ++k) {
-    const uint32_t v = bits[k];
-#if FLT_DEVICE_BUILD
-    const int n = __popc(v);
-    if (r < n) return (k << 5) + (int)__fns(v, 0, r + 1);
-#else
-    const int n = __builtin_popcount(v);
-    if (r < n) {
-      uint32_t u = v;
-      for (int z = 0; z < r; ++z) u &= u - 1;
-      return (k << 5) + __builtin_ctz(u);
-    }
-#endif
-    r -= n;
-  }
-  return -1;
-}
-
-// static schedule of walker ranks over warp-sized slots: ranks 0,1 a whole warp each; 2..5 sixteen
-// lanes; 6..21 eight; the tail four (the host model runs one walker per slot)
-FLT_DEV int gxWalkSlots(int nWalk) {
-#if FLT_DEVICE_BUILD
-  if (nWalk <= 2) return nWalk;
-  if (nWalk <= 6) return 2 + ((nWalk - 2 + 1) >> 1);
-  if (nWalk <= 22) return 4 + ((nWalk - 6 + 3) >> 2);
-  return 8 + ((nWalk - 22 + 7) >> 3);
-#else
-  return nWalk;
-#endif
-}
-FLT_DEV void gxWalkLane(int slot, int lane, int& r, int& width, int& sub) {
-#if FLT_DEVICE_BUILD
-  if (slot < 2) {
-    r = slot, width = 32;
-  } else if (slot < 4) {
-    r = 2 + ((slot - 2) << 1) + (lane >> 4), width = 16;
-  } else if (slot < 8) {
-    r = 6 + ((slot - 4) << 2) + (lane >> 3), width = 8;
-  } else {
-    r = 22 + ((slot - 8) << 3) + (lane >> 2), width = 4;
-  }
-  sub = lane & (width - 1);
-#else
-  (void)lane;
-  r = slot, width = 1, sub = 0;
-#endif
-}
-
-// One slot of walkers: each group of `width` lanes expands one hypothesis over the ranked list.
+// One slot of walkers: each group of kGxWalkLanes lanes expands one hypothesis over the ranked list.
 template <bool LEX>
 FLT_DEV void gxWalkSlot(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, const FrameIn& f,
-                        const GxFrame& fr, int set, int slot, int nWalk, int& cut) {
+                        const GxFrame& fr, int set, int slot, int nWalk) {
+#if FLT_DEVICE_BUILD
   const int lane = cta.tid & 31;
-  int r, width, sub;
-  gxWalkLane(slot, lane, r, width, sub);
+  const int width = kGxWalkLanes, sub = lane & (width - 1);
+  const int r = slot * (32 / width) + lane / width;
+#else
+  const int width = 1, sub = 0, r = slot;
+#endif
   int i = -1;
-  if (r < nWalk) i = LEX ? gxNthWalker(gxBits(w, set), (c.K + 31) >> 5, r) : r;
+  if (r < nWalk) i = LEX ? gxWalkList(w, set)[r] : r;
   bool active = i >= 0;
   double si = 0.0;
   int ti = 0, pbi = 0;
@@ -309,7 +322,7 @@ FLT_DEV void gxWalkSlot(const Cta& cta, const DecCfg& c, const Ws& w, const Beam
           const double a = (ev < 0 ? -(double)ev : (double)ev) + (lmPart < 0 ? -lmPart : lmPart);
           slack = 1e-3 + 1e-5 * a;
         }
-        cont = fr.mode == 1 || !(approx + slack < fr.G);
+        cont = !(approx + slack < fr.stop);
         if (cont && (!LEX || child >= 0)) {
           bool ok;
           if (LEX) ok = pbi || n != ti; // LexiconDecoder.cpp:89-90 (CTC)
@@ -319,28 +332,29 @@ FLT_DEV void gxWalkSlot(const Cta& cta, const DecCfg& c, const Ws& w, const Beam
             double score = base;
             if (n == c.sil) score += c.silScore;
             score = score + c.lmWeight * (double)d; // ZeroLM / root child: lmWeight * (maxScore - 0)
-            gxOffer(cta, c, w, cur, fr, set, score, i, n, -1, LEX ? child : 0, LEX ? 0 : CF_NEW, d, ev, eoff,
-                    degLab, msBits, cut);
+            gxOffer(cta, c, w, cur, fr, set, score, i, n, -1, LEX ? child : 0, LEX ? 0 : CF_NEW, d, ev, eoff, degLab,
+                    msBits);
           }
         }
       }
     }
 #if FLT_DEVICE_BUILD
     const unsigned b = __ballot_sync(0xffffffffu, cont);
-    const unsigned gm = width == 32 ? 0xffffffffu : (((1u << width) - 1u) << (lane - sub));
-    if (active && (b & gm) == 0) {
-      if (j - sub + width < M && fr.G > fr.floor) cut = 1; // stopped before the end of the list: the rest is below G
-      active = false;
-    }
+    const unsigned gm = ((1u << width) - 1u) << (lane - sub);
+    if ((b & gm) == 0) active = false; // the whole chunk is below the bound: so is the rest of the list
     if (b == 0) break;
 #else
-    if (!cont) {
-      if (active && j + 1 < M && fr.G > fr.floor) cut = 1;
-      break;
-    }
+    if (!cont) break;
 #endif
     j += width;
   }
+}
+FLT_DEV int gxWalkSlots(int nWalk) {
+#if FLT_DEVICE_BUILD
+  return (nWalk + (32 / kGxWalkLanes) - 1) / (32 / kGxWalkLanes);
+#else
+  return nWalk;
+#endif
 }
 
 /* ------------------------------------------------------------------ items ---------------------- */
@@ -357,11 +371,12 @@ FLT_DEV float gxWordLm(const DecCfg& c, const Beam& cur, int p, int label) {
   return ngramScore(c.lm, cur.ctx(p), cur.nctx(p), c.lm.usr2lm[label]);
 }
 
-// stage 3 of one item: scores and proposals
+// stage 3 of one item: scores and proposals. Returns 1 + the best bin a proposal reached, 0 if none,
+// 255 if a word end was not probed (its bin is unknown: the second pass must look again).
 template <bool LEX>
-FLT_DEV void gxItemFinish(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, const FrameIn& f,
-                          const GxFrame& fr, int set, const GxItem& it, int& cut) {
-  if (it.kind < 0) return;
+FLT_DEV int gxItemFinish(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, const FrameIn& f,
+                         const GxFrame& fr, int set, const GxItem& it) {
+  if (it.kind < 0) return 0;
   const int q = it.q;
   const double sq = cur.score(q);
   const int tq = cur.tok(q), pbq = cur.pb(q);
@@ -369,107 +384,91 @@ FLT_DEV void gxItemFinish(const Cta& cta, const DecCfg& c, const Ws& w, const Be
     if (it.kind == 1) { // repeat (LexiconFreeDecoder.cpp:98-110)
       const int n = tq;
       const bool isRepeat = c.ctc ? (!pbq && n != c.blank) : true;
-      if (!(isRepeat && n >= 0 && n < c.N && inTokenSetV(c, f, n, it.ev))) return;
+      if (!(isRepeat && n >= 0 && n < c.N && inTokenSetV(c, f, n, it.ev))) return 0;
       double score = sq + (double)it.ev;
       if (n == c.sil) score += c.silScore;
-      gxOffer(cta, c, w, cur, fr, set, score, q, n, -1, 0, 0, 0.0f, it.ev, 0, 0, 0, cut);
-    } else if (it.kind == 2) { // blank (:86-97)
-      if (!c.ctc || !inTokenSetV(c, f, c.blank, it.ev)) return;
+      return 1 + gxOffer(cta, c, w, cur, fr, set, score, q, n, -1, 0, 0, 0.0f, it.ev, 0, 0, 0);
+    }
+    if (it.kind == 2) { // blank (:86-97)
+      if (!c.ctc || !inTokenSetV(c, f, c.blank, it.ev)) return 0;
       double score = sq + (double)it.ev;
       if (c.blank == c.sil) score += c.silScore;
-      gxOffer(cta, c, w, cur, fr, set, score, q, c.blank, -1, 0, CF_PB, 0.0f, it.ev, 0, 0, 0, cut);
-    } else { // boosted sil as a new token (:69-85)
-      const int n = c.sil;
-      const bool ok = c.ctc ? (n != c.blank && (n != tq || pbq)) : n != tq;
-      if (!ok || !inTokenSetV(c, f, n, it.ev)) return;
-      double score = sq + (double)it.ev;
-      score += c.silScore;
-      score = score + c.lmWeight * (double)0.0f;
-      gxOffer(cta, c, w, cur, fr, set, score, q, n, -1, 0, CF_NEW, 0.0f, it.ev, 0, 0, 0, cut);
+      return 1 + gxOffer(cta, c, w, cur, fr, set, score, q, c.blank, -1, 0, CF_PB, 0.0f, it.ev, 0, 0, 0);
     }
-    return;
+    // boosted sil as a new token (:69-85)
+    const int n = c.sil;
+    const bool ok = c.ctc ? (n != c.blank && (n != tq || pbq)) : n != tq;
+    if (!ok || !inTokenSetV(c, f, n, it.ev)) return 0;
+    double score = sq + (double)it.ev;
+    score += c.silScore;
+    score = score + c.lmWeight * (double)0.0f;
+    return 1 + gxOffer(cta, c, w, cur, fr, set, score, q, n, -1, 0, CF_NEW, 0.0f, it.ev, 0, 0, 0);
   }
   const int lex = cur.lex(q);
   const int eoffQ = cur.xv[q], degLabQ = cur.xv[c.K + q], msQ = cur.xv[2 * c.K + q];
   if (it.kind == 1) { // (2) same node, LexiconDecoder.cpp:167-194
-    if (!(!pbq || lex == 0)) return;
+    if (!(!pbq || lex == 0)) return 0;
     const int n = it.n;
     double score = sq + (double)it.ev;
     if (n == c.sil) score += c.silScore;
-    gxOffer(cta, c, w, cur, fr, set, score, q, n, -1, lex, 0, 0.0f, it.ev, eoffQ, degLabQ, msQ, cut);
-    return;
+    return 1 + gxOffer(cta, c, w, cur, fr, set, score, q, n, -1, lex, 0, 0.0f, it.ev, eoffQ, degLabQ, msQ);
   }
   if (it.kind == 2) { // (3) blank, :196-213
     const double score = sq + (double)it.ev;
-    gxOffer(cta, c, w, cur, fr, set, score, q, c.blank, -1, lex, CF_PB, 0.0f, it.ev, eoffQ, degLabQ, msQ, cut);
-    return;
+    return 1 + gxOffer(cta, c, w, cur, fr, set, score, q, c.blank, -1, lex, CF_PB, 0.0f, it.ev, eoffQ, degLabQ, msQ);
   }
   if (it.kind == 3) { // boosted sil from the root through root child `sil` (emitSilCell)
-    if (it.child < 0 || gxNodeDeg(it.nd.z) == 0) return;
+    if (it.child < 0 || gxNodeDeg(it.nd.z) == 0) return 0;
     const int n = c.sil;
-    if (!(pbq || n != tq) || n == c.blank) return;
-    if (!inTokenSetV(c, f, n, it.ev)) return;
+    if (!(pbq || n != tq) || n == c.blank) return 0;
+    if (!inTokenSetV(c, f, n, it.ev)) return 0;
     double score = sq + (double)it.ev;
     score += c.silScore;
     const float d = bitsF32((uint32_t)it.nd.x) - 0.0f;
     score = score + c.lmWeight * (double)d;
-    gxOffer(cta, c, w, cur, fr, set, score, q, n, -1, it.child, 0, d, it.ev, it.nd.y, it.nd.z, it.nd.x, cut);
-    return;
+    return 1 + gxOffer(cta, c, w, cur, fr, set, score, q, n, -1, it.child, 0, d, it.ev, it.nd.y, it.nd.z, it.nd.x);
   }
   // (1) one Trie edge: child node it.child reached by token it.n (LexiconDecoder.cpp:62-141)
   const int n = it.n;
   const float ev = it.ev;
-  if (!inTokenSetV(c, f, n, ev)) return;
+  if (!inTokenSetV(c, f, n, ev)) return 0;
   const float lexMax = lex == 0 ? 0.0f : bitsF32((uint32_t)msQ);
   double score = sq + (double)ev;
   if (n == c.sil) score += c.silScore;
   const int deg = gxNodeDeg(it.nd.z), nLab = gxNodeLabels(it.nd.z);
+  int best = -1;
   if (lex != 0 && deg > 0 && (pbq || n != tq)) { // (1a); root children with kids are the walkers' cells
     const float d = bitsF32((uint32_t)it.nd.x) - lexMax;
     const double s = score + c.lmWeight * (double)d;
-    gxOffer(cta, c, w, cur, fr, set, s, q, n, -1, it.child, 0, d, ev, it.nd.y, it.nd.z, it.nd.x, cut);
+    const int b = gxOffer(cta, c, w, cur, fr, set, s, q, n, -1, it.child, 0, d, ev, it.nd.y, it.nd.z, it.nd.x);
+    best = b > best ? b : best;
   }
   if (nLab > 0 && !(lex == 0 && tq == n)) { // (1b) word ends, :114-141
-    // with an n-gram LM: skip the probes when even the LM's best possible score cannot reach G
-    if (c.lm.kind != 0 && fr.mode == 0) {
+    // with an n-gram LM: no probes when even the LM's best possible score stays below the bound
+    if (c.lm.kind != 0 && c.lmWeight >= 0) {
       const float dUp = c.lmUpper - lexMax;
-      const double up = score + (c.lmWeight >= 0 ? c.lmWeight * (double)dUp : 0.0) + c.wordScore + 1e-6;
-      if (c.lmWeight >= 0 && up < fr.G) {
-        if (up >= fr.floor) cut = 1;
-        return;
-      }
+      const double up = score + c.lmWeight * (double)dUp + c.wordScore + 1e-6;
+      if (up < fr.stop) return fr.mode == 1 ? 255 : 1 + best;
     }
     for (int l = 0; l < nLab; ++l) {
       const int label = nLab == 1 ? it.nd.w : c.trie.labels[it.nd.w + l];
       const float d = gxWordLm(c, cur, q, label) - lexMax;
       const double s = score + c.lmWeight * (double)d + c.wordScore;
-      gxOffer(cta, c, w, cur, fr, set, s, q, n, label, 0, CF_NEW, d, ev, 0, 0, 0, cut);
+      const int b = gxOffer(cta, c, w, cur, fr, set, s, q, n, label, 0, CF_NEW, d, ev, 0, 0, 0);
+      best = b > best ? b : best;
     }
   }
+  return 1 + best;
 }
 
-/* ------------------------------------------------------------------ phase E --------------------- */
+/* ------------------------------------------------------------------ phase E (both passes) ------- */
 template <bool LEX>
 FLT_DEV void gxPhaseE(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, const FrameIn& f,
                       const GxFrame& fr, int set, int nH, float eBlank, float eSil) {
-  int cut = 0;
   const int warp = cta.tid >> 5, nw = (cta.nthr + 31) >> 5;
   const int nSpec = gxSpecials(c);
-  // walkers
-  int nWalk = nH;
-  if (LEX) {
-    nWalk = 0;
-    const uint32_t* bits = gxBits(w, set);
-    for (int k = 0; k < ((c.K + 31) >> 5); ++k) {
-#if FLT_DEVICE_BUILD
-      nWalk += __popc(bits[k]);
-#else
-      nWalk += __builtin_popcount(bits[k]);
-#endif
-    }
-  }
+  const int nWalk = LEX ? gxSc(w, set)[GX_NWALK] : nH;
   const int nSlots = gxWalkSlots(nWalk);
-  // items
   int nItems;
   int kp2 = 1;
   if (LEX) {
@@ -481,6 +480,7 @@ FLT_DEV void gxPhaseE(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& 
     nItems = nSpec * kp2;
   }
   const int* ch = LEX ? gxChunks(w, set) : nullptr;
+  unsigned char* stash = gxStash(w);
   bool walked = false;
   for (int x0 = 0; x0 < nItems || !walked; x0 += kGxSweep * cta.nthr) {
     GxItem it[kGxSweep];
@@ -498,6 +498,10 @@ FLT_DEV void gxPhaseE(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& 
       er[z].x = 0, er[z].y = -1;
       const int x = x0 + z * cta.nthr + cta.tid;
       if (x >= nItems) continue;
+      if (fr.mode == 0) { // second pass: only the items whose best proposal reached the cut
+        const int st = stash[x];
+        if (st == 0 || (st != 255 && st - 1 < fr.cutBin)) continue;
+      }
       if (!LEX) {
         const int kind = x / kp2, q = x & (kp2 - 1);
         if (q >= nH) continue;
@@ -544,7 +548,7 @@ FLT_DEV void gxPhaseE(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& 
     }
     // ---- the walkers run while those loads are in flight (first sweep only)
     if (!walked) {
-      for (int s = warp; s < nSlots; s += nw) gxWalkSlot<LEX>(cta, c, w, cur, f, fr, set, s, nWalk, cut);
+      for (int s = warp; s < nSlots; s += nw) gxWalkSlot<LEX>(cta, c, w, cur, f, fr, set, s, nWalk);
       walked = true;
     }
     // ---- stage 2: emission and node record of each edge
@@ -562,133 +566,112 @@ FLT_DEV void gxPhaseE(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& 
     }
     // ---- stage 3
 #pragma unroll
-    for (int z = 0; z < kGxSweep; ++z) gxItemFinish<LEX>(cta, c, w, cur, f, fr, set, it[z], cut);
-  }
-  if (fr.mode == 0) {
-#if FLT_DEVICE_BUILD
-    if (__any_sync(0xffffffffu, cut) && (cta.tid & 31) == 0) gxSc(w, set)[GX_CUT] = 1;
-#else
-    if (cut) gxSc(w, set)[GX_CUT] = 1;
-#endif
+    for (int z = 0; z < kGxSweep; ++z) {
+      const int x = x0 + z * cta.nthr + cta.tid;
+      const int st = gxItemFinish<LEX>(cta, c, w, cur, f, fr, set, it[z]);
+      if (fr.mode == 1 && x < nItems) stash[x] = (unsigned char)(st > 255 ? 255 : st);
+    }
   }
 }
 
-/* ------------------------------------------------------------------ the frame step ------------- */
-// highest bin b with at least `want` proposals in bins >= b (0 if there are fewer in total); *kept =
-// proposals in bins >= b. One warp; the histogram is left intact.
-FLT_DEV void gxFindCut(const Cta& cta, const Ws& w, int want, int* out) {
+/* ------------------------------------------------------------------ the cut -------------------- */
+// From the histogram: the highest bin b with at least `want` proposals in bins >= b (0 if there are
+// fewer in total). kept = proposals in bins >= b, above = proposals in bins > b. Every warp computes
+// this for itself from the same data (identical results; no barrier, no single-warp phase).
+FLT_DEV void gxFindCut(const Cta& cta, const Ws& w, int want, int& cutBin, int& kept, int& above) {
   const int* hist = w.hist();
 #if FLT_DEVICE_BUILD
-  if (cta.tid < 32) {
-    const int lane = cta.tid;
-    int h[8], part = 0;
+  const int lane = cta.tid & 31;
+  int h[8], part = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    h[k] = hist[255 - (lane * 8 + k)];
+    part += h[k];
+  }
+  int incl = part;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  const int excl = incl - part;
+  int found = -1, fk = 0, fa = 0;
+  if (excl < want && incl >= want) {
+    int cum = excl;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      h[k] = hist[255 - (lane * 8 + k)];
-      part += h[k];
-    }
-    int incl = part;
-    for (int o = 1; o < 32; o <<= 1) {
-      const int u = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += u;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (lane == 0 && total < want) {
-      out[0] = 0;
-      out[1] = total;
-    }
-    const int excl = incl - part;
-    if (excl < want && incl >= want) {
-      int cum = excl;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (cum < want && cum + h[k] >= want) {
-          out[0] = 255 - (lane * 8 + k);
-          out[1] = cum + h[k];
-        }
-        cum += h[k];
+      if (cum < want && cum + h[k] >= want) {
+        found = 255 - (lane * 8 + k);
+        fk = cum + h[k];
+        fa = cum;
       }
+      cum += h[k];
     }
+  }
+  const unsigned who = __ballot_sync(0xffffffffu, found >= 0);
+  const int bin0 = __shfl_sync(0xffffffffu, h[7], 31);
+  if (who) {
+    const int src = __ffs(who) - 1;
+    cutBin = __shfl_sync(0xffffffffu, found, src);
+    kept = __shfl_sync(0xffffffffu, fk, src);
+    above = __shfl_sync(0xffffffffu, fa, src);
+  } else {
+    cutBin = 0;
+    kept = total;
+    above = total - bin0;
   }
 #else
-  if (cta.tid == 0) {
-    int cum = 0;
-    out[0] = 0;
-    for (int b = 255; b >= 0; --b) {
-      cum += hist[b];
-      if (cum >= want) {
-        out[0] = b;
-        break;
-      }
+  (void)cta;
+  int cum = 0;
+  cutBin = 0;
+  for (int b = 255; b >= 1; --b) {
+    if (cum + hist[b] >= want) {
+      cutBin = b;
+      above = cum;
+      kept = cum + hist[b];
+      return;
     }
-    out[1] = cum;
+    cum += hist[b];
   }
+  above = cum;
+  kept = cum + hist[0];
 #endif
 }
 
-// C: compact the group representatives, empty the merge table, find the best score
-FLT_DEV void gxPhaseC(const Cta& cta, const DecCfg& c, const Ws& w, int set, int nCand) {
-  const Cand cd = w.cand();
-  int* sc = gxSc(w, set);
-  int* rep = w.rep();
-  u64* rkey = w.rkey();
-  int* mh = w.mh();
-  const int* cslot = w.cslot();
-  u64 best = 0;
-  for (int x = cta.tid; x < nCand; x += cta.nthr) {
-    if (!(cd.parflag(x) & CF_ALIVE)) continue;
-    const u64 k = orderedKey64(cd.score(x));
-    mh[cslot[x]] = -1;
-    const int r = aggInc(&sc[GX_NREP], cta.tid);
-    rep[r] = x;
-    rkey[r] = k; // keyA storage: every insert finished at the barrier before this phase
-    best = k > best ? k : best;
-  }
-#if FLT_DEVICE_BUILD
-  {
-    unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)(best >> 32));
-    unsigned lo = __reduce_max_sync(0xffffffffu, (unsigned)(best >> 32) == hi ? (unsigned)best : 0u);
-    best = ((u64)hi << 32) | lo;
-    if ((cta.tid & 31) == 0 && best) atomicMax((u64*)(w.base + c.lay.gxBest), best);
-  }
-#else
-  {
-    u64* gb = (u64*)(w.base + c.lay.gxBest);
-    if (best > *gb) *gb = best;
-  }
-#endif
-}
-
-// RF: rank the representatives by counting; the thread that finds rank q < K writes hypothesis q of
-// the new beam (phaseFinalize of beam_core.h, one hypothesis per thread) and registers it for the
-// next frame's E.
+/* ------------------------------------------------------------------ phase RF -------------------- */
+// Every live candidate ranks itself by counting larger score keys; the thread that finds rank q < K
+// writes hypothesis q of the new beam (phaseFinalize of beam_core.h, one hypothesis per thread),
+// registers it for the next frame's E, and frees its merge-table slot. The new beam's size
+// accumulates in the twin set's GX_NH.
 FLT_DEV void gxPhaseRF(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, const Beam& nxt,
-                       const FrameIn& f, int set, int nRep) {
+                       const FrameIn& f, int set, int nCand) {
   const Cand cd = w.cand();
   const int K = c.K;
-  int* sc = w.sc();
-  const int* rep = w.rep();
-  const u64* rkey = w.rkey();
+  int* gn = gxSc(w, set ^ 1);
+  const u64* skey = gxSkey(w);
+  int* mh = w.mh();
+  const int* cslot = w.cslot();
   const u64 bestKey = *(const u64*)(w.base + c.lay.gxBest);
   // candidatesBestScore_ - beamThreshold (Utils.h:161-165; a max-merge keeps the same groups when the
   // filter runs after the merge)
   const double thrScore = keyToDouble(bestKey) - c.beamThreshold;
   int lg = 0;
-  while (lg < 5 && ((long long)nRep << (lg + 1)) <= cta.nthr) ++lg;
+  while (lg < 5 && ((long long)nCand << (lg + 1)) <= cta.nthr) ++lg;
   const int parts = 1 << lg;
-  const int slice = (nRep + parts - 1) >> lg;
-  for (int base = 0; base < (nRep << lg); base += cta.nthr) {
+  const int slice = (nCand + parts - 1) >> lg;
+  for (int base = 0; base < (nCand << lg); base += cta.nthr) {
     const int t = base + cta.tid;
     const int a = t >> lg, part = t & (parts - 1);
-    const bool valid = a < nRep;
-    int cnt = 0, eq = 0;
     u64 ka = 0;
+    if (a < nCand) ka = skey[a];
+    const bool valid = ka != 0; // live
+    int cnt = 0, eq = 0;
     if (valid) {
-      ka = rkey[a];
-      const int lo = part * slice, hi = lo + slice < nRep ? lo + slice : nRep;
+      const int lo = part * slice, hi = lo + slice < nCand ? lo + slice : nCand;
 #pragma unroll 4
       for (int b = lo; b < hi; ++b) {
-        const u64 kb = rkey[b];
+        const u64 kb = skey[b];
         cnt += kb > ka ? 1 : 0;
         eq |= kb == ka ? (b != a ? 1 : 0) : 0;
       }
@@ -699,29 +682,39 @@ FLT_DEV void gxPhaseRF(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
       eq |= __shfl_xor_sync(0xffffffffu, eq, o);
     }
 #endif
-    if (!(valid && part == 0)) continue;
-    const int x = rep[a];
-    if (eq) { // another group with exactly this score: settle by the deterministic order (rare)
-      for (int b = 0; b < nRep; ++b)
-        if (b != a && rkey[b] == ka && candBetter(cd, rep[b], x)) ++cnt;
+    int keep = 0; // q + 1 if this thread writes hypothesis q
+    const int x = a;
+    if (valid && part == 0) {
+      mh[cslot[x]] = -1; // leave the merge table empty
+      if (eq) { // another group with exactly this score: settle by the deterministic order (rare)
+        for (int b = 0; b < nCand; ++b)
+          if (b != a && skey[b] == ka && gxBetter(c, cd, b, x)) ++cnt;
+      }
+      if (cnt < K && cd.score(x) >= thrScore) keep = cnt + 1;
     }
-    const int q = cnt;
-    if (q >= K) continue;
+#if FLT_DEVICE_BUILD
+    {
+      const int mx = __reduce_max_sync(0xffffffffu, keep);
+      if ((cta.tid & 31) == 0 && mx > 0) atomicMax(&gn[GX_NH], mx);
+    }
+#else
+    if (keep > gn[GX_NH]) gn[GX_NH] = keep;
+#endif
+    if (!keep) continue;
+    const int q = keep - 1;
     const double score = cd.score(x);
-    if (!(score >= thrScore)) continue;
-    atomMax(&sc[SC_NH], q + 1);
     const int p = cd.par(x);
     const int fl = cd.flags(x);
     const int n = cd.tok(x);
     nxt.score(q) = score;
     nxt.am(q) = (fl & CF_FINISH) ? cur.am(p) : cur.am(p) + amOf(c, f, cd.ce(x), n, cur.tok(p));
-    nxt.lm(q) = cur.lm(p) + (double)cd.lmd(x);
+    nxt.lm(q) = c.lexicon ? cur.lm(p) + (double)cd.lmd(x) : cur.lm(p) + (double)0.0f;
     const int lexNew = c.lexicon ? cd.lex(x) : 0;
     nxt.lex(q) = lexNew;
     nxt.tok(q) = n;
     nxt.pb(q) = (fl & CF_PB) ? 1 : 0;
     if (fl & CF_NEW) {
-      const int lab = candLabel(c, cd, x);
+      const int lab = (fl & CF_FINISH) ? -1 : ((c.lexicon && !c.lmToken) ? cd.word(x) : n);
       fpChild(cur.fpA(p), cur.fpB(p), lab, nxt.fpA(q), nxt.fpB(q));
       if (c.lm.kind) {
         const int wlm = lab < 0 ? c.lm.eos : c.lm.usr2lm[lab];
@@ -749,36 +742,42 @@ FLT_DEV void gxPhaseRF(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
     }
     if (c.lexicon && !(fl & CF_FINISH)) {
       const int* cx = gxCandX(w);
-      const int x0 = cx[x], x1 = cx[c.capC + x], x2 = cx[2 * c.capC + x];
-      gxSetNode(c, nxt, q, lexNew, x0, x1, x2);
+      const int x1 = cx[c.capC + x];
+      gxSetNode(nxt, q, cx[x], x1, cx[2 * c.capC + x]);
       gxRegister(c, w, set ^ 1, q, lexNew, x1);
     }
   }
 }
 
-// reference level of a frame: the best proposal of the best hypothesis (blank, or its best list cell)
+/* ------------------------------------------------------------------ the frame step ------------- */
+// emission level of a frame: the best raw proposal any hypothesis can make (blank, or the head of the
+// ranked list with its LM part)
 template <bool LEX>
-FLT_DEV double gxRefLevel(const DecCfg& c, const Beam& cur, const FrameIn& f, float eBlank, bool blankOk) {
-  const double s0 = cur.score(0);
-  double ref = negInf();
-  if (blankOk) ref = s0 + (double)eBlank;
-  if (f.listLen > 0 && f.topTok[0] >= 0) {
-    double v = s0 + (double)f.topVal[0];
-    if (LEX) v = v + c.lmWeight * (double)bitsF32((uint32_t)f.listInfo[0]);
-    ref = v > ref ? v : ref;
+FLT_DEV double gxLevel(const DecCfg& c, const FrameIn& f, float eBlank, bool blankOk, bool& known) {
+  double lv = negInf();
+  known = false;
+  if (blankOk) {
+    lv = (double)eBlank;
+    known = true;
   }
-  return ref;
+  if (f.listLen > 0 && f.topTok[0] >= 0) {
+    double v = (double)f.topVal[0];
+    if (LEX) v = v + c.lmWeight * (double)bitsF32((uint32_t)f.listInfo[0]);
+    lv = v > lv ? v : lv;
+    known = true;
+  }
+  return lv;
 }
 
-// One frame: cur (beam `set`) -> nxt (beam `set ^ 1`). All threads call this with identical arguments.
+// One frame: beam `set` -> beam `set ^ 1`. All threads call this with identical arguments; returns the
+// number of hypotheses in the new beam (0 = the beam died, Utils.h:155-158).
 template <bool LEX>
-FLT_DEV void gxFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, int set, const FrameIn& f, int* status,
-                         unsigned long long* stats, GxCarry& g) {
-  int* sc = w.sc();
-  const int nH = sc[SC_NH];
-  if (nH == 0) return; // the beam died (Utils.h:155-158)
-  const Beam cur = w.beam(set), nxt = w.beam(set ^ 1);
+FLT_DEV int gxFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, int set, const FrameIn& f, int* status,
+                        unsigned long long* stats, GxCarry& g) {
   int* gs = gxSc(w, set);
+  const int nH = gs[GX_NH];
+  if (nH == 0) return 0;
+  const Beam cur = w.beam(set), nxt = w.beam(set ^ 1);
   LfPhaseClock pc;
   pc.start(cta, stats);
   const int K = c.K;
@@ -802,9 +801,6 @@ FLT_DEV void gxFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, int set, 
   const bool blankOk = c.ctc && (LEX || inTokenSetV(c, f, c.blank, eBlank));
   const double s0 = cur.score(0);
   GxFrame fr;
-  fr.mode = 0;
-  fr.hlo = 0.0;
-  fr.hscale = 0.0f;
   // the best hypothesis' blank candidate always exists: the frame's best is at least that, and the
   // reference drops everything below it minus beamThreshold
   fr.floor = negInf();
@@ -813,130 +809,180 @@ FLT_DEV void gxFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, int set, 
     if (!LEX && c.blank == c.sil) sb += c.silScore;
     fr.floor = sb - c.beamThreshold;
   }
-  const double ref = gxRefLevel<LEX>(c, cur, f, eBlank, blankOk);
-  fr.G = ref - g.spread; // -inf while the spread is unknown
-  if (!(fr.G == fr.G)) fr.G = negInf(); // inf - inf
-  if (fr.G < fr.floor) fr.G = fr.floor;
-
-  int nCand = 0, nRep = 0;
-  int want = 2 * K + 32;
-  bool histReady = false, last = false;
-  int guessMiss = 0;
-  for (int attempt = 0;; ++attempt) {
+  bool levelKnown;
+  const double level = gxLevel<LEX>(c, f, eBlank, blankOk, levelKnown);
+  // histogram range: proposals lie below best hypothesis + best emission (+ bonuses)
+  double hi = s0 + (levelKnown ? level : 0.0);
+  if (c.silScore > 0) hi += c.silScore;
+  if (c.wordScore > 0) hi += c.wordScore;
+  hi += 0.25;
+  double span = (double)g.span;
+  if (c.beamThreshold + 4.0 < span) span = c.beamThreshold + 4.0;
+  fr.hlo = hi - span;
+  fr.hscale = (float)((double)kGxBins / span);
+  // Bound of the histogram pass for the walkers and the LM probes. Lexicon-free: the corner bound of
+  // beam_core.h — rows 1..a x columns 0..col hold >= K distinct groups, so the cut is never below the
+  // best corner (exact). Lexicon: the last cut moved by the emission level, minus a generous margin; a
+  // proposal it hides is only missing from the histogram (the cut comes out lower, never wrong).
+  double bound = negInf();
+  if (!LEX) {
+    for (int k = 0; k < c.nTau; ++k) {
+      const int i = 2 * c.tauA[k] - 2, col = c.tauCol[k];
+      if (i < nH && col < f.listLen && f.topTok[col] >= 0) {
+        const double corner = cur.score(i) + (double)f.topVal[col] + c.lmWeight * (double)0.0f;
+        bound = corner > bound ? corner : bound;
+      }
+    }
+    if (c.silScore < 0) bound += c.silScore; // keeps the bound valid if a counted cell is the sil one
+  } else if (g.have == 2 && levelKnown) {
+    bound = g.cutPrev + level + g.D - 4.0;
+  }
+  if (!(bound == bound)) bound = negInf();
+  int want = LEX ? K + (K >> 1) + 32 : 2 * K + 16;
+  int nCand = 0, nRep = 0, cutBin = 0, kept = 0, above = 0, redo = 0;
+  bool last = false;
+  for (int hpass = 0;; ++hpass) {
+    // ---- E1: histogram of every proposal
+    fr.mode = 1;
+    fr.cutBin = 0;
+    fr.stop = bound > fr.floor ? bound : fr.floor;
     gxPhaseE<LEX>(cta, c, w, cur, f, fr, set, nH, eBlank, eSil);
-    cta.sync(); // ---- A
-    if (attempt == 0) pc.mark(0);
-    nCand = gs[GX_NCAND];
-    const int ovf = gs[GX_OVF];
-    if (nCand > c.capC) nCand = c.capC;
-    gxPhaseC(cta, c, w, set, nCand);
-    cta.sync(); // ---- B
-    if (attempt == 0) pc.mark(1);
-    nRep = gs[GX_NREP];
-    const int cutAny = gs[GX_CUT];
-    const bool miss = nRep < K && cutAny; // fewer than K groups although proposals were left out
-    if ((!ovf && !miss) || last) break;
-    // ---- exact redo: a histogram of every proposal picks G (the kept set is verified again)
-    guessMiss = 1;
-    cta.sync(); // everyone has read the scalars
-    if (cta.tid == 0) {
-      gs[GX_NCAND] = 0;
-      gs[GX_OVF] = 0;
-      gs[GX_CUT] = 0;
-      gs[GX_NREP] = 0;
-      *(u64*)(w.base + c.lay.gxBest) = 0;
-    }
-    if (!histReady) {
-      double hi = s0;
-      if (c.silScore > 0) hi += c.silScore;
-      if (c.wordScore > 0) hi += c.wordScore;
-      double span = 2.0 * (s0 - cur.score(nH - 1)) + 16.0;
-      span = span > 128.0 ? 128.0 : span;
-      if (c.beamThreshold + 4.0 < span) span = c.beamThreshold + 4.0;
-      fr.hlo = hi - span;
-      fr.hscale = (float)kGxBins / (float)span;
-      fr.mode = 1;
-      gxPhaseE<LEX>(cta, c, w, cur, f, fr, set, nH, eBlank, eSil);
+    cta.sync(); // ---- B1
+    if (hpass == 0) pc.mark(0);
+    bool rehist = false;
+    for (int attempt = 0;; ++attempt) {
+      gxFindCut(cta, w, want, cutBin, kept, above);
+      if (kept > c.capC - 16 && !last) {
+        if (cutBin < kGxBins - 1 && above >= K + (K >> 2) && above <= c.capC - 16) {
+          // a crowded cut bin: the bins above it may hold the K groups on their own (verified below)
+          ++cutBin;
+          kept = above;
+        } else {
+          // more proposals in (and above) the cut bin than candidate slots: histogram again at a finer
+          // scale over the cut bin — or over a longer range if the cut fell below this one
+          const double binW = 1.0 / (double)fr.hscale;
+          if (cutBin == 0) {
+            const double len = (double)kGxBins * binW;
+            fr.hlo -= 7.0 * len;
+            fr.hscale = (float)(1.0 / (8.0 * binW));
+          } else {
+            const double nw = binW / (double)(kGxBins - 2);
+            fr.hlo = fr.hlo + (double)cutBin * binW - nw;
+            fr.hscale = (float)(1.0 / nw);
+          }
+          rehist = true;
+          break;
+        }
+      }
+      // ---- E2: materialise what reaches the cut
       fr.mode = 0;
-      histReady = true;
-    } else if (ovf) {
-      // the histogram's own choice overflowed (a crowded cut bin): aim lower; at K proposals nothing is
-      // left to try — the host grows the capacity and redoes the batch
-      if (want <= K + 16) last = true;
-      want = want / 2 > K + 16 ? want / 2 : K + 16;
-    } else {
+      fr.cutBin = cutBin;
+      const double edge = cutBin > 0 ? fr.hlo + ((double)cutBin - 0.01) / (double)fr.hscale : negInf();
+      fr.stop = edge > fr.floor ? edge : fr.floor;
+      if (!LEX && bound > fr.stop) fr.stop = bound; // exact: nothing below the corner bound is ever needed
+      gxPhaseE<LEX>(cta, c, w, cur, f, fr, set, nH, eBlank, eSil);
+      cta.sync(); // ---- B2
+      if (hpass == 0 && attempt == 0) pc.mark(1);
+      nCand = gs[GX_NCAND];
+      const int ovf = gs[GX_OVF];
+      if (nCand > c.capC) nCand = c.capC;
+      gxPhaseM(cta, c, w, set, nCand);
+      cta.sync(); // ---- B3
+      if (hpass == 0 && attempt == 0) pc.mark(2);
+      nRep = nCand - gs[GX_NDEAD];
+      // complete if nothing was left out (cut at bin 0; lexicon-free: and no corner bound in the way)
+      const bool all = cutBin == 0 && (LEX || !(bound > fr.floor));
+      const bool miss = nRep < K && !all;
+      if ((!ovf && !miss) || last) break;
+      // ---- rare: too few groups above the cut, or more candidates than the histogram promised. Undo.
+      redo = 1;
+      for (int x = cta.tid; x < nCand; x += cta.nthr)
+        if (gxSkey(w)[x]) w.mh()[w.cslot()[x]] = -1;
+      cta.sync();
+      if (cta.tid == 0) {
+        gs[GX_NCAND] = 0;
+        gs[GX_OVF] = 0;
+        gs[GX_NDEAD] = 0;
+        *(u64*)(w.base + c.lay.gxBest) = 0;
+      }
+#if FLT_DEVICE_BUILD
+      if (stats && cta.tid == 0) {
+        atomicAdd(stats + 13, (unsigned long long)(ovf ? 1 : 0));
+        atomicAdd(stats + 14, (unsigned long long)(miss ? 1 : 0));
+      }
+#endif
+      cta.sync();
+      if (ovf) { // proposals the bound hid from the histogram: count everything this time
+        if (!(bound > negInf())) last = true; // nothing was hidden: the capacity itself is too small
+        bound = negInf();
+        rehist = true;
+        break;
+      }
       want = want * 2;
+      if (attempt >= 8) last = true;
     }
-    if (attempt >= 12) last = true;
-    cta.sync();
-    gxFindCut(cta, w, want, sc + SC_GXCUTBIN);
-    cta.sync();
-    const int cutBin = sc[SC_GXCUTBIN];
-    if (cutBin <= 0) fr.G = fr.floor; // fewer proposals than wanted: take everything
-    else fr.G = fr.hlo + ((double)cutBin - 0.02) / (double)fr.hscale;
-    if (fr.G < fr.floor) fr.G = fr.floor;
-    if (last && cta.tid == 0) *status |= 1; // decode on with what fits; the host discards the result
-  }
-  if (histReady) {
+    if (!rehist) break;
+    redo = 1;
+    if (hpass >= 4) last = true; // ties en masse: the host grows the capacity and redoes the batch
     for (int b = cta.tid; b < kGxBins; b += cta.nthr) w.hist()[b] = 0;
+    cta.sync();
   }
-  // the new beam's tables are built below: reset their counters, and this frame's scalars' twin set
-  if (cta.tid == 0) {
-    int* gn = gxSc(w, set ^ 1);
-    gn[GX_NCAND] = 0;
-    gn[GX_OVF] = 0;
-    gn[GX_CUT] = 0;
-    gn[GX_NREP] = 0;
-    sc[SC_NH] = 0;
-  }
-  // (the twin set's chunk counter / walker bitmap were cleared in the previous frame's tail, below)
+  if (last && cta.tid == 0) *status |= 1;
+  // leave the histogram empty for the next frame
+  for (int b = cta.tid; b < kGxBins; b += cta.nthr) w.hist()[b] = 0;
 #if FLT_DEVICE_BUILD
   if (stats && cta.tid == 0) {
     atomicAdd(stats + 0, 1ull);
     atomicAdd(stats + 1, (unsigned long long)nCand);
     atomicAdd(stats + 2, (unsigned long long)nRep);
     atomicAdd(stats + 3, (unsigned long long)(nRep < K ? nRep : K));
-    if (guessMiss) atomicAdd(stats + 12, 1ull);
+    if (redo) atomicAdd(stats + 12, 1ull);
+    if (last) atomicAdd(stats + 15, 1ull);
     stats[30] = 1ull; // phase names of this step for the host
   }
 #endif
-  cta.sync(); // ---- (scalars reset before RF's atomics)
-  gxPhaseRF(cta, c, w, cur, nxt, f, set, nRep);
-  cta.sync(); // ---- C
-  pc.mark(2);
-  // tail: this frame's tables are dead — clear them for the frame after next; reset the best key
-  if (LEX) {
-    if (cta.tid == 0) gs[GX_NCHUNK] = 0;
-    for (int i = cta.tid; i < ((K + 31) >> 5); i += cta.nthr) gxBits(w, set)[i] = 0;
-  }
+  gxPhaseRF(cta, c, w, cur, nxt, f, set, nCand);
+  cta.sync(); // ---- B4
+  pc.mark(3);
+  // tail: this frame's tables are dead — clear their counters for the frame after next
+  const int nHn = gxSc(w, set ^ 1)[GX_NH];
   if (cta.tid == 0) {
+    gs[GX_NCHUNK] = 0;
+    gs[GX_NWALK] = 0;
     *(u64*)(w.base + c.lay.gxBest) = 0;
     if (LEX && gxSc(w, set ^ 1)[GX_NCHUNK] > c.capChunks) *status |= 1;
   }
-  // the guess for the next frame
-  const int nHn = sc[SC_NH];
-  if (nRep >= K && nHn == K) {
-    const double cutScore = nxt.score(K - 1);
-    const double exact = ref - cutScore;
-    if (nRep < K + (K >> 2) + 8) g.mu = g.mu * 1.5f < 4.0f ? g.mu * 1.5f : 4.0f;
-    else if (nRep > 2 * K + (K >> 1)) g.mu = g.mu * 0.8f > 0.04f ? g.mu * 0.8f : 0.04f;
-    if (guessMiss) g.mu = g.mu * 1.5f < 4.0f ? g.mu * 1.5f : 4.0f;
-    g.spread = exact > 0 ? exact * (1.0 + (double)g.mu) + 0.05 : 0.05;
+  // carry: where the cut went (bound of the next histogram pass, range of the next histogram)
+  if (nRep >= K && nHn == K && levelKnown) {
+    const double cutNow = nxt.score(K - 1);
+    if (g.have >= 1) {
+      g.D = cutNow - g.cutPrev - level;
+      g.have = 2;
+    } else {
+      g.have = 1;
+    }
+    g.cutPrev = cutNow;
+    float sp = (float)((hi - cutNow) * 1.5 + 2.0);
+    sp = sp < 4.0f ? 4.0f : (sp > 128.0f ? 128.0f : sp);
+    g.span = 0.5f * g.span + 0.5f * sp;
   } else {
-    g.spread = bitsF64(0x7FF0000000000000ull); // the beam is not full: nothing to cut against
+    g.have = 0;
+    g.span = 32.0f;
   }
   if (f.hCount && cta.tid == 0) *f.hCount = nHn;
+  return nHn;
 }
 
 // decodeEnd (LexiconFreeDecoder.cpp:127-158, LexiconDecoder.cpp:231-274) through the same phases:
 // one finish candidate per hypothesis (only those at the Trie root when any exists), merged, ranked.
+// Returns the number of final hypotheses (in beam set ^ 1, sorted).
 template <bool LEX>
-FLT_DEV void gxFinish(const Cta& cta, const DecCfg& c, const Ws& w, int set, const FrameIn& f) {
+FLT_DEV int gxFinish(const Cta& cta, const DecCfg& c, const Ws& w, int set, const FrameIn& f) {
   int* sc = w.sc();
-  const int nH = sc[SC_NH];
-  if (nH == 0) return;
-  const Beam cur = w.beam(set), nxt = w.beam(set ^ 1);
   int* gs = gxSc(w, set);
+  const int nH = gs[GX_NH];
+  if (nH == 0) return 0;
+  const Beam cur = w.beam(set), nxt = w.beam(set ^ 1);
   if (cta.tid == 0) sc[SC_NICE] = 0;
   cta.sync();
   if (LEX) {
@@ -950,8 +996,14 @@ FLT_DEV void gxFinish(const Cta& cta, const DecCfg& c, const Ws& w, int set, con
     cta.sync();
   }
   const bool nice = LEX && sc[SC_NICE] != 0;
+  GxFrame fr;
+  fr.mode = 0;
+  fr.floor = negInf();
+  fr.hlo = 0.0;
+  fr.hscale = 0.0f;
+  fr.cutBin = 0;
+  fr.stop = negInf();
   for (int i = cta.tid; i < nH; i += cta.nthr) {
-    w.cand().parflag(i) = 0;
     if (nice && cur.lex(i) != 0) continue;
     float ls = 0.0f;
     int flags = CF_FINISH;
@@ -960,33 +1012,24 @@ FLT_DEV void gxFinish(const Cta& cta, const DecCfg& c, const Ws& w, int set, con
       flags |= CF_NEW;
     }
     const double score = cur.score(i) + c.lmWeight * (double)ls;
-    putCand(c, w, cur, i, score, i, c.sil, -1, LEX ? cur.lex(i) : 0, flags, ls, 0.0f);
-    gxInsert(c, w, i);
-  }
-  if (cta.tid == 0) {
-    gs[GX_NREP] = 0;
-    *(u64*)(w.base + c.lay.gxBest) = 0;
+    gxOffer(cta, c, w, cur, fr, set, score, i, c.sil, -1, LEX ? cur.lex(i) : 0, flags, ls, 0.0f, 0, 0, 0);
   }
   cta.sync();
-  gxPhaseC(cta, c, w, set, nH);
+  const int nCand = gs[GX_NCAND] < c.capC ? gs[GX_NCAND] : c.capC; // <= K <= capC
+  gxPhaseM(cta, c, w, set, nCand);
   cta.sync();
-  const int nRep = gs[GX_NREP];
-  if (cta.tid == 0) sc[SC_NH] = 0;
+  gxPhaseRF(cta, c, w, cur, nxt, f, set, nCand);
   cta.sync();
-  gxPhaseRF(cta, c, w, cur, nxt, f, set, nRep);
-  cta.sync();
-  if (cta.tid == 0) {
-    gs[GX_NREP] = 0;
-    *(u64*)(w.base + c.lay.gxBest) = 0;
-  }
-  if (f.hCount && cta.tid == 0) *f.hCount = sc[SC_NH];
+  const int nFin = gxSc(w, set ^ 1)[GX_NH];
+  if (cta.tid == 0) *(u64*)(w.base + c.lay.gxBest) = 0;
+  if (f.hCount && cta.tid == 0) *f.hCount = nFin;
+  return nFin;
 }
 
 // once per CTA: tables that persist over its utterances
 FLT_DEV void gxInitWorkspace(const Cta& cta, const DecCfg& c, const Ws& w) {
   for (int i = cta.tid; i < c.capH; i += cta.nthr) w.mh()[i] = -1;
   for (int i = cta.tid; i < kGxBins; i += cta.nthr) w.hist()[i] = 0;
-  for (int i = cta.tid; i < 2 * ((c.K + 31) >> 5); i += cta.nthr) gxBits(w, 0)[i] = 0;
   if (cta.tid == 0) {
     for (int s = 0; s < 2; ++s)
       for (int k = 0; k < GX_SET; ++k) gxSc(w, s)[k] = 0;
@@ -999,8 +1042,9 @@ FLT_DEV void gxBeginUtterance(const Cta& cta, const DecCfg& c, const Ws& w, int 
   if (cta.tid == 0) {
     for (int s = 0; s < 2; ++s)
       for (int k = 0; k < GX_SET; ++k) gxSc(w, s)[k] = 0;
+    gxSc(w, 0)[GX_NH] = nH;
+    *(u64*)(w.base + c.lay.gxBest) = 0;
   }
-  for (int i = cta.tid; i < 2 * ((c.K + 31) >> 5); i += cta.nthr) gxBits(w, 0)[i] = 0;
   cta.sync();
   gxRebuild(cta, c, w, 0, nH);
 }
@@ -1049,7 +1093,8 @@ FLT_DEV void gxDecodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, ch
     if (a.streamBeam && a.streamRestore) streamRestoreBeam(cta, c, w, a);
     else if (cta.tid == 0) seedUtterance(c, w, a, b);
     cta.sync();
-    gxBeginUtterance(cta, c, w, w.sc()[SC_NH]);
+    int nHcur = w.sc()[SC_NH];
+    gxBeginUtterance(cta, c, w, nHcur);
     GxCarry g = gxCarryInit();
     const long long row0 = (long long)b * a.T;
     if (len > 0) gxLoadListDirect<LEX>(cta, c, w, a, row0, 0);
@@ -1108,7 +1153,7 @@ FLT_DEV void gxDecodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, ch
           asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + off));
       }
 #endif
-      gxFrameStep<LEX>(cta, c, w, set, f, a.status + b, a.stats, g);
+      nHcur = gxFrameStep<LEX>(cta, c, w, set, f, a.status + b, a.stats, g);
       if (pf) {
         const int nb = (t + 1) & 1;
 #if FLT_DEVICE_BUILD
@@ -1135,21 +1180,22 @@ FLT_DEV void gxDecodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, ch
         gxLoadListDirect<LEX>(cta, c, w, a, row + 1, nb);
 #endif
       }
-      if (w.sc()[SC_NH] == 0) break;
+      if (nHcur == 0) break; // the beam died; `set` still names the last beam that was read
       set ^= 1;
       cta.sync();
     }
     if (a.streamBeam && a.streamNoFinish) { // decodeStep chunk: keep the beam for the next launch
       cta.sync();
+      if (cta.tid == 0) w.sc()[SC_NH] = nHcur;
+      cta.sync();
       streamSaveBeam(cta, c, w, a, set);
       continue;
     }
     int nFin = 0;
-    if (w.sc()[SC_NH] != 0) {
+    if (nHcur != 0) {
       const FrameIn f = finishFrameIn(c, a, b, len);
-      gxFinish<LEX>(cta, c, w, set, f);
+      nFin = gxFinish<LEX>(cta, c, w, set, f);
       set ^= 1;
-      nFin = w.sc()[SC_NH];
     }
     cta.sync();
     writeFinals(cta, c, w, a, b, set, nFin);

@@ -692,8 +692,8 @@ void planFor(flt_decoder& d, int N) {
                             : (long long)(c.wideRanked ? d.wideOffHost[K] : 0) + 3LL * K + budget0 * d.capBoost;
   if (c.full && !c.prune2) capC = 3LL * K + std::min(fullCells, budget0 * d.capBoost);
   if (c.gx) {
-    // the guess aims at 1.25 K .. 2.5 K merge groups; duplicates of a group (members of one row) come on top
-    capC = getenv("FLT_TEST_CAP") ? std::max<long long>(K + 16, budget0) * d.capBoost : (3LL * K + 128) * d.capBoost;
+    // the guess aims at 1.5 K .. 3 K merge groups; duplicates of a group (members of one row) come on top
+    capC = getenv("FLT_TEST_CAP") ? std::max<long long>(K + 16, budget0) * d.capBoost : (4LL * K + 128) * d.capBoost;
     c.capChunks = (int)std::min<long long>((4LL * K + 64) * d.capBoost, 1 << 20);
   }
   capC = (capC + 63) / 64 * 64;

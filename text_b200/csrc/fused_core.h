@@ -501,6 +501,7 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
     GxCarry gcarry = gxCarryInit();
     cta.sync();
     if (c.gx) gxBeginUtterance(cta, c, w, 1);
+    int gxAlive = 1; // hypotheses in the current beam (beam_gx.h); 0 = the beam died, lists are still consumed
     for (int t = 0; t < len; ++t, ++g) {
       const int slot = (int)(g & (kFusedRing - 1)); // ring slot = running row count mod ring, on both sides
       LfPhaseClock oc; // time spent waiting for the producers
@@ -517,18 +518,29 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
       oc.mark(5);
       FrameIn f = fusedFrameIn(c, a, v, b, t, slot);
       f.eNext = t + 1 < len ? f.e + c.N : nullptr;
-      if (c.gx) gxFrameStep<false>(cta, c, w, curIdx, f, a.status + b, a.stats, gcarry);
-      else lfFrameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.stats, carry); // ends with a barrier
-      curIdx ^= 1;
+      if (c.gx) {
+        if (gxAlive) {
+          gxAlive = gxFrameStep<false>(cta, c, w, curIdx, f, a.status + b, a.stats, gcarry);
+          if (gxAlive) curIdx ^= 1;
+        }
+      } else {
+        lfFrameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.stats, carry); // ends with a barrier
+        curIdx ^= 1;
+      }
 #if FLT_DEVICE_BUILD
       if (cta.tid == 0) mbarArrive(v.mbar(MB_LIST_FREE0 + slot));
 #endif
     }
     int nFin = 0;
-    if (w.sc()[SC_NH] != 0) {
+    if (c.gx) {
+      if (gxAlive) {
+        const FrameIn f = finishFrameIn(c, a, b, len);
+        nFin = gxFinish<false>(cta, c, w, curIdx, f);
+        curIdx ^= 1;
+      }
+    } else if (w.sc()[SC_NH] != 0) {
       const FrameIn f = finishFrameIn(c, a, b, len);
-      if (c.gx) gxFinish<false>(cta, c, w, curIdx, f);
-      else lfFinish(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f);
+      lfFinish(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f);
       curIdx ^= 1;
       nFin = w.sc()[SC_NH];
     }
