@@ -9,7 +9,9 @@
  *
  * Threading: a decoder handle owns one CUDA stream and is single-owner, like the reference's
  * decoders (decoder/Utils.h:60-63). Tries and LMs are immutable once a decoder is created from
- * them and may be shared by several decoders.
+ * them and may be shared by several decoders, also across CUDA devices and threads: the flattened
+ * tables are built once per device, under a lock. Every call makes the decoder's device current for
+ * its own duration and restores the caller's current device before it returns.
  */
 #ifndef FLT_DECODER_H
 #define FLT_DECODER_H
@@ -107,7 +109,10 @@ int flt_decoder_set_nbest(flt_decoder* dec, int32_t nbest);
  * until flt_nbest_copy. B = 1 is the reference's single-utterance decode(). */
 int flt_decode_batch(flt_decoder* dec, const float* emissions, int32_t B, int32_t T, int32_t N,
                      const int32_t* lengths);
-/* Same, device emissions, enqueue only (no host synchronisation): for timing on a stream. */
+/* Same, device emissions, enqueue only (no host synchronisation): for timing on a stream. A frame whose
+ * (data-dependent) candidate count exceeds the planned capacity cannot be redone here: the error
+ * ("candidate capacity exceeded") surfaces at flt_nbest_copy, which also grows the capacity, so calling
+ * flt_decode_batch_async + flt_nbest_copy again succeeds. flt_decode_batch does that retry itself. */
 int flt_decode_batch_async(flt_decoder* dec, const float* dEmissions, int32_t B, int32_t T,
                            int32_t N, const int32_t* dLengths);
 int flt_decoder_synchronize(flt_decoder* dec);
@@ -118,8 +123,9 @@ void* flt_decoder_stream(flt_decoder* dec);
  * r < counts[b] (sorted by score, best first), tokens/words hold T+2 entries
  * (seed, T frames, finish record; -1 padded past lengths[b]+2):
  *   tokens[(b*nbest + r)*(T+2) + i], words[...], scores[(b*nbest + r)*3 + {0: score,
- *   1: emittingModelScore, 2: lmScore}]. nbest <= beamSize; host buffers. counts[b] is the
- * total number of final hypotheses (may exceed nbest). */
+ *   1: emittingModelScore, 2: lmScore}]. nbest <= the nbest setting the LAST BATCH was decoded with
+ * (flt_decoder_set_nbest calls made after that decode do not apply to it); host buffers. counts[b] is
+ * the total number of final hypotheses (may exceed nbest). */
 int flt_nbest_copy(flt_decoder* dec, int32_t nbest, int32_t* tokens, int32_t* words,
                    double* scores, int32_t* counts);
 

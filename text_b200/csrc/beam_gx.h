@@ -835,7 +835,7 @@ FLT_DEV int gxFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, int set, c
     }
     if (c.silScore < 0) bound += c.silScore; // keeps the bound valid if a counted cell is the sil one
   } else if (g.have == 2 && levelKnown) {
-    bound = g.cutPrev + level + g.D - 4.0;
+    bound = g.cutPrev + level + g.D - 0.75;
   }
   if (!(bound == bound)) bound = negInf();
   int want = LEX ? K + (K >> 1) + 32 : 2 * K + 16;

@@ -550,6 +550,7 @@ struct flt_decoder {
   rt::DevBuf topTok, topVal, thr, hPar, hTok, hWord, finScore, finCount, status, ws, outTok,
       outWord, dLengths, staging[2], dStats;
   int lastB = 0, lastT = 0, launches = 0;
+  int lastNbest = 0; // nbest the last batch's outTok / outWord rows were sized and strided with
   int capBoost = 1; // candidate-capacity multiplier, grown after an overflow
   bool useSmemFlag = false;
   std::vector<int> lastLengths;
@@ -661,8 +662,10 @@ void planFor(flt_decoder& d, int N) {
   t.fast = (N % 4 == 0) && N <= 4 * kFastVec * kThreads && want <= 256 && c.M <= 256;
   t.stage = !t.fast && (size_t)N * 4 <= 100 * 1024;
   // single-pass step with a guessed cut (beam_gx.h): max-merge, word-level LM; lexicon: CTC without unk
-  c.gx = !getenv("FLT_NO_GX") && !o.logAdd && K <= 4095 &&
-         (d.lexicon ? c.wideRanked != 0 : !c.full);
+  // (FLT_GX=1 / 0 forces it on / off where it applies)
+  const bool gxCan = !o.logAdd && K <= 4095 && (d.lexicon ? c.wideRanked != 0 : !c.full);
+  const bool gxAuto = false;
+  c.gx = gxCan && (getenv("FLT_GX") ? atoi(getenv("FLT_GX")) != 0 : gxAuto);
   // lexicon-free fast step (beam_lf.h): ZeroLM max-merge, candidate indices fit 16 bits
   c.lfFast = !c.gx && !d.lexicon && !c.full && K <= 256 && !getenv("FLT_NO_LF");
   c.lfBins = std::min(1024, std::max(256, nextPow2(4 * K)));
@@ -987,6 +990,7 @@ void prepareBatch(flt_decoder& d, int B, int T, int N) {
   d.outWord.reserve(sizeof(int) * (size_t)std::max(B, 1) * d.nbest * (T + 2));
   d.lastB = B;
   d.lastT = T;
+  d.lastNbest = d.nbest;
   d.launches = 0;
   if (d.counters) {
     d.dStats.reserve(sizeof(unsigned long long) * 32);
@@ -1025,27 +1029,45 @@ int guarded(F&& f) {
   }
 }
 
-void requireDevice(int device) {
+// Makes `device` current for the duration of one C-ABI call and restores the caller's current device
+// afterwards (a decoder is bound to the device it was created for; the caller's context is not ours to
+// change).
+struct DeviceScope {
+  int prev = -1;
+  explicit DeviceScope(int device) {
 #if FLT_DEVICE_BUILD
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess || n == 0) {
-    cudaGetLastError();
-    throw FltError(FLT_ERR_CUDA, "no CUDA device available: the decoder has no CPU path");
-  }
-  if (device < 0 || device >= n) throw FltError(FLT_ERR_INVALID, "bad CUDA device ordinal");
-  FLT_RT_TRY(cudaSetDevice(device));
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+      cudaGetLastError();
+      throw FltError(FLT_ERR_CUDA, "no CUDA device available: the decoder has no CPU path");
+    }
+    if (device < 0 || device >= n) throw FltError(FLT_ERR_INVALID, "bad CUDA device ordinal");
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      cudaGetLastError();
+      prev = -1;
+    }
+    if (prev != device) FLT_RT_TRY(cudaSetDevice(device));
+    else prev = -1; // nothing to restore
 #else
-  (void)device;
+    (void)device;
 #endif
-}
+  }
+  ~DeviceScope() {
+#if FLT_DEVICE_BUILD
+    if (prev >= 0) cudaSetDevice(prev);
+#endif
+  }
+  DeviceScope(const DeviceScope&) = delete;
+  DeviceScope& operator=(const DeviceScope&) = delete;
+};
 
 flt_decoder* makeDecoder(int lexicon, const flt_options* opt, const flt_trie* trie, const flt_lm* lm,
                          int sil, int blank, int unk, const float* trans, long long nTrans,
                          int isLmToken, int device) {
   if (!opt || !lm) throw FltError(FLT_ERR_INVALID, "null options or LM");
   if (lexicon && !trie) throw FltError(FLT_ERR_INVALID, "null trie");
-  requireDevice(device);
+  DeviceScope dev(device);
   std::unique_ptr<flt_decoder> d(new flt_decoder);
   d->lexicon = lexicon;
   d->opt = *opt;
@@ -1428,7 +1450,7 @@ int flt_decode_batch_async(flt_decoder* dec, const float* dEmissions, int32_t B,
                            int32_t N, const int32_t* dLengths) {
   return guarded([&] {
     if (!dec || (!dEmissions && (long long)B * T > 0)) throw FltError(FLT_ERR_INVALID, "null argument");
-    requireDevice(dec->device);
+    DeviceScope dev(dec->device);
     prepareBatch(*dec, B, T, N);
     dec->haveLengths = false;
     decodeDevice(*dec, dEmissions, B, T, N, dLengths);
@@ -1439,7 +1461,7 @@ int flt_decode_batch(flt_decoder* dec, const float* emissions, int32_t B, int32_
                      const int32_t* lengths) {
   return guarded([&] {
     if (!dec || (!emissions && (long long)B * T > 0)) throw FltError(FLT_ERR_INVALID, "null argument");
-    requireDevice(dec->device);
+    DeviceScope dev(dec->device);
     flt_decoder& d = *dec;
     for (int attempt = 0;; ++attempt) {
       prepareBatch(d, B, T, N);
@@ -1460,6 +1482,9 @@ int flt_decode_batch(flt_decoder* dec, const float* emissions, int32_t B, int32_
         // overlaps the kernels of slice i
         const long long perUtt = (long long)T * N * sizeof(float);
         long long slice = std::max<long long>(1, (1LL << 30) / std::max<long long>(perUtt, 1));
+        // ... and by the same history / list budget as decodeDevice (small N with a large beam)
+        const long long perUttHist = (long long)(T + 2) * d.cfg.K * 12 + (long long)T * d.cfg.M * 8 + 64;
+        slice = std::min<long long>(slice, std::max<long long>(1, (8LL << 30) / perUttHist));
         slice = std::min<long long>(slice, B);
         for (int i = 0; i < 2; ++i) d.staging[i].reserve((size_t)(slice * perUtt));
         int k = 0;
@@ -1505,19 +1530,33 @@ int flt_nbest_copy(flt_decoder* dec, int32_t nbest, int32_t* tokens, int32_t* wo
   return guarded([&] {
     if (!dec) throw FltError(FLT_ERR_INVALID, "null decoder");
     flt_decoder& d = *dec;
-    if (nbest < 1 || nbest > d.nbest) throw FltError(FLT_ERR_INVALID, "nbest exceeds the decoder's nbest setting");
+    DeviceScope dev(d.device);
     const int B = d.lastB, T = d.lastT, K = d.cfg.K;
+    // the rows of the last batch were sized and strided with the nbest setting of THAT decode, whatever
+    // flt_decoder_set_nbest has been told since
+    const int NB = d.lastNbest;
     if (B == 0) return;
-    checkStatus(d);
+    if (nbest < 1 || nbest > NB)
+      throw FltError(FLT_ERR_INVALID, "nbest exceeds the nbest setting the last batch was decoded with");
+    try {
+      checkStatus(d);
+    } catch (const FltError& e) {
+      // flt_decode_batch_async cannot redo the batch itself: grow the capacity for the caller's retry
+      if (std::string(e.what()) == "candidate capacity exceeded" && d.capBoost < 4096) {
+        d.capBoost *= 4;
+        d.planN = -1;
+      }
+      throw;
+    }
     const size_t L = (size_t)T + 2;
-    if (nbest == d.nbest) {
+    if (nbest == NB) {
       if (tokens) rt::d2h(tokens, d.outTok.p, sizeof(int) * B * nbest * L, d.stream);
       if (words) rt::d2h(words, d.outWord.p, sizeof(int) * B * nbest * L, d.stream);
     } else {
       for (int b = 0; b < B; ++b) {
-        if (tokens) rt::d2h(tokens + (size_t)b * nbest * L, d.outTok.as<int>() + (size_t)b * d.nbest * L,
+        if (tokens) rt::d2h(tokens + (size_t)b * nbest * L, d.outTok.as<int>() + (size_t)b * NB * L,
                             sizeof(int) * nbest * L, d.stream);
-        if (words) rt::d2h(words + (size_t)b * nbest * L, d.outWord.as<int>() + (size_t)b * d.nbest * L,
+        if (words) rt::d2h(words + (size_t)b * nbest * L, d.outWord.as<int>() + (size_t)b * NB * L,
                            sizeof(int) * nbest * L, d.stream);
       }
     }
@@ -1549,7 +1588,7 @@ int flt_nbest_device_ptrs(flt_decoder* dec, int32_t** tokens, int32_t** words, d
 int flt_stream_begin(flt_decoder* dec, int32_t N) {
   return guarded([&] {
     if (!dec) throw FltError(FLT_ERR_INVALID, "null decoder");
-    requireDevice(dec->device);
+    DeviceScope dev(dec->device);
     planFor(*dec, N);
     auto& on = dec->on;
     on = flt_decoder::Online{};
@@ -1563,14 +1602,14 @@ int flt_stream_step(flt_decoder* dec, const float* emissions, int32_t T, int32_t
     requireOnline(dec);
     if (N != dec->on.N) throw FltError(FLT_ERR_INVALID, "N differs from flt_stream_begin");
     if (T < 0 || (!emissions && T > 0)) throw FltError(FLT_ERR_INVALID, "bad chunk");
-    requireDevice(dec->device);
+    DeviceScope dev(dec->device);
     if (T > 0) runStream(*dec, emissions, T, N, false);
   });
 }
 int flt_stream_end(flt_decoder* dec) {
   return guarded([&] {
     requireOnline(dec);
-    requireDevice(dec->device);
+    DeviceScope dev(dec->device);
     runStream(*dec, nullptr, 0, dec->on.N, true);
   });
 }
