@@ -68,3 +68,28 @@ def test_topm_rows(kind, N, M, offset):
     etok, eval_ = expected(rows, M)
     np.testing.assert_array_equal(tok.cpu().numpy(), etok)
     np.testing.assert_array_equal(val.cpu().numpy(), eval_)
+
+
+@pytest.mark.parametrize("kind,N,M,R", [("logsoftmax", 2048, 53, 5000), ("gauss", 1000, 205, 3000),
+                                        ("few_values", 1024, 40, 2500), ("neg_inf", 4096, 100, 2000)])
+def test_topm_many_rows(kind, N, M, R):
+    """More rows than resident CTAs: every CTA of the streaming kernel goes through many rows with its stage,
+    its mbarrier phase and the running guess of the select bound carried from row to row."""
+    import torch
+
+    from text_b200 import capi
+
+    api = capi.Api()
+    rng = np.random.default_rng(N + M + R)
+    rows = make_rows(kind, R, N, rng)
+    # the level of the rows drifts and jumps, so that guesses miss and the exact modes engage
+    rows += (np.sin(np.arange(R) / 7.0) * 3.0 + (np.arange(R) % 97 == 0) * 20.0).astype(np.float32)[:, None]
+    dev = torch.from_numpy(rows).cuda()
+    tok = torch.full((R, M), -7, dtype=torch.int32, device="cuda")
+    val = torch.zeros((R, M), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    api.topm_rows(dev.data_ptr(), R, N, M, tok.data_ptr(), val.data_ptr(), None)
+    torch.cuda.synchronize()
+    etok, eval_ = expected(rows, M)
+    np.testing.assert_array_equal(tok.cpu().numpy(), etok)
+    np.testing.assert_array_equal(val.cpu().numpy(), eval_)

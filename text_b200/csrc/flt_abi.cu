@@ -24,6 +24,7 @@
 #include "beam_gx.h"
 #include "topm_core.h"
 #include "fused_core.h"
+#include "topm_stream.h"
 
 using namespace flt;
 
@@ -33,6 +34,12 @@ __global__ void __launch_bounds__(256, 3) flt_k_topm(TopMCfg c, TopMArgs a) {
   extern __shared__ __align__(128) char smem[];
   Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
   topmCta(cta, c, a, smem);
+}
+// streaming select (topm_stream.h): one TMA-staged row per 128-thread CTA, four CTAs per SM
+__global__ void __launch_bounds__(kStreamThreads, 4) flt_k_topm_stream(TopMCfg c, StreamLay sl, TopMArgs a) {
+  extern __shared__ __align__(128) char smem[];
+  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
+  topmStreamCta(cta, c, sl, a, smem);
 }
 // workspace in shared memory (the fast path: every access is an LDS/STS with constant-bank offsets)
 __global__ void __launch_bounds__(256) flt_k_decode(DecCfg c, BatchArgs a) {
@@ -137,6 +144,49 @@ void launchTopM(const TopMCfg& c, const TopMArgs& a, int grid, size_t smem, rt::
   }
   (void)s;
 #endif
+}
+void launchTopMStream(const TopMCfg& c, const StreamLay& sl, const TopMArgs& a, int grid, rt::Stream s) {
+#if FLT_DEVICE_BUILD
+  flt_k_topm_stream<<<grid, kStreamThreads, sl.total, s>>>(c, sl, a);
+  FLT_RT_TRY(cudaGetLastError());
+#else
+  std::vector<char> sm(sl.total + 128, (char)0x5A);
+  for (int b = 0; b < grid; ++b) {
+    Cta cta{0, 1, b, grid};
+    topmStreamCta(cta, c, sl, a, sm.data());
+  }
+  (void)s;
+#endif
+}
+// plan of the streaming select for a row length / list length / bias; false if the shape does not fit it
+bool planStream(int N, int M, int bst, const float* dBias, float biasMax, TopMCfg& t, StreamLay& sl) {
+  const bool restricted = bst < N;
+  const int want = restricted ? bst : M;
+  if (N % 4 != 0 || N < 64 || want > 340 || M > 2048 || (dBias && restricted) || getenv("FLT_NO_STREAM")) return false;
+  t = TopMCfg{};
+  t.N = N;
+  t.M = M;
+  t.bst = restricted ? bst : N;
+  t.bias = dBias;
+  t.biasMax = biasMax;
+  t.P = std::max(kStreamThreads, nextPow2(want));
+  t.capS = kStreamCap;
+  t.extra = 2 * kProdBins;
+  t.fast = 1;
+  t.stage = 0;
+  size_t off = 0;
+  auto take = [&](size_t bytes, size_t align) {
+    off = (off + align - 1) / align * align;
+    const size_t o = off;
+    off += bytes;
+    return (int)o;
+  };
+  TopMSmem ts;
+  sl.prod = take(carveTopM(nullptr, t, ts), 16);
+  sl.row = take((size_t)N * 4, 128);
+  sl.mbar = take(8, 8);
+  sl.total = (int)((off + 127) / 128 * 128);
+  return sl.total <= 200 * 1024;
 }
 void launchDecode(const DecCfg& c, const BatchArgs& a, int grid, size_t smem, rt::Stream s, int threads) {
 #if FLT_DEVICE_BUILD
@@ -540,6 +590,10 @@ struct flt_decoder {
   bool fused = false; // select + step in one kernel (fused_core.h)
   TopMCfg ftcfg{};
   FuseLay flay{};
+  bool streamSel = false; // token-beam select by the streaming kernel (topm_stream.h)
+  TopMCfg stcfg{};
+  StreamLay slay{};
+  int streamGridMax = 1;
   int fusedGridMax = 1;
   size_t wsBytes = 0, topmSmem = 0;
   int gridMax = 1, topmGridMax = 1;
@@ -753,6 +807,13 @@ void planFor(flt_decoder& d, int N) {
       bias[kv.first] = (float)(o.lmWeight * (double)tr.nodes[kv.second].maxScore);
     }
     t.bias = upload(d.dBias, bias, s);
+    t.biasMax = 0.0f;
+    bool any = false;
+    for (float b : bias)
+      if (!isNegInf(b)) {
+        t.biasMax = any ? std::max(t.biasMax, b) : b;
+        any = true;
+      }
   }
   rt::sync(s);
 
@@ -762,6 +823,7 @@ void planFor(flt_decoder& d, int N) {
   d.topmSmem = (carveTopM(nullptr, t, ts) + 255) / 256 * 256;
   d.cfg = c;
   d.tcfg = t;
+  d.streamSel = d.needTopM && planStream(N, c.M, t.bst, t.bias, t.biasMax, d.stcfg, d.slay);
   // fused select + step: the row stage, the producer scratch and the consumer workspace share the
   // CTA's shared memory; two CTAs per SM need <= 113 KB each
   d.fused = false;
@@ -807,6 +869,17 @@ void planFor(flt_decoder& d, int N) {
   int occ = 1;
   FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, flt_k_topm, kThreads, d.topmSmem));
   d.topmGridMax = std::max(1, occ) * d.numSMs;
+  if (d.streamSel) {
+    if ((size_t)d.slay.total > smemMax) {
+      d.streamSel = false;
+    } else {
+      FLT_RT_TRY(cudaFuncSetAttribute(flt_k_topm_stream, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      std::max(d.slay.total, 48 * 1024)));
+      int occS = 1;
+      FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, flt_k_topm_stream, kStreamThreads, d.slay.total));
+      d.streamGridMax = std::max(1, occS) * d.numSMs;
+    }
+  }
   // <= 110 KB keeps two CTAs per SM; FLT_SMEM_KB raises the limit (one CTA per SM) for experiments
   // (the single-pass step keeps large beams on chip with one CTA per SM rather than spilling to a slab)
   const size_t smemLimit = getenv("FLT_SMEM_KB") ? (size_t)atoi(getenv("FLT_SMEM_KB")) * 1024
@@ -848,16 +921,17 @@ void planFor(flt_decoder& d, int N) {
 #else
   d.gridMax = 4;
   d.topmGridMax = 4;
+  d.streamGridMax = 3;
   d.fusedGridMax = 3;
   d.useSmemFlag = true;
 #endif
   d.planN = N;
   if (getenv("FLT_DBG_PLAN"))
     fprintf(stderr, "[flt plan] lexicon=%d K=%d N=%d M=%d gx=%d lfFast=%d fused=%d wide=%d prune2=%d threads=%d capC=%d "
-                    "capChunks=%d ws=%zu B (%s) fusedSmem=%d grid<=%d\n",
+                    "capChunks=%d ws=%zu B (%s) fusedSmem=%d grid<=%d streamSelect=%d (%d B, grid<=%d)\n",
             c.lexicon, c.K, N, c.M, c.gx, c.lfFast, (int)d.fused, c.wide, c.prune2, d.threads, c.capC, c.capChunks,
             d.wsBytes, d.useSmemFlag ? "shared" : "global slab", d.fused ? d.flay.total : 0,
-            d.fused ? d.fusedGridMax : d.gridMax);
+            d.fused ? d.fusedGridMax : d.gridMax, (int)d.streamSel, d.streamSel ? d.slay.total : 0, d.streamGridMax);
 }
 
 } // namespace
@@ -915,11 +989,13 @@ void runChunk(flt_decoder& d, const float* dEmis, int Bc, int T, int N, const in
     ta.outVal = d.topVal.as<float>();
     ta.outThr = c.setAll ? nullptr : d.thr.as<float>();
     TopMCfg tc = d.tcfg;
-    if ((reinterpret_cast<uintptr_t>(dEmis) & 15) != 0) tc.fast = 0;
+    const bool aligned = (reinterpret_cast<uintptr_t>(dEmis) & 15) == 0;
+    if (!aligned) tc.fast = 0;
     const int grid = (int)std::min<long long>(rows, d.topmGridMax * 8LL);
     if (rows > 0) {
       KernelTimer kt(d, 0);
-      launchTopM(tc, ta, grid, d.topmSmem, s);
+      if (d.streamSel && aligned) launchTopMStream(d.stcfg, d.slay, ta, (int)std::min<long long>(rows, d.streamGridMax), s);
+      else launchTopM(tc, ta, grid, d.topmSmem, s);
       d.launches++;
     }
     a.topTok = ta.outTok;
@@ -1135,8 +1211,10 @@ bool runStreamOnce(flt_decoder& d, const float* emis, int T, int N, bool finish)
     ta.outVal = d.topVal.as<float>();
     ta.outThr = c.setAll ? nullptr : d.thr.as<float>();
     TopMCfg tc = d.tcfg;
-    if ((reinterpret_cast<uintptr_t>(dEmis) & 15) != 0) tc.fast = 0;
-    launchTopM(tc, ta, std::min(T, d.topmGridMax), d.topmSmem, s);
+    const bool aligned = (reinterpret_cast<uintptr_t>(dEmis) & 15) == 0;
+    if (!aligned) tc.fast = 0;
+    if (d.streamSel && aligned) launchTopMStream(d.stcfg, d.slay, ta, std::min(T, d.streamGridMax), s);
+    else launchTopM(tc, ta, std::min(T, d.topmGridMax), d.topmSmem, s);
     a.topTok = ta.outTok;
     a.topVal = ta.outVal;
     a.thrVal = ta.outThr;
@@ -1742,6 +1820,30 @@ int flt_topm_rows(const float* dEmissions, int64_t rows, int32_t N, int32_t M, i
                   float* dVal, void* stream) {
   return guarded([&] {
     if (M < 1 || M > 2048 || M > N) throw FltError(FLT_ERR_INVALID, "need 1 <= M <= min(N, 2048)");
+    {
+      TopMCfg st;
+      StreamLay sl;
+      if ((reinterpret_cast<uintptr_t>(dEmissions) & 15) == 0 && planStream(N, M, N, nullptr, 0.0f, st, sl)) {
+        TopMArgs sa{};
+        sa.emis = dEmissions;
+        sa.rows = rows;
+        sa.outTok = dTok;
+        sa.outVal = dVal;
+        sa.outThr = nullptr;
+        int gridS = 3;
+#if FLT_DEVICE_BUILD
+        int dev = 0, sms = 148, occ = 1;
+        FLT_RT_TRY(cudaGetDevice(&dev));
+        FLT_RT_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        FLT_RT_TRY(cudaFuncSetAttribute(flt_k_topm_stream, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        std::max(sl.total, 48 * 1024)));
+        FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, flt_k_topm_stream, kStreamThreads, sl.total));
+        gridS = std::max(1, occ) * sms;
+#endif
+        if (rows > 0) launchTopMStream(st, sl, sa, (int)std::min<int64_t>(rows, gridS), (rt::Stream)stream);
+        return;
+      }
+    }
     TopMCfg t{};
     t.N = N;
     t.M = M;

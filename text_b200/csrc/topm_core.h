@@ -27,6 +27,7 @@ struct TopMCfg {
   int M;          // list entries written per row
   int bst;        // token-set size (>= N: unrestricted)
   const float* bias; // [N] or null
+  float biasMax;     // largest finite bias (bound of the streaming kernel's first filter)
   int P;          // chunks (pow2, >= nthr, >= wanted)
   int capS;       // survivor capacity (pow2)
   int stage;      // 1 = stage the row in shared memory
