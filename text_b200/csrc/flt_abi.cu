@@ -162,7 +162,7 @@ void launchTopMStream(const TopMCfg& c, const StreamLay& sl, const TopMArgs& a, 
 bool planStream(int N, int M, int bst, const float* dBias, float biasMax, TopMCfg& t, StreamLay& sl) {
   const bool restricted = bst < N;
   const int want = restricted ? bst : M;
-  if (N % 4 != 0 || N < 64 || want > 340 || M > 2048 || (dBias && restricted) || getenv("FLT_NO_STREAM")) return false;
+  if (N % 4 != 0 || N < 64 || want > (getenv("FLT_STREAM_WANT") ? atoi(getenv("FLT_STREAM_WANT")) : 128) || M > 2048 || (dBias && restricted) || getenv("FLT_NO_STREAM")) return false;
   t = TopMCfg{};
   t.N = N;
   t.M = M;

@@ -135,17 +135,31 @@ struct ProdGuess {
 
 #if FLT_DEVICE_BUILD
 // collect every element >= bound of the row at r4 (shared or global) into sv[] (unordered keys);
-// returns this thread's maximum
+// returns this thread's maximum. The scan itself is branch-free: a thread only notes WHICH of its
+// 16-byte vectors hold a survivor (one bit each) and comes back for those few afterwards — a warp
+// whose 32 lanes each test 4 elements would otherwise run the (rare per lane, common per warp)
+// survivor path on most iterations.
 FLT_DEV float prodFilter(const Cta& p, const TopMCfg& c, TopMSmem& s, const float4* r4, float bound,
                          unsigned long long* sv) {
   const int nvec = c.N >> 2;
   float top = bitsF32(0xFF800000u);
-#pragma unroll 4
-  for (int v = p.tid; v < nvec; v += p.nthr) {
-    const float4 x = r4[v];
-    const float mx = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
-    top = fmaxf(top, mx);
-    if (mx >= bound) { // rare: ~1.5 x want elements of the row
+  for (int v0 = p.tid; v0 < nvec; v0 += 32 * p.nthr) {
+    unsigned hits = 0;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const int v = v0 + k * p.nthr;
+      if (v < nvec) {
+        const float4 x = r4[v];
+        const float mx = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+        top = fmaxf(top, mx);
+        hits |= (mx >= bound ? 1u : 0u) << k;
+      }
+    }
+    while (hits) {
+      const int k = __ffs(hits) - 1;
+      hits &= hits - 1;
+      const int v = v0 + k * p.nthr;
+      const float4 x = r4[v];
       const unsigned m4 = (x.x >= bound ? 1u : 0u) | (x.y >= bound ? 2u : 0u) | (x.z >= bound ? 4u : 0u) |
                           (x.w >= bound ? 8u : 0u);
       int pos = atomAdd(&s.cnt[0], __popc(m4));

@@ -161,10 +161,12 @@ FLT_DEV void streamRow(const Cta& p, const TopMCfg& c, TopMSmem& s, ProdGuess& p
       miss = miss || !okCount(ns) || (biased && ns < (want < N ? want : N) && bound > bitsF32(0xFF7FFFFFu));
       pg.missRate = 0.9f * pg.missRate + (miss ? 0.1f : 0.0f);
       if (miss) {
+        // too many survivors: guess closer to the want-th value next time; too few: further below it
+        pg.margin = fminf(fmaxf(pg.margin * (ns > want ? 0.7f : 1.4f), 0.02f), 4.0f);
         p.sync(); // everyone has read cnt[0]
         if (canExact) exactSelect((const float4*)grow, true); // exact two-pass select of this row from L2
         else generic = true;
-        if (pg.missRate > 0.2f) { // stop guessing for a while; the spell doubles each time (<= 4096 rows)
+        if (pg.missRate > 0.2f && canExact) { // stop guessing for a while; the spell doubles each time (<= 4096 rows)
           pg.exactRows = pg.exactSpell;
           pg.exactSpell = pg.exactSpell < 4096 ? pg.exactSpell * 2 : 4096;
           pg.missRate = 0.0f;
@@ -257,8 +259,11 @@ FLT_DEV void streamRow(const Cta& p, const TopMCfg& c, TopMSmem& s, ProdGuess& p
       if (p.tid == 0) s.cnt[0] = 0;
       // next row's guess: below this row's want-th value by a margin that tracks the survivor count
       const float wth = bitsF32((uint32_t)s.cnt[1]);
-      if (ns > 2 * want + want / 2) pg.margin *= 0.85f;
-      else if (ns < want + want / 2) pg.margin *= 1.25f;
+      // (aim between 1.5 x and 2.5 x want survivors, and well inside the survivor capacity)
+      const int hiT = 2 * want + want / 2 < (3 * c.capS) / 4 ? 2 * want + want / 2 : (3 * c.capS) / 4;
+      const int loT = want + want / 2 < hiT - want / 4 ? want + want / 2 : hiT - want / 4;
+      if (ns > hiT) pg.margin *= 0.85f;
+      else if (ns < loT) pg.margin *= 1.25f;
       pg.margin = fminf(fmaxf(pg.margin, 0.02f), 4.0f);
       pg.g = wth - pg.margin * (top - wth);
       p.sync();
