@@ -69,6 +69,10 @@ int flt_trie_smear(flt_trie* trie, int32_t mode);
 int flt_trie_search(const flt_trie* trie, const int32_t* indices, int32_t n, int32_t* found,
                     float* maxScore, int32_t* nLabels, int32_t* labels6, float* scores6);
 int flt_trie_num_nodes(const flt_trie* trie, int64_t* out);
+/* TrieNode::maxScore (decoder/Trie.h:50) of every node, in the order the nodes were created by
+ * flt_trie_insert (node 0 = the root): lets a host-side mirror of the node tree (TrieNode::children,
+ * decoder/Trie.h:39-54) take the smeared scores over after flt_trie_smear. n = flt_trie_num_nodes. */
+int flt_trie_max_scores(const flt_trie* trie, float* out, int64_t n);
 void flt_trie_destroy(flt_trie* trie);
 
 /* ---- LM: decoder/lm/LM.h:52-85. Two device-resident models:

@@ -180,3 +180,28 @@ def test_cpp_mirror_program(tmp_path):
                words=np.array([g["words"] for g in got], np.int32).reshape(len(got), T + 2))
     assert_same_nbest(ra, res, 1e-4, what="C++ mirror")
     ba.close()
+
+
+def test_lexfree_decoder_pickle_and_getters():
+    """LexiconFreeDecoder pickling (bindings/python/flashlight/lib/text/_decoder.cpp:409-441): a decoder
+    without state and with a ZeroLM round-trips through pickle and decodes the same; one that has decoded,
+    or that carries another LM, refuses with the reference's messages."""
+    import pickle
+
+    from flashlight.lib.text.decoder import CriterionType, LexiconFreeDecoder, LexiconFreeDecoderOptions, ZeroLM
+
+    N, T = 32, 25
+    opts = LexiconFreeDecoderOptions(beam_size=8, beam_size_token=N, beam_threshold=1e9, lm_weight=0.0,
+                                     sil_score=-0.2, log_add=False, criterion_type=CriterionType.CTC)
+    dec = LexiconFreeDecoder(opts, ZeroLM(), 0, N - 1, [])
+    assert dec.get_sil_idx() == 0 and dec.get_blank_idx() == N - 1 and dec.get_transitions() == []
+    assert dec.get_options().beam_size == 8 and dec.get_options().sil_score == -0.2
+    twin = pickle.loads(pickle.dumps(dec))
+    assert twin.get_blank_idx() == N - 1 and twin.get_options().beam_size_token == N
+    em = np.ascontiguousarray(synth.emissions(1, T, N, seed=3)[0])
+    a, b = dec.decode(em.ctypes.data, T, N), twin.decode(em.ctypes.data, T, N)
+    assert len(a) == len(b) > 0
+    for x, y in zip(a, b):
+        assert x.tokens == y.tokens and x.score == y.score
+    with pytest.raises(RuntimeError, match="has state"):
+        pickle.dumps(dec)

@@ -1,0 +1,97 @@
+"""The N > 1 path on hardware: text_b200.shard.decode_sharded over NCCL with one process per GPU — rank 0
+scatters a host-originated batch, every rank decodes its block with the CUDA library through the C-ABI, the
+n-best blocks are gathered back to rank 0 straight from the decoders' device buffers — must give, bit for bit,
+what one GPU decoding the whole batch gives (utterances are independent, nothing else is
+exchanged). Needs two GPUs on the box (`gpurun --gpus 2`); on a one-GPU box the test is skipped — the same
+functions are covered there with gloo and a stub decode (tests/test_shard_gloo.py), and bench.py checks the
+gathered result of its own multi-GPU e2e leg against every rank's local one."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, kind, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+
+    from cases import Built, spec_lexfree, spec_lexicon
+    from flt_backend import FltBackend
+    from text_b200 import shard, synth
+
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        N, T, B, K = 400, 60, 11, 30  # B not divisible by the world size: ragged blocks
+        if kind == "lexfree":
+            spec = spec_lexfree(N, K, N, 1e9)
+        else:
+            spec = spec_lexicon(N, K, N, synth.lexicon(3000, N, 2, 4, seed=7, exclude=(0, N - 1)), 25.0, word_score=0.3)
+        G = FltBackend("cuda")
+        G.api.device = rank
+        built = Built(G, spec)
+        api, dec = G.api, built.dec
+
+        def decode_local(block):
+            Bl = block.shape[0]
+            api.decode_batch_ptr(dec, block.data_ptr(), Bl, T, N)
+            api.synchronize(dec)
+            nb = api.nbest_device(dec, Bl, T, K, K)  # device tensors aliasing the decoder's buffers
+            return dict(tokens=nb["tokens"], words=nb["words"], scores=nb["scores"], counts=nb["counts"])
+
+        em = None
+        if rank == 0:
+            em = torch.from_numpy(synth.emissions(B, T, N, seed=5, sigma=2.0)).to(dev)
+        out = shard.decode_sharded(decode_local, em, (B, T, N), K, dev)
+        if rank == 0:
+            api.decode_batch_ptr(dec, em.data_ptr(), B, T, N)
+            full = api.nbest(dec, B, T, K)
+            ok = True
+            for b in range(B):
+                n = int(full["counts"][b])
+                ok = ok and int(out["counts"][b]) == n and n > 0
+                ok = ok and np.array_equal(out["tokens"][b, :n], full["tokens"][b, :n])
+                ok = ok and np.array_equal(out["words"][b, :n], full["words"][b, :n])
+                ok = ok and np.array_equal(out["scores"][b, :n], full["scores"][b, :n])
+            q.put(bool(ok))
+        built.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind", ["lexfree", "lexicon"])
+def test_nccl_sharded_decode_equals_one_gpu(kind):
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs on the box (run with gpurun --gpus 2)")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, kind, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True

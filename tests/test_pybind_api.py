@@ -132,3 +132,33 @@ def test_decoder_needs_cuda_and_device_lm(D):
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CUDA device"):
             D.LexiconFreeDecoder(opt, D.ZeroLM(), 0, 28, [])
+
+
+def test_trie_children_can_be_walked(D):
+    """TrieNode::children (decoder/Trie.h:39-54): the mirror keeps the reference's node tree, so code that
+    walks it from get_root() sees every inserted spelling, with labels, scores and smeared scores."""
+    trie = D.Trie(10, 0)
+    words = {(1, 2): (7, -1.0), (1, 2, 3): (8, -2.0), (1, 4): (9, -0.5), (5,): (3, -3.0)}
+    for sp, (label, score) in words.items():
+        trie.insert(list(sp), label, score)
+    trie.smear(D.SmearingMode.MAX)
+    root = trie.get_root()
+    assert sorted(root.children.keys()) == [1, 5]
+    found = {}
+
+    def walk(node, path):
+        for lab, sc in zip(node.labels, node.scores):
+            found[tuple(path)] = (lab, sc)
+        for tok, child in node.children.items():
+            assert child.idx == tok
+            walk(child, path + [tok])
+
+    walk(root, [])
+    assert found == {k: (v[0], v[1]) for k, v in words.items()}
+    n1 = root.children[1]
+    assert abs(n1.max_score - (-0.5)) < 1e-6 and abs(root.max_score - (-0.5)) < 1e-6
+    assert abs(n1.children[2].max_score - (-1.0)) < 1e-6
+    assert trie.search([1, 2, 3]).labels == [8] and trie.search([2]) is None
+    with pytest.raises(IndexError):
+        trie.insert([1, 99], 1, 0.0)
+    assert sorted(root.children[1].children.keys()) == [2, 4]  # nothing was added by the failed insert's tail

@@ -48,6 +48,7 @@ SYMBOLS = {
                                   C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                   C.POINTER(C.c_float)]),
     "flt_trie_num_nodes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "flt_trie_max_scores": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int64]),
     "flt_trie_destroy": (None, [C.c_void_p]),
     "flt_lm_zero_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "flt_lm_ngram_load_arpa": (C.c_int, [C.c_char_p, C.POINTER(C.c_char_p), C.c_int32,
@@ -161,6 +162,13 @@ class Api:
         n = C.c_int64()
         self._ck(self.lib.flt_trie_num_nodes(trie, C.byref(n)))
         return n.value
+
+    def trie_max_scores(self, trie):
+        """smeared score of every node, in creation order (node 0 = root)"""
+        n = self.trie_num_nodes(trie)
+        out = np.zeros(n, np.float32)
+        self._ck(self.lib.flt_trie_max_scores(trie, out.ctypes.data_as(C.POINTER(C.c_float)), n))
+        return out
 
     def trie_destroy(self, trie):
         self.lib.flt_trie_destroy(trie)

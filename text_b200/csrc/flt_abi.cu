@@ -363,16 +363,17 @@ struct flt_lm {
   int order = 0, vocab = 0, bos = -1, eos = -1;
   std::vector<F2> uni;
   std::vector<uint64_t> keys[kMaxOrder + 1];
+  std::vector<uint64_t> chk[kMaxOrder + 1];
   std::vector<F2> vals[kMaxOrder + 1];
   std::vector<int> usr2lm;
   LmDev host{}; // view over the host vectors (host-side scoring)
   float upper = 0.0f; // no word scores above this: best probability + the positive back-offs
   struct Image {
     LmDev dev{};
-    rt::DevBuf uni, usr, keys[kMaxOrder + 1], vals[kMaxOrder + 1];
+    rt::DevBuf uni, usr, keys[kMaxOrder + 1], chk[kMaxOrder + 1], vals[kMaxOrder + 1];
     ~Image() {
       uni.release(), usr.release();
-      for (int n = 0; n <= kMaxOrder; ++n) keys[n].release(), vals[n].release();
+      for (int n = 0; n <= kMaxOrder; ++n) keys[n].release(), chk[n].release(), vals[n].release();
     }
   };
   mutable std::mutex mu;
@@ -392,6 +393,7 @@ struct flt_lm {
     for (const F2& v : uni) best = std::max(best, v.x);
     for (int n = 2; n <= kMaxOrder; ++n) {
       host.keys[n] = keys[n].empty() ? nullptr : keys[n].data();
+      host.chk[n] = chk[n].empty() ? nullptr : chk[n].data();
       host.vals[n] = vals[n].empty() ? nullptr : vals[n].data();
       host.mask[n] = keys[n].empty() ? 0 : (uint32_t)keys[n].size() - 1;
       for (size_t i = 0; i < keys[n].size(); ++i)
@@ -423,6 +425,7 @@ struct flt_lm {
       for (int n = 2; n <= kMaxOrder; ++n) {
         if (keys[n].empty()) continue;
         im->dev.keys[n] = upload(im->keys[n], keys[n], s);
+        im->dev.chk[n] = upload(im->chk[n], chk[n], s);
         im->dev.vals[n] = upload(im->vals[n], vals[n], s);
       }
       rt::sync(s);
@@ -441,7 +444,7 @@ void loadArpa(const std::string& path, const char* const* usrWords, int nUsr, fl
   std::unordered_map<std::string, int> vocab;
   std::vector<long> counts(kMaxOrder + 2, 0);
   struct Entry {
-    uint64_t key;
+    uint64_t key, key2;
     F2 v;
   };
   std::vector<Entry> pending[kMaxOrder + 1];
@@ -504,13 +507,14 @@ void loadArpa(const std::string& path, const char* const* usrWords, int nUsr, fl
       }
     } else {
       // chain over the words in reversed order (tables.h)
-      uint64_t h = 0;
+      uint64_t h = 0, h2 = 0;
       for (int i = section; i >= 1; --i) {
         auto it = vocab.find(toks[i]);
         const int w = it == vocab.end() ? 0 : it->second;
         h = i == section ? ngramChainStart(w) : ngramChainExtend(h, w);
+        h2 = i == section ? ngramChain2Start(w) : ngramChain2Extend(h2, w);
       }
-      pending[section].push_back(Entry{ngramFinalKey(h), v});
+      pending[section].push_back(Entry{ngramFinalKey(h), h2, v});
     }
   }
   if (lm.order < 1 || lm.uni.empty()) throw FltError(FLT_ERR_RUNTIME, "[KenLM] LM loading failed: empty model");
@@ -525,12 +529,14 @@ void loadArpa(const std::string& path, const char* const* usrWords, int nUsr, fl
     size_t cap = 16;
     while (cap < pending[n].size() * 2) cap <<= 1;
     lm.keys[n].assign(cap, 0);
+    lm.chk[n].assign(cap, 0);
     lm.vals[n].assign(cap, F2{0, 0});
     const uint32_t mask = (uint32_t)cap - 1;
     for (const Entry& en : pending[n]) {
       uint32_t s = (uint32_t)(en.key >> 17) & mask;
-      while (lm.keys[n][s] != 0 && lm.keys[n][s] != en.key) s = (s + 1) & mask;
+      while (lm.keys[n][s] != 0 && !(lm.keys[n][s] == en.key && lm.chk[n][s] == en.key2)) s = (s + 1) & mask;
       lm.keys[n][s] = en.key; // a repeated n-gram keeps the last value, like a rebuilt table
+      lm.chk[n][s] = en.key2;
       lm.vals[n][s] = en.v;
     }
     std::vector<Entry>().swap(pending[n]);
@@ -558,8 +564,9 @@ struct flt_decoder {
   int nbest = 0;
   rt::Stream stream{};
   rt::Stream copyStream{};
+  rt::Stream copyStream2{}; // second copy queue: two host->device copies in flight (flt_decode_batch, host input)
 #if FLT_DEVICE_BUILD
-  cudaEvent_t evCopied[2]{}, evFree[2]{};
+  cudaEvent_t evCopied[3]{}, evFree[3]{};
   int numSMs = 148;
   std::vector<cudaEvent_t> evPool; // kernel timing: (start, stop) pairs, kind = index % 3
   size_t evUsed = 0;
@@ -602,7 +609,7 @@ struct flt_decoder {
   // batch buffers
   rt::DevBuf hSkip, hSkipFin;
   rt::DevBuf topTok, topVal, thr, hPar, hTok, hWord, finScore, finCount, status, ws, outTok,
-      outWord, dLengths, staging[2], dStats;
+      outWord, dLengths, staging[3], dStats;
   int lastB = 0, lastT = 0, launches = 0;
   int lastNbest = 0; // nbest the last batch's outTok / outWord rows were sized and strided with
   int capBoost = 1; // candidate-capacity multiplier, grown after an overflow
@@ -613,16 +620,17 @@ struct flt_decoder {
   ~flt_decoder() {
     for (rt::DevBuf* b : {&dWideOff, &dBias, &dTrans, &dLfDesc, &topTok, &topVal, &thr, &hPar, &hTok, &hWord,
                           &finScore, &finCount, &status, &ws, &outTok, &outWord, &dLengths,
-                          &staging[0], &staging[1], &dStats, &hSkip, &hSkipFin, &sBeam, &sBeamBackup, &sScore, &sCount, &sEmis})
+                          &staging[0], &staging[1], &staging[2], &dStats, &hSkip, &hSkipFin, &sBeam, &sBeamBackup, &sScore, &sCount, &sEmis})
       b->release();
 #if FLT_DEVICE_BUILD
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
       if (evCopied[i]) cudaEventDestroy(evCopied[i]);
       if (evFree[i]) cudaEventDestroy(evFree[i]);
     }
     for (cudaEvent_t e : evPool) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
     if (copyStream) cudaStreamDestroy(copyStream);
+    if (copyStream2) cudaStreamDestroy(copyStream2);
 #endif
   }
 };
@@ -1159,7 +1167,8 @@ flt_decoder* makeDecoder(int lexicon, const flt_options* opt, const flt_trie* tr
 #if FLT_DEVICE_BUILD
   FLT_RT_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
   FLT_RT_TRY(cudaStreamCreateWithFlags(&d->copyStream, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; ++i) {
+  FLT_RT_TRY(cudaStreamCreateWithFlags(&d->copyStream2, cudaStreamNonBlocking));
+  for (int i = 0; i < 3; ++i) {
     FLT_RT_TRY(cudaEventCreateWithFlags(&d->evCopied[i], cudaEventDisableTiming));
     FLT_RT_TRY(cudaEventCreateWithFlags(&d->evFree[i], cudaEventDisableTiming));
   }
@@ -1448,6 +1457,13 @@ int flt_trie_num_nodes(const flt_trie* trie, int64_t* out) {
     *out = (int64_t)trie->nodes.size();
   });
 }
+int flt_trie_max_scores(const flt_trie* trie, float* out, int64_t n) {
+  return guarded([&] {
+    if (!trie || (!out && n > 0)) throw FltError(FLT_ERR_INVALID, "null argument");
+    if (n != (int64_t)trie->nodes.size()) throw FltError(FLT_ERR_INVALID, "n must equal flt_trie_num_nodes");
+    for (int64_t i = 0; i < n; ++i) out[i] = trie->nodes[(size_t)i].maxScore;
+  });
+}
 void flt_trie_destroy(flt_trie* trie) { delete trie; }
 
 int flt_lm_zero_create(flt_lm** out) {
@@ -1556,22 +1572,25 @@ int flt_decode_batch(flt_decoder* dec, const float* emissions, int32_t B, int32_
         decodeDevice(d, emissions, B, T, N, dLen);
       } else {
 #if FLT_DEVICE_BUILD
-        // host emissions: stream them through two staging buffers so the PCIe copy of slice i+1
-        // overlaps the kernels of slice i
+        // host emissions: stream them through staging buffers so the PCIe copy of slice i+1 overlaps the
+        // kernels of slice i. Three buffers on two copy queues keep two copies in flight, so the link never
+        // idles between slices; the slices are 512 MiB (the step is latency-bound: a small last slice costs
+        // as much device time as a large one, so the tail that cannot overlap is one step either way).
         const long long perUtt = (long long)T * N * sizeof(float);
-        long long slice = std::max<long long>(1, (1LL << 30) / std::max<long long>(perUtt, 1));
+        long long slice = std::max<long long>(1, (512LL << 20) / std::max<long long>(perUtt, 1));
         // ... and by the same history / list budget as decodeDevice (small N with a large beam)
         const long long perUttHist = (long long)(T + 2) * d.cfg.K * 12 + (long long)T * d.cfg.M * 8 + 64;
         slice = std::min<long long>(slice, std::max<long long>(1, (8LL << 30) / perUttHist));
         slice = std::min<long long>(slice, B);
-        for (int i = 0; i < 2; ++i) d.staging[i].reserve((size_t)(slice * perUtt));
+        for (int i = 0; i < 3; ++i) d.staging[i].reserve((size_t)(slice * perUtt));
         int k = 0;
-        for (long long b0 = 0; b0 < B; b0 += slice, k ^= 1) {
+        for (long long b0 = 0; b0 < B; b0 += slice, k = (k + 1) % 3) {
           const int Bc = (int)std::min<long long>(slice, B - b0);
-          FLT_RT_TRY(cudaStreamWaitEvent(d.copyStream, d.evFree[k], 0));
+          rt::Stream cs = (k & 1) ? d.copyStream2 : d.copyStream;
+          FLT_RT_TRY(cudaStreamWaitEvent(cs, d.evFree[k], 0));
           FLT_RT_TRY(cudaMemcpyAsync(d.staging[k].p, emissions + b0 * T * N, (size_t)(Bc * perUtt),
-                                     cudaMemcpyHostToDevice, d.copyStream));
-          FLT_RT_TRY(cudaEventRecord(d.evCopied[k], d.copyStream));
+                                     cudaMemcpyHostToDevice, cs));
+          FLT_RT_TRY(cudaEventRecord(d.evCopied[k], cs));
           FLT_RT_TRY(cudaStreamWaitEvent(d.stream, d.evCopied[k], 0));
           runChunk(d, d.staging[k].as<float>(), Bc, T, N, dLen ? dLen + b0 : nullptr, b0);
           FLT_RT_TRY(cudaEventRecord(d.evFree[k], d.stream));
@@ -1810,7 +1829,7 @@ int flt_decoder_workspace_bytes(const flt_decoder* dec, int64_t* out) {
     int64_t t = 0;
     for (const rt::DevBuf* b : {&dec->topTok, &dec->topVal, &dec->thr, &dec->hPar, &dec->hTok,
                                 &dec->hWord, &dec->finScore, &dec->finCount, &dec->status, &dec->ws,
-                                &dec->outTok, &dec->outWord, &dec->staging[0], &dec->staging[1]})
+                                &dec->outTok, &dec->outWord, &dec->staging[0], &dec->staging[1], &dec->staging[2]})
       t += (int64_t)b->cap;
     *out = t;
   });

@@ -17,7 +17,8 @@
 // ::setNbest. Differences, all loud:
 //   * LM objects other than ZeroLM / KenLM (ARPA file) cannot be used by the decoders
 //     (std::invalid_argument): a user-defined LM::score cannot run on the device.
-//   * TrieNode objects returned by insert / search are value snapshots (children not populated).
+//   * The Trie keeps the reference's node tree on the host as well (TrieNode::children can be walked);
+//     the smeared scores are taken over from the library after smear().
 #pragma once
 #include <cmath>
 #include <cstdlib>
@@ -74,18 +75,23 @@ struct TrieNode {
     labels.reserve(kTrieMaxLabel);
     scores.reserve(kTrieMaxLabel);
   }
-  std::unordered_map<int, std::shared_ptr<TrieNode>> children; // not populated by this mirror
+  std::unordered_map<int, std::shared_ptr<TrieNode>> children; // letter index -> child, as in Trie.h:45
   int idx;
   std::vector<int> labels;
   std::vector<float> scores;
   float maxScore;
+  int id_ = 0; // creation order (= node index inside the library): not part of the reference's struct
 };
 using TrieNodePtr = std::shared_ptr<TrieNode>;
 
+// The node tree lives twice: here, with the reference's layout, for code that walks TrieNode::children
+// (decoder/Trie.h:39-54), and flattened inside the library for the kernels. Both are built by the same
+// sequence of inserts, so a node's creation index is its index in the library.
 class Trie {
  public:
   Trie(int maxChildren, int rootIdx) : maxChildren_(maxChildren), root_(std::make_shared<TrieNode>(rootIdx)) {
     detail::check(flt_trie_create(maxChildren, rootIdx, &h_));
+    byId_.push_back(root_.get());
   }
   ~Trie() { flt_trie_destroy(h_); }
   Trie(const Trie&) = delete;
@@ -93,31 +99,62 @@ class Trie {
 
   const TrieNode* getRoot() const { return root_.get(); }
 
-  // Trie.cpp:26-48 (throws std::out_of_range on a token index outside [0, maxChildren))
+  // Trie.cpp:26-48 (throws std::out_of_range on a token index outside [0, maxChildren); the nodes
+  // created before the bad index stay, here as in the library)
   TrieNodePtr insert(const std::vector<int>& indices, int label, float score) {
-    detail::check(flt_trie_insert(h_, indices.data(), (int)indices.size(), label, score));
-    return search(indices);
+    TrieNodePtr node = root_;
+    bool bad = false;
+    for (int idx : indices) {
+      if (idx < 0 || idx >= maxChildren_) {
+        bad = true;
+        break;
+      }
+      auto it = node->children.find(idx);
+      if (it == node->children.end()) {
+        auto child = std::make_shared<TrieNode>(idx);
+        child->id_ = (int)byId_.size();
+        byId_.push_back(child.get());
+        node->children[idx] = child;
+        node = child;
+      } else {
+        node = it->second;
+      }
+    }
+    detail::check(flt_trie_insert(h_, indices.data(), (int)indices.size(), label, score)); // throws if bad
+    (void)bad;
+    if (node->labels.size() < (size_t)kTrieMaxLabel) { // Trie.cpp:40-46 (the library prints the notice)
+      node->labels.push_back(label);
+      node->scores.push_back(score);
+    }
+    return node;
   }
   // Trie.cpp:50-64 (nullptr when the path does not exist)
   TrieNodePtr search(const std::vector<int>& indices) {
-    int found = 0, nLabels = 0, labels[kTrieMaxLabel];
-    float maxScore = 0, scores[kTrieMaxLabel];
-    detail::check(flt_trie_search(h_, indices.data(), (int)indices.size(), &found, &maxScore, &nLabels, labels, scores));
-    if (!found) return nullptr;
-    auto node = std::make_shared<TrieNode>(indices.empty() ? root_->idx : indices.back());
-    node->labels.assign(labels, labels + nLabels);
-    node->scores.assign(scores, scores + nLabels);
-    node->maxScore = maxScore;
+    TrieNodePtr node = root_;
+    for (int idx : indices) {
+      if (idx < 0 || idx >= maxChildren_)
+        throw std::out_of_range("[Trie] Invalid letter index: " + std::to_string(idx));
+      auto it = node->children.find(idx);
+      if (it == node->children.end()) return nullptr;
+      node = it->second;
+    }
     return node;
   }
-  // Trie.cpp:79-101
-  void smear(const SmearingMode smearMode) { detail::check(flt_trie_smear(h_, (int)smearMode)); }
+  // Trie.cpp:79-101: computed by the library (float arithmetic of the reference), mirrored here
+  void smear(const SmearingMode smearMode) {
+    detail::check(flt_trie_smear(h_, (int)smearMode));
+    if (smearMode == SmearingMode::NONE) return;
+    std::vector<float> ms(byId_.size());
+    detail::check(flt_trie_max_scores(h_, ms.data(), (int64_t)ms.size()));
+    for (size_t i = 0; i < byId_.size(); ++i) byId_[i]->maxScore = ms[i];
+  }
 
   flt_trie* handle() const { return h_; }
 
  private:
   int maxChildren_;
   TrieNodePtr root_;
+  std::vector<TrieNode*> byId_;
   flt_trie* h_ = nullptr;
 };
 using TriePtr = std::shared_ptr<Trie>;

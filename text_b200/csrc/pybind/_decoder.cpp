@@ -210,4 +210,26 @@ PYBIND11_MODULE(flashlight_lib_text_decoder, m) {
   lexfree.def(py::init<LexiconFreeDecoderOptions, const LMPtr, const int, const int, const std::vector<float>&>(),
               "options"_a, "lm"_a, "sil_token_idx"_a, "blank_token_idx"_a, "transitions"_a);
   defDecoderMethods<LexiconFreeDecoder>(lexfree);
+  lexfree.def("get_options", &LexiconFreeDecoder::getOptions)
+      .def("get_sil_idx", &LexiconFreeDecoder::getSilIdx)
+      .def("get_blank_idx", &LexiconFreeDecoder::getBlankIdx)
+      .def("get_transitions", &LexiconFreeDecoder::getTransitions)
+      // same rules as the reference's pickling (bindings/python/flashlight/lib/text/_decoder.cpp:409-441): only a
+      // decoder without state and with a ZeroLM can be pickled; the copy gets a ZeroLM of its own
+      .def(py::pickle(
+          [](const LexiconFreeDecoder& p) {
+            if (p.getAllFinalHypothesis().size() != 0)
+              throw std::runtime_error("LexiconFreeDecoder: cannot pickle decoder that has state");
+            if (!std::dynamic_pointer_cast<ZeroLM>(p.getLMPtr()))
+              throw std::runtime_error("LexiconFreeDecoder: cannot pickle a decoder with an "
+                                       "integrated language model that is not ZeroLM");
+            return py::make_tuple(p.getOptions(), p.getSilIdx(), p.getBlankIdx(), p.getTransitions());
+          },
+          [](py::tuple t) {
+            if (t.size() != 4)
+              throw std::runtime_error("Cannot run __setstate__ on LexiconFreeDecoder - insufficient arguments provided.");
+            return std::make_unique<LexiconFreeDecoder>(t[0].cast<LexiconFreeDecoderOptions>(), std::make_shared<ZeroLM>(),
+                                                        t[1].cast<int>(), t[2].cast<int>(),
+                                                        t[3].cast<std::vector<float>>());
+          }));
 }

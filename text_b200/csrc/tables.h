@@ -40,21 +40,29 @@ struct LmDev {
   const int* usr2lm;              // [nUsr] user word index -> LM vocabulary id (OOV -> 0 = <unk>)
   const F2* uni;                  // [vocab]
   const uint64_t* keys[kMaxOrder + 1]; // [n] -> open-addressing table of order n (n >= 2); 0 = empty
+  const uint64_t* chk[kMaxOrder + 1];  // [n] -> second, independent 64-bit key of the same slot (verification)
   const F2* vals[kMaxOrder + 1];
   uint32_t mask[kMaxOrder + 1];
 };
 
 // Key of an n-gram = chained 64-bit mix over its words in REVERSED order (most recent first), so
 // that growing the context by one older word extends the chain. KenLM's probing model likewise
-// keys n-grams by a 64-bit hash of the word ids; the oracle uses exact keys, so a collision here
-// would surface as a parity failure.
+// keys n-grams by a 64-bit hash of the word ids. A second chain with other constants is stored next to
+// every entry and compared on a hit, so an n-gram is identified by 128 bits: two distinct n-grams (or
+// a queried one that is not in the model and a stored one) are confused with probability 2^-128 per
+// pair — against 2^-64 with one key, which at 5 M entries and ~1e9 probes per batch would have been a
+// wrong LM score every few thousand batches.
 FLT_HD uint64_t ngramChainStart(int w) { return mix64(0x9E3779B97F4A7C15ull + (uint64_t)(uint32_t)w); }
 FLT_HD uint64_t ngramChainExtend(uint64_t h, int w) {
   return mix64(h * 0x100000001B3ull + (uint64_t)(uint32_t)w + 0x632BE59BD9B4E019ull);
 }
 FLT_HD uint64_t ngramFinalKey(uint64_t h) { return h == 0 ? 1 : h; }
+FLT_HD uint64_t ngramChain2Start(int w) { return mix64(0xD6E8FEB86659FD93ull ^ ((uint64_t)(uint32_t)w << 1)); }
+FLT_HD uint64_t ngramChain2Extend(uint64_t h, int w) {
+  return mix64((h ^ 0xC2B2AE3D27D4EB4Full) * 0xFF51AFD7ED558CCDull + (uint64_t)(uint32_t)w);
+}
 
-FLT_HD bool ngramFind(const LmDev& lm, int n, uint64_t chain, F2& out) {
+FLT_HD bool ngramFind(const LmDev& lm, int n, uint64_t chain, uint64_t chain2, F2& out) {
   const uint64_t key = ngramFinalKey(chain);
   const uint32_t mask = lm.mask[n];
   const uint64_t* keys = lm.keys[n];
@@ -62,7 +70,7 @@ FLT_HD bool ngramFind(const LmDev& lm, int n, uint64_t chain, F2& out) {
   uint32_t s = (uint32_t)(key >> 17) & mask;
   for (;;) {
     uint64_t k = keys[s];
-    if (k == key) {
+    if (k == key && lm.chk[n][s] == chain2) {
       out = lm.vals[n][s];
       return true;
     }
@@ -78,24 +86,26 @@ FLT_HD float ngramScore(const LmDev& lm, const int* ctx, int nctx, int w) {
   const int L = nctx < lm.order - 1 ? nctx : lm.order - 1;
   float ret = lm.uni[w].x;
   int matchLen = 1;
-  uint64_t h = ngramChainStart(w);
+  uint64_t h = ngramChainStart(w), h2 = ngramChain2Start(w);
   for (int k = 1; k <= L; ++k) {
     h = ngramChainExtend(h, ctx[k - 1]);
+    h2 = ngramChain2Extend(h2, ctx[k - 1]);
     F2 v;
-    if (!ngramFind(lm, k + 1, h, v)) break;
+    if (!ngramFind(lm, k + 1, h, h2, v)) break;
     ret = v.x;
     matchLen = k + 1;
   }
   if (matchLen - 1 < L) {
-    uint64_t g = 0;
+    uint64_t g = 0, g2 = 0;
     for (int i = 0; i < L; ++i) {
       g = i == 0 ? ngramChainStart(ctx[0]) : ngramChainExtend(g, ctx[i]);
+      g2 = i == 0 ? ngramChain2Start(ctx[0]) : ngramChain2Extend(g2, ctx[i]);
       if (i < matchLen - 1) continue;
       if (i == 0) {
         ret += lm.uni[ctx[0]].y;
       } else {
         F2 v;
-        if (ngramFind(lm, i + 1, g, v)) ret += v.y;
+        if (ngramFind(lm, i + 1, g, g2, v)) ret += v.y;
       }
     }
   }
