@@ -348,11 +348,6 @@ def measure(a, ctx, with_cpu):
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
-    if not os.environ.get("BENCH_NO_PRESTEP"):
-        # one untimed step between the barrier and the first event: ranks idle in the barrier until the slowest
-        # arrives and the GPU's clocks sag meanwhile, which the first timed step would pay for (SCALE_r01: a flat
-        # 0.32 ms per step from N = 2 on with identical per-kernel times). The events still bracket exactly K steps.
-        step()
     ev0.record(stream)
     for _ in range(a.steps):
         step()
@@ -639,9 +634,7 @@ def run_ours(a):
            "config": {"workload": main["workload"], "emissions": f"log_softmax({a.sigma}*N(0,1)) fp32",
                       "nbest": main["nbest"], "beamThreshold": a.threshold,
                       "l2": f"inputs ({h2d / 1e9:.2f} GB/step/GPU) exceed L2 (126 MB); no flush needed",
-                      "timing": "CUDA events on the decoder's stream around exactly K steps, max over ranks; one "
-                                "untimed step is enqueued between the barrier and the first event so that the "
-                                "timed region starts on a busy GPU"},
+                      "timing": "CUDA events on the decoder's stream around exactly K steps, max over ranks"},
            "roofline": main["roofline"], "kernels": main["kernels"], "beam_step_work": main["beam_step_work"],
            "cpu_baseline": main["cpu_baseline"], "cpu_baseline_bst_beam": main["cpu_baseline_bst_beam"],
            "e2e": main["e2e"], "gpu_launches": main["launches"], "clocks": main["clocks"], "parity": main["parity"],

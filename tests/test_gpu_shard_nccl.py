@@ -95,3 +95,41 @@ def test_nccl_sharded_decode_equals_one_gpu(kind):
         p.join(300)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def test_one_trie_and_lm_shared_by_decoders_on_two_devices():
+    """include/flt_decoder.h: a Trie / LM may be shared by several decoders, also across CUDA devices — the
+    flattened tables are built once per device (they used to be built once, on the first decoder's
+    device). Same process, one lexicon + n-gram LM, one decoder per GPU: identical n-best; and the caller's
+    current device is what it was before each call."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs on the box (run with gpurun --gpus 2)")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity_cases
+    from flt_backend import FltBackend
+
+    name, spec, em = next(c for c in parity_cases.lexicon_cases() if c[0] == "arpa3_ctc")
+    G = FltBackend("cuda")
+    api = G.api
+    lm = api.lm_arpa(spec["lm"][1], spec["lm"][2])
+    trie = api.trie_create(spec["N"], spec["sil"])
+    for sp, wid in zip(spec["spellings"], spec["word_ids"]):
+        api.trie_insert(trie, sp, wid, float(api.lm_score_seq(lm, [wid])[0]))
+    api.trie_smear(trie, spec["smear"])
+    torch.cuda.set_device(0)
+    res = []
+    for device in (0, 1, 0):
+        api.device = device
+        dec = G.decoder_lexicon(spec["opt"], trie, lm, spec["sil"], spec["blank"], spec["unk"])
+        res.append(G.decode_batch(dec, em, spec["opt"].beamSize))
+        assert torch.cuda.current_device() == 0, "an ABI call left another device current"
+        api.decoder_destroy(dec)
+    for other in res[1:]:
+        for a, b in zip(res[0], other):
+            assert a["n"] == b["n"] and a["n"] > 0
+            assert np.array_equal(a["tokens"], b["tokens"]) and np.array_equal(a["words"], b["words"])
+            assert np.array_equal(a["scores"], b["scores"])
+    api.trie_destroy(trie)
+    api.lm_destroy(lm)

@@ -1573,11 +1573,13 @@ int flt_decode_batch(flt_decoder* dec, const float* emissions, int32_t B, int32_
       } else {
 #if FLT_DEVICE_BUILD
         // host emissions: stream them through staging buffers so the PCIe copy of slice i+1 overlaps the
-        // kernels of slice i. Three buffers on two copy queues keep two copies in flight, so the link never
-        // idles between slices. The step is latency-bound — a slice of 13 utterances costs as much device
+        // kernels of slice i. Three buffers keep the copy queue from ever waiting for the kernels to free one
+        // (two copy queues were measured slower: concurrent copies share the link and every slice arrives
+        // later). The step is latency-bound — a slice of 13 utterances costs as much device
         // time as one of 52 — so FEW LARGE slices (2 GiB) keep the kernels hidden behind the copies, and the
         // part that cannot overlap is one step (the last slice's) either way. Measured at cfg 2 / cfg 3:
-        // 512 MiB slices 1.10 k / 0.48 k utt/s, 1 GiB (two buffers, one queue) 1.21 k / 0.83 k.
+        // 512 MiB slices on two queues 1.10 k / 0.48 k utt/s, 2 GiB on two queues 1.15 k / 1.15 k,
+        // 1 GiB on one queue (two buffers) 1.21 k / 0.83 k.
         const long long perUtt = (long long)T * N * sizeof(float);
         long long slice = std::max<long long>(1, (2LL << 30) / std::max<long long>(perUtt, 1));
         // ... and by the same history / list budget as decodeDevice (small N with a large beam)
@@ -1588,7 +1590,7 @@ int flt_decode_batch(flt_decoder* dec, const float* emissions, int32_t B, int32_
         int k = 0;
         for (long long b0 = 0; b0 < B; b0 += slice, k = (k + 1) % 3) {
           const int Bc = (int)std::min<long long>(slice, B - b0);
-          rt::Stream cs = (k & 1) ? d.copyStream2 : d.copyStream;
+          rt::Stream cs = d.copyStream; // ONE queue: slices must arrive in order, each as early as possible
           FLT_RT_TRY(cudaStreamWaitEvent(cs, d.evFree[k], 0));
           FLT_RT_TRY(cudaMemcpyAsync(d.staging[k].p, emissions + b0 * T * N, (size_t)(Bc * perUtt),
                                      cudaMemcpyHostToDevice, cs));
