@@ -246,15 +246,17 @@ def run_reference(a):
 
 
 def src_hash():
-    """sha256 over the kernel sources: ties a committed ncu capture (profiles/traffic.json) to the build."""
+    """sha256 over the device code of the kernels (the headers the __global__ wrappers instantiate): ties a
+    committed ncu capture (profiles/traffic.json) to the build. Host-side files (flt_abi.cu, table_io.h,
+    runtime.h, host/) are left out so that an ABI change does not make the capture look stale."""
     import hashlib
 
     h = hashlib.sha256()
     d = os.path.join(ROOT, "text_b200", "csrc")
-    for f in sorted(os.listdir(d)):
-        if f.endswith((".h", ".cu")):
-            with open(os.path.join(d, f), "rb") as fh:
-                h.update(fh.read())
+    for f in ("spmd.h", "tables.h", "topm_core.h", "topm_stream.h", "beam_core.h", "beam_lf.h", "beam_gx.h",
+              "fused_core.h"):
+        with open(os.path.join(d, f), "rb") as fh:
+            h.update(fh.read())
     return h.hexdigest()[:16]
 
 
