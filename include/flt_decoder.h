@@ -74,6 +74,16 @@ int flt_trie_num_nodes(const flt_trie* trie, int64_t* out);
  * decoder/Trie.h:39-54) take the smeared scores over after flt_trie_smear. n = flt_trie_num_nodes. */
 int flt_trie_max_scores(const flt_trie* trie, float* out, int64_t n);
 void flt_trie_destroy(flt_trie* trie);
+/* Table file of a built (inserted + smeared) Trie: what test/decoder/DecoderTest.cpp:126-146 rebuilds in every
+ * process with one Trie::insert per word — saved once, loaded with a few reads (format: csrc/table_io.h). */
+int flt_trie_save(const flt_trie* trie, const char* path);
+int flt_trie_load(const char* path, flt_trie** out);
+/* The node tree as CSR arrays, nodes in creation order (node 0 = the root), edges of a node ascending by
+ * token: meta5 = {maxChildren, rootIdx, nNodes, nEdges, nLabels}; with childOff == NULL only meta5 is filled
+ * (sizes for the second call). childOff / labelOff hold nNodes+1 entries. Lets a host mirror rebuild
+ * TrieNode::children (decoder/Trie.h:39-54) for a Trie that came from flt_trie_load. */
+int flt_trie_export(const flt_trie* trie, int32_t* meta5, int32_t* childOff, int32_t* childTok, int32_t* childNode,
+                    int32_t* labelOff, int32_t* labels, float* scores, float* maxScore);
 
 /* ---- LM: decoder/lm/LM.h:52-85. Two device-resident models:
  *   zero  = ZeroLM (lm/ZeroLM.cpp:14-26): score 0, a child state per (state, index)
@@ -83,6 +93,10 @@ void flt_trie_destroy(flt_trie* trie);
 int flt_lm_zero_create(flt_lm** out);
 int flt_lm_ngram_load_arpa(const char* path, const char* const* usrWords, int32_t nUsrWords,
                            flt_lm** out);
+/* The hashed n-gram tables + vocabulary as a table file (the role of KenLM's binary format, which the
+ * reference's KenLM constructor accepts in place of ARPA text, lm/KenLM.cpp:32-47): flt_lm_ngram_load_arpa
+ * recognises such a file by its magic and loads it without parsing text. */
+int flt_lm_save(const flt_lm* lm, const char* path);
 /* LM::start(false) then LM::score per index (and LM::finish when withFinish): host-side query used
  * for Trie insertion scores (test/decoder/DecoderTest.cpp:126-141) and tests. out[n(+1)]. */
 int flt_lm_score_seq(const flt_lm* lm, const int32_t* usrIdx, int32_t n, int32_t withFinish,

@@ -50,6 +50,12 @@ SYMBOLS = {
     "flt_trie_num_nodes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "flt_trie_max_scores": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int64]),
     "flt_trie_destroy": (None, [C.c_void_p]),
+    "flt_trie_save": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "flt_trie_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "flt_trie_export": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                  C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                  C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "flt_lm_save": (C.c_int, [C.c_void_p, C.c_char_p]),
     "flt_lm_zero_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "flt_lm_ngram_load_arpa": (C.c_int, [C.c_char_p, C.POINTER(C.c_char_p), C.c_int32,
                                          C.POINTER(C.c_void_p)]),
@@ -173,6 +179,32 @@ class Api:
     def trie_destroy(self, trie):
         self.lib.flt_trie_destroy(trie)
 
+    def trie_save(self, trie, path):
+        self._ck(self.lib.flt_trie_save(trie, path.encode()))
+
+    def trie_load(self, path):
+        h = C.c_void_p()
+        self._ck(self.lib.flt_trie_load(path.encode(), C.byref(h)))
+        return h
+
+    def trie_export(self, trie):
+        """CSR arrays of the node tree (creation order; edges ascending by token)"""
+        meta = np.zeros(5, np.int32)
+        nul_i, nul_f = C.POINTER(C.c_int32)(), C.POINTER(C.c_float)()
+        self._ck(self.lib.flt_trie_export(trie, _i32p(meta), nul_i, nul_i, nul_i, nul_i, nul_i, nul_f, nul_f))
+        nn, ne, nl = int(meta[2]), int(meta[3]), int(meta[4])
+        out = dict(childOff=np.zeros(nn + 1, np.int32), childTok=np.zeros(max(ne, 1), np.int32),
+                   childNode=np.zeros(max(ne, 1), np.int32), labelOff=np.zeros(nn + 1, np.int32),
+                   labels=np.zeros(max(nl, 1), np.int32), scores=np.zeros(max(nl, 1), np.float32),
+                   maxScore=np.zeros(nn, np.float32))
+        self._ck(self.lib.flt_trie_export(trie, _i32p(meta), _i32p(out["childOff"]), _i32p(out["childTok"]),
+                                          _i32p(out["childNode"]), _i32p(out["labelOff"]), _i32p(out["labels"]),
+                                          _f32p(out["scores"]), _f32p(out["maxScore"])))
+        out["childTok"], out["childNode"] = out["childTok"][:ne], out["childNode"][:ne]
+        out["labels"], out["scores"] = out["labels"][:nl], out["scores"][:nl]
+        out.update(maxChildren=int(meta[0]), rootIdx=int(meta[1]))
+        return out
+
     # ---- LM
     def lm_zero(self):
         h = C.c_void_p()
@@ -184,6 +216,9 @@ class Api:
         h = C.c_void_p()
         self._ck(self.lib.flt_lm_ngram_load_arpa(path.encode(), arr, len(words), C.byref(h)))
         return h
+
+    def lm_save(self, lm, path):
+        self._ck(self.lib.flt_lm_save(lm, path.encode()))
 
     def lm_score_seq(self, lm, usr_idx, with_finish=False):
         a = np.ascontiguousarray(usr_idx, np.int32)

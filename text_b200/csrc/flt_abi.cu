@@ -366,6 +366,7 @@ struct flt_lm {
   std::vector<uint64_t> chk[kMaxOrder + 1];
   std::vector<F2> vals[kMaxOrder + 1];
   std::vector<int> usr2lm;
+  std::vector<std::string> words; // vocabulary by LM id (kept for the table file, table_io.h)
   LmDev host{}; // view over the host vectors (host-side scoring)
   float upper = 0.0f; // no word scores above this: best probability + the positive back-offs
   struct Image {
@@ -524,6 +525,8 @@ void loadArpa(const std::string& path, const char* const* usrWords, int nUsr, fl
   lm.bos = b->second;
   lm.eos = e->second;
   lm.vocab = (int)lm.uni.size();
+  lm.words.assign(lm.uni.size(), std::string());
+  for (auto& kv : vocab) lm.words[(size_t)kv.second] = kv.first;
   for (int n = 2; n <= lm.order; ++n) {
     if (pending[n].empty()) continue;
     size_t cap = 16;
@@ -550,6 +553,8 @@ void loadArpa(const std::string& path, const char* const* usrWords, int nUsr, fl
 }
 
 } // namespace
+
+#include "table_io.h"
 
 /* ============================================================================== decoder ===== */
 struct flt_decoder {
@@ -1465,6 +1470,42 @@ int flt_trie_max_scores(const flt_trie* trie, float* out, int64_t n) {
   });
 }
 void flt_trie_destroy(flt_trie* trie) { delete trie; }
+int flt_trie_save(const flt_trie* trie, const char* path) {
+  return guarded([&] {
+    if (!trie || !path) throw FltError(FLT_ERR_INVALID, "null argument");
+    saveTrie(*trie, path);
+  });
+}
+int flt_trie_export(const flt_trie* trie, int32_t* meta5, int32_t* childOff, int32_t* childTok, int32_t* childNode,
+                    int32_t* labelOff, int32_t* labels, float* scores, float* maxScore) {
+  return guarded([&] {
+    if (!trie || !meta5) throw FltError(FLT_ERR_INVALID, "null argument");
+    const size_t nn = trie->nodes.size();
+    size_t ne = 0, nl = 0;
+    for (const HNode& nd : trie->nodes) ne += nd.kids.size(), nl += nd.labels.size();
+    meta5[0] = trie->maxChildren, meta5[1] = trie->rootIdx, meta5[2] = (int32_t)nn, meta5[3] = (int32_t)ne,
+    meta5[4] = (int32_t)nl;
+    if (!childOff) return; // sizes only
+    if (!childTok || !childNode || !labelOff || !labels || !scores || !maxScore)
+      throw FltError(FLT_ERR_INVALID, "null argument");
+    size_t e = 0, l = 0;
+    for (size_t i = 0; i < nn; ++i) {
+      const HNode& nd = trie->nodes[i];
+      childOff[i] = (int32_t)e, labelOff[i] = (int32_t)l, maxScore[i] = nd.maxScore;
+      for (auto& kv : nd.kids) childTok[e] = kv.first, childNode[e] = kv.second, ++e;
+      for (size_t k = 0; k < nd.labels.size(); ++k) labels[l] = nd.labels[k], scores[l] = nd.scores[k], ++l;
+    }
+    childOff[nn] = (int32_t)e, labelOff[nn] = (int32_t)l;
+  });
+}
+int flt_trie_load(const char* path, flt_trie** out) {
+  return guarded([&] {
+    if (!out || !path) throw FltError(FLT_ERR_INVALID, "null argument");
+    std::unique_ptr<flt_trie> t(new flt_trie);
+    loadTrie(path, *t);
+    *out = t.release();
+  });
+}
 
 int flt_lm_zero_create(flt_lm** out) {
   return guarded([&] {
@@ -1480,8 +1521,16 @@ int flt_lm_ngram_load_arpa(const char* path, const char* const* usrWords, int32_
   return guarded([&] {
     if (!out || !path) throw FltError(FLT_ERR_INVALID, "null argument");
     std::unique_ptr<flt_lm> m(new flt_lm);
-    loadArpa(path, usrWords, nUsrWords, *m);
+    // like KenLM's constructor, which takes ARPA text or its own binary format and tells them apart by magic
+    if (isTableFile(path)) loadLmTables(path, usrWords, nUsrWords, *m);
+    else loadArpa(path, usrWords, nUsrWords, *m);
     *out = m.release();
+  });
+}
+int flt_lm_save(const flt_lm* lm, const char* path) {
+  return guarded([&] {
+    if (!lm || !path) throw FltError(FLT_ERR_INVALID, "null argument");
+    saveLm(*lm, path);
   });
 }
 int flt_lm_score_seq(const flt_lm* lm, const int32_t* usrIdx, int32_t n, int32_t withFinish,

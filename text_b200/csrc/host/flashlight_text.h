@@ -151,7 +151,51 @@ class Trie {
 
   flt_trie* handle() const { return h_; }
 
+  // Additive: the built (inserted + smeared) Trie as a table file (csrc/table_io.h) — written once, loaded by
+  // every later process instead of repeating one insert per lexicon word.
+  void save(const std::string& path) const { detail::check(flt_trie_save(h_, path.c_str())); }
+  static std::shared_ptr<Trie> load(const std::string& path) {
+    flt_trie* h = nullptr;
+    detail::check(flt_trie_load(path.c_str(), &h));
+    std::shared_ptr<Trie> t(new Trie(h));
+    return t;
+  }
+
  private:
+  // takes over a library Trie and rebuilds the host node tree from its CSR export
+  explicit Trie(flt_trie* h) : maxChildren_(0), h_(h) {
+    int32_t meta[5];
+    try {
+      detail::check(flt_trie_export(h_, meta, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+      const size_t nn = (size_t)meta[2], ne = (size_t)meta[3], nl = (size_t)meta[4];
+      std::vector<int32_t> childOff(nn + 1), childTok(ne + 1), childNode(ne + 1), labelOff(nn + 1), labels(nl + 1);
+      std::vector<float> scores(nl + 1), maxScore(nn);
+      detail::check(flt_trie_export(h_, meta, childOff.data(), childTok.data(), childNode.data(), labelOff.data(),
+                                    labels.data(), scores.data(), maxScore.data()));
+      maxChildren_ = meta[0];
+      std::vector<TrieNodePtr> nodes(nn);
+      nodes[0] = std::make_shared<TrieNode>(meta[1]);
+      byId_.assign(nn, nullptr);
+      // a child is always created after its parent, so parents come first in creation order
+      for (size_t i = 0; i < nn; ++i) {
+        TrieNode* nd = nodes[i].get();
+        nd->id_ = (int)i;
+        nd->maxScore = maxScore[i];
+        nd->labels.assign(labels.begin() + labelOff[i], labels.begin() + labelOff[i + 1]);
+        nd->scores.assign(scores.begin() + labelOff[i], scores.begin() + labelOff[i + 1]);
+        byId_[i] = nd;
+        for (int e = childOff[i]; e < childOff[i + 1]; ++e) {
+          auto child = std::make_shared<TrieNode>(childTok[e]);
+          nodes[(size_t)childNode[e]] = child;
+          nd->children[childTok[e]] = child;
+        }
+      }
+      root_ = nodes[0];
+    } catch (...) {
+      flt_trie_destroy(h_);
+      throw;
+    }
+  }
   int maxChildren_;
   TrieNodePtr root_;
   std::vector<TrieNode*> byId_;
@@ -218,7 +262,7 @@ class ZeroLM : public LM {
 };
 using ZeroLMPtr = std::shared_ptr<ZeroLM>;
 
-// lm/KenLM.cpp:32-83 for ARPA files: log10 scores, OOV -> <unk>, start = <s> context, finish = </s>
+// lm/KenLM.cpp:32-83 for ARPA files (or a table file written by save()): log10 scores, OOV -> <unk>, start = <s> context, finish = </s>
 struct KenLMState : LMState {};
 class KenLM : public LM {
  public:
@@ -250,6 +294,9 @@ class KenLM : public LM {
     return std::make_pair(std::static_pointer_cast<LMState>(out), s.back());
   }
   const flt_lm* handle() const override { return h_; }
+  // Additive: write the hashed n-gram tables + vocabulary as a table file (csrc/table_io.h); the constructor
+  // above loads such a file in place of ARPA text, the way the reference's takes a KenLM binary.
+  void save(const std::string& path) const { detail::check(flt_lm_save(h_, path.c_str())); }
 
  private:
   flt_lm* h_ = nullptr;

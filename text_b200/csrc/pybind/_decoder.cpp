@@ -89,7 +89,10 @@ PYBIND11_MODULE(flashlight_lib_text_decoder, m) {
       .def("get_root", &Trie::getRoot, py::return_value_policy::reference_internal)
       .def("insert", &Trie::insert, "indices"_a, "label"_a, "score"_a)
       .def("search", &Trie::search, "indices"_a)
-      .def("smear", &Trie::smear, "smear_mode"_a);
+      .def("smear", &Trie::smear, "smear_mode"_a)
+      // additive: table file of the built Trie (csrc/table_io.h)
+      .def("save", &Trie::save, "path"_a)
+      .def_static("load", &Trie::load, "path"_a);
 
   py::class_<LM, LMPtr, PyLM>(m, "LM")
       .def(py::init<>())
@@ -131,7 +134,8 @@ PYBIND11_MODULE(flashlight_lib_text_decoder, m) {
         "max_reps"_a = 0, "smear_mode"_a = SmearingMode::MAX);
 
   py::class_<KenLM, KenLMPtr, LM>(m, "KenLM")
-      .def(py::init<const std::string&, const Dictionary&>(), "path"_a, "usr_token_dict"_a);
+      .def(py::init<const std::string&, const Dictionary&>(), "path"_a, "usr_token_dict"_a)
+      .def("save", &KenLM::save, "path"_a); // additive: table file; the constructor loads it in place of ARPA
 
   py::enum_<CriterionType>(m, "CriterionType")
       .value("ASG", CriterionType::ASG)
