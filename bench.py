@@ -50,6 +50,8 @@ def parse():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-secondary", action="store_true", help="skip the cfg 3 (lexicon) block of the default run")
+    p.add_argument("--no-tertiary", action="store_true",
+                   help="skip the cfg 4 (lexicon + 4-gram, beam 200, T=1500, B=512) block of the default run")
     p.add_argument("--cpu-seconds", type=float, default=20.0)
     return p.parse_args()
 
@@ -324,8 +326,28 @@ def measure(a, ctx, with_cpu):
     B, T, N = a.batch, a.frames, a.tokens
     nbest = a.nbest or beam
     spec = build_spec(a, beam, bst)
+    G.setup_times = {}
+    t0 = time.perf_counter()
     built = Built(G, spec)
+    setup = {"build_tables_s": time.perf_counter() - t0,
+             "note": "build_tables_s = LM load + one Trie insert per lexicon word + smear through the C-ABI from Python; "
+                     "*_file_load_s = the same objects from their table files (csrc/table_io.h); first_decode_s = "
+                     "planning + flattening / upload of the tables to HBM + one decode of the batch"}
     api, dec = G.api, built.dec
+    if built.trie is not None and rank == 0:
+        from text_b200 import synth
+
+        tp = os.path.join(synth.cache_dir(), f"bench_trie_{os.getpid()}.flt")
+        t0 = time.perf_counter()
+        api.trie_save(built.trie, tp)
+        setup["trie_file_save_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        t2 = api.trie_load(tp)
+        setup["trie_file_load_s"] = time.perf_counter() - t0
+        setup["trie_file_bytes"] = os.path.getsize(tp)
+        setup["trie_nodes"] = api.trie_num_nodes(t2)
+        api.trie_destroy(t2)
+        os.remove(tp)
     api.set_nbest(dec, nbest)
     stream = torch.cuda.ExternalStream(api.stream(dec), device=dev)
 
@@ -334,19 +356,23 @@ def measure(a, ctx, with_cpu):
 
     def barrier():
         torch.cuda.synchronize()
-        if world > 1:
+        if world > 1 or os.environ.get("BENCH_FORCE_PG"):
             dist.barrier()
         torch.cuda.synchronize()
 
     # one synchronous decode first: data-dependent candidate capacities (lexicon enumeration, full
     # expansion) are grown by flt_decode_batch's overflow retry and then stay for the async steps
+    t0 = time.perf_counter()
     api.decode_batch_ptr(dec, em.data_ptr(), B, T, N)
+    setup["first_decode_s"] = time.perf_counter() - t0
+    setup.update(G.setup_times)
     for _ in range(a.warmup):
         step()
     api.synchronize(dec)
     api.set_timing(dec, 1)  # CUDA events around each launch; in-kernel counters stay off while timing
     clocks = ClockSampler(local)
-    clocks.start()
+    if not os.environ.get("BENCH_NO_CLOCKS"):
+        clocks.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
@@ -388,13 +414,13 @@ def measure(a, ctx, with_cpu):
             res = None
             for _ in range(min(a.warmup, 2)):
                 api.decode_batch_ptr(dec, host.data_ptr(), B, T, N)
-                res = api.nbest(dec, B, T, nbest)
+                res = api.nbest(dec, B, T, nbest, pinned=True)
 
             def collect():
                 # N > 1: the n-best blocks of every rank go to rank 0 over NCCL (device buffers, no host round
                 # trip), rank 0 then reads the job's result; N = 1: plain device->host copy
                 if world == 1:
-                    return api.nbest(dec, B, T, nbest)
+                    return api.nbest(dec, B, T, nbest, pinned=True)  # page-locked result buffers, like the input
                 api.synchronize(dec)
                 nb = api.nbest_device(dec, B, T, nbest, beam)
                 mine = dict(tokens=nb["tokens"], words=nb["words"], scores=nb["scores"][:, :nbest].contiguous(),
@@ -442,7 +468,7 @@ def measure(a, ctx, with_cpu):
                            + "; bound by the host link (see host_link: plain pinned cudaMemcpyAsync ceiling of this box)"}
 
     out = {"value": value, "ms_per_step": ms_step, "launches": launches, "clocks": clk, "e2e": e2e,
-           "workload": workload_name(a, beam, bst), "beam": beam, "bst": bst, "nbest": nbest}
+           "workload": workload_name(a, beam, bst), "beam": beam, "bst": bst, "nbest": nbest, "setup": setup}
     if rank != 0:
         built.close()
         return out
@@ -568,12 +594,18 @@ def run_ours(a):
         pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
     except Exception:
         pass
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world > 1 or os.environ.get("BENCH_FORCE_PG"):  # BENCH_FORCE_PG: a 1-rank NCCL group, to study its side effects
+        if world == 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29533")
+            dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     B, T, N = a.batch, a.frames, a.tokens
     G = FltBackend("cuda")
     G.api.device = local
+    G.table_cache = True  # n-gram tables are parsed from ARPA text once and then loaded from their table file
 
     # synthetic emissions, generated where they are consumed
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -623,7 +655,34 @@ def run_ours(a):
                          "kernels": sec["kernels"], "roofline": sec["roofline"], "parity": sec["parity"],
                          "e2e": sec["e2e"], "cpu_baseline": sec["cpu_baseline"],
                          "cpu_baseline_bst_beam": sec["cpu_baseline_bst_beam"], "beam_step_work": sec["beam_step_work"],
-                         "gpu_launches": sec["launches"], "clocks": sec["clocks"]}
+                         "gpu_launches": sec["launches"], "clocks": sec["clocks"], "setup": sec["setup"]}
+    # ---- tertiary: BASELINE configs[3] (LexiconDecoder, 200k-word Trie + 4-gram LM, beam 200, beamThreshold 25,
+    # T=1500, B=512 per GPU) with a synthetic ARPA of the SURVEY's size (2M/2M/1M 2/3/4-grams): device-timed
+    tertiary = None
+    if a.workload == "lexfree" and not a.no_tertiary and not a.no_secondary and not a.log_add:
+        a3 = copy.copy(a)
+        a3.workload, a3.beam, a3.nbest, a3.threshold = "lexicon_lm", 200, 0, 25.0
+        a3.batch, a3.frames, a3.ngrams = 512, 1500, "2000000,2000000,1000000"
+        a3.steps, a3.warmup, a3.no_e2e = 2, 1, True
+        del em, ctx["em"]
+        torch.cuda.empty_cache()
+        if world > 1:
+            if rank == 0:
+                build_spec(a3, 200, a3.tokens)
+            dist.barrier()
+        em3 = torch.empty((a3.batch, a3.frames, N), dtype=torch.float32, device=dev)
+        for b0 in range(0, a3.batch, 16):
+            z = torch.randn((min(16, a3.batch - b0), a3.frames, N), generator=gen, device=dev, dtype=torch.float32)
+            em3[b0:b0 + z.shape[0]] = torch.log_softmax(z * a.sigma, dim=-1)
+        del z
+        ctx3 = dict(ctx, em=em3, host=None)
+        ter = measure(a3, ctx3, with_cpu=False)
+        if rank == 0:
+            tertiary = {"config": {"workload": ter["workload"]}, "metric": "utterances/sec", "value": ter["value"],
+                        "unit": "utt/s", "ms_per_step": ter["ms_per_step"], "steps": a3.steps, "warmup": a3.warmup,
+                        "kernels": ter["kernels"], "roofline": ter["roofline"], "parity": ter["parity"],
+                        "beam_step_work": ter["beam_step_work"], "gpu_launches": ter["launches"],
+                        "clocks": ter["clocks"], "setup": ter["setup"], "workspace_bytes": ter["workspace_bytes"]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -640,7 +699,8 @@ def run_ours(a):
            "roofline": main["roofline"], "kernels": main["kernels"], "beam_step_work": main["beam_step_work"],
            "cpu_baseline": main["cpu_baseline"], "cpu_baseline_bst_beam": main["cpu_baseline_bst_beam"],
            "e2e": main["e2e"], "gpu_launches": main["launches"], "clocks": main["clocks"], "parity": main["parity"],
-           "workspace_bytes": main["workspace_bytes"], "secondary": secondary}
+           "workspace_bytes": main["workspace_bytes"], "setup": main["setup"], "secondary": secondary,
+           "tertiary": tertiary}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

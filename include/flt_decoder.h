@@ -192,6 +192,12 @@ int flt_decoder_workspace_bytes(const flt_decoder* dec, int64_t* out);
  * dEmissions [rows,N] device; outputs device: dTok/dVal [rows,M] sorted by value descending. */
 int flt_topm_rows(const float* dEmissions, int64_t rows, int32_t N, int32_t M, int32_t* dTok,
                   float* dVal, void* stream);
+/* The same with the lexicon decoder's ranking offset (decoder/LexiconDecoder.cpp:41-52 sorts raw emissions; the
+ * device path ranks the root's children by e[n] + bias[n], bias[n] = lmWeight * smeared score of root child n,
+ * -inf = token n does not start a word): tokens by e + bias descending (fp32 sum), dVal = the raw e[tok];
+ * rows with fewer than M eligible tokens are padded with tok = -1, val = 0. dBias [N] device, may be NULL. */
+int flt_topm_rows_bias(const float* dEmissions, int64_t rows, int32_t N, int32_t M, const float* dBias,
+                       int32_t* dTok, float* dVal, void* stream);
 
 #ifdef __cplusplus
 }

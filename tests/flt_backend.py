@@ -26,10 +26,29 @@ class FltBackend:
         else:
             self.api = capi.Api()
         self.kind = kind
+        self.table_cache = False  # bench.py: keep the hashed n-gram tables next to the ARPA file (table_io.h)
+        self.setup_times = {}
         a = self.api
         for name in ("trie_create", "trie_insert", "trie_smear", "trie_search", "trie_destroy",
-                     "lm_zero", "lm_arpa", "lm_score_seq", "lm_destroy", "decoder_destroy"):
+                     "lm_zero", "lm_score_seq", "lm_destroy", "decoder_destroy"):
             setattr(self, name, getattr(a, name))
+
+    def lm_arpa(self, path, words):
+        import time
+
+        tbl = path + ".flt"
+        t0 = time.perf_counter()
+        if self.table_cache and os.path.exists(tbl):
+            h = self.api.lm_arpa(tbl, words)
+            self.setup_times["lm_table_file_load_s"] = time.perf_counter() - t0
+            return h
+        h = self.api.lm_arpa(path, words)
+        self.setup_times["lm_arpa_parse_s"] = time.perf_counter() - t0
+        if self.table_cache:
+            tmp = f"{tbl}.tmp{os.getpid()}"
+            self.api.lm_save(h, tmp)
+            os.replace(tmp, tbl)
+        return h
 
     @staticmethod
     def _opt(o):

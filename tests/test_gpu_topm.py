@@ -93,3 +93,63 @@ def test_topm_many_rows(kind, N, M, R):
     etok, eval_ = expected(rows, M)
     np.testing.assert_array_equal(tok.cpu().numpy(), etok)
     np.testing.assert_array_equal(val.cpu().numpy(), eval_)
+
+
+@pytest.mark.parametrize("N,M,R,spread", [(10000, 105, 1500, 6.0), (10000, 205, 1500, 6.0), (10000, 205, 900, 0.5),
+                                          (10000, 505, 900, 0.0), (10000, 505, 900, 6.0), (4096, 600, 700, 3.0),
+                                          (1000, 53, 600, 6.0), (10000, 1000, 300, 0.0)])
+def test_topm_biased_and_long_lists(N, M, R, spread):
+    """The lexicon decoder's select: rank by e[n] + bias[n] (bias = lmWeight * smeared LM score of root child n,
+    spread wider than the emissions when an n-gram LM is smeared into the Trie; -inf = not a word start), and
+    the long lists of wide beams (beam 200 / 500: M = 205 / 505; M = 1000 takes the generic kernel). Values
+    returned are the raw emissions of the selected tokens."""
+    import torch
+
+    from text_b200 import capi
+
+    api = capi.Api()
+    rng = np.random.default_rng(N + M + R)
+    rows = make_rows("logsoftmax", R, N, rng)
+    rows += (np.sin(np.arange(R) / 9.0) * 2.0 + (np.arange(R) % 131 == 0) * 15.0).astype(np.float32)[:, None]
+    bias = None
+    if spread > 0:
+        bias = (-rng.random(N) * spread).astype(np.float32)
+        bias[rng.random(N) < 0.03] = -np.inf
+    dev = torch.from_numpy(rows).cuda()
+    dbias = torch.from_numpy(bias).cuda() if bias is not None else None
+    tok = torch.full((R, M), -7, dtype=torch.int32, device="cuda")
+    val = torch.zeros((R, M), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    api.topm_rows(dev.data_ptr(), R, N, M, tok.data_ptr(), val.data_ptr(), None,
+                  dbias.data_ptr() if dbias is not None else None)
+    torch.cuda.synchronize()
+    key = rows if bias is None else (rows + bias[None, :]).astype(np.float32)
+    etok, _ = expected(key, M)
+    np.testing.assert_array_equal(tok.cpu().numpy(), etok)
+    np.testing.assert_array_equal(val.cpu().numpy(), np.take_along_axis(rows, etok, axis=1))
+
+
+def test_topm_biased_few_eligible():
+    """fewer word-starting tokens than the list is long: the list holds them all, then -1 / 0 padding"""
+    import torch
+
+    from text_b200 import capi
+
+    api = capi.Api()
+    N, M, R = 2048, 105, 400
+    rng = np.random.default_rng(5)
+    rows = make_rows("logsoftmax", R, N, rng)
+    bias = np.full(N, -np.inf, np.float32)
+    ok = rng.choice(N, size=40, replace=False)
+    bias[ok] = -rng.random(40).astype(np.float32)
+    dev, dbias = torch.from_numpy(rows).cuda(), torch.from_numpy(bias).cuda()
+    tok = torch.full((R, M), -7, dtype=torch.int32, device="cuda")
+    val = torch.zeros((R, M), dtype=torch.float32, device="cuda")
+    api.topm_rows(dev.data_ptr(), R, N, M, tok.data_ptr(), val.data_ptr(), None, dbias.data_ptr())
+    torch.cuda.synchronize()
+    key = (rows + bias[None, :]).astype(np.float32)
+    etok, _ = expected(key, 40)
+    got = tok.cpu().numpy()
+    np.testing.assert_array_equal(got[:, :40], etok)
+    assert (got[:, 40:] == -1).all() and (val.cpu().numpy()[:, 40:] == 0).all()
+    np.testing.assert_array_equal(val.cpu().numpy()[:, :40], np.take_along_axis(rows, etok, axis=1))

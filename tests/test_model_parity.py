@@ -149,3 +149,17 @@ def run_widened(A, G, spec, em, exact, tol):
 def test_widened_modes(A, M, name, spec, em, exact):
     # same libm on both sides here: logAdd scores are bit-equal too
     run_widened(A, M, spec, em, True, 1e-9)
+
+
+def test_lexicon_split_workspace(A, M, monkeypatch):
+    """The generic step with its capacity-sized arrays (candidate records, merge table, representatives) in a
+    region of their own, as the device places them in a global slab when a wide beam outgrows shared memory
+    (FLT_TEST_HYBRID makes the logic harness do the same): results unchanged. Includes a word-LM case, whose
+    n-gram probes are bounded before they are made, and a histogram-ranked select (groups > K)."""
+    monkeypatch.setenv("FLT_TEST_HYBRID", "1")
+    cases = parity_cases.lexicon_cases()
+    ran = 0
+    for name, spec, em in cases[::3] + [c for c in cases if c[1]["lm"][0] == "arpa"][:3]:
+        run_case(A, M, spec, em)
+        ran += 1
+    assert ran >= 4

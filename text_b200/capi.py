@@ -98,6 +98,8 @@ SYMBOLS = {
     "flt_decoder_last_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "flt_topm_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_void_p]),
+    "flt_topm_rows_bias": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
 }
 
 _libs = {}
@@ -274,11 +276,30 @@ class Api:
     def stream(self, dec):
         return self.lib.flt_decoder_stream(dec)
 
-    def nbest(self, dec, B, T, nbest):
-        tokens = np.empty((B, nbest, T + 2), np.int32)
-        words = np.empty((B, nbest, T + 2), np.int32)
-        scores = np.empty((B, nbest, 3), np.float64)
-        counts = np.empty(B, np.int32)
+    def _pinned_out(self, B, T, nbest):
+        """page-locked result buffers, allocated once per shape and reused (numpy views of pinned torch tensors)"""
+        import torch
+
+        key = (B, T, nbest)
+        cache = self.__dict__.setdefault("_pinned", {})
+        if key not in cache:
+            cache.clear()  # one shape at a time: these are hundreds of MB
+            mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
+            cache[key] = (mk((B, nbest, T + 2), torch.int32), mk((B, nbest, T + 2), torch.int32),
+                          mk((B, nbest, 3), torch.float64), mk((B,), torch.int32))
+        return tuple(t.numpy() for t in cache[key])
+
+    def nbest(self, dec, B, T, nbest, pinned=False):
+        """n-best of the last batch. pinned=True: the arrays are page-locked buffers owned by this Api object and
+        overwritten by the next pinned call of the same shape (the device->host copy of a few hundred MB then runs
+        at the link rate instead of the pageable-memory rate)."""
+        if pinned:
+            tokens, words, scores, counts = self._pinned_out(B, T, nbest)
+        else:
+            tokens = np.empty((B, nbest, T + 2), np.int32)
+            words = np.empty((B, nbest, T + 2), np.int32)
+            scores = np.empty((B, nbest, 3), np.float64)
+            counts = np.empty(B, np.int32)
         self._ck(self.lib.flt_nbest_copy(dec, nbest, _i32p(tokens), _i32p(words),
                                          scores.ctypes.data_as(C.POINTER(C.c_double)), _i32p(counts)))
         return dict(tokens=tokens, words=words, scores=scores, counts=counts)
@@ -400,5 +421,9 @@ class Api:
         self._ck(self.lib.flt_decoder_workspace_bytes(dec, C.byref(n)))
         return n.value
 
-    def topm_rows(self, dev_emis_ptr, rows, N, M, dev_tok_ptr, dev_val_ptr, stream=None):
-        self._ck(self.lib.flt_topm_rows(dev_emis_ptr, rows, N, M, dev_tok_ptr, dev_val_ptr, stream))
+    def topm_rows(self, dev_emis_ptr, rows, N, M, dev_tok_ptr, dev_val_ptr, stream=None, dev_bias_ptr=None):
+        if dev_bias_ptr is None:
+            self._ck(self.lib.flt_topm_rows(dev_emis_ptr, rows, N, M, dev_tok_ptr, dev_val_ptr, stream))
+        else:
+            self._ck(self.lib.flt_topm_rows_bias(dev_emis_ptr, rows, N, M, dev_bias_ptr, dev_tok_ptr, dev_val_ptr,
+                                                 stream))

@@ -69,7 +69,10 @@ struct Lay {
   int gxStash;    // u8 per work item: 1 + best histogram bin its proposals reached in the first pass
   int gxList;     // int4 [2][Mwide]: root child of each list entry (lexicon), double-buffered
   int gxBest;     // u64: best representative score key of the frame
-  int total;
+  int total;      // bytes of both regions back to back (one region for the lexicon-free / single-pass steps)
+  int small;      // bytes of the small region (Ws::base), 128-byte aligned
+  int bigOff;     // offset of the capacity-sized region (Ws::big) from `base` when both sit together
+  int bigBytes;   // its size: offsets of candScore / candKey / candI / mh / rep / cslot / lnk / lhead count from `big`
 };
 
 struct DecCfg {
@@ -104,6 +107,7 @@ struct DecCfg {
   int lfBins;     // histogram bins of its select (pow2, multiple of 32)
   int gx;         // 1 = single-pass step with a guessed cut (beam_gx.h)
   int capChunks;  // its item chunk descriptors per beam
+  int bigGlobal;  // 1 = the capacity-sized region (Ws::big) is the CTA's global slab, `base` is shared memory
   float lmUpper;  // n-gram LM: no word scores above this (log10): bound used to skip hopeless probes
   int nTau;       // pruning rectangles: rows 1..tauA[k] x columns 0..tauCol[k] hold >= K regular cells
   int tauA[16];
@@ -218,10 +222,16 @@ enum { // ws.sc[] scalars
 
 // The workspace is addressed as base + constant-bank offset on every access (no pointer table in
 // local memory; with the shared-memory base the compiler emits LDS/STS with immediate offsets).
+// Two regions: `base` holds the small, hot arrays (beams, histogram, scalars, lists, row tables); `big` holds
+// the arrays sized by the candidate capacity (candidate records, merge table, representatives). Both sit in
+// shared memory when they fit (big = base + lay.bigOff); when the candidate capacity outgrows it, only `big`
+// moves to the CTA's global slab (DecCfg::bigGlobal) and the per-item traffic of the expansion passes —
+// histogram atomics, beam reads — stays on chip.
 struct Ws {
   char* base;
   const DecCfg* c;
   int* itemBin = nullptr; // pass 1 of the two-pass pruning: best bin reached by the current work item
+  char* big = nullptr;
   FLT_DEV Beam beam(int b) const {
     const Lay& L = c->lay;
     return Beam{(double*)(base + L.beamD[b]), (u64*)(base + L.beamFp[b]), (int*)(base + L.beamI[b]), c->K,
@@ -232,10 +242,10 @@ struct Ws {
   }
   FLT_DEV Cand cand() const {
     const Lay& L = c->lay;
-    return Cand{(double*)(base + L.candScore), (u64*)(base + L.candKey), (int*)(base + L.candI), c->capC};
+    return Cand{(double*)(big + L.candScore), (u64*)(big + L.candKey), (int*)(big + L.candI), c->capC};
   }
-  FLT_DEV int* mh() const { return (int*)(base + c->lay.mh); }       // [capH] merge table
-  FLT_DEV int* rep() const { return (int*)(base + c->lay.rep); }     // [capC] group representatives
+  FLT_DEV int* mh() const { return (int*)(big + c->lay.mh); }       // [capH] merge table
+  FLT_DEV int* rep() const { return (int*)(big + c->lay.rep); }     // [capC] group representatives
   FLT_DEV int* surv() const { return (int*)(base + c->lay.surv); }   // [2][capP] selected / ranked
   FLT_DEV u64* skey() const { return (u64*)(base + c->lay.skey); }   // [capP] ordered score keys
   FLT_DEV int* pos() const { return (int*)(base + c->lay.pos); }     // [capP] rank counters
@@ -247,19 +257,19 @@ struct Ws {
   FLT_DEV float* spec() const { return (float*)(base + c->lay.spec); } // [K+2] e[own], e[blank], e[sil]
   FLT_DEV int* wideOff() const { return (int*)(base + c->lay.wideOff); } // [K+1]
   FLT_DEV short* itemRow() const { return (short*)(base + c->lay.itemRow); }
-  FLT_DEV int* cslot() const { return (int*)(base + c->lay.cslot); }
+  FLT_DEV int* cslot() const { return (int*)(big + c->lay.cslot); }
   FLT_DEV int* gath() const { return (int*)(base + c->lay.gath); }
   FLT_DEV int* listNode() const { return (int*)(base + c->lay.listNode); }
   FLT_DEV float* listMax() const { return (float*)(base + c->lay.listMax); }
-  FLT_DEV int* lnk() const { return (int*)(base + c->lay.lnk); }
-  FLT_DEV int* lhead() const { return (int*)(base + c->lay.lhead); }
-  FLT_DEV u64* rkey() const { return (u64*)(base + c->lay.candKey); } // reps' score keys (reuses keyA)
+  FLT_DEV int* lnk() const { return (int*)(big + c->lay.lnk); }
+  FLT_DEV int* lhead() const { return (int*)(big + c->lay.lhead); }
+  FLT_DEV u64* rkey() const { return (u64*)(big + c->lay.candKey); } // reps' score keys (reuses keyA)
 };
 
 FLT_HD size_t alignUp(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 FLT_HD void makeLayout(DecCfg& c) {
-  size_t off = 0;
+  size_t off = 0, offBig = 0;
   auto take = [&](size_t bytes) {
     const size_t o = off;
     off = alignUp(off + bytes, 16);
@@ -270,6 +280,15 @@ FLT_HD void makeLayout(DecCfg& c) {
   const bool lf = c.lfFast != 0;
   const bool gx = c.gx != 0;
   const bool gxl = gx && c.lexicon;
+  // the generic step keeps the capacity-sized arrays in a region of their own (Ws::big); the lexicon-free and
+  // single-pass steps use one region (offsets from `base`, big == base)
+  const bool split = !lf && !gx;
+  auto takeBig = [&](size_t bytes) {
+    if (!split) return take(bytes);
+    const size_t o = offBig;
+    offBig = alignUp(offBig + bytes, 16);
+    return (int)o;
+  };
   for (int b = 0; b < 2; ++b) {
     L.beamD[b] = take(sizeof(double) * 3 * K);
     L.beamFp[b] = take(sizeof(u64) * (lf ? 4 : 2) * K);
@@ -278,11 +297,11 @@ FLT_HD void makeLayout(DecCfg& c) {
   }
   L.rowHash = take(gx ? 0 : sizeof(int) * c.capRH);
   L.rowI = take(lf || gx ? 0 : sizeof(int) * (kRowsInts * K + 8));
-  L.candScore = take(sizeof(double) * c.capC);
-  L.candKey = take(sizeof(u64) * (lf ? 1 : 2) * c.capC);
-  L.candI = take(sizeof(int) * (lf ? 3 : 6) * c.capC);
-  L.mh = take(lf ? 0 : sizeof(int) * c.capH);
-  L.rep = take(gx ? 0 : sizeof(int) * c.capC);
+  L.candScore = takeBig(sizeof(double) * c.capC);
+  L.candKey = takeBig(sizeof(u64) * (lf ? 1 : 2) * c.capC);
+  L.candI = takeBig(sizeof(int) * (lf ? 3 : 6) * c.capC);
+  L.mh = takeBig(lf ? 0 : sizeof(int) * c.capH);
+  L.rep = takeBig(gx ? 0 : sizeof(int) * c.capC);
   L.surv = take(gx ? 0 : sizeof(int) * 2 * c.capP);
   L.skey = take(lf ? 0 : sizeof(u64) * (gx ? c.capC : c.capP));
   L.pos = take(lf || gx ? 0 : sizeof(int) * c.capP);
@@ -293,7 +312,7 @@ FLT_HD void makeLayout(DecCfg& c) {
   L.spec = take(gx ? 0 : sizeof(float) * (K + 2));
   L.wideOff = take(gx ? 0 : sizeof(int) * (K + 1));
   L.itemRow = take(gx ? 0 : sizeof(short) * (c.wideTotal + 2));
-  L.cslot = take(lf ? 0 : sizeof(int) * c.capC);
+  L.cslot = takeBig(lf ? 0 : sizeof(int) * c.capC);
   L.gath = take(gx ? 0 : sizeof(int) * 64);
   L.gxCandX = take(gxl ? sizeof(int) * 3 * c.capC : 0);
   L.gxChunk = take(gxl ? sizeof(int) * 2 * 2 * (size_t)c.capChunks : 0);
@@ -308,10 +327,21 @@ FLT_HD void makeLayout(DecCfg& c) {
   L.lfDesc = take(lf ? sizeof(int) * c.capC : 0);                      // static work-item descriptors
   L.listNode = take(c.lexicon && c.wideRanked && !gx ? sizeof(int) * c.Mwide : 0);
   L.listMax = take(c.lexicon && c.wideRanked && !gx ? sizeof(float) * c.Mwide : 0);
-  L.lnk = take(c.logAdd ? sizeof(int) * c.capC : 0);
-  L.lhead = take(c.logAdd ? sizeof(int) * c.capC : 0);
+  L.lnk = takeBig(c.logAdd ? sizeof(int) * c.capC : 0);
+  L.lhead = takeBig(c.logAdd ? sizeof(int) * c.capC : 0);
   L.pruneCache = take(c.prune2 ? (size_t)c.wideTotal + c.K + kPruneEdgeCap : 0);
-  L.total = (int)off;
+  L.small = (int)alignUp(off, 128);
+  L.bigOff = split ? L.small : 0;
+  L.bigBytes = (int)alignUp(offBig, 128);
+  L.total = split ? L.small + L.bigBytes : (int)off; // both regions back to back
+}
+
+// the workspace views of a CTA: `base` = shared memory or the CTA's slab; with DecCfg::bigGlobal the
+// capacity-sized region lives in the slab while `base` is shared memory
+FLT_DEV Ws wsOf(char* base, const DecCfg& c, char* slab) {
+  Ws w{base, &c};
+  w.big = c.bigGlobal ? slab : base + c.lay.bigOff;
+  return w;
 }
 
 FLT_HD double negInf() { return bitsF64(0xFFF0000000000000ull); }
@@ -828,8 +858,32 @@ FLT_DEV void emitEdge(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& 
       if (slot >= 0) putCand(c, w, cur, slot, s, i, n, -1, child, 0, d, ev);
     }
   }
+  // n-gram word LM under the two-pass pruning: a word end's score is bounded from above with the LM's best
+  // possible score (c.lmUpper) BEFORE the table probes (a chain of dependent DRAM reads each). Every step from
+  // the LM score to the bin is monotone in floating point (float subtraction of lexMax, product with
+  // lmWeight >= 0, the two additions, pruneBin), so bin(bound) >= bin(score):
+  //   pass 1  the word end is not probed and not counted; only its bound's bin goes into the item's cache byte.
+  //           The cut is then chosen from the other candidates alone and can only sit lower than with the word
+  //           ends counted: pass 2 keeps a superset of what it kept before — still everything at or above the
+  //           cut, so the frame stays exact (and is verified to hold >= K groups as before);
+  //   pass 2  probed only if the bound reaches the cut.
+  const int pmode = w.sc()[SC_PMODE];
+  const bool lmBound = c.lm.kind != 0 && pmode != 0 && c.lmWeight >= 0;
+  auto boundSkips = [&](double extra) __attribute__((always_inline)) { // true: this word end needs no probe now
+    if (!lmBound) return false;
+    const float dub = c.lmUpper - lexMax;
+    const double sub = score + c.lmWeight * (double)dub + extra;
+    if (sub < tau) return true;
+    const int bub = pruneBin(w.sc(), sub);
+    if (pmode == 1) {
+      if (w.itemBin && bub > *w.itemBin) *w.itemBin = bub;
+      return true;
+    }
+    return bub < w.sc()[SC_PCUT];
+  };
   if (!(lex == 0 && cur.tok(i) == n)) { // LexiconDecoder.cpp:114-122
     for (int l = l0; l < l1; ++l) {
+      if (boundSkips(c.wordScore)) break; // the bound is the same for every label of this node
       const int label = t.labels[l];
       const float d = lmWordScore(c, cur, i, label) - lexMax;
       const double s = score + c.lmWeight * (double)d + c.wordScore;
@@ -838,7 +892,7 @@ FLT_DEV void emitEdge(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& 
       if (slot >= 0) putCand(c, w, cur, slot, s, i, n, label, 0, CF_NEW, d, ev);
     }
   }
-  if (l0 == l1 && c.hasUnk) { // LexiconDecoder.cpp:145-164
+  if (l0 == l1 && c.hasUnk && !boundSkips(c.unkScore)) { // LexiconDecoder.cpp:145-164
     const float d = lmWordScore(c, cur, i, c.unk) - lexMax;
     const double s = score + c.lmWeight * (double)d + c.unkScore;
     if (!(s < tau)) {
@@ -1061,7 +1115,9 @@ FLT_DEV void findCutBin(const Cta& cta, const Ws& w, int need) {
 // descending, deterministic ties) into surv[capP..], and return how many there are.
 // Radix select on the score keys, most significant *varying* bit first (from the AND/OR of the
 // keys); a cut bin with <= 32 members is finished by one warp.
-FLT_DEV int phaseSelect(const Cta& cta, const DecCfg& c, const Ws& w, int nRep) {
+// `binned`: the groups come out of the two-pass pruning, i.e. their scores lie in the bins [SC_PCUT, 255) of
+// the frame's monotone map (pruneBin) — the select then ranks by histogram instead of by counting.
+FLT_DEV int phaseSelect(const Cta& cta, const DecCfg& c, const Ws& w, int nRep, bool binned = false) {
   const Cand cd = w.cand();
   const int K = c.K;
   int* sc = w.sc();
@@ -1075,6 +1131,83 @@ FLT_DEV int phaseSelect(const Cta& cta, const DecCfg& c, const Ws& w, int nRep) 
   int* mh = w.mh();
   const int* cslot = w.cslot();
   int nSel;
+  if (binned && nRep > K && nRep < 65536 && !(c.dbg & 4)) {
+    // Histogram rank (as in beam_lf.h): the kept score range [lower edge of the cut bin, top] is spread over
+    // 256 fine bins; a suffix scan gives every group the number of groups in higher bins, groups with fewer
+    // than K above them are listed grouped by bin (position = groups above + arrival order in the bin) and
+    // settle their exact rank against the members of their own bin only. O(groups x bin occupancy) instead
+    // of O(groups^2); crowded bins only lengthen the comparisons, the order is the deterministic one.
+    const double lo = bitsF64(((u64)(unsigned)sc[SC_PLO_HI] << 32) | (unsigned)sc[SC_PLO_LO]);
+    const float pscale = bitsF32((uint32_t)sc[SC_PSCALE]);
+    const float cutF = (float)sc[SC_PCUT];
+    const float fine = 256.0f / (256.0f - cutF);
+    int* bs = (int*)(w.rkey() + c.capC); // the merge keys' second half is dead by now: [capC] bin | slot, [capC] list
+    int* list = bs + c.capC;
+    for (int r = cta.tid; r < nRep; r += cta.nthr) {
+      const int x = rep[r];
+      mh[cslot[x]] = -1; // leave the merge table empty
+      const float p = ((float)(cd.score(x) - lo) * pscale - cutF) * fine; // monotone in the score
+      const int bin = p >= 255.0f ? 255 : (p > 0.0f ? (int)p : 0);
+      bs[r] = (bin << 16) | atomAdd(&hist[bin], 1);
+    }
+    cta.sync();
+#if FLT_DEVICE_BUILD
+    if (cta.tid < 32) { // hist[b] <- groups in bins above b
+      const int lane = cta.tid;
+      int h[8], part = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        h[k] = hist[255 - (lane * 8 + k)];
+        part += h[k];
+      }
+      int incl = part;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+      }
+      int cum = incl - part;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        hist[255 - (lane * 8 + k)] = cum;
+        cum += h[k];
+      }
+    }
+#else
+    if (cta.tid == 0) {
+      int cum = 0;
+      for (int b = 255; b >= 0; --b) {
+        const int h = hist[b];
+        hist[b] = cum;
+        cum += h;
+      }
+    }
+#endif
+    cta.sync();
+    for (int r = cta.tid; r < nRep; r += cta.nthr) {
+      const int ab = hist[bs[r] >> 16];
+      if (ab < K) list[ab + (bs[r] & 0xFFFF)] = r;
+    }
+    cta.sync();
+    for (int r = cta.tid; r < nRep; r += cta.nthr) {
+      const int bin = bs[r] >> 16;
+      const int ab = hist[bin];
+      if (ab >= K) continue; // K groups score strictly higher
+      const int end = bin == 0 ? nRep : hist[bin - 1]; // members of the bin sit at list[ab .. end)
+      const u64 ka = rkey[r];
+      const int xa = rep[r];
+      int cnt = ab;
+      for (int q = ab; q < end; ++q) {
+        const int rb = list[q];
+        const u64 kb = rkey[rb];
+        cnt += (kb > ka || (kb == ka && rb != r && candBetter(cd, rep[rb], xa))) ? 1 : 0;
+      }
+      if (cnt < K) ranked[cnt] = xa;
+    }
+    cta.sync();
+    for (int b = cta.tid; b < 256; b += cta.nthr) hist[b] = 0; // the next frame's first pass counts from zero
+    cta.sync();
+    return K;
+  }
   if (nRep <= K) {
     for (int r = cta.tid; r < nRep; r += cta.nthr) {
       const int x = rep[r];
@@ -1647,7 +1780,7 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
   if (prune && cta.tid == 0) sc[SC_PMODE] = 0; // decodeEnd's candidates are not pruned
   const int nRep = sc[SC_NREP];
   mark(5); // merge
-  const int nSel = phaseSelect(cta, c, w, nRep);
+  const int nSel = phaseSelect(cta, c, w, nRep, prune);
   mark(6); // select
 #if FLT_DEVICE_BUILD
   if (stats && cta.tid == 0) {
@@ -1839,7 +1972,7 @@ FLT_DEV void streamRestoreBeam(const Cta& cta, const DecCfg& c, const Ws& w, con
 
 template <bool W>
 FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char* base) {
-  const Ws w{base, &c};
+  const Ws w = wsOf(base, c, a.wsGlobal ? a.wsGlobal + (long long)cta.bid * a.wsStride : nullptr);
   const int K = c.K;
   ctaInitWorkspace(cta, c, w, base);
   for (int b = cta.bid; b < a.B; b += cta.nblk) {

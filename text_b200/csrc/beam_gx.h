@@ -1083,7 +1083,7 @@ FLT_DEV void gxLoadListDirect(const Cta& cta, const DecCfg& c, const Ws& w, cons
 
 template <bool LEX>
 FLT_DEV void gxDecodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char* base) {
-  const Ws w{base, &c};
+  const Ws w = wsOf(base, c, nullptr); // one region
   const int K = c.K;
   gxInitWorkspace(cta, c, w);
   for (int b = cta.bid; b < a.B; b += cta.nblk) {

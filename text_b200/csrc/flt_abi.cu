@@ -36,6 +36,12 @@ __global__ void __launch_bounds__(256, 3) flt_k_topm(TopMCfg c, TopMArgs a) {
   topmCta(cta, c, a, smem);
 }
 // streaming select (topm_stream.h): one TMA-staged row per 128-thread CTA, four CTAs per SM
+// long lists (341..680 entries wanted): twice the threads rank twice the survivors, two CTAs per SM
+__global__ void __launch_bounds__(2 * kStreamThreads, 2) flt_k_topm_stream256(TopMCfg c, StreamLay sl, TopMArgs a) {
+  extern __shared__ __align__(128) char smem[];
+  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
+  topmStreamCta(cta, c, sl, a, smem);
+}
 __global__ void __launch_bounds__(kStreamThreads, 4) flt_k_topm_stream(TopMCfg c, StreamLay sl, TopMArgs a) {
   extern __shared__ __align__(128) char smem[];
   Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
@@ -147,7 +153,8 @@ void launchTopM(const TopMCfg& c, const TopMArgs& a, int grid, size_t smem, rt::
 }
 void launchTopMStream(const TopMCfg& c, const StreamLay& sl, const TopMArgs& a, int grid, rt::Stream s) {
 #if FLT_DEVICE_BUILD
-  flt_k_topm_stream<<<grid, kStreamThreads, sl.total, s>>>(c, sl, a);
+  if (sl.threads == kStreamThreads) flt_k_topm_stream<<<grid, kStreamThreads, sl.total, s>>>(c, sl, a);
+  else flt_k_topm_stream256<<<grid, 2 * kStreamThreads, sl.total, s>>>(c, sl, a);
   FLT_RT_TRY(cudaGetLastError());
 #else
   std::vector<char> sm(sl.total + 128, (char)0x5A);
@@ -162,15 +169,18 @@ void launchTopMStream(const TopMCfg& c, const StreamLay& sl, const TopMArgs& a, 
 bool planStream(int N, int M, int bst, const float* dBias, float biasMax, TopMCfg& t, StreamLay& sl) {
   const bool restricted = bst < N;
   const int want = restricted ? bst : M;
-  if (N % 4 != 0 || N < 64 || want > (getenv("FLT_STREAM_WANT") ? atoi(getenv("FLT_STREAM_WANT")) : 340) || M > 2048 || (dBias && restricted) || getenv("FLT_NO_STREAM")) return false;
+  // survivors aimed at: 1.5 .. 2.5 x want, inside 3/4 of the capacity (4 per thread)
+  const int wantShort = getenv("FLT_STREAM_WANT") ? atoi(getenv("FLT_STREAM_WANT")) : 340;
+  if (N % 4 != 0 || N < 64 || want > 2 * wantShort || M > 2048 || (dBias && restricted) || getenv("FLT_NO_STREAM")) return false;
+  sl.threads = want > wantShort ? 2 * kStreamThreads : kStreamThreads;
   t = TopMCfg{};
   t.N = N;
   t.M = M;
   t.bst = restricted ? bst : N;
   t.bias = dBias;
   t.biasMax = biasMax;
-  t.P = std::max(kStreamThreads, nextPow2(want));
-  t.capS = kStreamCap;
+  t.P = std::max(sl.threads, nextPow2(want));
+  t.capS = kStreamSPT * sl.threads;
   t.extra = 2 * kProdBins;
   t.fast = 1;
   t.stage = 0;
@@ -607,7 +617,8 @@ struct flt_decoder {
   StreamLay slay{};
   int streamGridMax = 1;
   int fusedGridMax = 1;
-  size_t wsBytes = 0, topmSmem = 0;
+  size_t wsBytes = 0, topmSmem = 0; // wsBytes: whole workspace (both regions)
+  size_t smemBytes = 0, slabBytes = 0; // dynamic shared memory per CTA / global slab per CTA of the step kernel
   int gridMax = 1, topmGridMax = 1;
   std::vector<int> wideOffHost;
   rt::DevBuf dWideOff, dBias, dTrans, dLfDesc;
@@ -886,10 +897,10 @@ void planFor(flt_decoder& d, int N) {
     if ((size_t)d.slay.total > smemMax) {
       d.streamSel = false;
     } else {
-      FLT_RT_TRY(cudaFuncSetAttribute(flt_k_topm_stream, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      std::max(d.slay.total, 48 * 1024)));
+      auto* ks = d.slay.threads == kStreamThreads ? flt_k_topm_stream : flt_k_topm_stream256;
+      FLT_RT_TRY(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(d.slay.total, 48 * 1024)));
       int occS = 1;
-      FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, flt_k_topm_stream, kStreamThreads, d.slay.total));
+      FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, ks, d.slay.threads, d.slay.total));
       d.streamGridMax = std::max(1, occS) * d.numSMs;
     }
   }
@@ -897,28 +908,37 @@ void planFor(flt_decoder& d, int N) {
   // (the single-pass step keeps large beams on chip with one CTA per SM rather than spilling to a slab)
   const size_t smemLimit = getenv("FLT_SMEM_KB") ? (size_t)atoi(getenv("FLT_SMEM_KB")) * 1024
                                                  : (c.gx ? smemMax : 110 * 1024);
+  // three placements of the workspace (beam_core.h Ws): everything in shared memory; the small region in
+  // shared memory and the capacity-sized arrays in the CTA's global slab (the candidate capacity of a wide
+  // beam, or one grown by the overflow retry, must not push the histogram and the beams off the chip: the
+  // small region may then take a whole SM's shared memory); everything in the slab
+  const size_t smallBytes = ((size_t)c.lay.small + 255) / 256 * 256;
   const bool smemOk = d.wsBytes <= std::min<size_t>(smemMax, smemLimit);
+  const bool hybrid = !smemOk && c.lay.bigBytes > 0 && smallBytes <= smemMax && !getenv("FLT_NO_HYBRID");
+  d.cfg.bigGlobal = c.bigGlobal = hybrid ? 1 : 0;
+  d.smemBytes = smemOk ? d.wsBytes : (hybrid ? smallBytes : 0);
+  d.slabBytes = smemOk ? 0 : (hybrid ? ((size_t)c.lay.bigBytes + 255) / 256 * 256 : d.wsBytes);
   int occ2 = 1;
   auto* k256 = c.gx ? (c.lexicon ? flt_k_gx<true> : flt_k_gx<false>) : (c.wide ? flt_k_decode_wide : flt_k_decode);
   auto* k512 = c.gx ? (c.lexicon ? flt_k_gx512<true> : flt_k_gx512<false>)
                     : (c.wide ? flt_k_decode512_wide : flt_k_decode512);
   auto* kGmem = c.gx ? (c.lexicon ? flt_k_gx_gmem<true> : flt_k_gx_gmem<false>)
                      : (c.wide ? flt_k_decode_gmem_wide : flt_k_decode_gmem);
-  if (smemOk) {
+  if (d.smemBytes) {
     FLT_RT_TRY(cudaFuncSetAttribute(k256, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)std::max<size_t>(d.wsBytes, 48 * 1024)));
+                                    (int)std::max<size_t>(d.smemBytes, 48 * 1024)));
     FLT_RT_TRY(cudaFuncSetAttribute(k512, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)std::max<size_t>(d.wsBytes, 48 * 1024)));
+                                    (int)std::max<size_t>(d.smemBytes, 48 * 1024)));
     if (d.threads == 512)
-      FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k512, 512, d.wsBytes));
+      FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k512, 512, d.smemBytes));
     else
-      FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k256, d.threads, d.wsBytes));
+      FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k256, d.threads, d.smemBytes));
   } else {
     FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, kGmem, d.threads > 256 ? 256 : d.threads, 0));
     occ2 = std::min(occ2, 4);
   }
   d.gridMax = std::max(1, occ2) * d.numSMs;
-  d.useSmemFlag = smemOk;
+  d.useSmemFlag = d.smemBytes != 0;
   if (d.fused) {
     if ((size_t)d.flay.total > smemMax) {
       d.fused = false;
@@ -937,13 +957,18 @@ void planFor(flt_decoder& d, int N) {
   d.streamGridMax = 3;
   d.fusedGridMax = 3;
   d.useSmemFlag = true;
+  // host model: FLT_TEST_HYBRID=1 puts the capacity-sized region into a separate slab, as the device does
+  // when the workspace outgrows shared memory
+  d.cfg.bigGlobal = c.bigGlobal = (getenv("FLT_TEST_HYBRID") && c.lay.bigBytes > 0) ? 1 : 0;
+  d.smemBytes = c.bigGlobal ? (size_t)c.lay.small : d.wsBytes;
+  d.slabBytes = c.bigGlobal ? (size_t)c.lay.bigBytes : 0;
 #endif
   d.planN = N;
   if (getenv("FLT_DBG_PLAN"))
     fprintf(stderr, "[flt plan] lexicon=%d K=%d N=%d M=%d gx=%d lfFast=%d fused=%d wide=%d prune2=%d threads=%d capC=%d "
                     "capChunks=%d ws=%zu B (%s) fusedSmem=%d grid<=%d streamSelect=%d (%d B, grid<=%d)\n",
             c.lexicon, c.K, N, c.M, c.gx, c.lfFast, (int)d.fused, c.wide, c.prune2, d.threads, c.capC, c.capChunks,
-            d.wsBytes, d.useSmemFlag ? "shared" : "global slab", d.fused ? d.flay.total : 0,
+            d.wsBytes, d.slabBytes == 0 ? "shared" : (d.smemBytes ? "small region shared, capacity-sized arrays in a global slab" : "global slab"), d.fused ? d.flay.total : 0,
             d.fused ? d.fusedGridMax : d.gridMax, (int)d.streamSel, d.streamSel ? d.slay.total : 0, d.streamGridMax);
 }
 
@@ -1037,13 +1062,13 @@ void runChunk(flt_decoder& d, const float* dEmis, int Bc, int T, int N, const in
     launchFused(c, d.ftcfg, d.flay, a, grid, s);
     d.launches++;
   } else {
-    if (!d.useSmemFlag) {
-      d.ws.reserve(d.wsBytes * grid);
+    if (d.slabBytes) {
+      d.ws.reserve(d.slabBytes * grid);
       a.wsGlobal = d.ws.as<char>();
-      a.wsStride = (long long)d.wsBytes;
+      a.wsStride = (long long)d.slabBytes;
     }
     KernelTimer kt(d, 1);
-    launchDecode(c, a, grid, d.useSmemFlag ? d.wsBytes : 0, s, d.threads);
+    launchDecode(c, a, grid, d.smemBytes, s, d.threads);
     d.launches++;
   }
   BacktraceArgs b{};
@@ -1268,12 +1293,12 @@ bool runStreamOnce(flt_decoder& d, const float* emis, int T, int N, bool finish)
   a.streamShift = d.on.shift;
   a.hScore = d.sScore.as<double>();
   a.hCount = d.sCount.as<int>();
-  if (!d.useSmemFlag) {
-    d.ws.reserve(d.wsBytes);
+  if (d.slabBytes) {
+    d.ws.reserve(d.slabBytes);
     a.wsGlobal = d.ws.as<char>();
-    a.wsStride = (long long)d.wsBytes;
+    a.wsStride = (long long)d.slabBytes;
   }
-  launchDecode(c, a, 1, d.useSmemFlag ? d.wsBytes : 0, s, d.threads);
+  launchDecode(c, a, 1, d.smemBytes, s, d.threads);
   // mirror the new rows: frames 1..T (+ the finish row T+1)
   const int nNew = T + (finish ? 1 : 0);
   std::vector<int> par(rows * K), tok(rows * K), wrd(rows * K, -1), cnt(rows), st(1);
@@ -1890,12 +1915,18 @@ int flt_decoder_workspace_bytes(const flt_decoder* dec, int64_t* out) {
 
 int flt_topm_rows(const float* dEmissions, int64_t rows, int32_t N, int32_t M, int32_t* dTok,
                   float* dVal, void* stream) {
+  return flt_topm_rows_bias(dEmissions, rows, N, M, nullptr, dTok, dVal, stream);
+}
+
+int flt_topm_rows_bias(const float* dEmissions, int64_t rows, int32_t N, int32_t M, const float* dBias,
+                       int32_t* dTok, float* dVal, void* stream) {
   return guarded([&] {
     if (M < 1 || M > 2048 || M > N) throw FltError(FLT_ERR_INVALID, "need 1 <= M <= min(N, 2048)");
     {
       TopMCfg st;
       StreamLay sl;
-      if ((reinterpret_cast<uintptr_t>(dEmissions) & 15) == 0 && planStream(N, M, N, nullptr, 0.0f, st, sl)) {
+      if ((reinterpret_cast<uintptr_t>(dEmissions) & 15) == 0 && (reinterpret_cast<uintptr_t>(dBias) & 15) == 0 &&
+          planStream(N, M, N, dBias, 0.0f, st, sl)) {
         TopMArgs sa{};
         sa.emis = dEmissions;
         sa.rows = rows;
@@ -1907,9 +1938,9 @@ int flt_topm_rows(const float* dEmissions, int64_t rows, int32_t N, int32_t M, i
         int dev = 0, sms = 148, occ = 1;
         FLT_RT_TRY(cudaGetDevice(&dev));
         FLT_RT_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        FLT_RT_TRY(cudaFuncSetAttribute(flt_k_topm_stream, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        std::max(sl.total, 48 * 1024)));
-        FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, flt_k_topm_stream, kStreamThreads, sl.total));
+        auto* ks = sl.threads == kStreamThreads ? flt_k_topm_stream : flt_k_topm_stream256;
+        FLT_RT_TRY(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(sl.total, 48 * 1024)));
+        FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ks, sl.threads, sl.total));
         gridS = std::max(1, occ) * sms;
 #endif
         if (rows > 0) launchTopMStream(st, sl, sa, (int)std::min<int64_t>(rows, gridS), (rt::Stream)stream);
@@ -1920,11 +1951,11 @@ int flt_topm_rows(const float* dEmissions, int64_t rows, int32_t N, int32_t M, i
     t.N = N;
     t.M = M;
     t.bst = N;
-    t.bias = nullptr;
+    t.bias = dBias;
     t.capS = 2048;
     t.P = std::max(kThreads, nextPow2(M));
     t.fast = (N % 4 == 0) && N <= 4 * kFastVec * kThreads && M <= 256 &&
-             (reinterpret_cast<uintptr_t>(dEmissions) & 15) == 0;
+             (reinterpret_cast<uintptr_t>(dEmissions) & 15) == 0 && (reinterpret_cast<uintptr_t>(dBias) & 15) == 0;
     t.stage = !t.fast && (size_t)N * 4 <= 100 * 1024;
     TopMSmem ts;
     const size_t smem = (carveTopM(nullptr, t, ts) + 255) / 256 * 256;

@@ -427,7 +427,7 @@ FLT_DEV FrameIn fusedFrameIn(const DecCfg& c, const BatchArgs& a, const FusedVie
 FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, const FuseLay& fl,
                       const BatchArgs& a, char* smem) {
   const FusedView v{smem, &fl};
-  const Ws w{smem + fl.ws, &c};
+  const Ws w = wsOf(smem + fl.ws, c, nullptr); // one region (lexicon-free step)
   TopMSmem ps;
   carveTopM(smem + fl.prod, tc, ps);
 #if FLT_DEVICE_BUILD

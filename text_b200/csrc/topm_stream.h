@@ -10,8 +10,7 @@
 //      want-th value minus an adaptive margin), collecting the few elements that reach it
 //   -> the stage is free: one thread issues the bulk copy of the CTA's NEXT row, which streams in
 //      from HBM behind the rest of the select
-//   -> (lexicon decoder) the survivors' ranking keys e[n] + bias[n] are formed — bias is gathered for
-//      the survivors only — and filtered against the bound again
+//      (lexicon decoder: of the ranking keys e[n] + bias[n]; the bias row is read through L1 alongside)
 //   -> the survivors are ranked exactly (128-bin histogram over [bound, maximum], suffix scan,
 //      comparison inside bins) and the list is written.
 // If at least `want` elements passed, the result is exact (every element >= the want-th largest was
@@ -28,41 +27,56 @@ namespace flt {
 
 constexpr int kStreamThreads = 128;
 constexpr int kStreamSPT = 4;    // survivors a thread ranks: up to 512 per row
-constexpr int kStreamCap = 512;  // survivor capacity (TopMCfg::capS)
+                                 // (survivor capacity TopMCfg::capS = kStreamSPT x threads: 512, or 1024 for long lists)
 
 #if FLT_DEVICE_BUILD
-// survivors of the raw-emission filter -> ranking keys e + bias that reach `bound` (compacted in place);
-// returns their number and this thread's largest key value
-FLT_DEV int streamRekey(const Cta& p, const TopMCfg& c, TopMSmem& s, int n1, float bound, float& top) {
-  unsigned long long* sv = s.sortBuf + c.capS;
-  unsigned long long mine[kStreamSPT];
+// prodFilter (fused_core.h) on the ranking keys e[n] + bias[n] of the lexicon decoder: the bias row (4N bytes,
+// the same for every row and every CTA) is read through L1 next to the staged emissions, so the one pass
+// collects exactly the keys that reach `bound` — filtering raw emissions against bound - max(bias) lets almost
+// the whole row through when the bias spreads wider than the emissions do (a smeared n-gram LM).
+FLT_DEV float4 streamKeyed(const float4 x, const float4 b) {
   const float ninf = bitsF32(0xFF800000u);
-  top = ninf;
-#pragma unroll
-  for (int z = 0; z < kStreamSPT; ++z) {
-    const int a = p.tid + z * p.nthr;
-    mine[z] = 0ull;
-    if (a < n1) {
-      const unsigned long long k = sv[a];
-      const int tok = topmKeyTok(k);
-      const float b = __ldg(c.bias + tok);
-      if (!isNegInf(b)) {
-        const float kv = topmKeyVal(k) + b;
-        if (kv >= bound) {
-          mine[z] = topmKey(kv, tok);
-          top = fmaxf(top, kv);
-        }
+  float4 k;
+  k.x = isNegInf(b.x) ? ninf : x.x + b.x;
+  k.y = isNegInf(b.y) ? ninf : x.y + b.y;
+  k.z = isNegInf(b.z) ? ninf : x.z + b.z;
+  k.w = isNegInf(b.w) ? ninf : x.w + b.w;
+  return k;
+}
+FLT_DEV float prodFilterBiased(const Cta& p, const TopMCfg& c, TopMSmem& s, const float4* r4, const float4* b4,
+                               float bound, unsigned long long* sv) {
+  const int nvec = c.N >> 2;
+  float top = bitsF32(0xFF800000u);
+  for (int v0 = p.tid; v0 < nvec; v0 += 32 * p.nthr) {
+    unsigned hits = 0;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const int v = v0 + k * p.nthr;
+      if (v < nvec) {
+        const float4 x = streamKeyed(r4[v], __ldg(b4 + v));
+        const float mx = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+        top = fmaxf(top, mx);
+        hits |= (mx >= bound ? 1u : 0u) << k;
       }
     }
-  }
-  p.sync(); // every entry has been read
-  if (p.tid == 0) s.cnt[0] = 0;
-  p.sync();
+    while (hits) {
+      const int k = __ffs(hits) - 1;
+      hits &= hits - 1;
+      const int v = v0 + k * p.nthr;
+      const float4 x = streamKeyed(r4[v], __ldg(b4 + v));
+      const float xs[4] = {x.x, x.y, x.z, x.w};
+      const unsigned m4 = (x.x >= bound ? 1u : 0u) | (x.y >= bound ? 2u : 0u) | (x.z >= bound ? 4u : 0u) |
+                          (x.w >= bound ? 8u : 0u);
+      int pos = atomAdd(&s.cnt[0], __popc(m4));
 #pragma unroll
-  for (int z = 0; z < kStreamSPT; ++z)
-    if (mine[z]) sv[atomAdd(&s.cnt[0], 1)] = mine[z];
-  p.sync();
-  return s.cnt[0];
+      for (int q = 0; q < 4; ++q)
+        if (m4 & (1u << q)) {
+          if (pos < c.capS) sv[pos] = topmKey(xs[q], v * 4 + q);
+          ++pos;
+        }
+    }
+  }
+  return top;
 }
 #endif
 
@@ -151,21 +165,63 @@ FLT_DEV void streamRow(const Cta& p, const TopMCfg& c, TopMSmem& s, ProdGuess& p
       stageFree();
     } else {
       // ---- guess mode: one pass over the stage against the running guess, stage released at once
-      const float fb = biased ? bound - c.biasMax : bound;
-      top = prodFilter(p, c, s, (const float4*)row, fb, sv);
+      top = biased ? prodFilterBiased(p, c, s, (const float4*)row, b4, bound, sv)
+                   : prodFilter(p, c, s, (const float4*)row, bound, sv);
       p.sync(); // every thread is done reading the stage
       stageFree();
       ns = s.cnt[0];
       bool miss = ns > c.capS || ns > kStreamSPT * p.nthr;
-      if (!miss && biased) ns = streamRekey(p, c, s, ns, bound, top);
       miss = miss || !okCount(ns) || (biased && ns < (want < N ? want : N) && bound > bitsF32(0xFF7FFFFFu));
       pg.missRate = 0.9f * pg.missRate + (miss ? 0.1f : 0.0f);
       if (miss) {
         // too many survivors: guess closer to the want-th value next time; too few: further below it
         pg.margin = fminf(fmaxf(pg.margin * (ns > want ? 0.7f : 1.4f), 0.02f), 4.0f);
         p.sync(); // everyone has read cnt[0]
-        if (canExact) exactSelect((const float4*)grow, true); // exact two-pass select of this row from L2
-        else generic = true;
+        if (canExact) {
+          exactSelect((const float4*)grow, true); // exact two-pass select of this row from L2
+        } else {
+          // long lists: filter the row again from L2 with the bound moved towards the side that missed (a
+          // bracket once both sides are known); exact as soon as want <= survivors <= capacity
+          generic = true;
+          const float lowest = bitsF32(0xFF7FFFFFu);
+          const int wantN = want < N ? want : N;
+          float bLo = ninf, bHi = bitsF32(0x7F800000u); // too many at bLo, too few at bHi
+          auto ctaTop = [&](float t) { // row maximum, uniform over the CTA (prodFilter returns per-thread maxima)
+            const unsigned tk = __reduce_max_sync(0xffffffffu, orderedKey32(t));
+            if (lane == 0) bnd[32 + warp] = orderedKey32Inv(tk);
+            p.sync();
+            float m = bnd[32];
+            for (int i = 1; i < nw; ++i) m = fmaxf(m, bnd[32 + i]);
+            p.sync();
+            return m;
+          };
+          top = ctaTop(top);
+          for (int tries = 0; tries < 6 && generic; ++tries) {
+            const bool tooFew = ns < wantN;
+            float nb;
+            if (!(bound < 3.0e38f)) { // no guess yet (first row of the CTA): start just below the maximum
+              nb = top - 0.5f;
+            } else {
+              if (tooFew) bHi = bound;
+              else bLo = bound;
+              const float span = fmaxf(top - bound, 1e-3f);
+              nb = tooFew ? bound - 1.5f * span : bound + 0.4f * span;
+              if (!isNegInf(bLo) && bHi < 3.0e38f) nb = 0.5f * (bLo + bHi);
+              if (tooFew && tries >= 4) nb = lowest; // (biased) fewer expandable tokens than wanted: take them all
+              if (!(nb < bHi) || !(nb > bLo)) break;
+            }
+            if (!(nb > lowest)) nb = lowest;
+            bound = nb;
+            if (p.tid == 0) s.cnt[0] = 0;
+            p.sync();
+            top = biased ? prodFilterBiased(p, c, s, (const float4*)grow, b4, bound, sv)
+                         : prodFilter(p, c, s, (const float4*)grow, bound, sv);
+            p.sync();
+            ns = s.cnt[0];
+            top = ctaTop(top);
+            generic = !okCount(ns) || (ns < wantN && (!biased || bound > lowest));
+          }
+        }
         if (pg.missRate > 0.2f && canExact) { // stop guessing for a while; the spell doubles each time (<= 4096 rows)
           pg.exactRows = pg.exactSpell;
           pg.exactSpell = pg.exactSpell < 4096 ? pg.exactSpell * 2 : 4096;
@@ -311,6 +367,7 @@ FLT_DEV void streamRow(const Cta& p, const TopMCfg& c, TopMSmem& s, ProdGuess& p
 }
 
 struct StreamLay { // byte offsets from the CTA's shared-memory base
+  int threads;     // 128 (lists up to ~340 entries) or 256
   int prod;        // scratch (TopMSmem)
   int row;         // staged emission row [N] fp32, 128-byte aligned
   int mbar;        // rowFull

@@ -48,11 +48,31 @@ def _global(group, r):
     return r if group is None else dist.get_global_rank(group, r)
 
 
+_pinned = {}
+
+
+def _to_host(t, name):
+    """device tensor -> numpy; CUDA tensors land in a page-locked buffer that is reused per (name, shape) —
+    a pageable destination would cap the copy of the gathered blocks (hundreds of MB per rank) far below the link"""
+    if t.device.type != "cuda":
+        return t.cpu().numpy()
+    key = (name, tuple(t.shape), t.dtype)
+    if key not in _pinned:
+        if len(_pinned) > 8:
+            _pinned.clear()
+        _pinned[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h = _pinned[key]
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return h.numpy()
+
+
 def gather_nbest(local, B, T, K, device, dst=0, group=None):
     """`local` = dict(tokens [Bl,K,T+2] int32, words [Bl,K,T+2] int32, scores [Bl,K,3] f64,
     counts [Bl] int32) as numpy arrays or tensors for this rank's block. Returns the same dict for
     the whole batch on rank `dst` (None elsewhere). Blocks are padded to ceil(B/world) rows so the
-    collective moves fixed-size buffers."""
+    collective moves fixed-size buffers. On CUDA the returned arrays are page-locked buffers owned by this module
+    and overwritten by the next gather of the same shape."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     per = (B + world - 1) // world
     L = T + 2
@@ -77,7 +97,7 @@ def gather_nbest(local, B, T, K, device, dst=0, group=None):
             for r in range(world):
                 lo, hi = block(B, world, r)
                 rows.append(bufs[r][: hi - lo])
-            out[name] = torch.cat(rows, dim=0).cpu().numpy()
+            out[name] = _to_host(torch.cat(rows, dim=0), name)
     return out if rank == dst else None
 
 
