@@ -409,10 +409,14 @@ class Api:
             names = ("rows", "degrees_scan", "pass1_histogram", "cut_bin", "pass2_emit", "merge", "select",
                      "new_beam")
             out["phase_cycles_per_frame"] = {n: round(v[4 + i] / frames, 1) for i, n in enumerate(names)}
+            # frames decided in one pass against a guessed cut / frames whose guess missed (redone in two passes)
+            out["guessed_cut_frames"], out["guessed_cut_misses"] = int(v[12]), int(v[13])
         elif any(v[4:11]):
             names = ("insert", "emit", "scan", "rank", "new_beam", "wait_list", "handover_gather")
             out["phase_cycles_per_frame"] = {n: round(v[4 + i] / frames, 1) for i, n in enumerate(names)}
             out["select_guess_misses"] = int(v[11])
+            # frames expanded against the guessed pruning bound / frames whose guess cut too deep (expanded twice)
+            out["guessed_bound_frames"], out["guessed_bound_misses"] = int(v[12]), int(v[13])
             out["emit_cycles_per_warp"] = [round(v[16 + i] / frames, 1) for i in range(12) if v[16 + i]]
         return out
 

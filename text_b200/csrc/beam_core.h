@@ -153,7 +153,8 @@ struct BatchArgs {
 struct Beam {
   double* d;  // [3][K] score, emittingModelScore, lmScore
   u64* fp;    // [2][K] LM-state fingerprint (+ [2][K] fingerprint of the parent state, beam_lf.h)
-  int* iv;    // [5][K] lex, tok, prevBlank, nctx, anc; then ctx [K][kMaxCtx]
+  int* iv;    // [5][K] lex, tok, prevBlank, nctx, anc; then (n-gram LM) ctx [K][kMaxCtx], the context's
+              // back-off weights bo [K][kMaxCtx] (float bits) and their presence mask boMask [K]
   int K;
   int* xv = nullptr; // [3][K] Trie cache (beam_gx.h)
   FLT_DEV double& score(int i) const { return d[i]; }
@@ -169,6 +170,8 @@ struct Beam {
   FLT_DEV int& nctx(int i) const { return iv[3 * K + i]; }
   FLT_DEV int& anc(int i) const { return iv[4 * K + i]; } // ancestor at the last checkpoint row (backtrace)
   FLT_DEV int* ctx(int i) const { return iv + 5 * K + i * kMaxCtx; }
+  FLT_DEV float* bo(int i) const { return (float*)(iv + 5 * K + K * kMaxCtx) + i * kMaxCtx; } // tables.h
+  FLT_DEV int& boMask(int i) const { return iv[5 * K + 2 * K * kMaxCtx + i]; }
 };
 
 constexpr int kPruneEdgeCap = 4096; // trie-edge work items whose pass-1 result is cached
@@ -214,6 +217,8 @@ enum { // ws.sc[] scalars
   SC_PMODE, SC_PCUT, SC_PLO_LO, SC_PLO_HI, SC_PSCALE, // two-pass candidate pruning (frameStep)
   SC_TLO, SC_THI, // previous phase stamp of thread 0 (counters on)
   SC_WANT, SC_WHOLD, // two-pass pruning: candidates to keep this frame; frames left at the wide setting
+  SC_GSPAN, SC_GHOLD, SC_GBIN, // guessed cut: kept score span below the top (float bits, 0 = none), frames left
+                               // without guessing after a miss, this frame's guessed cut bin (0 = two passes)
   SC_GXCUTBIN, SC_GXKEPT, // beam_gx.h: cut bin of the exact redo and the proposals it keeps
   SC_GX,                  // beam_gx.h: two sets of scalars (2 x 8 ints)
   SC_WCNT = SC_GX + 16 /* 32 warp counters follow */,
@@ -292,10 +297,10 @@ FLT_HD void makeLayout(DecCfg& c) {
   for (int b = 0; b < 2; ++b) {
     L.beamD[b] = take(sizeof(double) * 3 * K);
     L.beamFp[b] = take(sizeof(u64) * (lf ? 4 : 2) * K);
-    L.beamI[b] = take(sizeof(int) * (5 * K + (c.lm.kind ? K * kMaxCtx : 0)));
+    L.beamI[b] = take(sizeof(int) * (5 * K + (c.lm.kind ? K * (2 * kMaxCtx + 1) : 0)));
     L.beamX[b] = take(gxl ? sizeof(int) * 3 * K : 0); // inside the beam block: saved / restored with it
   }
-  L.rowHash = take(gx ? 0 : sizeof(int) * c.capRH);
+  L.rowHash = take(gx ? 0 : sizeof(int) * (lf ? 2 : 1) * c.capRH); // beam_lf.h: one fingerprint table per beam
   L.rowI = take(lf || gx ? 0 : sizeof(int) * (kRowsInts * K + 8));
   L.candScore = takeBig(sizeof(double) * c.capC);
   L.candKey = takeBig(sizeof(u64) * (lf ? 1 : 2) * c.capC);
@@ -320,8 +325,8 @@ FLT_HD void makeLayout(DecCfg& c) {
   L.gxStash = take(gx ? (gxl ? (size_t)c.capChunks * 8 : 3 * (size_t)c.capP) : 0);
   L.gxList = take(gxl ? sizeof(int) * 4 * 2 * (size_t)c.Mwide : 0);
   L.gxBest = take(gx ? 16 : 0);
-  L.lfSlotB = take(lf ? sizeof(int) * c.capRH : 0);
-  L.lfSlotOf = take(lf ? sizeof(int) * K : 0);
+  L.lfSlotB = take(lf ? sizeof(int) * 2 * c.capRH : 0);
+  L.lfSlotOf = take(lf ? sizeof(int) * 2 * K : 0);
   L.lfCbin = take(lf ? sizeof(unsigned short) * 2 * c.capC : 0); // bin, arrival order in the bin
   L.lfAbove = take(lf ? sizeof(unsigned short) * 16 * c.lfBins : 0); // one copy per warp (<= 16)
   L.lfDesc = take(lf ? sizeof(int) * c.capC : 0);                      // static work-item descriptors
@@ -807,7 +812,8 @@ FLT_DEV void emitSpecials(const Cta& cta, const DecCfg& c, const Ws& w, const Be
 
 FLT_DEV float lmWordScore(const DecCfg& c, const Beam& cur, int p, int usrIdx) {
   if (c.lm.kind == 0) return 0.0f;
-  return ngramScore(c.lm, cur.ctx(p), cur.nctx(p), c.lm.usr2lm[usrIdx]);
+  // the back-offs of hypothesis p's LM state were looked up when the state was created (phaseFinalize)
+  return ngramScoreCached(c.lm, cur.ctx(p), cur.nctx(p), c.lm.usr2lm[usrIdx], cur.bo(p), cur.boMask(p));
 }
 
 // one trie edge of hypothesis i: child node `child` reached by token n (LexiconDecoder.cpp:62-164)
@@ -1459,6 +1465,7 @@ FLT_DEV void phaseFinalize(const Cta& cta, const DecCfg& c, const Ws& w, const B
         if (c.lm.kind) {
           const int wlm = lab < 0 ? c.lm.eos : c.lm.usr2lm[lab];
           nxt.nctx(q) = ngramAdvanceCtx(c.lm, cur.ctx(p), cur.nctx(p), wlm, nxt.ctx(q));
+          nxt.boMask(q) = ngramContextBackoffs(c.lm, nxt.ctx(q), nxt.nctx(q), nxt.bo(q)); // once per new LM state
         }
       } else {
         nxt.fpA(q) = cur.fpA(p);
@@ -1466,7 +1473,11 @@ FLT_DEV void phaseFinalize(const Cta& cta, const DecCfg& c, const Ws& w, const B
         if (c.lm.kind) {
           const int nc = cur.nctx(p);
           nxt.nctx(q) = nc;
-          for (int k = 0; k < nc; ++k) nxt.ctx(q)[k] = cur.ctx(p)[k];
+          for (int k = 0; k < nc; ++k) {
+            nxt.ctx(q)[k] = cur.ctx(p)[k];
+            nxt.bo(q)[k] = cur.bo(p)[k];
+          }
+          nxt.boMask(q) = cur.boMask(p);
         }
       }
       f.hParent[q] = p;
@@ -1633,7 +1644,9 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
   int localBin = -1;
   Ws wp = w;
   unsigned char* pcache = c.prune2 ? (unsigned char*)(w.base + c.lay.pruneCache) : nullptr;
-  auto emitAll = [&](int pass) __attribute__((always_inline)) { // 0 = no pruning, 1 = histogram pass, 2 = materialise
+  // pass: 0 = no pruning, 1 = histogram pass, 2 = materialise (items that cannot reach the cut are skipped from
+  // the first pass' cache), 3 = materialise against a guessed cut (no first pass, every item is evaluated)
+  auto emitAll = [&](int pass) __attribute__((always_inline)) {
     const int cut = pass == 2 ? sc[SC_PCUT] : 0;
     wp.itemBin = pass == 1 ? &localBin : nullptr;
     auto skip = [&](int slot) { return pass == 2 && pcache && (int)pcache[slot] <= cut; };
@@ -1708,6 +1721,8 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
   // Two-pass pruning for the lexicon decoder (no corner bound there): histogram the scores of
   // everything the frame would propose, keep the bins that hold the best ~3K candidates.
   const bool prune = c.prune2 != 0;
+  int nCand = 0;
+  bool done = false;
   if (prune) {
     if (cta.tid == 0) {
       // candidate scores lie below best hypothesis + bonuses for log-probability emissions; the
@@ -1720,62 +1735,131 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
       if (c.beamThreshold + 4.0 < span) span = c.beamThreshold + 4.0;
       const double lo = hi - span;
       const u64 lb = f64Bits(lo);
+      const float scale = (float)kPruneBins / (float)span;
       sc[SC_PLO_LO] = (int)(unsigned)lb;
       sc[SC_PLO_HI] = (int)(unsigned)(lb >> 32);
-      sc[SC_PSCALE] = (int)f32Bits((float)kPruneBins / (float)span);
-      sc[SC_PMODE] = 1;
+      sc[SC_PSCALE] = (int)f32Bits(scale);
       sc[SC_BIN] = 0; // fewer candidates than wanted: keep every bin
       // keep ~1.5 K candidates; after a frame whose kept bins held fewer than K merge groups (it was
       // redone without the cut) fall back to 3K+64 for a while
       const int hold = sc[SC_WHOLD];
       sc[SC_WANT] = hold > 0 ? 3 * c.K + 64 : c.pruneWant;
       if (hold > 0) sc[SC_WHOLD] = hold - 1;
+      // Guessed cut (experiment, FLT_DBG=8; OFF by default): in steady state the K-th best candidate sits about
+      // as far below the top as it did in the previous frame, so the frame is first tried in ONE pass against
+      // the bin of (top - that span): if the kept candidates fit the capacity and form >= K merge groups the
+      // result is exact (everything at or above the cut was kept, as with a cut chosen from a histogram) and
+      // the histogram pass is saved; otherwise the frame is done again with the two exact passes and guessing
+      // pauses for a few frames. Measured on cfg 3 (B200): the kept count moves by a whole bin's worth of
+      // candidates (~30) from frame to frame, 44 % of the guesses missed, 7.90 k utt/s against 8.27 k without.
+      const float gspan = bitsF32((uint32_t)sc[SC_GSPAN]);
+      const int ghold = sc[SC_GHOLD];
+      int gbin = 0;
+      if ((c.dbg & 8) && gspan > 0.0f && ghold == 0 && hold == 0 && nH == c.K) {
+        const float pos = ((float)span - gspan) * scale;
+        gbin = pos >= (float)(kPruneBins - 3) ? kPruneBins - 3 : (pos > 1.0f ? (int)pos : 0);
+      }
+      if (ghold > 0) sc[SC_GHOLD] = ghold - 1;
+      sc[SC_GBIN] = gbin;
+      sc[SC_PMODE] = gbin > 0 ? 2 : 1;
+      sc[SC_PCUT] = gbin;
     }
     cta.sync();
     mark(1); // degrees + scan
-    emitAll(1); // pass 1: histogram only
-    mark(2); // pass 1
-    // cut = lowest bin with fewer than `want` candidates in higher bins (one warp; bins re-zeroed)
-    findCutBin(cta, w, sc[SC_WANT]);
-    cta.sync();
-    if (cta.tid == 0) {
-      sc[SC_PMODE] = 2;
-      sc[SC_PCUT] = sc[SC_BIN];
+    const int gbin = sc[SC_GBIN];
+    if (gbin > 0) {
+      emitAll(3);
+      mark(4); // the single pass
+      nCand = sc[SC_NCAND];
+      const bool ovf = sc[SC_OVF] != 0;
+      if (!ovf) {
+        phaseMerge<W>(cta, c, w, nCand);
+        done = sc[SC_NREP] >= c.K;
+      }
+      cta.sync();
+      if (!done) { // undo: empty the merge table, reset the counters, exact passes below
+        if (!ovf)
+          for (int x = cta.tid; x < nCand; x += cta.nthr)
+            if (w.cand().parflag(x) & CF_ALIVE) w.mh()[w.cslot()[x]] = -1;
+        if (cta.tid == 0) {
+          sc[SC_NREP] = 0;
+          sc[SC_OR_LO] = 0;
+          sc[SC_OR_HI] = 0;
+          sc[SC_AND_LO] = -1;
+          sc[SC_AND_HI] = -1;
+          sc[SC_NCAND] = 0;
+          sc[SC_OVF] = 0;
+          sc[SC_PCUT] = 0;
+          sc[SC_PMODE] = 1;
+          sc[SC_GHOLD] = 8;
+#if FLT_DEVICE_BUILD
+          if (stats) atomicAdd(stats + 13, 1ull);
+#endif
+        }
+      } else if (cta.tid == 0) {
+        // steer the kept count towards 1.25 K .. 1.5 K + 32 candidates (merge groups ~ candidates)
+        float g = bitsF32((uint32_t)sc[SC_GSPAN]);
+        if (nCand > c.K + c.K / 2 + 32) g *= 0.95f;
+        else if (nCand < c.K + c.K / 4) g *= 1.05f;
+        sc[SC_GSPAN] = (int)f32Bits(g);
+#if FLT_DEVICE_BUILD
+        if (stats) atomicAdd(stats + 12, 1ull);
+#endif
+      }
+      cta.sync();
     }
-    cta.sync();
-  }
-  mark(3); // cut bin
-  emitAll(prune ? 2 : 0);
-  mark(4); // pass 2 (or the only pass)
-  int nCand = sc[SC_NCAND];
-  if (sc[SC_OVF]) {
-    if (cta.tid == 0) *status |= 1;
-    nCand = nCand < c.capC ? nCand : c.capC;
-  }
-  phaseMerge<W>(cta, c, w, nCand);
-  if (prune && sc[SC_PCUT] > 0 && sc[SC_NREP] < c.K) {
-    // the kept bins hold fewer than K merge groups: take everything (rare)
-    cta.sync();
-    for (int x = cta.tid; x < nCand; x += cta.nthr)
-      if (w.cand().parflag(x) & CF_ALIVE) w.mh()[w.cslot()[x]] = -1;
-    if (cta.tid == 0) {
-      sc[SC_NREP] = 0;
-      sc[SC_OR_LO] = 0;
-      sc[SC_OR_HI] = 0;
-      sc[SC_AND_LO] = -1;
-      sc[SC_AND_HI] = -1;
-      sc[SC_NCAND] = 0;
-      sc[SC_PCUT] = 0;
-      sc[SC_WHOLD] = 64;
+    if (!done) {
+      emitAll(1); // pass 1: histogram only
+      mark(2); // pass 1
+      // cut = lowest bin with fewer than `want` candidates in higher bins (one warp; bins re-zeroed)
+      findCutBin(cta, w, sc[SC_WANT]);
+      cta.sync();
+      if (cta.tid == 0) {
+        sc[SC_PMODE] = 2;
+        sc[SC_PCUT] = sc[SC_BIN];
+        // next frame's guess: the span this exact cut keeps, widened to about twice the candidates
+        const float scale = bitsF32((uint32_t)sc[SC_PSCALE]);
+        const float kept = (float)(kPruneBins - sc[SC_BIN]) / scale;
+        sc[SC_GSPAN] = sc[SC_BIN] > 0 ? (int)f32Bits(kept * 1.05f) : 0;
+      }
+      cta.sync();
     }
-    cta.sync();
-    emitAll(2);
+  }
+  if (!done) {
+    mark(3); // cut bin
+    emitAll(prune ? 2 : 0);
+    mark(4); // pass 2 (or the only pass)
     nCand = sc[SC_NCAND];
     if (sc[SC_OVF]) {
       if (cta.tid == 0) *status |= 1;
       nCand = nCand < c.capC ? nCand : c.capC;
     }
     phaseMerge<W>(cta, c, w, nCand);
+    if (prune && sc[SC_PCUT] > 0 && sc[SC_NREP] < c.K) {
+      // the kept bins hold fewer than K merge groups: take everything (rare)
+      cta.sync();
+      for (int x = cta.tid; x < nCand; x += cta.nthr)
+        if (w.cand().parflag(x) & CF_ALIVE) w.mh()[w.cslot()[x]] = -1;
+      if (cta.tid == 0) {
+        sc[SC_NREP] = 0;
+        sc[SC_OR_LO] = 0;
+        sc[SC_OR_HI] = 0;
+        sc[SC_AND_LO] = -1;
+        sc[SC_AND_HI] = -1;
+        sc[SC_NCAND] = 0;
+        sc[SC_PCUT] = 0;
+        sc[SC_WHOLD] = 64;
+        sc[SC_GSPAN] = 0;
+      }
+      cta.sync();
+      emitAll(2);
+      nCand = sc[SC_NCAND];
+      if (sc[SC_OVF]) {
+        if (cta.tid == 0) *status |= 1;
+        nCand = nCand < c.capC ? nCand : c.capC;
+      }
+      phaseMerge<W>(cta, c, w, nCand);
+    }
   }
   if (prune && cta.tid == 0) sc[SC_PMODE] = 0; // decodeEnd's candidates are not pruned
   const int nRep = sc[SC_NREP];
@@ -1818,7 +1902,7 @@ FLT_DEV void finishStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam
     float ls = 0.0f;
     int flags = CF_FINISH;
     if (c.lm.kind) { // KenLM::finish: score </s>, state = child(-1); ZeroLM: same state, 0
-      ls = ngramScore(c.lm, cur.ctx(i), cur.nctx(i), c.lm.eos);
+      ls = ngramScoreCached(c.lm, cur.ctx(i), cur.nctx(i), c.lm.eos, cur.bo(i), cur.boMask(i));
       flags |= CF_NEW;
     }
     const double score = cur.score(i) + c.lmWeight * (double)ls;
@@ -1835,11 +1919,17 @@ FLT_DEV void finishStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam
 struct LfCarry { // emissions of the NEXT frame, loaded while the current one retires (registers)
   float eOwn, eBlank, eSil;
   int valid;
+  // guessed pruning bound of the lexicon-free step (uniform over the CTA): distance of the K-th best candidate
+  // below the frame's upper bound in the previous frame (< 0: none yet), the safety factor applied to it, and
+  // the frames left without guessing after a miss
+  float gap = -1.0f, gfac = 1.3f;
+  int ghold = 0;
 };
-FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur,
-                         const Beam& nxt, const FrameIn& f, unsigned long long* stats, LfCarry& carry);
-FLT_DEV void lfFinish(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, const Beam& nxt,
-                      const FrameIn& f);
+FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, int curIdx, const FrameIn& f,
+                         unsigned long long* stats, LfCarry& carry);
+FLT_DEV void lfFinish(const Cta& cta, const DecCfg& c, const Ws& w, int curIdx, const FrameIn& f);
+FLT_DEV void lfTabBuild(const Cta& cta, const Ws& w, int beamIdx, int nH);
+FLT_DEV void lfTabClear(const Cta& cta, const Ws& w, int beamIdx, int nH);
 FLT_DEV void lfBuildItemDesc(const Cta& cta, const DecCfg& c, const Ws& w);
 
 // One CTA decodes utterances bid, bid+nblk, ... start to finish. `base` is the CTA's workspace:
@@ -1848,10 +1938,10 @@ FLT_DEV void lfBuildItemDesc(const Cta& cta, const DecCfg& c, const Ws& w);
 FLT_DEV void ctaInitWorkspace(const Cta& cta, const DecCfg& c, const Ws& w, char* base) {
   const int K = c.K;
   for (int i = cta.tid; i <= K; i += cta.nthr) w.wideOff()[i] = c.wideOff[i];
-  for (int i = cta.tid; i < c.capRH; i += cta.nthr) w.rows().hash[i] = -1;
+  for (int i = cta.tid; i < (c.lfFast ? 2 : 1) * c.capRH; i += cta.nthr) w.rows().hash[i] = -1;
   if (c.lfFast) {
     int* slotB = (int*)(base + c.lay.lfSlotB);
-    for (int i = cta.tid; i < c.capRH; i += cta.nthr) slotB[i] = -1;
+    for (int i = cta.tid; i < 2 * c.capRH; i += cta.nthr) slotB[i] = -1;
     for (int i = cta.tid; i < c.lfBins; i += cta.nthr) w.hist()[i] = 0;
     lfBuildItemDesc(cta, c, w);
   } else {
@@ -1868,6 +1958,8 @@ FLT_DEV void ctaInitWorkspace(const Cta& cta, const DecCfg& c, const Ws& w, char
     sc[SC_AND_LO] = -1;
     sc[SC_AND_HI] = -1;
     sc[SC_WHOLD] = 0;
+    sc[SC_GSPAN] = 0;
+    sc[SC_GHOLD] = 0;
     sc[SC_PMODE] = 0; // allocCand reads these in every mode; only the two-pass pruning sets them
     sc[SC_PCUT] = 0;
     sc[SC_BIN] = 0;
@@ -1892,11 +1984,16 @@ FLT_DEV void seedUtterance(const DecCfg& c, const Ws& w, const BatchArgs& a, int
   B0.tok(0) = c.sil;
   B0.pb(0) = 0;
   B0.nctx(0) = 0;
-  if (c.lm.kind && c.lm.order > 1) {
-    B0.ctx(0)[0] = c.lm.bos;
-    B0.nctx(0) = 1;
+  if (c.lm.kind) {
+    if (c.lm.order > 1) {
+      B0.ctx(0)[0] = c.lm.bos;
+      B0.nctx(0) = 1;
+    }
+    B0.boMask(0) = ngramContextBackoffs(c.lm, B0.ctx(0), B0.nctx(0), B0.bo(0));
   }
   w.sc()[SC_NH] = 1;
+  w.sc()[SC_GSPAN] = 0; // the guessed cut of the two-pass pruning starts over with every utterance
+  w.sc()[SC_GHOLD] = 0;
   a.status[b] = 0;
   const long long h0 = ((long long)b * (a.T + 2)) * K;
   a.hParent[h0] = -1;
@@ -1982,6 +2079,10 @@ FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char
     if (a.streamBeam && a.streamRestore) streamRestoreBeam(cta, c, w, a);
     else if (cta.tid == 0) seedUtterance(c, w, a, b);
     LfCarry carry{0.0f, 0.0f, 0.0f, 0};
+    if (c.lfFast) { // fingerprint table of the first beam (beam_lf.h keeps one per beam from then on)
+      cta.sync();
+      lfTabBuild(cta, w, 0, w.sc()[SC_NH]);
+    }
     // token list of frame 0 into the workspace
     const long long row0 = (long long)b * a.T;
     if (c.listInSmem && len > 0) {
@@ -2040,7 +2141,7 @@ FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char
           asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + off));
       }
 #endif
-      if (c.lfFast) lfFrameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.stats, carry);
+      if (c.lfFast) lfFrameStep(cta, c, w, curIdx, f, a.stats, carry);
       else frameStep<W>(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.status + b, a.stats);
       if (pf) {
 #if FLT_DEVICE_BUILD
@@ -2068,12 +2169,13 @@ FLT_DEV void decodeCta(const Cta& cta, const DecCfg& c, const BatchArgs& a, char
     if (a.streamBeam && a.streamNoFinish) { // decodeStep chunk: keep the beam for the next launch
       cta.sync();
       streamSaveBeam(cta, c, w, a, curIdx);
+      if (c.lfFast) lfTabClear(cta, w, curIdx, w.sc()[SC_NH]);
       continue;
     }
     int nFin = 0;
     if (w.sc()[SC_NH] != 0) {
       const FrameIn f = finishFrameIn(c, a, b, len);
-      if (c.lfFast) lfFinish(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f);
+      if (c.lfFast) lfFinish(cta, c, w, curIdx, f);
       else finishStep<W>(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f);
       curIdx ^= 1;
       nFin = w.sc()[SC_NH];

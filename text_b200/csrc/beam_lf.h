@@ -35,10 +35,41 @@ struct LfTab { // fingerprint -> row members
   uint32_t mask;
 };
 
-FLT_DEV LfTab lfTab(const Ws& w) {
+// One table per beam (index = beam index): the table of the NEXT beam is filled by the threads that create its
+// hypotheses (end of lfFrameStep) while the current beam's is emptied, so a frame starts with its table ready.
+FLT_DEV LfTab lfTab(const Ws& w, int beamIdx) {
   const Lay& L = w.c->lay;
-  return LfTab{(int*)(w.base + L.rowHash), (int*)(w.base + L.lfSlotB), (int*)(w.base + L.lfSlotOf),
-               (uint32_t)w.c->capRH - 1};
+  const int cap = w.c->capRH;
+  return LfTab{(int*)(w.base + L.rowHash) + beamIdx * cap, (int*)(w.base + L.lfSlotB) + beamIdx * cap,
+               (int*)(w.base + L.lfSlotOf) + beamIdx * w.c->K, (uint32_t)cap - 1};
+}
+// hypothesis i of `beam` (fingerprint fa, fb already stored in the beam) into its table
+FLT_DEV void lfTabInsert(const LfTab& t, const Beam& beam, int i, u64 fa, u64 fb) {
+  uint32_t s = (uint32_t)fa & t.mask;
+  for (;;) {
+    const int old = atomCAS(&t.a[s], -1, i);
+    if (old == -1) break;
+    if (beam.fpA(old) == fa && beam.fpB(old) == fb) {
+      t.b[s] = i; // a row has at most two members
+      break;
+    }
+    s = (s + 1) & t.mask;
+  }
+  t.slotOf[i] = (int)s;
+}
+// table of a beam that was not produced by lfFrameStep (seed, restored stream beam); the caller synchronises
+FLT_DEV void lfTabBuild(const Cta& cta, const Ws& w, int beamIdx, int nH) {
+  const LfTab t = lfTab(w, beamIdx);
+  const Beam beam = w.beam(beamIdx);
+  for (int i = cta.tid; i < nH; i += cta.nthr) lfTabInsert(t, beam, i, beam.fpA(i), beam.fpB(i));
+}
+FLT_DEV void lfTabClear(const Cta& cta, const Ws& w, int beamIdx, int nH) {
+  const LfTab t = lfTab(w, beamIdx);
+  for (int i = cta.tid; i < nH; i += cta.nthr) {
+    const int s = t.slotOf[i];
+    t.a[s] = -1;
+    t.b[s] = -1;
+  }
 }
 FLT_DEV unsigned short* lfCbin(const Ws& w) { return (unsigned short*)(w.base + w.c->lay.lfCbin); }
 
@@ -208,9 +239,11 @@ struct LfPhaseClock {
 };
 
 FLT_DEV int* lfItemDesc(const Ws& w) { return (int*)(w.base + w.c->lay.lfDesc); }
-// Work items of a frame: [0, wideTotal) = cells (hypothesis, ranked column) of all K hypotheses,
-// column-major; then K repeat items, K blank items and (silScore > 0 only) K sil cells. Item x owns candidate
-// slot x; items of hypotheses >= nH are dead. desc = hypothesis | column << 12 | kind << 24.
+// Work items of a frame: K repeat items, K blank items and (silScore > 0 only) K sil cells first — the repeat
+// item of hypothesis p is item p, i.e. it belongs to thread p, which created the hypothesis and already holds
+// its emission of this frame in a register — then the cells (hypothesis, ranked column) of all K hypotheses,
+// column-major. Item x owns candidate slot x; items of hypotheses >= nH are dead.
+// desc = hypothesis | column << 12 | kind << 24.
 FLT_DEV void lfBuildItemDesc(const Cta& cta, const DecCfg& c, const Ws& w) {
   // the host orders the cells column-major (column 0 of every hypothesis, then column 1, ...): the
   // cells most likely to survive the bound sit together in the first warps' first sweep, and the
@@ -219,49 +252,54 @@ FLT_DEV void lfBuildItemDesc(const Cta& cta, const DecCfg& c, const Ws& w) {
   for (int x = cta.tid; x < c.capC; x += cta.nthr) desc[x] = c.lfDesc[x];
 }
 
-FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur,
-                         const Beam& nxt, const FrameIn& f, unsigned long long* stats, LfCarry& carry) {
+FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, int curIdx, const FrameIn& f,
+                         unsigned long long* stats, LfCarry& carry) {
   int* sc = w.sc();
   const int nH = sc[SC_NH];
   if (nH == 0) return; // the beam died (Utils.h:155-158)
   LfPhaseClock pc;
   pc.start(cta, stats);
   const int K = c.K;
-  const LfTab t = lfTab(w);
+  const Beam cur = w.beam(curIdx), nxt = w.beam(curIdx ^ 1);
+  const LfTab t = lfTab(w, curIdx);     // filled when this beam was created
+  const LfTab tn = lfTab(w, curIdx ^ 1); // empty; filled below with the new beam
   const Cand cd = w.cand();
   float* spec = w.spec();
   int* hist = w.hist();
   const int NB = c.lfBins;
 
-  // scattered emission reads, published for the threads that own the special items (the fused
-  // kernel has already gathered them from the staged row: f.specReady)
-  if (carry.valid) { // loaded while the previous frame retired
-    if (cta.tid < nH) spec[cta.tid] = carry.eOwn;
-    for (int i = cta.tid + cta.nthr; i < nH; i += cta.nthr) { // beams wider than the CTA
-      const int n = cur.tok(i);
-      spec[i] = (n >= 0 && n < c.N) ? f.e[n] : 0.0f;
+  // The scattered emission reads of the special items (e[own token] per hypothesis, e[blank], e[sil]). With
+  // K <= threads every special item is processed by a thread that holds its value in a register: thread p
+  // created hypothesis p at the end of the previous frame and loaded e_next[token] then (carry); every thread
+  // loaded e_next[blank] and e_next[sil]. No shared-memory hand-over, no barrier before the expansion.
+  const bool direct = K <= cta.nthr;
+  float eOwnR = 0.0f, eBlankR = 0.0f, eSilR = 0.0f;
+  if (direct) {
+    if (carry.valid) {
+      eOwnR = carry.eOwn;
+      eBlankR = carry.eBlank;
+      eSilR = carry.eSil;
+    } else { // first frame of the utterance (or of a stream chunk)
+      const int n = cta.tid < nH ? cur.tok(cta.tid) : -1;
+      eOwnR = (n >= 0 && n < c.N) ? f.e[n] : 0.0f;
+      eBlankR = c.ctc ? f.e[c.blank] : 0.0f;
+      eSilR = f.e[c.sil];
     }
-    if (cta.tid == cta.nthr - 1) {
-      spec[K] = carry.eBlank;
-      spec[K + 1] = carry.eSil;
-    }
-  } else if (!f.specReady) {
-    lfGatherSpec(cta, c, w, cur, nH, f.e);
-  }
-  // (1) fingerprint table of the beam
-  for (int i = cta.tid; i < nH; i += cta.nthr) {
-    const u64 fa = cur.fpA(i), fb = cur.fpB(i);
-    uint32_t s = (uint32_t)fa & t.mask;
-    for (;;) {
-      const int old = atomCAS(&t.a[s], -1, i);
-      if (old == -1) break;
-      if (cur.fpA(old) == fa && cur.fpB(old) == fb) {
-        t.b[s] = i; // a row has at most two members
-        break;
+  } else { // beams wider than the CTA: published through shared memory
+    if (carry.valid) {
+      if (cta.tid < nH) spec[cta.tid] = carry.eOwn;
+      for (int i = cta.tid + cta.nthr; i < nH; i += cta.nthr) {
+        const int n = cur.tok(i);
+        spec[i] = (n >= 0 && n < c.N) ? f.e[n] : 0.0f;
       }
-      s = (s + 1) & t.mask;
+      if (cta.tid == cta.nthr - 1) {
+        spec[K] = carry.eBlank;
+        spec[K + 1] = carry.eSil;
+      }
+    } else {
+      lfGatherSpec(cta, c, w, cur, nH, f.e);
     }
-    t.slotOf[i] = (int)s;
+    cta.sync();
   }
 
   // corner bound (beam_core.h frameStep): lanes 0..nTau-1 of every warp take one rectangle each
@@ -294,21 +332,41 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
   const float eTop = (f.listLen > 0 && f.topTok[0] >= 0) ? f.topVal[0] : 0.0f;
   double upper = cur.score(0) + (double)eTop;
   if (c.silScore > 0) upper += c.silScore;
+  // Guessed bound. The corner bound is safe but loose (about six candidates pass it for every survivor). In
+  // steady state the K-th best candidate sits about as far below `upper` as it did one frame earlier, so the
+  // frame is first expanded against upper - gfac * (that distance): if at least K candidates pass, they contain
+  // the K best (every materialised candidate is a distinct merge group) and the result is exact; if fewer
+  // pass, the frame is expanded again against the corner bound and guessing pauses for a few frames.
+  const double tauCorner = tau;
+  bool guessed = false;
+  if (carry.gap >= 0.0f && carry.ghold == 0 && nH == K && !(c.dbg & 16)) {
+    const double g = upper - (double)(carry.gap * carry.gfac);
+    if (g > tau) {
+      tau = g;
+      guessed = true;
+    }
+  }
+  if (carry.ghold > 0) --carry.ghold;
+  pc.mark(0); // (no barrier: the beam, its table and the zeroed histogram were published by the previous frame's last one)
+
+  // (2) candidates, each in the slot of its work item, and the histogram of their scores
+  // item x -> (hypothesis, column | kind) is fixed for the CTA's lifetime (lfItemDesc, built once):
+  // K repeat, K blank and K sil-cell items first, then the cells of all K hypotheses
+  const int* desc = lfItemDesc(w);
+  const int items = c.wideTotal + (c.silScore > 0 ? 3 : 2) * K;
+  unsigned short* cbin = lfCbin(w);
+  unsigned short* cslot = cbin + c.capC;
+  int* list = w.rep();  // [capC] relevant candidates
+  u64* lkey = w.rkey(); // [capC] their ordered score keys
+  int total = 0;        // live candidates of the frame
+  int nRel = 0;         // relevant ones (list length)
+  unsigned short* above;
+  for (;;) { // at most twice: against the guessed bound, then (on a miss) against the corner bound
   // (double -> float conversion, the float subtraction of a constant and the multiplication by a
   // positive constant are all monotone, so bins never invert the score order)
   const float rangeF = (float)(upper - tau);
   const bool binned = rangeF > 0.0f && rangeF < 3.0e38f; // finite, non-degenerate
   const float scaleF = binned ? (float)NB / rangeF : 0.0f;
-  cta.sync(); // ---- B1
-  pc.mark(0);
-
-  // (2) candidates, each in the slot of its work item, and the histogram of their scores
-  // item x -> (hypothesis, column | kind) is fixed for the CTA's lifetime (lfItemDesc, built once):
-  // cells of hypothesis p first (all K hypotheses), then K repeat, K blank and K sil-cell items
-  const int* desc = lfItemDesc(w);
-  const int items = c.wideTotal + (c.silScore > 0 ? 3 : 2) * K;
-  unsigned short* cbin = lfCbin(w);
-  unsigned short* cslot = cbin + c.capC;
   for (int x = cta.tid; x < items; x += cta.nthr) {
     bool alive = false;
     double score = 0.0;
@@ -333,16 +391,16 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
     } else {
       if (kind == 1) {
         tok = h.tok;
-        ev = spec[par];
+        ev = direct ? eOwnR : spec[par]; // direct: item par belongs to thread par
         alive = lfRepeat(c, cur, t, f, h, ev, tau, score);
       } else if (kind == 2) {
         tok = c.blank;
-        ev = spec[K];
+        ev = direct ? eBlankR : spec[K];
         flags = CF_PB;
         alive = lfBlank(c, f, h, ev, tau, score);
       } else {
         tok = c.sil;
-        ev = spec[K + 1];
+        ev = direct ? eSilR : spec[K + 1];
         flags = CF_NEW;
         if (inTokenSetV(c, f, tok, ev)) alive = lfCell(c, cur, t, h, tok, ev, tau, score);
       }
@@ -371,12 +429,10 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
   // warp does for itself into a private copy (lane L owns NB/32 consecutive bins). Candidates with
   // above < K (the K best and the rest of the cut bin) are "relevant" and go to list position
   // above[bin] + arrival order: the list is grouped by bin, best bins first, with no further atomics.
-  int* list = w.rep();  // [capC] relevant candidates
-  u64* lkey = w.rkey(); // [capC] their ordered score keys
-  int total = 0;        // live candidates of the frame
-  int nRel = 0;         // relevant ones (list length)
+  total = 0;
+  nRel = 0;
 #if FLT_DEVICE_BUILD
-  unsigned short* above = (unsigned short*)(w.base + c.lay.lfAbove) + (cta.tid >> 5) * NB;
+  above = (unsigned short*)(w.base + c.lay.lfAbove) + (cta.tid >> 5) * NB;
   {
     const int lane = cta.tid & 31;
     if (NB == 256) {
@@ -430,12 +486,28 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
     __syncwarp();
   }
 #else
-  unsigned short* above = (unsigned short*)(w.base + c.lay.lfAbove);
+  above = (unsigned short*)(w.base + c.lay.lfAbove);
   for (int bn = NB - 1; bn >= 0; --bn) {
     above[bn] = (unsigned short)(total > 65535 ? 65535 : total);
     if (total < K) nRel += hist[bn];
     total += hist[bn];
   }
+#endif
+  if (!(guessed && total < K)) break;
+  // the guess cut too deep (fewer than K candidates passed): the same frame against the corner bound
+  cta.sync(); // every warp has read the histogram
+  for (int bn = cta.tid; bn < NB; bn += cta.nthr) hist[bn] = 0;
+  tau = tauCorner;
+  guessed = false;
+  carry.ghold = 8;
+  carry.gfac = carry.gfac * 1.25f < 3.0f ? carry.gfac * 1.25f : 3.0f;
+#if FLT_DEVICE_BUILD
+  if (stats && cta.tid == 0) atomicAdd(stats + 13, 1ull);
+#endif
+  cta.sync();
+  } // for (;;)
+#if FLT_DEVICE_BUILD
+  if (stats && cta.tid == 0 && guessed) atomicAdd(stats + 12, 1ull);
 #endif
   const int nSel = total < K ? total : K;
   for (int x = cta.tid; x < items; x += cta.nthr) {
@@ -495,8 +567,9 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
   (void)stats;
 #endif
 
-  // (5) the new beam (Utils.h:161-165 threshold against the best, then the K best in rank order)
-  for (int i = cta.tid; i < nH; i += cta.nthr) { // leave the fingerprint table empty
+  // (5) the new beam (Utils.h:161-165 threshold against the best, then the K best in rank order) and its
+  // fingerprint table; the current beam's table is emptied for the beam after next
+  for (int i = cta.tid; i < nH; i += cta.nthr) {
     const int s = t.slotOf[i];
     t.a[s] = -1;
     t.b[s] = -1;
@@ -505,6 +578,17 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
     if (cta.tid == 0) sc[SC_NH] = 0;
   } else {
     const double thrScore = cd.score(ranked[0]) - c.beamThreshold;
+    // next frame's guess: how far below `upper` the K-th best candidate was; the factor follows how many
+    // candidates passed (aim: 1.5 K .. 3 K)
+    if (nSel == K) {
+      carry.gap = (float)(upper - cd.score(ranked[K - 1]));
+      if (guessed) {
+        if (total > 3 * K) carry.gfac = carry.gfac * 0.97f > 1.05f ? carry.gfac * 0.97f : 1.05f;
+        else if (total < K + K / 2) carry.gfac *= 1.04f;
+      }
+    } else {
+      carry.gap = -1.0f;
+    }
     for (int q = cta.tid; q < nSel; q += cta.nthr) {
       const int x = ranked[q];
       const double score = cd.score(x);
@@ -519,16 +603,23 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
       nxt.lex(q) = 0;
       nxt.tok(q) = n;
       nxt.pb(q) = (fl & CF_PB) ? 1 : 0;
+      u64 fa, fb;
       if (fl & CF_NEW) {
-        fpChild(cur.fpA(p), cur.fpB(p), n, nxt.fpA(q), nxt.fpB(q));
+        fpChild(cur.fpA(p), cur.fpB(p), n, fa, fb);
         nxt.pfpA(q) = cur.fpA(p);
         nxt.pfpB(q) = cur.fpB(p);
       } else {
-        nxt.fpA(q) = cur.fpA(p);
-        nxt.fpB(q) = cur.fpB(p);
+        fa = cur.fpA(p);
+        fb = cur.fpB(p);
         nxt.pfpA(q) = cur.pfpA(p);
         nxt.pfpB(q) = cur.pfpB(p);
       }
+      nxt.fpA(q) = fa;
+      nxt.fpB(q) = fb;
+#if FLT_DEVICE_BUILD
+      __threadfence_block(); // the fingerprint is visible before the table slot names this hypothesis
+#endif
+      lfTabInsert(tn, nxt, q, fa, fb);
       f.hParent[q] = p;
       f.hTok[q] = n;
       const int an = skipCarry(cur, f.hRow, p);
@@ -545,7 +636,7 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
     }
   }
   carry.valid = f.eNext != nullptr;
-  if (f.eNext && cta.tid == cta.nthr - 1) {
+  if (f.eNext && (direct || cta.tid == cta.nthr - 1)) { // direct: every thread keeps its own copy
     carry.eBlank = c.ctc ? f.eNext[c.blank] : 0.0f;
     carry.eSil = f.eNext[c.sil];
   }
@@ -557,28 +648,13 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Bea
 // decodeEnd (LexiconFreeDecoder.cpp:127-158) with ZeroLM: finish() returns the same state and 0,
 // every hypothesis proposes (state, sil, prevBlank=0); the two members of a row merge (max).
 // The beam is already sorted, so the survivors keep their order.
-FLT_DEV void lfFinish(const Cta& cta, const DecCfg& c, const Ws& w, const Beam& cur, const Beam& nxt,
-                      const FrameIn& f) {
+FLT_DEV void lfFinish(const Cta& cta, const DecCfg& c, const Ws& w, int curIdx, const FrameIn& f) {
   int* sc = w.sc();
   const int nH = sc[SC_NH];
   if (nH == 0) return;
-  const LfTab t = lfTab(w);
+  const Beam cur = w.beam(curIdx), nxt = w.beam(curIdx ^ 1);
+  const LfTab t = lfTab(w, curIdx); // filled when the beam was created (the caller has synchronised since)
   int* keep = w.surv(); // [capP] flags
-  for (int i = cta.tid; i < nH; i += cta.nthr) {
-    const u64 fa = cur.fpA(i), fb = cur.fpB(i);
-    uint32_t s = (uint32_t)fa & t.mask;
-    for (;;) {
-      const int old = atomCAS(&t.a[s], -1, i);
-      if (old == -1) break;
-      if (cur.fpA(old) == fa && cur.fpB(old) == fb) {
-        t.b[s] = i;
-        break;
-      }
-      s = (s + 1) & t.mask;
-    }
-    t.slotOf[i] = (int)s;
-  }
-  cta.sync();
   const double best = cur.score(0) + c.lmWeight * (double)0.0f;
   for (int i = cta.tid; i < nH; i += cta.nthr) {
     const int s = t.slotOf[i];

@@ -166,7 +166,8 @@ void launchTopMStream(const TopMCfg& c, const StreamLay& sl, const TopMArgs& a, 
 #endif
 }
 // plan of the streaming select for a row length / list length / bias; false if the shape does not fit it
-bool planStream(int N, int M, int bst, const float* dBias, float biasMax, TopMCfg& t, StreamLay& sl) {
+bool planStream(int N, int M, int bst, const float* dBias, float biasMax, TopMCfg& t, StreamLay& sl,
+                float biasSpread = 1e30f) {
   const bool restricted = bst < N;
   const int want = restricted ? bst : M;
   // survivors aimed at: 1.5 .. 2.5 x want, inside 3/4 of the capacity (4 per thread)
@@ -179,6 +180,7 @@ bool planStream(int N, int M, int bst, const float* dBias, float biasMax, TopMCf
   t.bst = restricted ? bst : N;
   t.bias = dBias;
   t.biasMax = biasMax;
+  t.biasKeyed = biasSpread > 0.5f ? 1 : 0;
   t.P = std::max(sl.threads, nextPow2(want));
   t.capS = kStreamSPT * sl.threads;
   t.extra = 2 * kProdBins;
@@ -618,6 +620,7 @@ struct flt_decoder {
   int streamGridMax = 1;
   int fusedGridMax = 1;
   size_t wsBytes = 0, topmSmem = 0; // wsBytes: whole workspace (both regions)
+  float biasSpread = 0.0f; // max - min of the finite rank offsets of the root children (lexicon decoder)
   size_t smemBytes = 0, slabBytes = 0; // dynamic shared memory per CTA / global slab per CTA of the step kernel
   int gridMax = 1, topmGridMax = 1;
   std::vector<int> wideOffHost;
@@ -804,12 +807,12 @@ void planFor(flt_decoder& d, int N) {
   c.wideOff = upload(d.dWideOff, d.wideOffHost, s);
   c.lfDesc = nullptr;
   if (c.lfFast) {
-    std::vector<int> desc;
+    std::vector<int> desc; // beam_lf.h: repeat, blank (and boosted-sil) items first, then the cells column-major
+    for (int kind = 1; kind <= (o.silScore > 0 ? 3 : 2); ++kind)
+      for (int p = 0; p < K; ++p) desc.push_back(p | (kind << 24));
     for (int j = 0; j < c.Mwide; ++j)
       for (int p = 0; p < K; ++p)
         if (j < d.wideOffHost[p + 1] - d.wideOffHost[p]) desc.push_back(p | (j << 12));
-    for (int kind = 1; kind <= 3; ++kind)
-      for (int p = 0; p < K; ++p) desc.push_back(p | (kind << 24));
     desc.resize(c.capC, 0xFFF); // padding: hypothesis 4095 >= nH, dead
     c.lfDesc = upload(d.dLfDesc, desc, s);
   }
@@ -832,12 +835,15 @@ void planFor(flt_decoder& d, int N) {
     }
     t.bias = upload(d.dBias, bias, s);
     t.biasMax = 0.0f;
+    float biasMin = 0.0f;
     bool any = false;
     for (float b : bias)
       if (!isNegInf(b)) {
         t.biasMax = any ? std::max(t.biasMax, b) : b;
+        biasMin = any ? std::min(biasMin, b) : b;
         any = true;
       }
+    d.biasSpread = any ? t.biasMax - biasMin : 0.0f;
   }
   rt::sync(s);
 
@@ -847,7 +853,7 @@ void planFor(flt_decoder& d, int N) {
   d.topmSmem = (carveTopM(nullptr, t, ts) + 255) / 256 * 256;
   d.cfg = c;
   d.tcfg = t;
-  d.streamSel = d.needTopM && planStream(N, c.M, t.bst, t.bias, t.biasMax, d.stcfg, d.slay);
+  d.streamSel = d.needTopM && planStream(N, c.M, t.bst, t.bias, t.biasMax, d.stcfg, d.slay, d.biasSpread);
   // fused select + step: the row stage, the producer scratch and the consumer workspace share the
   // CTA's shared memory; two CTAs per SM need <= 113 KB each
   d.fused = false;

@@ -515,6 +515,10 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
     GxCarry gcarry = gxCarryInit();
     cta.sync();
     if (c.gx) gxBeginUtterance(cta, c, w, 1);
+    else {
+      lfTabBuild(cta, w, 0, w.sc()[SC_NH]); // fingerprint table of the seed beam
+      cta.sync();
+    }
     int gxAlive = 1; // hypotheses in the current beam (beam_gx.h); 0 = the beam died, lists are still consumed
     for (int t = 0; t < len; ++t, ++g) {
       const int slot = (int)(g & (kFusedRing - 1)); // ring slot = running row count mod ring, on both sides
@@ -538,7 +542,7 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
           if (gxAlive) curIdx ^= 1;
         }
       } else {
-        lfFrameStep(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f, a.stats, carry); // ends with a barrier
+        lfFrameStep(cta, c, w, curIdx, f, a.stats, carry); // ends with a barrier
         curIdx ^= 1;
       }
 #if FLT_DEVICE_BUILD
@@ -554,7 +558,7 @@ FLT_DEV void fusedCta(const Cta& whole, const DecCfg& c, const TopMCfg& tc, cons
       }
     } else if (w.sc()[SC_NH] != 0) {
       const FrameIn f = finishFrameIn(c, a, b, len);
-      lfFinish(cta, c, w, w.beam(curIdx), w.beam(curIdx ^ 1), f);
+      lfFinish(cta, c, w, curIdx, f);
       curIdx ^= 1;
       nFin = w.sc()[SC_NH];
     }

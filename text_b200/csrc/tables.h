@@ -112,6 +112,52 @@ FLT_HD float ngramScore(const LmDev& lm, const int* ctx, int nctx, int w) {
   return ret;
 }
 
+// The back-off weights of a context, which ngramScore adds whenever the n-gram ending in the scored word is
+// shorter than the context: they depend on the LM state only, so a decoder computes them once when the state
+// is created and every word scored from that state reuses them (typically one table probe per word instead
+// of three). bo[i] = back-off of the context's first i+1 words (bo[0] from the unigram table); bit i of the
+// returned mask says whether that context is in the model (absent = nothing is added, as in ngramScore).
+FLT_HD int ngramContextBackoffs(const LmDev& lm, const int* ctx, int nctx, float* bo) {
+  const int L = nctx < lm.order - 1 ? nctx : lm.order - 1;
+  int mask = 0;
+  uint64_t g = 0, g2 = 0;
+  for (int i = 0; i < L; ++i) {
+    g = i == 0 ? ngramChainStart(ctx[0]) : ngramChainExtend(g, ctx[i]);
+    g2 = i == 0 ? ngramChain2Start(ctx[0]) : ngramChain2Extend(g2, ctx[i]);
+    bo[i] = 0.0f;
+    if (i == 0) {
+      bo[0] = lm.uni[ctx[0]].y;
+      mask |= 1;
+    } else {
+      F2 v;
+      if (ngramFind(lm, i + 1, g, g2, v)) {
+        bo[i] = v.y;
+        mask |= 1 << i;
+      }
+    }
+  }
+  return mask;
+}
+// ngramScore with the context's back-offs taken from ngramContextBackoffs (same float operations in the same
+// order: bit-identical)
+FLT_HD float ngramScoreCached(const LmDev& lm, const int* ctx, int nctx, int w, const float* bo, int mask) {
+  const int L = nctx < lm.order - 1 ? nctx : lm.order - 1;
+  float ret = lm.uni[w].x;
+  int matchLen = 1;
+  uint64_t h = ngramChainStart(w), h2 = ngramChain2Start(w);
+  for (int k = 1; k <= L; ++k) {
+    h = ngramChainExtend(h, ctx[k - 1]);
+    h2 = ngramChain2Extend(h2, ctx[k - 1]);
+    F2 v;
+    if (!ngramFind(lm, k + 1, h, h2, v)) break;
+    ret = v.x;
+    matchLen = k + 1;
+  }
+  for (int i = matchLen - 1; i < L; ++i)
+    if ((mask >> i) & 1) ret += bo[i];
+  return ret;
+}
+
 // Context of the child state: (w, ctx...) truncated to order-1 words.
 FLT_HD int ngramAdvanceCtx(const LmDev& lm, const int* ctx, int nctx, int w, int* out) {
   const int keep = lm.order - 1;

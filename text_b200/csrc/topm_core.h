@@ -27,7 +27,9 @@ struct TopMCfg {
   int M;          // list entries written per row
   int bst;        // token-set size (>= N: unrestricted)
   const float* bias; // [N] or null
-  float biasMax;     // largest finite bias (bound of the streaming kernel's first filter)
+  float biasMax;     // largest finite bias (bound of the streaming kernel's raw-emission filter)
+  int biasKeyed;     // streaming kernel: 1 = the one-pass filter runs on e + bias (bias spread wider than ~0.5),
+                     // 0 = on raw emissions against bound - biasMax, survivors re-keyed
   int P;          // chunks (pow2, >= nthr, >= wanted)
   int capS;       // survivor capacity (pow2)
   int stage;      // 1 = stage the row in shared memory

@@ -78,6 +78,41 @@ FLT_DEV float prodFilterBiased(const Cta& p, const TopMCfg& c, TopMSmem& s, cons
   }
   return top;
 }
+// survivors of the raw-emission filter -> ranking keys e + bias that reach `bound` (compacted in place);
+// returns their number and this thread's largest key value. Used when the bias is (nearly) constant over the
+// tokens that start a word (ZeroLM: all zero), where filtering raw emissions against bound - max(bias) is as
+// tight as the keyed filter and saves reading the bias row.
+FLT_DEV int streamRekey(const Cta& p, const TopMCfg& c, TopMSmem& s, int n1, float bound, float& top) {
+  unsigned long long* sv = s.sortBuf + c.capS;
+  unsigned long long mine[kStreamSPT];
+  const float ninf = bitsF32(0xFF800000u);
+  top = ninf;
+#pragma unroll
+  for (int z = 0; z < kStreamSPT; ++z) {
+    const int a = p.tid + z * p.nthr;
+    mine[z] = 0ull;
+    if (a < n1) {
+      const unsigned long long k = sv[a];
+      const int tok = topmKeyTok(k);
+      const float b = __ldg(c.bias + tok);
+      if (!isNegInf(b)) {
+        const float kv = topmKeyVal(k) + b;
+        if (kv >= bound) {
+          mine[z] = topmKey(kv, tok);
+          top = fmaxf(top, kv);
+        }
+      }
+    }
+  }
+  p.sync(); // every entry has been read
+  if (p.tid == 0) s.cnt[0] = 0;
+  p.sync();
+#pragma unroll
+  for (int z = 0; z < kStreamSPT; ++z)
+    if (mine[z]) sv[atomAdd(&s.cnt[0], 1)] = mine[z];
+  p.sync();
+  return s.cnt[0];
+}
 #endif
 
 // One row. `row` = the shared-memory stage, `grow` = the same row in global memory (L2).
@@ -165,12 +200,16 @@ FLT_DEV void streamRow(const Cta& p, const TopMCfg& c, TopMSmem& s, ProdGuess& p
       stageFree();
     } else {
       // ---- guess mode: one pass over the stage against the running guess, stage released at once
-      top = biased ? prodFilterBiased(p, c, s, (const float4*)row, b4, bound, sv)
-                   : prodFilter(p, c, s, (const float4*)row, bound, sv);
+      // c.biasKeyed: the bias spreads over the tokens (a smeared n-gram LM) -> filter the keys e + bias;
+      // else (constant bias, ZeroLM) filter the raw emissions against bound - max(bias) and re-key the survivors
+      const bool useKeyed = biased && c.biasKeyed;
+      top = useKeyed ? prodFilterBiased(p, c, s, (const float4*)row, b4, bound, sv)
+                  : prodFilter(p, c, s, (const float4*)row, biased ? bound - c.biasMax : bound, sv);
       p.sync(); // every thread is done reading the stage
       stageFree();
       ns = s.cnt[0];
       bool miss = ns > c.capS || ns > kStreamSPT * p.nthr;
+      if (!miss && biased && !useKeyed) ns = streamRekey(p, c, s, ns, bound, top);
       miss = miss || !okCount(ns) || (biased && ns < (want < N ? want : N) && bound > bitsF32(0xFF7FFFFFu));
       pg.missRate = 0.9f * pg.missRate + (miss ? 0.1f : 0.0f);
       if (miss) {
