@@ -412,9 +412,6 @@ def measure(a, ctx, with_cpu):
         else:
             torch.cuda.synchronize()
             res = None
-            for _ in range(min(a.warmup, 2)):
-                api.decode_batch_ptr(dec, host.data_ptr(), B, T, N)
-                res = api.nbest(dec, B, T, nbest, pinned=True)
 
             def collect():
                 # N > 1: the n-best blocks of every rank go to rank 0 over NCCL (device buffers, no host round
@@ -427,6 +424,11 @@ def measure(a, ctx, with_cpu):
                             counts=nb["counts"])
                 return shard.gather_nbest(mine, world * B, T, nbest, dev)
 
+            # warm-up through the same path as the timed steps: the page-locked result buffers and the NCCL
+            # channels of the gather are set up here, not inside the timed region
+            for _ in range(min(a.warmup, 2)):
+                api.decode_batch_ptr(dec, host.data_ptr(), B, T, N)
+                res = collect()
             barrier()
             t0 = time.perf_counter()
             for _ in range(a.steps):

@@ -217,6 +217,9 @@ enum { // ws.sc[] scalars
   SC_PMODE, SC_PCUT, SC_PLO_LO, SC_PLO_HI, SC_PSCALE, // two-pass candidate pruning (frameStep)
   SC_TLO, SC_THI, // previous phase stamp of thread 0 (counters on)
   SC_WANT, SC_WHOLD, // two-pass pruning: candidates to keep this frame; frames left at the wide setting
+  SC_LFGAP, SC_LFFAC, SC_LFHOLD, // beam_lf.h guessed pruning bound: distance of the K-th best candidate below the
+                                 // frame's upper bound in the previous frame (float bits, < 0: none yet), the
+                                 // safety factor applied to it (float bits), frames left without guessing
   SC_GSPAN, SC_GHOLD, SC_GBIN, // guessed cut: kept score span below the top (float bits, 0 = none), frames left
                                // without guessing after a miss, this frame's guessed cut bin (0 = two passes)
   SC_GXCUTBIN, SC_GXKEPT, // beam_gx.h: cut bin of the exact redo and the proposals it keeps
@@ -1919,11 +1922,6 @@ FLT_DEV void finishStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam
 struct LfCarry { // emissions of the NEXT frame, loaded while the current one retires (registers)
   float eOwn, eBlank, eSil;
   int valid;
-  // guessed pruning bound of the lexicon-free step (uniform over the CTA): distance of the K-th best candidate
-  // below the frame's upper bound in the previous frame (< 0: none yet), the safety factor applied to it, and
-  // the frames left without guessing after a miss
-  float gap = -1.0f, gfac = 1.3f;
-  int ghold = 0;
 };
 FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, int curIdx, const FrameIn& f,
                          unsigned long long* stats, LfCarry& carry);
@@ -1960,6 +1958,9 @@ FLT_DEV void ctaInitWorkspace(const Cta& cta, const DecCfg& c, const Ws& w, char
     sc[SC_WHOLD] = 0;
     sc[SC_GSPAN] = 0;
     sc[SC_GHOLD] = 0;
+    sc[SC_LFGAP] = (int)f32Bits(-1.0f);
+    sc[SC_LFFAC] = (int)f32Bits(1.3f);
+    sc[SC_LFHOLD] = 0;
     sc[SC_PMODE] = 0; // allocCand reads these in every mode; only the two-pass pruning sets them
     sc[SC_PCUT] = 0;
     sc[SC_BIN] = 0;
@@ -1994,6 +1995,9 @@ FLT_DEV void seedUtterance(const DecCfg& c, const Ws& w, const BatchArgs& a, int
   w.sc()[SC_NH] = 1;
   w.sc()[SC_GSPAN] = 0; // the guessed cut of the two-pass pruning starts over with every utterance
   w.sc()[SC_GHOLD] = 0;
+  w.sc()[SC_LFGAP] = (int)f32Bits(-1.0f); // and so does the lexicon-free step's guessed bound
+  w.sc()[SC_LFFAC] = (int)f32Bits(1.3f);
+  w.sc()[SC_LFHOLD] = 0;
   a.status[b] = 0;
   const long long h0 = ((long long)b * (a.T + 2)) * K;
   a.hParent[h0] = -1;

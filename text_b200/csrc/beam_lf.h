@@ -303,6 +303,7 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, int curId
   }
 
   // corner bound (beam_core.h frameStep): lanes 0..nTau-1 of every warp take one rectangle each
+  auto cornerBound = [&]() {
   double tau = negInf();
   {
 #if FLT_DEVICE_BUILD
@@ -328,6 +329,9 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, int curId
 #endif
     if (c.silScore < 0) tau += c.silScore; // keeps the bound valid if a counted cell is the sil one
   }
+  return tau;
+  };
+  double tau = cornerBound();
   // candidate scores lie in [tau, upper]: monotone linear map to NB bins
   const float eTop = (f.listLen > 0 && f.topTok[0] >= 0) ? f.topVal[0] : 0.0f;
   double upper = cur.score(0) + (double)eTop;
@@ -337,16 +341,18 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, int curId
   // frame is first expanded against upper - gfac * (that distance): if at least K candidates pass, they contain
   // the K best (every materialised candidate is a distinct merge group) and the result is exact; if fewer
   // pass, the frame is expanded again against the corner bound and guessing pauses for a few frames.
-  const double tauCorner = tau;
+  // (the three scalars of the guess live in the workspace, not in registers: the kernel is at its register cap)
   bool guessed = false;
-  if (carry.gap >= 0.0f && carry.ghold == 0 && nH == K && !(c.dbg & 16)) {
-    const double g = upper - (double)(carry.gap * carry.gfac);
-    if (g > tau) {
-      tau = g;
-      guessed = true;
+  {
+    const float gap = bitsF32((uint32_t)sc[SC_LFGAP]);
+    if (gap >= 0.0f && sc[SC_LFHOLD] == 0 && nH == K && !(c.dbg & 16)) {
+      const double g = upper - (double)(gap * bitsF32((uint32_t)sc[SC_LFFAC]));
+      if (g > tau) {
+        tau = g;
+        guessed = true;
+      }
     }
   }
-  if (carry.ghold > 0) --carry.ghold;
   pc.mark(0); // (no barrier: the beam, its table and the zeroed histogram were published by the previous frame's last one)
 
   // (2) candidates, each in the slot of its work item, and the histogram of their scores
@@ -497,13 +503,16 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, int curId
   // the guess cut too deep (fewer than K candidates passed): the same frame against the corner bound
   cta.sync(); // every warp has read the histogram
   for (int bn = cta.tid; bn < NB; bn += cta.nthr) hist[bn] = 0;
-  tau = tauCorner;
+  tau = cornerBound();
   guessed = false;
-  carry.ghold = 8;
-  carry.gfac = carry.gfac * 1.25f < 3.0f ? carry.gfac * 1.25f : 3.0f;
+  if (cta.tid == 0) {
+    const float fac = bitsF32((uint32_t)sc[SC_LFFAC]) * 1.25f;
+    sc[SC_LFFAC] = (int)f32Bits(fac < 3.0f ? fac : 3.0f);
+    sc[SC_LFHOLD] = 9; // decremented below: 8 frames without guessing
 #if FLT_DEVICE_BUILD
-  if (stats && cta.tid == 0) atomicAdd(stats + 13, 1ull);
+    if (stats) atomicAdd(stats + 13, 1ull);
 #endif
+  }
   cta.sync();
   } // for (;;)
 #if FLT_DEVICE_BUILD
@@ -580,14 +589,19 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, int curId
     const double thrScore = cd.score(ranked[0]) - c.beamThreshold;
     // next frame's guess: how far below `upper` the K-th best candidate was; the factor follows how many
     // candidates passed (aim: 1.5 K .. 3 K)
-    if (nSel == K) {
-      carry.gap = (float)(upper - cd.score(ranked[K - 1]));
-      if (guessed) {
-        if (total > 3 * K) carry.gfac = carry.gfac * 0.97f > 1.05f ? carry.gfac * 0.97f : 1.05f;
-        else if (total < K + K / 2) carry.gfac *= 1.04f;
+    if (cta.tid == 0) {
+      if (sc[SC_LFHOLD] > 0) --sc[SC_LFHOLD];
+      if (nSel == K) {
+        sc[SC_LFGAP] = (int)f32Bits((float)(upper - cd.score(ranked[K - 1])));
+        if (guessed) {
+          float fac = bitsF32((uint32_t)sc[SC_LFFAC]);
+          if (total > 3 * K) fac = fac * 0.97f > 1.05f ? fac * 0.97f : 1.05f;
+          else if (total < K + K / 2) fac *= 1.04f;
+          sc[SC_LFFAC] = (int)f32Bits(fac);
+        }
+      } else {
+        sc[SC_LFGAP] = (int)f32Bits(-1.0f);
       }
-    } else {
-      carry.gap = -1.0f;
     }
     for (int q = cta.tid; q < nSel; q += cta.nthr) {
       const int x = ranked[q];
