@@ -22,7 +22,7 @@ except Exception as ex:
 PY
   tail -2 $OUT/$1.err | cut -c1-300
 }
-( time NCCL_DEBUG=INFO FLT_DBG_PLAN=1 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $G --steps 2 --warmup 1 --workload lexicon_lm --beam 500 --batch 512 --frames 1500 --threshold 25 --ngrams 2000000,2000000,1000000 --no-e2e --no-cpu-baseline ) > $OUT/bench_cfg5_g$G.json 2> $OUT/bench_cfg5_g$G.err; show bench_cfg5_g$G
-grep -a "NCCL INFO.*\(NVLS\|nranks\|Connected all\)" $OUT/bench_cfg5_g$G.err | head -5 > $OUT/nccl_info.txt; cut -c1-200 $OUT/nccl_info.txt; grep -a "flt plan" $OUT/bench_cfg5_g$G.err | head -1 | cut -c1-330; grep real $OUT/bench_cfg5_g$G.err
+( time NCCL_DEBUG=INFO NCCL_DEBUG_FILE=$OUT/nccl_debug.%p.txt FLT_DBG_PLAN=1 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $G --steps 2 --warmup 1 --workload lexicon_lm --beam 500 --batch 512 --frames 1500 --threshold 25 --ngrams 2000000,2000000,1000000 --no-e2e --no-cpu-baseline ) > $OUT/bench_cfg5_g$G.json 2> $OUT/bench_cfg5_g$G.err; show bench_cfg5_g$G
+cat $OUT/nccl_debug.*.txt | grep -a "NCCL INFO.*\(NVLS\|nranks\|Connected all\)" | head -5 > $OUT/nccl_info.txt; cut -c1-200 $OUT/nccl_info.txt; grep -a "flt plan" $OUT/bench_cfg5_g$G.err | head -1 | cut -c1-330; grep real $OUT/bench_cfg5_g$G.err
 grep -av "NCCL INFO" $OUT/bench_cfg5_g$G.err > $OUT/bench_cfg5_g$G.err.short; mv $OUT/bench_cfg5_g$G.err.short $OUT/bench_cfg5_g$G.err
 ( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $G --steps 3 --warmup 3 --no-cpu-baseline --no-secondary ) > $OUT/bench_g$G.json 2> $OUT/bench_g$G.err; show bench_g$G; grep real $OUT/bench_g$G.err
