@@ -92,3 +92,33 @@ def test_widened_modes(A, G, name, spec, em, exact):
         if not (A.tie_events(ba.dec) or has_ties(ra)):
             assert np.array_equal(ra["scores"], rg["scores"]), "scores not bit-equal"
         ba.close(), bg.close()
+
+
+def test_lexicon_split_workspace(A, G, monkeypatch):
+    """The generic step with its capacity-sized arrays in the CTA's global slab and the small region in shared
+    memory (what a wide beam or a grown candidate capacity gets on the device), forced here on small cases by
+    lowering the shared-memory budget of the plan (FLT_SMEM_KB): same bits as everything in shared memory."""
+    monkeypatch.setenv("FLT_SMEM_KB", "16")
+    ran = 0
+    for name, spec, em in parity_cases.lexicon_cases():
+        if name in ("cfg3_scaled_bstN", "arpa3_ctc", "zero_unk", "arpa3_ctc_bst", "arpa_asg", "cfg4_scaled"):
+            run_case(A, G, spec, em)
+            ran += 1
+    assert ran >= 3
+
+
+def test_very_wide_beam(A, G, tmp_path):
+    """beam 500 (BASELINE configs[4]): the small workspace region leaves one CTA per SM, which then runs the
+    step with 1024 threads (flt_k_decode1024), the capacity-sized arrays in its global slab, the long-list
+    select (M = 505) and the histogram-rank select; lexicon + 3-gram LM and lexicon + ZeroLM."""
+    from cases import spec_lexicon
+    from text_b200 import synth
+
+    N, W, T = 640, 3000, 24
+    sp = synth.lexicon(W, N, 2, 4, seed=21, exclude=(0, N - 1))
+    path = str(tmp_path / "lm3.arpa")
+    synth.write_arpa(path, W, order=3, counts=[0, 6000, 3000], seed=5)
+    em = synth.emissions(3, T, N, seed=31, sigma=1.5)
+    for lm, lw in ((("arpa", path, synth.word_names(W) + ["<unk>"]), 1.5), (("zero",), 0.0)):
+        spec = spec_lexicon(N, 500, N, sp, 40.0, lm_weight=lw, word_score=0.2, lm=lm, unk=W)
+        run_case(A, G, spec, em)

@@ -630,10 +630,25 @@ FLT_DEV void lfFrameStep(const Cta& cta, const DecCfg& c, const Ws& w, int curId
       }
       nxt.fpA(q) = fa;
       nxt.fpB(q) = fb;
-#if FLT_DEVICE_BUILD
-      __threadfence_block(); // the fingerprint is visible before the table slot names this hypothesis
-#endif
-      lfTabInsert(tn, nxt, q, fa, fb);
+      { // into the new beam's table. A slot already claimed by another new hypothesis q2 is compared through
+        // what q2 was made FROM (its candidate and parent, all written before the last barrier), not through
+        // the fingerprint q2's thread is storing in this very phase: no ordering between the two threads needed
+        uint32_t s = (uint32_t)fa & tn.mask;
+        for (;;) {
+          const int q2 = atomCAS(&tn.a[s], -1, q);
+          if (q2 == -1) break;
+          const int x2 = ranked[q2];
+          const int p2 = cd.par(x2);
+          u64 oa = cur.fpA(p2), ob = cur.fpB(p2);
+          if (cd.flags(x2) & CF_NEW) fpChild(oa, ob, cd.tok(x2), oa, ob);
+          if (oa == fa && ob == fb) {
+            tn.b[s] = q; // a row has at most two members
+            break;
+          }
+          s = (s + 1) & tn.mask;
+        }
+        tn.slotOf[q] = (int)s;
+      }
       f.hParent[q] = p;
       f.hTok[q] = n;
       const int an = skipCarry(cur, f.hRow, p);

@@ -59,6 +59,13 @@ __global__ void __launch_bounds__(512, 2) flt_k_decode512(DecCfg c, BatchArgs a)
   Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
   decodeCta<false>(cta, c, a, smem);
 }
+// 1024 threads per utterance: beams so wide (K = 500) that the small workspace region leaves room for one
+// CTA per SM only — the items of a frame (thousands) are then spread over all 32 warps the SM can hold
+__global__ void __launch_bounds__(1024, 1) flt_k_decode1024(DecCfg c, BatchArgs a) {
+  extern __shared__ __align__(128) char smem[];
+  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
+  decodeCta<false>(cta, c, a, smem);
+}
 // workspace in a global slab per CTA (beams / candidate sets too large for shared memory)
 __global__ void __launch_bounds__(256) flt_k_decode_gmem(DecCfg c, BatchArgs a) {
   Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
@@ -206,7 +213,8 @@ void launchDecode(const DecCfg& c, const BatchArgs& a, int grid, size_t smem, rt
     if (smem && threads == 512) (c.lexicon ? flt_k_gx512<true> : flt_k_gx512<false>)<<<grid, 512, smem, s>>>(c, a);
     else if (smem) (c.lexicon ? flt_k_gx<true> : flt_k_gx<false>)<<<grid, threads, smem, s>>>(c, a);
     else (c.lexicon ? flt_k_gx_gmem<true> : flt_k_gx_gmem<false>)<<<grid, threads > 256 ? 256 : threads, 0, s>>>(c, a);
-  } else if (smem && threads == 512) (c.wide ? flt_k_decode512_wide : flt_k_decode512)<<<grid, 512, smem, s>>>(c, a);
+  } else if (smem && threads == 1024 && !c.wide) flt_k_decode1024<<<grid, 1024, smem, s>>>(c, a);
+  else if (smem && threads >= 512) (c.wide ? flt_k_decode512_wide : flt_k_decode512)<<<grid, 512, smem, s>>>(c, a);
   else if (smem) (c.wide ? flt_k_decode_wide : flt_k_decode)<<<grid, threads, smem, s>>>(c, a);
   else (c.wide ? flt_k_decode_gmem_wide : flt_k_decode_gmem)<<<grid, threads > 256 ? 256 : threads, 0, s>>>(c, a);
   FLT_RT_TRY(cudaGetLastError());
@@ -935,9 +943,17 @@ void planFor(flt_decoder& d, int N) {
                                     (int)std::max<size_t>(d.smemBytes, 48 * 1024)));
     FLT_RT_TRY(cudaFuncSetAttribute(k512, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)std::max<size_t>(d.smemBytes, 48 * 1024)));
-    if (d.threads == 512)
+    if (d.threads == 512) {
       FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k512, 512, d.smemBytes));
-    else
+      // one CTA per SM only (the small region of a very wide beam): give it all 32 warps of the SM
+      if (occ2 == 1 && !c.gx && !c.wide && !decThreadsEnv() && !getenv("FLT_NO_1024")) {
+        FLT_RT_TRY(cudaFuncSetAttribute(flt_k_decode1024, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)std::max<size_t>(d.smemBytes, 48 * 1024)));
+        int occ1k = 0;
+        FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1k, flt_k_decode1024, 1024, d.smemBytes));
+        if (occ1k >= 1) d.threads = 1024;
+      }
+    } else
       FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k256, d.threads, d.smemBytes));
   } else {
     FLT_RT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, kGmem, d.threads > 256 ? 256 : d.threads, 0));
