@@ -217,6 +217,7 @@ enum { // ws.sc[] scalars
   SC_PMODE, SC_PCUT, SC_PLO_LO, SC_PLO_HI, SC_PSCALE, // two-pass candidate pruning (frameStep)
   SC_TLO, SC_THI, // previous phase stamp of thread 0 (counters on)
   SC_WANT, SC_WHOLD, // two-pass pruning: candidates to keep this frame; frames left at the wide setting
+  SC_NACT, // active work items of the compacted second pruning pass
   SC_LFGAP, SC_LFFAC, SC_LFHOLD, // beam_lf.h guessed pruning bound: distance of the K-th best candidate below the
                                  // frame's upper bound in the previous frame (float bits, < 0: none yet), the
                                  // safety factor applied to it (float bits), frames left without guessing
@@ -1657,14 +1658,70 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
       if (pass == 1) pcache[slot] = (unsigned char)(localBin + 1);
       localBin = -1;
     };
+    // the three kinds of work items (cache slots: [0, wideTotal) wide cells, then K specials, then the
+    // first kPruneEdgeCap trie edges)
+    auto doWide = [&](int x) __attribute__((always_inline)) {
+      const int r = w.itemRow()[x]; // row rank (0-based)
+      emitWide(cta, c, wp, cur, f, w.rows().leaderOfRank(r), x - w.wideOff()[r], tau);
+    };
+    auto doSpecial = [&](int i) __attribute__((always_inline)) {
+      emitSpecials(cta, c, wp, cur, f, i, tau);
+      if (c.wideRanked) emitSilCell(cta, c, wp, cur, f, i, tau);
+    };
+    auto doEdge = [&](int x) __attribute__((always_inline)) {
+      const TrieDev& t = c.trie;
+      const int* deg = w.rows().deg();
+      const int i = searchOffsets(deg, nH + 1, x);
+      const int k = x - deg[i];
+      const int lex = cur.lex(i);
+      if (c.wideRanked && lex == 0) {
+        const int n = t.rootLabTok[k];
+        emitEdge<W>(cta, c, wp, cur, f, i, n, t.rootChild[n], true, tau);
+      } else if (rootList && lex == 0) {
+        const int n = f.topTok[k];
+        const int child = n >= 0 ? t.rootChild[n] : -1;
+        if (child >= 0) emitEdge<W>(cta, c, wp, cur, f, i, n, child, false, tau);
+      } else {
+        const int e = t.childOff[lex] + k;
+        emitEdge<W>(cta, c, wp, cur, f, i, t.childTok[e], t.childNode[e], false, tau);
+      }
+    };
+    if (pass == 2 && pcache && !full && !(c.dbg & 32)) {
+      // Second pass, compacted: only about one item in ten reaches the cut, and a thread that owned two or
+      // three of them ran their gather chains one after the other while most threads had none. The items
+      // whose cached bin reaches the cut are listed first (one byte read per item) and then dealt out one per
+      // thread. (The list reuses the representatives' array, idle until the merge; an item on it yields at
+      // least one kept candidate, so the list is no longer than the candidate set.)
+      int* act = w.rep();
+      const int cachedEdges = edgeItems < kPruneEdgeCap ? edgeItems : kPruneEdgeCap;
+      const int slots = c.wideTotal + c.K + (c.lexicon ? cachedEdges : 0);
+      for (int sl = cta.tid; sl < slots; sl += cta.nthr) {
+        const bool valid = sl < c.wideTotal ? (c.wideRanked && sl < wideItems)
+                                            : (sl < c.wideTotal + c.K ? sl - c.wideTotal < nH : true);
+        if (valid && (int)pcache[sl] > cut) {
+          const int pos = aggInc(&sc[SC_NACT], cta.tid);
+          if (pos < c.capC) act[pos] = sl;
+          else sc[SC_OVF] = 1;
+        }
+      }
+      cta.sync();
+      const int nAct = sc[SC_NACT] < c.capC ? sc[SC_NACT] : c.capC;
+      for (int a = cta.tid; a < nAct; a += cta.nthr) {
+        const int sl = act[a];
+        if (sl < c.wideTotal) doWide(sl);
+        else if (sl < c.wideTotal + c.K) doSpecial(sl - c.wideTotal);
+        else doEdge(sl - c.wideTotal - c.K);
+      }
+      for (int x = kPruneEdgeCap + cta.tid; x < edgeItems; x += cta.nthr) doEdge(x); // beyond the cache: all
+      cta.sync();
+      if (cta.tid == 0) sc[SC_NACT] = 0;
+      return;
+    }
     // wide cells
     if (c.wideRanked) {
-      const short* itemRow = w.itemRow();
-      const int* wideOff = w.wideOff();
       for (int x = cta.tid; x < wideItems; x += cta.nthr) {
         if (skip(x)) continue;
-        const int r = itemRow[x]; // row rank (0-based)
-        emitWide(cta, c, wp, cur, f, w.rows().leaderOfRank(r), x - wideOff[r], tau);
+        doWide(x);
         note(x);
       }
     }
@@ -1690,31 +1747,15 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
     // stay / repeat / blank
     for (int i = cta.tid; i < (full ? 0 : nH); i += cta.nthr) {
       if (skip(c.wideTotal + i)) continue;
-      emitSpecials(cta, c, wp, cur, f, i, tau);
-      if (c.wideRanked) emitSilCell(cta, c, wp, cur, f, i, tau);
+      doSpecial(i);
       note(c.wideTotal + i);
     }
     // trie edges
     if (c.lexicon) {
-      const TrieDev& t = c.trie;
-      const int* deg = w.rows().deg();
       for (int x = cta.tid; x < edgeItems; x += cta.nthr) {
         const bool cached = x < kPruneEdgeCap;
         if (cached && skip(c.wideTotal + c.K + x)) continue;
-        const int i = searchOffsets(deg, nH + 1, x);
-        const int k = x - deg[i];
-        const int lex = cur.lex(i);
-        if (c.wideRanked && lex == 0) {
-          const int n = t.rootLabTok[k];
-          emitEdge<W>(cta, c, wp, cur, f, i, n, t.rootChild[n], true, tau);
-        } else if (rootList && lex == 0) {
-          const int n = f.topTok[k];
-          const int child = n >= 0 ? t.rootChild[n] : -1;
-          if (child >= 0) emitEdge<W>(cta, c, wp, cur, f, i, n, child, false, tau);
-        } else {
-          const int e = t.childOff[lex] + k;
-          emitEdge<W>(cta, c, wp, cur, f, i, t.childTok[e], t.childNode[e], false, tau);
-        }
+        doEdge(x);
         if (cached) note(c.wideTotal + c.K + x);
         else localBin = -1;
       }
@@ -1961,6 +2002,7 @@ FLT_DEV void ctaInitWorkspace(const Cta& cta, const DecCfg& c, const Ws& w, char
     sc[SC_LFGAP] = (int)f32Bits(-1.0f);
     sc[SC_LFFAC] = (int)f32Bits(1.3f);
     sc[SC_LFHOLD] = 0;
+    sc[SC_NACT] = 0;
     sc[SC_PMODE] = 0; // allocCand reads these in every mode; only the two-pass pruning sets them
     sc[SC_PCUT] = 0;
     sc[SC_BIN] = 0;

@@ -127,11 +127,8 @@ FLT_DEV void streamRow(const Cta& p, const TopMCfg& c, TopMSmem& s, ProdGuess& p
   {
     const int lane = p.tid & 31, warp = p.tid >> 5, nw = p.nthr >> 5;
     float* bnd = (float*)s.red;          // [nw] per-warp bound, [32 + nw] per-warp maximum
-    // ranking histogram: 128 bins for short lists, 512 for long ones (TopMCfg::extra = 2 x bins) — a few hundred
-    // survivors over 128 bins crowd the bins next to the bound, and the comparisons inside a bin are quadratic
-    const int NBk = c.extra >> 1, perLane = NBk >> 5; // bins, bins per lane of the scan (4 or 16)
-    int* hist = s.rankCnt;         // [NBk] zero on entry, re-zeroed below
-    int* above = s.rankCnt + NBk;  // [NBk]
+    int* hist = s.rankCnt;               // [kProdBins] zero on entry, re-zeroed below
+    int* above = s.rankCnt + kProdBins;  // [kProdBins]
     unsigned long long* sv = s.sortBuf + c.capS;
     const int minExpected = biased ? 1 : (want < N ? want : N);
     const float ninf = bitsF32(0xFF800000u);
@@ -281,7 +278,7 @@ FLT_DEV void streamRow(const Cta& p, const TopMCfg& c, TopMSmem& s, ProdGuess& p
       top = bnd[32];
       for (int i = 1; i < nw; ++i) top = fmaxf(top, bnd[32 + i]);
       const float range = top - bound;
-      const float scale = (range > 0.0f && range < 3.0e38f) ? (float)NBk / range : 0.0f;
+      const float scale = (range > 0.0f && range < 3.0e38f) ? (float)kProdBins / range : 0.0f;
       unsigned long long mine[kStreamSPT];
       int myBin[kStreamSPT], mySlot[kStreamSPT];
 #pragma unroll
@@ -293,35 +290,31 @@ FLT_DEV void streamRow(const Cta& p, const TopMCfg& c, TopMSmem& s, ProdGuess& p
         if (a < ns) {
           mine[z] = sv[a];
           int bin = (int)((topmKeyVal(mine[z]) - bound) * scale);
-          bin = bin > NBk - 1 ? NBk - 1 : (bin < 0 ? 0 : bin);
+          bin = bin > kProdBins - 1 ? kProdBins - 1 : (bin < 0 ? 0 : bin);
           myBin[z] = bin;
           mySlot[z] = atomAdd(&hist[bin], 1);
         }
       }
       p.sync();
       { // above[bin] = survivors in higher bins; every warp scans, warp 0 publishes
-        int h[16];
-        int own = 0;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          h[k] = k < perLane ? hist[lane * perLane + k] : 0;
-          own += h[k];
-        }
+        const int4 h4 = *(const int4*)(hist + lane * 4);
+        const int own = (h4.x + h4.y) + (h4.z + h4.w);
         int suf = own;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const int u = __shfl_down_sync(0xffffffffu, suf, o);
           if (lane + o < 32) suf += u;
         }
+        int4 a4;
         int ab = suf - own;
-        if (warp == 0) {
-#pragma unroll
-          for (int k = 15; k >= 0; --k)
-            if (k < perLane) {
-              above[lane * perLane + k] = ab;
-              ab += h[k];
-            }
-        }
+        a4.w = ab;
+        ab += h4.w;
+        a4.z = ab;
+        ab += h4.z;
+        a4.y = ab;
+        ab += h4.y;
+        a4.x = ab;
+        if (warp == 0) *(int4*)(above + lane * 4) = a4;
       }
       p.sync();
       // survivors grouped by bin (best bins first); only those that can rank < want are placed
@@ -357,7 +350,7 @@ FLT_DEV void streamRow(const Cta& p, const TopMCfg& c, TopMSmem& s, ProdGuess& p
         outVal[j] = 0.0f;
       }
       p.sync();
-      for (int bn = p.tid; bn < NBk; bn += p.nthr) hist[bn] = 0;
+      for (int bn = p.tid; bn < kProdBins; bn += p.nthr) hist[bn] = 0;
       if (p.tid == 0) s.cnt[0] = 0;
       // next row's guess: below this row's want-th value by a margin that tracks the survivor count
       const float wth = bitsF32((uint32_t)s.cnt[1]);
@@ -373,7 +366,7 @@ FLT_DEV void streamRow(const Cta& p, const TopMCfg& c, TopMSmem& s, ProdGuess& p
     }
     // adversarial row (ties en masse, -inf padding) or a long list in exact mode: generic path below
     p.sync(); // everyone has read cnt[0]
-    for (int bn = p.tid; bn < NBk; bn += p.nthr) hist[bn] = 0;
+    for (int bn = p.tid; bn < kProdBins; bn += p.nthr) hist[bn] = 0;
     if (p.tid == 0) s.cnt[0] = 0;
     pg.g = bitsF32(0x7F800000u);
     p.sync();
@@ -424,7 +417,7 @@ struct StreamLay { // byte offsets from the CTA's shared-memory base
 FLT_DEV void topmStreamCta(const Cta& p, const TopMCfg& tc, const StreamLay& sl, const TopMArgs& a, char* smem) {
   TopMSmem ps;
   carveTopM(smem + sl.prod, tc, ps);
-  for (int i = p.tid; i < tc.extra + tc.capS; i += p.nthr) ps.rankCnt[i] = 0;
+  for (int i = p.tid; i < 2 * kProdBins + tc.capS; i += p.nthr) ps.rankCnt[i] = 0;
   if (p.tid < 4) ps.cnt[p.tid] = 0;
   float dummyThr = 0.0f;
   ProdGuess pg{bitsF32(0x7F800000u), 0.25f, 0.0f, 0, 64};

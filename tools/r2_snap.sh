@@ -31,3 +31,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --cs
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:flt_k_fused -s 1 -c 1 \
   -o $OUT/prof python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-secondary > $OUT/prof.log 2>&1
 du -sh $OUT; ls -la $OUT
+# the lexicon step (cfg 3, T = 100): full capture for the source-level counters of the north star's target kernel
+( timeout 900 ncu --set full --clock-control none --import-source on -k regex:flt_k_decode512 -s 1 -c 1 \
+  -o $OUT/prof_lexicon python bench.py --steps 1 --warmup 1 --frames 100 --workload lexicon --no-e2e --no-cpu-baseline ) > $OUT/prof_lexicon.log 2>&1
+ls -la $OUT | tail -5
