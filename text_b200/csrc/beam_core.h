@@ -208,8 +208,11 @@ struct Rows {
   FLT_DEV int* deg() const { return iv + 5 * K + 2; }          // [K+1]
   FLT_DEV int* degTmp() const { return iv + 6 * K + 3; }       // [K+1]
   FLT_DEV int& slotOf(int i) const { return iv[7 * K + 4 + i]; } // row-table slot of hyp i
+  // [K] first Trie edge of hyp i's node. (64 ints further on: the scan's scratch degTmp() takes up to 64 ints
+  // whatever K is and may run over slotOf(), which is dead by then — but must not reach this array.)
+  FLT_DEV int* eoff() const { return iv + 8 * K + 4 + 64; }
 };
-constexpr int kRowsInts = 8; // K-sized int arrays (+ slack) behind Rows::iv
+constexpr int kRowsInts = 9; // K-sized int arrays (+ slack) behind Rows::iv
 
 enum { // ws.sc[] scalars
   SC_NH = 0, SC_NCAND, SC_NREP, SC_NSEL, SC_NROWS, SC_OVF, SC_BIN, SC_NEED, SC_BINCOUNT, SC_NICE,
@@ -305,7 +308,7 @@ FLT_HD void makeLayout(DecCfg& c) {
     L.beamX[b] = take(gxl ? sizeof(int) * 3 * K : 0); // inside the beam block: saved / restored with it
   }
   L.rowHash = take(gx ? 0 : sizeof(int) * (lf ? 2 : 1) * c.capRH); // beam_lf.h: one fingerprint table per beam
-  L.rowI = take(lf || gx ? 0 : sizeof(int) * (kRowsInts * K + 8));
+  L.rowI = take(lf || gx ? 0 : sizeof(int) * (kRowsInts * K + 8 + 64));
   L.candScore = takeBig(sizeof(double) * c.capC);
   L.candKey = takeBig(sizeof(u64) * (lf ? 1 : 2) * c.capC);
   L.candI = takeBig(sizeof(int) * (lf ? 3 : 6) * c.capC);
@@ -1529,6 +1532,17 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
     if (c.ctc) eBlank = f.e[c.blank];
     eSil = f.e[c.sil];
   }
+  // ... and the Trie offsets of this thread's hypothesis (two L2 loads): degree and first edge, consumed by the
+  // degree scan after the row grouping; the first edge is kept per hypothesis so that an edge item does not
+  // chase childOff[lex] again (one L2 level less in every edge item of both passes)
+  int myDeg = 0, myEoff = 0;
+  if (c.lexicon && cta.tid < nH) {
+    const int lex = cur.lex(cta.tid);
+    if (!(lex == 0 && (c.wideRanked || rootList))) {
+      myEoff = c.trie.childOff[lex];
+      myDeg = c.trie.childOff[lex + 1] - myEoff;
+    }
+  }
   // lexicon, ranked rows: what the ~K ln K wide cells need to know about the root child of each list
   // token (node, has children, smeared score) is gathered ONCE per list entry, by the threads at the
   // far end of the CTA, instead of once per cell
@@ -1633,11 +1647,18 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
   if (c.lexicon) {
     const TrieDev& t = c.trie;
     int* deg = w.rows().deg();
+    int* eoff = w.rows().eoff();
     for (int i = cta.tid; i < nH; i += cta.nthr) {
       const int lex = cur.lex(i);
       if (lex == 0 && c.wideRanked) deg[i] = t.nRootLab;
       else if (lex == 0 && rootList) deg[i] = f.listLen;
-      else deg[i] = t.childOff[lex + 1] - t.childOff[lex];
+      else if (i == cta.tid) { // loaded at the top of the frame
+        deg[i] = myDeg;
+        eoff[i] = myEoff;
+      } else { // beams wider than the CTA
+        eoff[i] = t.childOff[lex];
+        deg[i] = t.childOff[lex + 1] - eoff[i];
+      }
     }
     cta.sync();
     ctaExclusiveScan(cta, deg, w.rows().degTmp(), nH);
@@ -1682,7 +1703,7 @@ FLT_DEV void frameStep(const Cta& cta, const DecCfg& c, const Ws& w, const Beam&
         const int child = n >= 0 ? t.rootChild[n] : -1;
         if (child >= 0) emitEdge<W>(cta, c, wp, cur, f, i, n, child, false, tau);
       } else {
-        const int e = t.childOff[lex] + k;
+        const int e = w.rows().eoff()[i] + k;
         emitEdge<W>(cta, c, wp, cur, f, i, t.childTok[e], t.childNode[e], false, tau);
       }
     };

@@ -25,6 +25,7 @@
 #include "topm_core.h"
 #include "fused_core.h"
 #include "topm_stream.h"
+#include "kernels.h"
 
 using namespace flt;
 
@@ -47,64 +48,8 @@ __global__ void __launch_bounds__(kStreamThreads, 4) flt_k_topm_stream(TopMCfg c
   Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
   topmStreamCta(cta, c, sl, a, smem);
 }
-// workspace in shared memory (the fast path: every access is an LDS/STS with constant-bank offsets)
-__global__ void __launch_bounds__(256) flt_k_decode(DecCfg c, BatchArgs a) {
-  extern __shared__ __align__(128) char smem[];
-  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
-  decodeCta<false>(cta, c, a, smem);
-}
-// same, 512 threads per utterance (two CTAs per SM): small batches leave SMs under-occupied
-__global__ void __launch_bounds__(512, 2) flt_k_decode512(DecCfg c, BatchArgs a) {
-  extern __shared__ __align__(128) char smem[];
-  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
-  decodeCta<false>(cta, c, a, smem);
-}
-// 1024 threads per utterance: beams so wide (K = 500) that the small workspace region leaves room for one
-// CTA per SM only — the items of a frame (thousands) are then spread over all 32 warps the SM can hold
-__global__ void __launch_bounds__(1024, 1) flt_k_decode1024(DecCfg c, BatchArgs a) {
-  extern __shared__ __align__(128) char smem[];
-  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
-  decodeCta<false>(cta, c, a, smem);
-}
-// workspace in a global slab per CTA (beams / candidate sets too large for shared memory)
-__global__ void __launch_bounds__(256) flt_k_decode_gmem(DecCfg c, BatchArgs a) {
-  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
-  decodeCta<false>(cta, c, a, a.wsGlobal + (long long)blockIdx.x * a.wsStride);
-}
-// the same three with the full-expansion paths compiled in (DecCfg::wide: logAdd merging, token-level
-// LMs, unranked rows walking the token list); kept out of the kernels above, which they slowed by 6 %
-__global__ void __launch_bounds__(256) flt_k_decode_wide(DecCfg c, BatchArgs a) {
-  extern __shared__ __align__(128) char smem[];
-  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
-  decodeCta<true>(cta, c, a, smem);
-}
-__global__ void __launch_bounds__(512, 2) flt_k_decode512_wide(DecCfg c, BatchArgs a) {
-  extern __shared__ __align__(128) char smem[];
-  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
-  decodeCta<true>(cta, c, a, smem);
-}
-__global__ void __launch_bounds__(256) flt_k_decode_gmem_wide(DecCfg c, BatchArgs a) {
-  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
-  decodeCta<true>(cta, c, a, a.wsGlobal + (long long)blockIdx.x * a.wsStride);
-}
-// the single-pass step with a guessed cut (beam_gx.h), two-kernel path: token lists from flt_k_topm
-template <bool LEX>
-__global__ void __launch_bounds__(256) flt_k_gx(DecCfg c, BatchArgs a) {
-  extern __shared__ __align__(128) char smem[];
-  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
-  gxDecodeCta<LEX>(cta, c, a, smem);
-}
-template <bool LEX>
-__global__ void __launch_bounds__(512, 2) flt_k_gx512(DecCfg c, BatchArgs a) {
-  extern __shared__ __align__(128) char smem[];
-  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
-  gxDecodeCta<LEX>(cta, c, a, smem);
-}
-template <bool LEX>
-__global__ void __launch_bounds__(256) flt_k_gx_gmem(DecCfg c, BatchArgs a) {
-  Cta cta{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
-  gxDecodeCta<LEX>(cta, c, a, a.wsGlobal + (long long)blockIdx.x * a.wsStride);
-}
+// the beam-step kernels live in their own translation units (kern_step.cu, one object per kernel, and
+// kern_gx.cu: declared in kernels.h) so that the library's device code compiles in parallel
 // token-beam select + beam step fused: 8 consumer + 4 producer warps per utterance (fused_core.h)
 __global__ void __launch_bounds__(kFusedConsumers + kFusedProducers, 2)
     flt_k_fused(DecCfg c, TopMCfg tc, FuseLay fl, BatchArgs a) {
@@ -210,9 +155,9 @@ bool planStream(int N, int M, int bst, const float* dBias, float biasMax, TopMCf
 void launchDecode(const DecCfg& c, const BatchArgs& a, int grid, size_t smem, rt::Stream s, int threads) {
 #if FLT_DEVICE_BUILD
   if (c.gx) {
-    if (smem && threads == 512) (c.lexicon ? flt_k_gx512<true> : flt_k_gx512<false>)<<<grid, 512, smem, s>>>(c, a);
-    else if (smem) (c.lexicon ? flt_k_gx<true> : flt_k_gx<false>)<<<grid, threads, smem, s>>>(c, a);
-    else (c.lexicon ? flt_k_gx_gmem<true> : flt_k_gx_gmem<false>)<<<grid, threads > 256 ? 256 : threads, 0, s>>>(c, a);
+    if (smem && threads == 512) (c.lexicon ? flt_k_gx512_lex : flt_k_gx512_lf)<<<grid, 512, smem, s>>>(c, a);
+    else if (smem) (c.lexicon ? flt_k_gx_lex : flt_k_gx_lf)<<<grid, threads, smem, s>>>(c, a);
+    else (c.lexicon ? flt_k_gx_gmem_lex : flt_k_gx_gmem_lf)<<<grid, threads > 256 ? 256 : threads, 0, s>>>(c, a);
   } else if (smem && threads == 1024 && !c.wide) flt_k_decode1024<<<grid, 1024, smem, s>>>(c, a);
   else if (smem && threads >= 512) (c.wide ? flt_k_decode512_wide : flt_k_decode512)<<<grid, 512, smem, s>>>(c, a);
   else if (smem) (c.wide ? flt_k_decode_wide : flt_k_decode)<<<grid, threads, smem, s>>>(c, a);
@@ -933,10 +878,10 @@ void planFor(flt_decoder& d, int N) {
   d.smemBytes = smemOk ? d.wsBytes : (hybrid ? smallBytes : 0);
   d.slabBytes = smemOk ? 0 : (hybrid ? ((size_t)c.lay.bigBytes + 255) / 256 * 256 : d.wsBytes);
   int occ2 = 1;
-  auto* k256 = c.gx ? (c.lexicon ? flt_k_gx<true> : flt_k_gx<false>) : (c.wide ? flt_k_decode_wide : flt_k_decode);
-  auto* k512 = c.gx ? (c.lexicon ? flt_k_gx512<true> : flt_k_gx512<false>)
+  auto* k256 = c.gx ? (c.lexicon ? flt_k_gx_lex : flt_k_gx_lf) : (c.wide ? flt_k_decode_wide : flt_k_decode);
+  auto* k512 = c.gx ? (c.lexicon ? flt_k_gx512_lex : flt_k_gx512_lf)
                     : (c.wide ? flt_k_decode512_wide : flt_k_decode512);
-  auto* kGmem = c.gx ? (c.lexicon ? flt_k_gx_gmem<true> : flt_k_gx_gmem<false>)
+  auto* kGmem = c.gx ? (c.lexicon ? flt_k_gx_gmem_lex : flt_k_gx_gmem_lf)
                      : (c.wide ? flt_k_decode_gmem_wide : flt_k_decode_gmem);
   if (d.smemBytes) {
     FLT_RT_TRY(cudaFuncSetAttribute(k256, cudaFuncAttributeMaxDynamicSharedMemorySize,

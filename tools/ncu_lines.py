@@ -16,8 +16,9 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(root, "text_b200", "lib", "libflt_decoder.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+# (the library holds one cubin per translation unit: all of them)
+dis = "".join(subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cb)], capture_output=True, text=True).stdout
+              for cb in sorted(os.listdir(tmp)) if cb.endswith(".cubin"))
 # offset -> (file,line) for the kernel
 line_of, cur, inside = {}, None, False
 for l in dis.splitlines():
