@@ -15,15 +15,23 @@ top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(root, "text_b200", "lib", "libflt_decoder.so")
 tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, capture_output=True)
-# (the library holds one cubin per translation unit: all of them)
-dis = "".join(subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cb)], capture_output=True, text=True).stdout
-              for cb in sorted(os.listdir(tmp)) if cb.endswith(".cubin"))
+# one cubin per translation unit; the seven objects of kern_step.cu carry cubins of the same name, so each
+# object file (text_b200/build/*.o, else the library) is unpacked into a directory of its own
+build = os.path.join(root, "text_b200", "build")
+units = sorted(os.path.join(build, f) for f in os.listdir(build) if f.endswith(".o")) if os.path.isdir(build) else [so]
+dis = ""
+for k, unit in enumerate(units):
+    d = os.path.join(tmp, str(k))
+    os.makedirs(d)
+    subprocess.run(["cuobjdump", "-xelf", "all", unit], cwd=d, capture_output=True)
+    for cb in sorted(os.listdir(d)):
+        if cb.endswith(".cubin"):
+            dis += subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cb)], capture_output=True, text=True).stdout
 # offset -> (file,line) for the kernel
 line_of, cur, inside = {}, None, False
 for l in dis.splitlines():
     if l.startswith("\t.section\t.text."):
-        inside = kern in l
+        inside = re.search(re.escape(kern) + r"(N3flt|[^A-Za-z0-9_])", l) is not None  # not flt_k_x_wide for flt_k_x
     if not inside:
         continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
