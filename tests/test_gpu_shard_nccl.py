@@ -2,9 +2,10 @@
 scatters a host-originated batch, every rank decodes its block with the CUDA library through the C-ABI, the
 n-best blocks are gathered back to rank 0 straight from the decoders' device buffers — must give, bit for bit,
 what one GPU decoding the whole batch gives (utterances are independent, nothing else is
-exchanged). Needs two GPUs on the box (`gpurun --gpus 2`); on a one-GPU box the test is skipped — the same
-functions are covered there with gloo and a stub decode (tests/test_shard_gloo.py), and bench.py checks the
-gathered result of its own multi-GPU e2e leg against every rank's local one."""
+exchanged). With two GPUs on the box (`gpurun --gpus 2`) the ranks use one GPU each and NCCL; on a one-GPU box
+the same test runs with two gloo ranks that both decode on cuda:0 and exchange host tensors (NCCL refuses two
+ranks on one device), so the sharding logic is still checked against a real decode; bench.py checks the gathered
+result of its own multi-GPU e2e leg against every rank's local one."""
 import os
 import socket
 import sys
@@ -24,7 +25,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, kind, q):
+def _worker(rank, world, port, kind, q, one_gpu=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -36,9 +37,14 @@ def _worker(rank, world, port, kind, q):
     from flt_backend import FltBackend
     from text_b200 import shard, synth
 
-    torch.cuda.set_device(rank)
-    dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    ordinal = 0 if one_gpu else rank
+    torch.cuda.set_device(ordinal)
+    dev = torch.device("cuda", ordinal)
+    if one_gpu:  # two ranks share the GPU: gloo, host tensors on the wire
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    else:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    wire = torch.device("cpu") if one_gpu else dev
     try:
         N, T, B, K = 400, 60, 11, 30  # B not divisible by the world size: ragged blocks
         if kind == "lexfree":
@@ -46,12 +52,16 @@ def _worker(rank, world, port, kind, q):
         else:
             spec = spec_lexicon(N, K, N, synth.lexicon(3000, N, 2, 4, seed=7, exclude=(0, N - 1)), 25.0, word_score=0.3)
         G = FltBackend("cuda")
-        G.api.device = rank
+        G.api.device = ordinal
         built = Built(G, spec)
         api, dec = G.api, built.dec
 
         def decode_local(block):
             Bl = block.shape[0]
+            if one_gpu:  # the block arrived as a host tensor: flt_decode_batch takes host pointers too
+                block = block.contiguous()
+                api.decode_batch_ptr(dec, block.data_ptr(), Bl, T, N)
+                return api.nbest(dec, Bl, T, K)
             api.decode_batch_ptr(dec, block.data_ptr(), Bl, T, N)
             api.synchronize(dec)
             nb = api.nbest_device(dec, Bl, T, K, K)  # device tensors aliasing the decoder's buffers
@@ -59,9 +69,10 @@ def _worker(rank, world, port, kind, q):
 
         em = None
         if rank == 0:
-            em = torch.from_numpy(synth.emissions(B, T, N, seed=5, sigma=2.0)).to(dev)
-        out = shard.decode_sharded(decode_local, em, (B, T, N), K, dev)
+            em = torch.from_numpy(synth.emissions(B, T, N, seed=5, sigma=2.0)).to(wire)
+        out = shard.decode_sharded(decode_local, em, (B, T, N), K, wire)
         if rank == 0:
+            em = em.to(dev)
             api.decode_batch_ptr(dec, em.data_ptr(), B, T, N)
             full = api.nbest(dec, B, T, K)
             ok = True
@@ -82,13 +93,12 @@ def test_nccl_sharded_decode_equals_one_gpu(kind):
     import torch
     import torch.multiprocessing as mp
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs on the box (run with gpurun --gpus 2)")
+    one_gpu = torch.cuda.device_count() < 2
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, kind, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, kind, q, one_gpu)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
@@ -104,8 +114,7 @@ def test_one_trie_and_lm_shared_by_decoders_on_two_devices():
     current device is what it was before each call."""
     import torch
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs on the box (run with gpurun --gpus 2)")
+    second = 1 if torch.cuda.device_count() >= 2 else 0  # one GPU: two decoders share the tables on it
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import parity_cases
     from flt_backend import FltBackend
@@ -120,7 +129,7 @@ def test_one_trie_and_lm_shared_by_decoders_on_two_devices():
     api.trie_smear(trie, spec["smear"])
     torch.cuda.set_device(0)
     res = []
-    for device in (0, 1, 0):
+    for device in (0, second, 0):
         api.device = device
         dec = G.decoder_lexicon(spec["opt"], trie, lm, spec["sil"], spec["blank"], spec["unk"])
         res.append(G.decode_batch(dec, em, spec["opt"].beamSize))

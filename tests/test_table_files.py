@@ -188,3 +188,27 @@ def test_load_is_faster_than_rebuilding(api, tmp_path):
     assert api.trie_num_nodes(t2) == api.trie_num_nodes(t)
     assert load < build, (load, build)
     api.trie_destroy(t), api.trie_destroy(t2)
+
+
+@pytest.mark.gpu
+def test_decode_from_loaded_tables_cuda(tmp_path):
+    """the same on the device: tables loaded from their files are flattened / uploaded like built ones"""
+    G, A = FltBackend("cuda"), po.Oracle("ora")
+    N, W = 64, 400
+    path, words = _arpa(tmp_path, vocab=W, counts=(0, 2500, 1200))
+    sp = synth.lexicon(W, N, 1, 4, seed=9, exclude=(0, N - 1))
+    spec = spec_lexicon(N, 20, N, sp, 50.0, lm_weight=1.5, word_score=0.4, lm=("arpa", path, words), unk=W)
+    em = synth.emissions(4, 40, N, seed=4)
+    ba, bg = Built(A, spec), Built(G, spec)
+    want = [ba.decode(em[b]) for b in range(len(em))]
+    got = bg.O.decode_batch(bg.dec, em, 20)
+    lp, tp = str(tmp_path / "lm.flt"), str(tmp_path / "trie.flt")
+    G.api.lm_save(bg.lm, lp), G.api.trie_save(bg.trie, tp)
+    lm2, trie2 = G.api.lm_arpa(lp, words), G.api.trie_load(tp)
+    dec2 = G.decoder_lexicon(spec["opt"], trie2, lm2, spec["sil"], spec["blank"], spec["unk"])
+    got2 = G.decode_batch(dec2, em, 20)
+    for b in range(len(em)):
+        assert_same_nbest(want[b], got[b], 1e-4, what=f"built {b}")
+        assert_same_nbest(got[b], got2[b], 0.0, what=f"loaded {b}")
+    G.decoder_destroy(dec2), G.api.trie_destroy(trie2), G.api.lm_destroy(lm2)
+    ba.close(), bg.close()
