@@ -72,6 +72,14 @@ def workload_name(a, beam, bst):
             f"batch={a.batch}/GPU")
 
 
+def config_of(a, beam, bst, nbest):
+    """the workload description both arms print (identical dicts: the driver compares them)"""
+    h2d = a.batch * a.frames * a.tokens * 4
+    return {"workload": workload_name(a, beam, bst), "emissions": f"log_softmax({a.sigma}*N(0,1)) fp32",
+            "nbest": nbest, "beamThreshold": a.threshold,
+            "l2": f"inputs ({h2d / 1e9:.2f} GB/step/GPU) exceed L2 (126 MB); no flush needed"}
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -238,7 +246,8 @@ def run_reference(a):
            "frames_per_s": v * a.frames, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": float(np.mean(walls)) * 1e3,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-           "data": "synthetic", "config": {"workload": workload_name(a, beam, bst)},
+           "data": "synthetic", "config": config_of(a, beam, bst, a.nbest or beam),
+           "timing": "wall clock of the multi-threaded decode of a bounded sample (see cpu_baseline.sample)",
            "cpu_baseline": {"value": v, "unit": "utt/s", "cores": threads, "kind": kind, "sample": desc,
                             "note": "one step = the timed multi-threaded decode of that sample; beamSizeToken = N is "
                                     "the CPU-hostile setting (the reference expands beam x N candidates per frame), "
@@ -694,10 +703,8 @@ def run_ours(a):
            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": main["ms_per_step"],
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic",
-           "config": {"workload": main["workload"], "emissions": f"log_softmax({a.sigma}*N(0,1)) fp32",
-                      "nbest": main["nbest"], "beamThreshold": a.threshold,
-                      "l2": f"inputs ({h2d / 1e9:.2f} GB/step/GPU) exceed L2 (126 MB); no flush needed",
-                      "timing": "CUDA events on the decoder's stream around exactly K steps, max over ranks"},
+           "config": config_of(a, main["beam"], main["bst"], main["nbest"]),
+           "timing": "CUDA events on the decoder's stream around exactly K steps, max over ranks",
            "roofline": main["roofline"], "kernels": main["kernels"], "beam_step_work": main["beam_step_work"],
            "cpu_baseline": main["cpu_baseline"], "cpu_baseline_bst_beam": main["cpu_baseline_bst_beam"],
            "e2e": main["e2e"], "gpu_launches": main["launches"], "clocks": main["clocks"], "parity": main["parity"],
