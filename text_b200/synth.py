@@ -88,9 +88,15 @@ def write_arpa(path, W, order=4, counts=None, seed=11, with_unk=True):
         nxt = rng.integers(0, V, size=len(pick))
         nxt[nxt == bos] = eos
         cand = np.concatenate([pick, nxt[:, None]], axis=1)
-        cand = np.unique(cand, axis=0)
+        # distinct rows in lexicographic order (= np.unique(cand, axis=0), several times faster)
+        order_ = np.lexsort(cand.T[::-1])
+        cand = cand[order_]
+        keep = np.ones(len(cand), dtype=bool)
+        keep[1:] = (cand[1:] != cand[:-1]).any(axis=1)
+        cand = cand[keep]
         rng.shuffle(cand)
         levels.append(cand[:want])
+    varr = np.array(vocab, dtype=object)
     with open(path, "w") as f:
         f.write("\\data\\\n")
         for k, lv in enumerate(levels):
@@ -100,16 +106,21 @@ def write_arpa(path, W, order=4, counts=None, seed=11, with_unk=True):
             probs = -(rng.random(len(lv)) * 5.9 + 0.1)
             bows = -rng.random(len(lv))
             last = k == order - 1
-            lines = []
-            for i, row in enumerate(lv):
-                ws = " ".join(vocab[j] for j in row)
-                if k == 0 and vocab[row[0]] == "<s>":
-                    lines.append(f"-99\t{ws}\t{bows[i]:.6f}\n")
-                elif last or vocab[row[-1]] == "</s>":
-                    lines.append(f"{probs[i]:.6f}\t{ws}\n")
-                else:
-                    lines.append(f"{probs[i]:.6f}\t{ws}\t{bows[i]:.6f}\n")
-            f.writelines(lines)
+            # vectorised formatting (5 M lines in a Python loop took most of the benchmark's set-up time)
+            ws = varr[lv[:, 0]]
+            for col in range(1, lv.shape[1]):
+                ws = ws + " " + varr[lv[:, col]]
+            ps = np.char.mod("%.6f", probs).astype(object)
+            bs = np.char.mod("%.6f", bows).astype(object)
+            with_bow = ps + "\t" + ws + "\t" + bs + "\n"
+            without = ps + "\t" + ws + "\n"
+            ends_eos = lv[:, -1] == eos
+            lines = without if last else np.where(ends_eos, without, with_bow)
+            if k == 0:
+                i_bos = int(np.nonzero(lv[:, 0] == bos)[0][0])
+                lines = lines.copy()
+                lines[i_bos] = "-99\t" + ws[i_bos] + "\t" + bs[i_bos] + "\n"
+            f.write("".join(lines.tolist()))
         f.write("\n\\end\\\n")
     return [len(lv) for lv in levels]
 
