@@ -157,7 +157,8 @@ void loadTrie(const std::string& path, flt_trie& t) {
   const size_t nn = meta.size() == 3 ? (size_t)meta[2] : 0;
   if (nn == 0 || childOff.size() != nn + 1 || labelOff.size() != nn + 1 || maxScore.size() != nn ||
       childTok.size() != childNode.size() || labels.size() != scores.size() ||
-      (size_t)childOff[nn] != childTok.size() || (size_t)labelOff[nn] != labels.size())
+      childOff[0] != 0 || labelOff[0] != 0 || (size_t)childOff[nn] != childTok.size() ||
+      (size_t)labelOff[nn] != labels.size())
     throw FltError(FLT_ERR_RUNTIME, path + ": inconsistent Trie sections");
   t.maxChildren = meta[0];
   t.rootIdx = meta[1];
@@ -168,7 +169,9 @@ void loadTrie(const std::string& path, flt_trie& t) {
       throw FltError(FLT_ERR_RUNTIME, path + ": inconsistent Trie offsets");
     auto hint = nd.kids.end();
     for (int e = childOff[i]; e < childOff[i + 1]; ++e) {
-      if (childNode[e] <= 0 || (size_t)childNode[e] >= nn) throw FltError(FLT_ERR_RUNTIME, path + ": bad Trie edge");
+      // (an edge's token indexes the emission row on the device: same range as Trie::insert enforces)
+      if (childNode[e] <= 0 || (size_t)childNode[e] >= nn || childTok[e] < 0 || childTok[e] >= meta[0])
+        throw FltError(FLT_ERR_RUNTIME, path + ": bad Trie edge");
       hint = nd.kids.emplace_hint(hint, childTok[e], childNode[e]);
     }
     nd.labels.assign(labels.begin() + labelOff[i], labels.begin() + labelOff[i + 1]);
