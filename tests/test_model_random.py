@@ -153,3 +153,12 @@ def test_lexicon_random(A, M, seed):
 @pytest.mark.parametrize("seed", [20, 21])
 def test_widened_random(A, M, seed):
     run_random(A, M, draw_widened, seed, 40, 1e-9)
+
+
+@pytest.mark.parametrize("seed", [12, 22])
+def test_random_split_workspace(A, M, seed, monkeypatch):
+    """the same draws with the capacity-sized arrays in a region of their own (what the device does when a wide
+    beam outgrows shared memory; FLT_TEST_HYBRID makes the logic harness do it for every configuration):
+    lexicon decoder incl. n-gram LMs, and the full-expansion modes"""
+    monkeypatch.setenv("FLT_TEST_HYBRID", "1")
+    run_random(A, M, draw_lexicon if seed < 20 else draw_widened, seed, 25, 1e-9)
